@@ -1,0 +1,401 @@
+// C ABI of libclasspose_b200.so (see include/classpose_b200.h).  Host side only: argument
+// checks, workspace carving, kernel launch sequences.  No host synchronisation, no global
+// mutable state; every call runs on the caller's stream with the caller's workspace.
+#include "classpose_b200.h"
+
+#include "cpb_platform.h"
+#include "cpb_common.cuh"
+#include "cpb_flow.cuh"
+#include "cpb_masks.cuh"
+#include "cpb_tables.cuh"
+#include "cpb_qc.cuh"
+#include "cpb_post.cuh"
+
+#ifndef CPB_SIM
+#include <mutex>
+#endif
+
+namespace {
+
+constexpr int kLabelBlocksPerTile = 24;   // per-label kernels: grid (kLabelBlocksPerTile, B)
+constexpr int kVoteSmemInts = 16 * 1024;  // 64 KB table for the class vote
+constexpr size_t kAlign = 256;
+
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct Carver {
+    char* base; size_t off;
+    template <class T> T* take(size_t n) {
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off = align_up(off + n * sizeof(T));
+        return p;
+    }
+};
+
+struct Workspace {
+    float2* flow;        // [B*N]
+    int* pfinal;         // [B*N]
+    int* hist;           // [B*N]
+    int* M;              // [B*N]
+    double* T;           // [B*N]
+    double* T2;          // [B*N]   (aliases holekey)
+    u64* holekey;        // [B*N]
+    unsigned* list;      // [B*N]
+    unsigned* list_n;    // [1] (+ status word)
+    int* status;
+    u64* skey;           // [B*LC]
+    int* sidx;           // [B*LC]
+    int* vote;           // [B*LC*C]
+    LabelTables t;
+    size_t bytes;
+};
+
+Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
+    Workspace w{};
+    const size_t N = (size_t)H * W, BN = (size_t)B * N;
+    const int LC = lcap > 0 ? lcap : cpb_label_capacity(H, W);
+    const size_t BL = (size_t)B * LC;
+    Carver c{reinterpret_cast<char*>(base), 0};
+    w.flow = c.take<float2>(BN);
+    w.pfinal = c.take<int>(BN);
+    w.hist = c.take<int>(BN);
+    w.M = c.take<int>(BN);
+    w.T = c.take<double>(BN);
+    w.T2 = c.take<double>(BN);
+    w.holekey = reinterpret_cast<u64*>(w.T2);
+    w.list = c.take<unsigned>(BN);
+    w.list_n = c.take<unsigned>(64);
+    w.status = reinterpret_cast<int*>(w.list_n) + 1;
+    w.skey = c.take<u64>(BL);
+    w.sidx = c.take<int>(BL);
+    w.vote = c.take<int>(C > 0 ? BL * C : 0);
+    LabelTables& t = w.t;
+    t.LC = LC;
+    t.cnt = c.take<int>(BL); t.first = c.take<int>(BL);
+    t.ymin = c.take<int>(BL); t.ymax = c.take<int>(BL); t.xmin = c.take<int>(BL); t.xmax = c.take<int>(BL);
+    t.sumy = c.take<u64>(BL); t.sumx = c.take<u64>(BL);
+    t.remap = c.take<int>(BL); t.flag = c.take<int>(BL);
+    t.cy = c.take<int>(BL); t.cx = c.take<int>(BL);
+    t.err = c.take<double>(BL);
+    t.lbound = c.take<int>(B); t.nlab = c.take<int>(B); t.niter = c.take<int>(B); t.misc = c.take<int>(B);
+    w.bytes = c.off;
+    return w;
+}
+
+int check_geom(int B, int H, int W) {
+    if (B <= 0 || H < 2 || W < 2 || H > 32767 || W > 32767) return CPB_E_ARG;
+    if ((long long)B * H * W >= (1LL << 31)) return CPB_E_RANGE;
+    return 0;
+}
+
+inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+#ifndef CPB_SIM
+void ensure_attributes() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaFuncSetAttribute(k_fill_holes, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CPB_FILL_WORDS * 4);
+        cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, kVoteSmemInts * 4);
+    });
+}
+int sm_count() {
+    static int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev);
+                        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v > 0 ? v : 148; }();
+    return n;
+}
+#else
+void ensure_attributes() {}
+int sm_count() { return 4; }
+#endif
+
+#define CPB_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+// ---- stage launch sequences (all asynchronous on `st`) ---------------------------------------
+
+int run_init_tables(const Workspace& w, int B, cudaStream_t st) {
+    CPB_LAUNCH(k_init_tables, dim3(blocks_for(w.t.LC, 256), B), dim3(256), 0, st, w.t);
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
+int run_set_lbound(const Workspace& w, int B, int v, cudaStream_t st) {
+    CPB_LAUNCH(k_fill_i32, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t.lbound, B, v);
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
+// map labels (remap / drop flags / hole keys) and optionally regather statistics
+int run_map_stats(const Workspace& w, int32_t* lab, int B, int H, int W, int nch, const int* map,
+                  const int* drop, const u64* holekey, bool stats, cudaStream_t st) {
+    if (stats) { int e = run_init_tables(w, B, st); if (e) return e; }
+    CPB_LAUNCH(k_map_stats, dim3(blocks_for((long long)B * H * W, 256)), dim3(256), 0, st, lab, B, H, W, nch,
+               map, drop, holekey, stats ? 1 : 0, w.t);
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
+int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B, int H, int W, int niter,
+               float thr, int32_t* pfinal, float* pfloat, int* hist, cudaStream_t st) {
+    const long long BN = (long long)B * H * W;
+    cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
+    if (hist) cudaMemsetAsync(hist, 0, BN * sizeof(int), st);
+    const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
+    CPB_LAUNCH(k_prep_flow, dim3(blocks_for(BN, 256)), dim3(256), 0, st, dP, cellprob, B, H, W, thr, sx, sy,
+               w.flow, pfinal, w.list, w.list_n);
+    CPB_CHECK_LAUNCH();
+    const unsigned grid = (unsigned)std::min<long long>(blocks_for(BN, 256), (long long)sm_count() * 8);
+    CPB_LAUNCH(k_follow, dim3(grid), dim3(256), 0, st, w.flow, w.list, w.list_n, H, W, niter, pfinal, pfloat, hist);
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
+// end points (+ histogram already in w.hist) -> contiguous labels in `masks`
+int run_get_masks(const Workspace& w, const int32_t* pfinal, int B, int H, int W, double msf, int32_t* masks,
+                  int32_t* counts, cudaStream_t st) {
+    const long long BN = (long long)B * H * W;
+    cudaMemsetAsync(w.M, 0, BN * sizeof(int), st);
+    CPB_LAUNCH(k_seeds, dim3(B), dim3(256), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.M, w.t.lbound);
+    CPB_CHECK_LAUNCH();
+    int e = run_init_tables(w, B, st); if (e) return e;
+    CPB_LAUNCH(k_lookup, dim3(blocks_for(BN, 256)), dim3(256), 0, st, pfinal, w.M, B, H, W, masks, w.t);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH(k_gm_finalize, dim3(B), dim3(256), 0, st, w.t, H, W, msf, w.skey, w.sidx, counts);
+    CPB_CHECK_LAUNCH();
+    return 0;   // caller applies w.t.remap
+}
+
+// labels with statistics in the tables -> T (and mu / err / bad flags)
+int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B, int H, int W, double thr,
+                double* mu_out, cudaStream_t st) {
+    cudaMemsetAsync(w.t.niter, 0, B * sizeof(int), st);
+    const dim3 grid(kLabelBlocksPerTile, B);
+    CPB_LAUNCH(k_centres, grid, dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t);
+    CPB_CHECK_LAUNCH();
+    const size_t smem = (size_t)CPB_DIFF_SMEM_CELLS * 17;
+    CPB_LAUNCH(k_diffuse, grid, dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH(k_flow_err, grid, dim3(CPB_QC_THREADS), 0, st, masks, dP, H, W, w.t, w.T, thr, mu_out);
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
+// fill_holes_and_remove_small_masks on `masks` whose statistics are NOT yet in the tables
+int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int min_size, int32_t* counts,
+                   bool have_stats, cudaStream_t st) {
+    const long long BN = (long long)B * H * W;
+    int e;
+    if (!have_stats) { e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, nullptr, true, st); if (e) return e; }
+    const int mode = min_size > 0 ? 1 : 0;
+    CPB_LAUNCH(k_size_renumber, dim3(B), dim3(256), 0, st, w.t, H, W, min_size, mode, w.skey, w.sidx, (int*)nullptr);
+    CPB_CHECK_LAUNCH();
+    e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, true, st); if (e) return e;
+    cudaMemsetAsync(w.holekey, 0, BN * sizeof(u64), st);
+    CPB_LAUNCH(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
+               masks, H, W, w.t, w.holekey, w.status);
+    CPB_CHECK_LAUNCH();
+    e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, w.holekey, true, st); if (e) return e;
+    if (mode == 1) {
+        CPB_LAUNCH(k_size_renumber, dim3(B), dim3(256), 0, st, w.t, H, W, min_size, 1, w.skey, w.sidx, counts);
+        CPB_CHECK_LAUNCH();
+        e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, false, st); if (e) return e;
+    } else if (counts) {
+        cudaMemcpyAsync(counts, w.t.lbound, B * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    }
+    return 0;
+}
+
+int run_vote(const Workspace& w, const int32_t* masks, const float* logits, int B, int H, int W, int C,
+             int32_t* cell_class, uint8_t* class_masks, cudaStream_t st) {
+    CPB_LAUNCH(k_vote, dim3(B), dim3(512), kVoteSmemInts * 4, st, masks, logits, H, W, C, w.t.LC, w.t.lbound,
+               kVoteSmemInts, w.vote, cell_class, class_masks);
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
+int run_border(const Workspace& w, int32_t* masks, int B, int H, int W, int nch, cudaStream_t st) {
+    int e = run_init_tables(w, B, st); if (e) return e;
+    CPB_LAUNCH(k_border_flags, dim3(B), dim3(256), 0, st, masks, H, W, nch, w.t);
+    CPB_CHECK_LAUNCH();
+    return run_map_stats(w, masks, B, H, W, nch, nullptr, w.t.flag, nullptr, false, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpb_abi_version(void) { return CPB_ABI_VERSION; }
+
+int cpb_label_capacity(int H, int W) {
+    // every seed needs more than 10 end points, so a tile yields at most H*W/11 labels
+    return (int)((long long)H * W / 11) + 2;
+}
+
+size_t cpb_workspace_bytes(int B, int H, int W, int C, int lcap) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return carve(nullptr, B, H, W, C < 0 ? 0 : C, lcap).bytes + kAlign;
+}
+
+#define CPB_PROLOGUE(Cval, lcapval)                                                            \
+    { int e_ = check_geom(B, H, W); if (e_) return e_; }                                       \
+    if (!workspace) return CPB_E_ARG;                                                          \
+    ensure_attributes();                                                                       \
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);                                  \
+    const uintptr_t wsa_ = (reinterpret_cast<uintptr_t>(workspace) + kAlign - 1) / kAlign * kAlign; \
+    Workspace w = carve(reinterpret_cast<void*>(wsa_), B, H, W, (Cval), (lcapval));            \
+    if (w.bytes + (wsa_ - reinterpret_cast<uintptr_t>(workspace)) > workspace_bytes) return CPB_E_WORKSPACE;
+
+int cpb_follow_flows_device(const float* dP, const float* cellprob, int B, int H, int W, int niter,
+                            float cellprob_threshold, int32_t* p_final, float* p_float, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    if (!dP || !cellprob || !p_final || niter < 0) return CPB_E_ARG;
+    CPB_PROLOGUE(0, 0)
+    return run_follow(w, dP, cellprob, B, H, W, niter, cellprob_threshold, p_final, p_float, nullptr, st);
+}
+
+CPB_KERNEL k_hist_from_pfinal(const int* CPB_RESTRICT pfinal, int B, int H, int W, int* CPB_RESTRICT hist) {
+    const int N = H * W;
+    const long long total = (long long)B * N;
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= total) return;
+    const int pf = pfinal[gi];
+    if (pf < 0) return;
+    const int b = (int)(gi / N);
+    const int y = min(pf >> 16, H - 1), x = min(pf & 0xffff, W - 1);
+    atomicAdd(&hist[(size_t)b * N + y * W + x], 1);
+}
+
+int cpb_get_masks_device(const int32_t* p_final, int B, int H, int W, double max_size_fraction, int32_t* masks,
+                         int32_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!p_final || !masks) return CPB_E_ARG;
+    CPB_PROLOGUE(0, 0)
+    const long long BN = (long long)B * H * W;
+    cudaMemsetAsync(w.hist, 0, BN * sizeof(int), st);
+    CPB_LAUNCH(k_hist_from_pfinal, dim3(blocks_for(BN, 256)), dim3(256), 0, st, p_final, B, H, W, w.hist);
+    CPB_CHECK_LAUNCH();
+    int e = run_get_masks(w, p_final, B, H, W, max_size_fraction, masks, counts, st); if (e) return e;
+    return run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, false, st);
+}
+
+int cpb_masks_to_flows_device(const int32_t* masks, int B, int H, int W, int lcap, double* mu, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    if (!masks || !mu || lcap < 2) return CPB_E_ARG;
+    CPB_PROLOGUE(0, lcap)
+    const long long BN = (long long)B * H * W;
+    int e = run_set_lbound(w, B, lcap - 1, st); if (e) return e;
+    e = run_map_stats(w, const_cast<int32_t*>(masks), B, H, W, 1, nullptr, nullptr, nullptr, true, st); if (e) return e;
+    cudaMemsetAsync(mu, 0, 2 * BN * sizeof(double), st);
+    return run_flow_qc(w, masks, nullptr, B, H, W, 0.0, mu, st);
+}
+
+int cpb_remove_bad_flow_masks_device(int32_t* masks, const float* dP, int B, int H, int W, int lcap,
+                                     double threshold, double* flow_err, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    if (!masks || !dP || lcap < 2) return CPB_E_ARG;
+    CPB_PROLOGUE(0, lcap)
+    int e = run_set_lbound(w, B, lcap - 1, st); if (e) return e;
+    e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, nullptr, true, st); if (e) return e;
+    if (flow_err) cudaMemsetAsync(w.t.err, 0, (size_t)B * w.t.LC * sizeof(double), st);
+    e = run_flow_qc(w, masks, dP, B, H, W, threshold, nullptr, st); if (e) return e;
+    if (flow_err) cudaMemcpyAsync(flow_err, w.t.err, (size_t)B * w.t.LC * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    return run_map_stats(w, masks, B, H, W, 1, nullptr, w.t.flag, nullptr, false, st);
+}
+
+int cpb_fill_holes_and_remove_small_masks_device(int32_t* masks, int B, int H, int W, int lcap, int min_size,
+                                                 int32_t* counts, void* workspace, size_t workspace_bytes,
+                                                 void* stream) {
+    if (!masks || lcap < 2) return CPB_E_ARG;
+    CPB_PROLOGUE(0, lcap)
+    int e = run_set_lbound(w, B, lcap - 1, st); if (e) return e;
+    return run_fill_small(w, masks, B, H, W, min_size, counts, false, st);
+}
+
+int cpb_class_vote_device(const int32_t* masks, const float* logits, int B, int H, int W, int C, int lcap,
+                          int32_t* cell_class, uint8_t* class_masks, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+    if (!masks || !logits || !cell_class || C < 1 || C > 255 || lcap < 2) return CPB_E_ARG;
+    CPB_PROLOGUE(C, lcap)
+    int e = run_set_lbound(w, B, lcap - 1, st); if (e) return e;
+    return run_vote(w, masks, logits, B, H, W, C, cell_class, class_masks, st);
+}
+
+int cpb_remove_border_instances_device(int32_t* masks, int B, int H, int W, int nch, int lcap, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+    if (!masks || nch < 1 || lcap < 2) return CPB_E_ARG;
+    { int e_ = check_geom(B, H, W); if (e_) return e_; }
+    if ((long long)B * H * W * nch >= (1LL << 31)) return CPB_E_RANGE;
+    CPB_PROLOGUE(0, lcap)
+    int e = run_set_lbound(w, B, lcap - 1, st); if (e) return e;
+    return run_border(w, masks, B, H, W, nch, st);
+}
+
+int cpb_compute_masks_device(const float* dP, const float* cellprob, const float* logits, int B, int H, int W,
+                             int C, const cpb_params* prm, int32_t* masks, int32_t* counts, int32_t* cell_class,
+                             uint8_t* class_masks, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!dP || !cellprob || !prm || !masks || !counts) return CPB_E_ARG;
+    if (logits && (!cell_class || C < 1 || C > 255)) return CPB_E_ARG;
+    if (prm->niter < 0) return CPB_E_ARG;
+    CPB_PROLOGUE(logits ? C : 0, 0)
+    int e;
+    // (2) Euler integration + end-point histogram
+    e = run_follow(w, dP, cellprob, B, H, W, prm->niter, prm->cellprob_threshold, w.pfinal, nullptr, w.hist, st);
+    if (e) return e;
+    // (3) seeds -> labels; apply the first-appearance remap while gathering label statistics
+    e = run_get_masks(w, w.pfinal, B, H, W, prm->max_size_fraction, masks, counts, st); if (e) return e;
+    e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, true, st); if (e) return e;
+    // (4) flow-error check; dropped labels become 0 in the pass that regathers statistics
+    bool have_stats = true;
+    if (prm->flow_threshold > 0.0) {
+        e = run_flow_qc(w, masks, dP, B, H, W, prm->flow_threshold, nullptr, st); if (e) return e;
+        if (prm->fill_holes) {
+            // k_map_stats resets `flag` via init_tables before reading it, so copy the flags out first
+            cudaMemcpyAsync(w.sidx, w.t.flag, (size_t)B * w.t.LC * sizeof(int), cudaMemcpyDeviceToDevice, st);
+            e = run_map_stats(w, masks, B, H, W, 1, nullptr, w.sidx, nullptr, true, st); if (e) return e;
+        } else {
+            e = run_map_stats(w, masks, B, H, W, 1, nullptr, w.t.flag, nullptr, false, st); if (e) return e;
+            have_stats = false;
+        }
+    }
+    // (5) hole fill + size filters
+    if (prm->fill_holes) {
+        e = run_fill_small(w, masks, B, H, W, prm->min_size, counts, have_stats, st); if (e) return e;
+    } else {
+        cudaMemcpyAsync(counts, w.t.lbound, B * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    }
+    // (7) optional border-instance removal (labels are not renumbered afterwards, as in the reference)
+    if (prm->remove_border) { e = run_border(w, masks, B, H, W, 1, st); if (e) return e; }
+    // (6) class vote
+    if (logits) { e = run_vote(w, masks, logits, B, H, W, C, cell_class, class_masks, st); if (e) return e; }
+    return 0;
+}
+
+int cpb_average_tiles_device(const float* y, int B, int ntiles, int nch, int ly, int lx, const int32_t* y0,
+                             const int32_t* x0, const int32_t* flip, int negate_flow, const double* taper_y,
+                             const double* taper_x, int Ly, int Lx, int cy0, int cy1, int cx0, int cx1, float* yf,
+                             void* stream) {
+    if (!y || !y0 || !x0 || !flip || !taper_y || !taper_x || !yf) return CPB_E_ARG;
+    const int oH = Ly - cy0 - cy1, oW = Lx - cx0 - cx1;
+    if (B <= 0 || ntiles <= 0 || nch <= 0 || ly <= 0 || lx <= 0 || oH <= 0 || oW <= 0 || cy0 < 0 || cx0 < 0)
+        return CPB_E_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long total = (long long)B * nch * oH * oW;
+    CPB_LAUNCH(k_average_tiles, dim3(blocks_for(total, 256)), dim3(256), 0, st, y, B, ntiles, nch, ly, lx, y0, x0,
+               flip, negate_flow, taper_y, taper_x, cy0, cx0, oH, oW, yf);
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
+int cpb_label_offsets_device(const int32_t* counts, int B, int64_t base, int64_t* offsets, int64_t* total,
+                             void* stream) {
+    if (!counts || !offsets || B <= 0) return CPB_E_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CPB_LAUNCH(k_label_offsets, dim3(1), dim3(256), 0, st, counts, B, (long long)base,
+               reinterpret_cast<long long*>(offsets), reinterpret_cast<long long*>(total));
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"
+
+#ifndef CPB_SIM
+#include "cpb_host.inl"
+#endif

@@ -1,0 +1,78 @@
+// Shared device helpers and the per-tile label-table layout.
+#pragma once
+#include "cpb_platform.h"
+
+#define CPB_FULL 0xffffffffu
+#define CPB_IMAX 0x7fffffff
+
+typedef unsigned long long u64;
+
+// Per-tile, per-label tables (struct of arrays, each [B][LC]); entry 0 is background.
+struct LabelTables {
+    int LC;          // entries per tile
+    int* cnt;        // pixel count
+    int* first;      // smallest raster index (first appearance)
+    int* ymin; int* ymax; int* xmin; int* xmax;   // bounding box (inclusive)
+    u64* sumy; u64* sumx;                          // coordinate sums
+    int* remap;      // label -> new label (0 = dropped)
+    int* flag;       // scratch flags (bad flow / removed-by-position / border)
+    int* cy; int* cx;                              // diffusion centre
+    double* err;     // flow error
+    int* lbound;     // [B] highest label value that may be present in the tile
+    int* nlab;       // [B] number of instances after the last renumbering
+    int* niter;      // [B] diffusion iterations (2 * max ext)
+    int* misc;       // [B] stage scratch (seed count, hole flag, ...)
+};
+
+CPB_DEVICE int cpb_lane() { return threadIdx.x & 31; }
+
+// Block-wide inclusive scan of one int per thread (blockDim.x multiple of 32, <= 1024).
+// `warp_tot` must point to >= 33 ints of shared memory.  Returns inclusive prefix;
+// *block_total receives the sum.  Contains __syncthreads().
+CPB_DEVICE int cpb_block_scan_incl(int v, int* warp_tot, int* block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int x = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(CPB_FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int t = lane < nw ? warp_tot[lane] : 0;
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(CPB_FULL, t, d);
+            if (lane >= d) t += y;
+        }
+        if (lane < nw) warp_tot[lane] = t;
+        if (lane == 31) warp_tot[32] = t;
+    }
+    __syncthreads();
+    int base = warp > 0 ? warp_tot[warp - 1] : 0;
+    *block_total = warp_tot[32];
+    return base + x;
+}
+
+// Warp-aggregated update of the label tables for one pixel per lane.
+// All 32 lanes must call; `lab` <= 0 lanes contribute nothing.  key = tile*LC + lab.
+CPB_DEVICE void cpb_stats_accum(const LabelTables& t, int b, int lab, int ridx, int y, int x) {
+    const int lane = threadIdx.x & 31;
+    const bool act = lab > 0;
+    const unsigned amask = __ballot_sync(CPB_FULL, act);
+    if (!act) return;
+    const int key = b * t.LC + lab;
+    const unsigned peers = __match_any_sync(amask, key);
+    const int leader = __ffs((int)peers) - 1;
+    const int n = __popc(peers);
+    const int fmin = __reduce_min_sync(peers, ridx);
+    const int y0 = __reduce_min_sync(peers, y), y1 = __reduce_max_sync(peers, y);
+    const int x0 = __reduce_min_sync(peers, x), x1 = __reduce_max_sync(peers, x);
+    const int sy = __reduce_add_sync(peers, y), sx = __reduce_add_sync(peers, x);
+    if (lane == leader) {
+        atomicAdd(&t.cnt[key], n);
+        atomicMin(&t.first[key], fmin);
+        atomicMin(&t.ymin[key], y0); atomicMax(&t.ymax[key], y1);
+        atomicMin(&t.xmin[key], x0); atomicMax(&t.xmax[key], x1);
+        atomicAdd(&t.sumy[key], (u64)sy); atomicAdd(&t.sumx[key], (u64)sx);
+    }
+}

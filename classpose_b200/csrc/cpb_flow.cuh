@@ -1,0 +1,108 @@
+// Row (2): follow_flows -- Euler integration of every foreground pixel through the
+// bilinearly sampled flow field, then the end-point histogram of row (3).
+// Semantics follow cellpose.dynamics.steps_interp with the arithmetic of
+// torch's grid_sample (bilinear, zero padding, align_corners=False) on coordinates that
+// were normalised by (L-1).
+#pragma once
+#include "cpb_common.cuh"
+
+// k_prep_flow: one thread per pixel.
+//   flow[b][y][x] = ( dX*fg/5 * 2/(W-1) , dY*fg/5 * 2/(H-1) )   (x component first)
+//   p_final[b][y][x] = -1 on background
+//   foreground pixels are appended to `list` (global pixel index), block-contiguous.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, int B, int H, int W,
+            float thr, float sx, float sy, float2* CPB_RESTRICT flow, int* CPB_RESTRICT pfinal,
+            unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n) {
+    CPB_SHARED int s_scan[33];
+    CPB_SHARED unsigned s_base;
+    const int N = H * W;
+    const long long total = (long long)B * N;
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool fg = false;
+    if (gi < total) {
+        const int b = (int)(gi / N);
+        const int r = (int)(gi - (long long)b * N);
+        const float cp = cellprob[gi];
+        fg = cp > thr;
+        const float m = fg ? 1.0f : 0.0f;
+        const float dy = dP[((size_t)b * 2 + 0) * N + r];
+        const float dx = dP[((size_t)b * 2 + 1) * N + r];
+        // (dP * fg) / 5.  then  *= 2/(L-1)   -- each a separately rounded float32 op
+        const float fy = __fmul_rn(__fdiv_rn(__fmul_rn(dy, m), 5.0f), sy);
+        const float fx = __fmul_rn(__fdiv_rn(__fmul_rn(dx, m), 5.0f), sx);
+        flow[gi] = make_float2(fx, fy);
+        if (!fg) pfinal[gi] = -1;
+    }
+    int tot;
+    const int incl = cpb_block_scan_incl(fg ? 1 : 0, s_scan, &tot);
+    if (threadIdx.x == 0 && tot > 0) s_base = atomicAdd(list_n, (unsigned)tot);
+    __syncthreads();
+    if (fg) list[s_base + incl - 1] = (unsigned)gi;
+}
+
+// One Euler step in normalised coordinates, arithmetic order as ATen's grid_sampler_2d.
+CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int H, int W, float fH, float fW,
+                               float& px, float& py) {
+    const float ix = ((px + 1.f) * fW - 1.f) / 2.f;
+    const float iy = ((py + 1.f) * fH - 1.f) / 2.f;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+    const float wnw = (fx1 - ix) * (fy1 - iy);
+    const float wne = (ix - fx0) * (fy1 - iy);
+    const float wsw = (fx1 - ix) * (iy - fy0);
+    const float wse = (ix - fx0) * (iy - fy0);
+    float ox = 0.f, oy = 0.f;
+    const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
+    const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
+    if (yin0 && xin0) { const float2 v = __ldg(&f[y0 * W + x0]);           ox += v.x * wnw; oy += v.y * wnw; }
+    if (yin0 && xin1) { const float2 v = __ldg(&f[y0 * W + x0 + 1]);       ox += v.x * wne; oy += v.y * wne; }
+    if (yin1 && xin0) { const float2 v = __ldg(&f[(y0 + 1) * W + x0]);     ox += v.x * wsw; oy += v.y * wsw; }
+    if (yin1 && xin1) { const float2 v = __ldg(&f[(y0 + 1) * W + x0 + 1]); ox += v.x * wse; oy += v.y * wse; }
+    px = fminf(fmaxf(px + ox, -1.f), 1.f);
+    py = fminf(fmaxf(py + oy, -1.f), 1.f);
+}
+
+// k_follow: grid-stride over the compacted foreground list, one pixel per thread.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
+         const unsigned* CPB_RESTRICT list_n, int H, int W, int niter,
+         int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
+    const unsigned total = *list_n;
+    const int N = H * W;
+    const float fW = (float)W, fH = (float)H;
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const int lane = threadIdx.x & 31;
+    for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {
+        const unsigned i = i0 + threadIdx.x;
+        const bool act = i < total;
+        const unsigned amask = __ballot_sync(CPB_FULL, act);
+        if (!act) continue;
+        const unsigned gi = list[i];
+        const int b = (int)(gi / (unsigned)N);
+        const int r = (int)(gi - (unsigned)b * (unsigned)N);
+        const int y = r / W, x = r - y * W;
+        const float2* f = flow + (size_t)b * N;
+        // pt = idx / (L-1) * 2 - 1
+        float px = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, wm1), 2.f), 1.f);
+        float py = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, hm1), 2.f), 1.f);
+        for (int t = 0; t < niter; t++) cpb_euler_step(f, H, W, fH, fW, px, py);
+        // undo: (pt + 1) * 0.5 * (L-1)
+        const float ex = __fmul_rn(__fmul_rn(__fadd_rn(px, 1.f), 0.5f), wm1);
+        const float ey = __fmul_rn(__fmul_rn(__fadd_rn(py, 1.f), 0.5f), hm1);
+        int xi = __float2int_rz(ex), yi = __float2int_rz(ey);
+        xi = min(max(xi, 0), W - 1);
+        yi = min(max(yi, 0), H - 1);
+        pfinal[gi] = (yi << 16) | xi;
+        if (pfloat) {
+            pfloat[((size_t)b * 2 + 0) * N + r] = ey;
+            pfloat[((size_t)b * 2 + 1) * N + r] = ex;
+        }
+        if (hist) {
+            const int key = b * N + yi * W + xi;
+            const unsigned peers = __match_any_sync(amask, key);
+            if (lane == __ffs((int)peers) - 1) atomicAdd(&hist[key], __popc(peers));
+        }
+    }
+}

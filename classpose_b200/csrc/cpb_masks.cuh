@@ -1,0 +1,161 @@
+// Row (3): get_masks -- seeds of the end-point histogram, constrained 11x11 growth,
+// label lookup, over-sized label removal, first-appearance renumbering.
+// Semantics follow cellpose.dynamics.get_masks_torch.  The reference pads
+// the histogram by rpad=20 so that windows never leave the array; end points never fall in
+// the padding, so here the histogram lives on the H x W tile and out-of-tile reads are 0.
+#pragma once
+#include "cpb_common.cuh"
+
+#define CPB_SEED_MIN 10
+#define CPB_GROW_MIN 2
+#define CPB_RANK_CHUNK 1024
+
+// rank[k] = #{ j : key[j] < key[k] } for n distinct 64-bit keys (block-cooperative, O(n^2/blockDim)).
+// s_keys: CPB_RANK_CHUNK u64 of shared memory.  out[k] = rank + 1 for k < n.
+CPB_DEVICE void cpb_block_rank(const u64* CPB_RESTRICT keys, int n, int* CPB_RESTRICT out, u64* s_keys) {
+    for (int kb = 0; kb < n; kb += blockDim.x) {
+        const int k = kb + threadIdx.x;
+        const u64 mine = k < n ? keys[k] : 0;
+        int rank = 0;
+        for (int c0 = 0; c0 < n; c0 += CPB_RANK_CHUNK) {
+            const int cn = min(CPB_RANK_CHUNK, n - c0);
+            __syncthreads();
+            for (int j = threadIdx.x; j < cn; j += blockDim.x) s_keys[j] = keys[c0 + j];
+            __syncthreads();
+            if (k < n)
+                for (int j = 0; j < cn; j++) rank += s_keys[j] < mine ? 1 : 0;
+        }
+        if (k < n) out[k] = rank + 1;
+    }
+    __syncthreads();
+}
+
+CPB_DEVICE int cpb_hist_at(const int* CPB_RESTRICT h, int H, int W, int y, int x) {
+    return (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(&h[y * W + x]) : 0;
+}
+
+// k_seeds: one block per tile.
+//  1. seeds = pixels with h > 10 that equal the maximum of their 5x5 neighbourhood
+//  2. order: ascending count, ties by raster position (stable sort of a raster-ordered list)
+//  3. each seed grows inside its 11x11 window: 5 x { 3x3 dilation ; &= h > 2 }
+//  4. paint label = order+1; later (larger) labels overwrite -> atomicMax
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_seeds(const int* CPB_RESTRICT hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
+        int* CPB_RESTRICT seed_lab, int* CPB_RESTRICT M, int* CPB_RESTRICT nseeds) {
+    CPB_SHARED int s_n;
+    CPB_SHARED u64 s_keys[CPB_RANK_CHUNK];
+    const int b = blockIdx.x;
+    const int N = H * W;
+    const int* h = hist + (size_t)b * N;
+    u64* keys = seed_key + (size_t)b * LC;
+    int* labs = seed_lab + (size_t)b * LC;
+    int* Mb = M + (size_t)b * N;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        const int v = h[p];
+        if (v > CPB_SEED_MIN) {
+            const int y = p / W, x = p - y * W;
+            bool ismax = true;
+            for (int dy = -2; dy <= 2 && ismax; dy++)
+                for (int dx = -2; dx <= 2; dx++)
+                    if (cpb_hist_at(h, H, W, y + dy, x + dx) > v) { ismax = false; break; }
+            if (ismax) {
+                const int k = atomicAdd(&s_n, 1);
+                if (k < LC) keys[k] = ((u64)(unsigned)v << 32) | (unsigned)p;
+            }
+        }
+    }
+    __syncthreads();
+    const int n = min(s_n, LC - 1);
+    if (threadIdx.x == 0) nseeds[b] = n;
+    cpb_block_rank(keys, n, labs, s_keys);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int s = warp; s < n; s += nw) {
+        const u64 key = keys[s];
+        const int p = (int)(key & 0xffffffffu);
+        const int label = labs[s];
+        const int sy = p / W, sx = p - sy * W;
+        const int y = sy - 5 + lane;
+        unsigned allowed = 0;
+        if (lane < 11)
+            for (int c = 0; c < 11; c++)
+                if (cpb_hist_at(h, H, W, y, sx - 5 + c) > CPB_GROW_MIN) allowed |= 1u << c;
+        unsigned m = (lane == 5) ? (1u << 5) : 0u;
+        for (int it = 0; it < 5; it++) {
+            const unsigned d = m | (m << 1) | (m >> 1);
+            unsigned up = __shfl_up_sync(CPB_FULL, d, 1);
+            unsigned dn = __shfl_down_sync(CPB_FULL, d, 1);
+            if (lane == 0) up = 0;
+            if (lane == 31) dn = 0;
+            m = (d | up | dn) & allowed;
+        }
+        while (m) {
+            const int c = __ffs((int)m) - 1;
+            m &= m - 1;
+            atomicMax(&Mb[y * W + sx - 5 + c], label);
+        }
+    }
+}
+
+// k_lookup: label of every foreground pixel = painted label at its end point; also fills
+// the label tables (count / first appearance / bbox / sums) of the raw labels.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_lookup(const int* CPB_RESTRICT pfinal, const int* CPB_RESTRICT M, int B, int H, int W,
+         int* CPB_RESTRICT lab, LabelTables t) {
+    const int N = H * W;
+    const long long total = (long long)B * N;
+    const long long base = (long long)blockIdx.x * blockDim.x;
+    if (base >= total) return;
+    const long long gi = base + threadIdx.x;
+    int l = 0, b = 0, r = 0, y = 0, x = 0;
+    if (gi < total) {
+        b = (int)(gi / N);
+        r = (int)(gi - (long long)b * N);
+        const int pf = pfinal[gi];
+        if (pf >= 0) l = M[(size_t)b * N + (pf >> 16) * W + (pf & 0xffff)];
+        lab[gi] = l;
+        y = r / W; x = r - y * W;
+    }
+    cpb_stats_accum(t, b, l, r, y, x);
+}
+
+// k_gm_finalize: one block per tile.  Drop labels larger than max_size_fraction of the tile,
+// renumber the rest 1..n in order of first appearance.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_gm_finalize(LabelTables t, int H, int W, double max_size_fraction, u64* CPB_RESTRICT scratch_key,
+              int* CPB_RESTRICT scratch_idx, int* CPB_RESTRICT counts_out) {
+    CPB_SHARED int s_n;
+    CPB_SHARED u64 s_keys[CPB_RANK_CHUNK];
+    const int b = blockIdx.x;
+    const int LC = t.LC;
+    const int lb = t.lbound[b];
+    const double big = (double)((long long)H * W) * max_size_fraction;
+    const int* cnt = t.cnt + (size_t)b * LC;
+    const int* first = t.first + (size_t)b * LC;
+    int* remap = t.remap + (size_t)b * LC;
+    u64* keys = scratch_key + (size_t)b * LC;   // (first << 32) | label of kept labels
+    int* rank = scratch_idx + (size_t)b * LC;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int l = threadIdx.x; l <= lb; l += blockDim.x) {
+        remap[l] = 0;
+        if (l >= 1) {
+            const int c = cnt[l];
+            if (c > 0 && !((double)c > big)) {
+                const int k = atomicAdd(&s_n, 1);
+                keys[k] = ((u64)(unsigned)first[l] << 32) | (unsigned)l;
+            }
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    cpb_block_rank(keys, n, rank, s_keys);
+    for (int k = threadIdx.x; k < n; k += blockDim.x) remap[(int)(keys[k] & 0xffffffffu)] = rank[k];
+    if (threadIdx.x == 0) {
+        t.nlab[b] = n;
+        t.lbound[b] = n;   // labels are 1..n after the remap is applied
+        if (counts_out) counts_out[b] = n;
+    }
+}

@@ -1,0 +1,208 @@
+// Rows (5)-(7), (1) and (e): hole filling, class vote, border-instance removal,
+// taper blending of sub-tiles, global label offsets.
+#pragma once
+#include "cpb_common.cuh"
+
+#define CPB_FILL_THREADS 128
+#define CPB_FILL_WORDS 8192          // 32-bit words per bitmap in shared memory (2 bitmaps = 64 KB)
+
+// k_fill_holes: one block per label (labels strided over gridDim.x, tile = blockIdx.y).
+// Holes of label l = pixels of its bbox crop that are not l and are not 4-connected, through
+// non-l pixels, to the border of the crop (fill_voids.fill on `crop == l`).
+// Every hole pixel proposes (bbox area, l) into holekey with atomicMax: when holes nest, the
+// outermost instance -- the one the reference's sequential loop ends with -- wins.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FILL_THREADS, 3)
+k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_RESTRICT holekey,
+             int* CPB_RESTRICT status) {
+    CPB_DYN_SMEM(unsigned, s_bits);     // free[CPB_FILL_WORDS] | reach[CPB_FILL_WORDS]
+    CPB_SHARED int s_changed;
+    const int b = blockIdx.y, LC = t.LC, N = H * W;
+    const int lb = t.lbound[b];
+    const int* L = lab + (size_t)b * N;
+    u64* HK = holekey + (size_t)b * N;
+    unsigned* fr = s_bits;
+    unsigned* rc = s_bits + CPB_FILL_WORDS;
+    for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
+        const size_t k = (size_t)b * LC + l;
+        if (t.cnt[k] <= 0) continue;
+        const int y0 = t.ymin[k], x0 = t.xmin[k];
+        const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        if (h < 3 || w < 3) continue;
+        const int wpr = (w + 31) >> 5;
+        if (h * wpr > CPB_FILL_WORDS) { if (threadIdx.x == 0) atomicOr(status, 1); continue; }
+        __syncthreads();
+        // bitmaps: fr = pixel is not l ; rc = fr on the crop border
+        for (int i = threadIdx.x; i < h * wpr; i += blockDim.x) {
+            const int r = i / wpr, j = i - r * wpr;
+            unsigned f = 0, e = 0;
+            const int cmax = min(32, w - j * 32);
+            for (int c = 0; c < cmax; c++) {
+                const int x = j * 32 + c;
+                if (L[(y0 + r) * W + x0 + x] != l) {
+                    f |= 1u << c;
+                    if (r == 0 || r == h - 1 || x == 0 || x == w - 1) e |= 1u << c;
+                }
+            }
+            fr[i] = f; rc[i] = e;
+        }
+        __syncthreads();
+        // flood from the border through free pixels (4-connectivity), monotone in-place sweeps
+        for (;;) {
+            if (threadIdx.x == 0) s_changed = 0;
+            __syncthreads();
+            bool ch = false;
+            for (int i = threadIdx.x; i < h * wpr; i += blockDim.x) {
+                const int r = i / wpr, j = i - r * wpr;
+                const unsigned f = fr[i];
+                unsigned cur = rc[i];
+                unsigned n = cur;
+                if (r > 0) n |= rc[i - wpr];
+                if (r < h - 1) n |= rc[i + wpr];
+                if (j > 0) n |= rc[i - 1] >> 31;
+                if (j < wpr - 1) n |= rc[i + 1] << 31;
+                n &= f;
+                for (;;) {   // smear along the row inside the word
+                    const unsigned m = (n | (n << 1) | (n >> 1)) & f;
+                    if (m == n) break;
+                    n = m;
+                }
+                if (n != cur) { rc[i] = n; ch = true; }
+            }
+            if (ch) s_changed = 1;
+            __syncthreads();
+            const int any = s_changed;
+            __syncthreads();
+            if (!any) break;
+        }
+        const u64 prio = (u64)((unsigned)(h * w)) << 32;
+        for (int i = threadIdx.x; i < h * wpr; i += blockDim.x) {
+            unsigned hole = fr[i] & ~rc[i];
+            const int r = i / wpr, j = i - r * wpr;
+            while (hole) {
+                const int c = __ffs((int)hole) - 1;
+                hole &= hole - 1;
+                atomicMax(&HK[(y0 + r) * W + x0 + j * 32 + c], prio | (unsigned)l);
+            }
+        }
+    }
+}
+
+// k_vote: one block per tile.  Per-pixel arg-max over the C logits (first maximum wins),
+// histogram (instance, class) in shared memory, per-instance arg-max (first maximum wins).
+// Falls back to a global table when (lbound+1)*C ints exceed the shared-memory budget.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(512, 2)
+k_vote(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT logits, int H, int W, int C, int LC,
+       const int* CPB_RESTRICT lbound, int smem_ints, int* CPB_RESTRICT gtable,
+       int* CPB_RESTRICT cell_class, unsigned char* CPB_RESTRICT class_masks) {
+    CPB_DYN_SMEM(int, s_tab);
+    const int b = blockIdx.x, N = H * W;
+    const int lb = min(lbound[b], LC - 1);
+    const int* L = lab + (size_t)b * N;
+    const float* G = logits + (size_t)b * C * N;
+    int* cc = cell_class + (size_t)b * LC;
+    const int need = (lb + 1) * C;
+    int* tab = need <= smem_ints ? s_tab : gtable + (size_t)b * LC * C;
+    for (int i = threadIdx.x; i < need; i += blockDim.x) tab[i] = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        const int l = L[p];
+        if (l <= 0 || l > lb) continue;
+        float best = G[p];
+        int arg = 0;
+        for (int c = 1; c < C; c++) {
+            const float v = G[(size_t)c * N + p];
+            if (v > best) { best = v; arg = c; }
+        }
+        atomicAdd(&tab[l * C + arg], 1);
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l <= lb; l += blockDim.x) {
+        int arg = 0;
+        if (l > 0) {
+            int best = tab[l * C];
+            for (int c = 1; c < C; c++) {
+                const int v = tab[l * C + c];
+                if (v > best) { best = v; arg = c; }
+            }
+        }
+        cc[l] = arg;
+    }
+    if (class_masks) {
+        __syncthreads();
+        unsigned char* CM = class_masks + (size_t)b * N;
+        for (int p = threadIdx.x; p < N; p += blockDim.x) {
+            const int l = L[p];
+            CM[p] = (l > 0 && l <= lb) ? (unsigned char)cc[l] : 0;
+        }
+    }
+}
+
+// k_border_flags: one block per tile; flag every label that owns a pixel on the tile border.
+CPB_KERNEL k_border_flags(const int* CPB_RESTRICT lab, int H, int W, int nch, LabelTables t) {
+    const int b = blockIdx.x, N = H * W;
+    const int* L = lab + (size_t)b * N * nch;
+    int* flag = t.flag + (size_t)b * t.LC;
+    for (int i = threadIdx.x; i < 2 * (H + W); i += blockDim.x) {
+        int y, x;
+        if (i < W) { y = 0; x = i; }
+        else if (i < 2 * W) { y = H - 1; x = i - W; }
+        else if (i < 2 * W + H) { y = i - 2 * W; x = 0; }
+        else { y = i - 2 * W - H; x = W - 1; }
+        const int l = L[((size_t)y * W + x) * nch];
+        if (l > 0 && l < t.LC) flag[l] = 1;
+    }
+}
+
+// k_average_tiles: one thread per output element (b, ch, Y, X) of the cropped blend.
+// Mirrors numpy's arithmetic in cellpose.transforms.average_tiles: the float32 accumulator
+// is updated as float32(double(acc) + double(v) * w) per covering tile in tile order, the
+// weight sum is float64, the final division is float32(double(acc) / Navg).
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_average_tiles(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly, int lx,
+                const int* CPB_RESTRICT ty0, const int* CPB_RESTRICT tx0, const int* CPB_RESTRICT flip,
+                int negate_flow, const double* CPB_RESTRICT taper_y, const double* CPB_RESTRICT taper_x,
+                int cy0, int cx0, int oH, int oW, float* CPB_RESTRICT yf) {
+    const long long total = (long long)B * nch * oH * oW;
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= total) return;
+    const int X = (int)(gi % oW);
+    const int Y = (int)((gi / oW) % oH);
+    const int ch = (int)((gi / ((long long)oW * oH)) % nch);
+    const int b = (int)(gi / ((long long)oW * oH * nch));
+    const int gy = Y + cy0, gx = X + cx0;
+    float acc = 0.f;
+    double navg = 0.0;
+    for (int j = 0; j < ntiles; j++) {
+        const int ry = gy - ty0[j], rx = gx - tx0[j];
+        if (ry < 0 || ry >= ly || rx < 0 || rx >= lx) continue;
+        const int f = flip[j];
+        const int sy = (f & 1) ? ly - 1 - ry : ry;
+        const int sx = (f & 2) ? lx - 1 - rx : rx;
+        float v = y[((((size_t)b * ntiles + j) * nch + ch) * ly + sy) * lx + sx];
+        if (negate_flow && ((ch == 0 && (f & 1)) || (ch == 1 && (f & 2)))) v = -v;
+        const double wgt = __dmul_rn(taper_y[ry], taper_x[rx]);
+        acc = (float)__dadd_rn((double)acc, __dmul_rn((double)v, wgt));
+        navg = __dadd_rn(navg, wgt);
+    }
+    yf[gi] = (float)__ddiv_rn((double)acc, navg);
+}
+
+// k_label_offsets: single block; offsets[b] = base + sum(counts[0..b)), total = sum(counts).
+CPB_KERNEL k_label_offsets(const int* CPB_RESTRICT counts, int B, long long base,
+                           long long* CPB_RESTRICT offsets, long long* CPB_RESTRICT total) {
+    CPB_SHARED int s_scan[33];
+    CPB_SHARED long long s_carry;
+    if (threadIdx.x == 0) s_carry = base;
+    __syncthreads();
+    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+        const int b = b0 + threadIdx.x;
+        const int c = b < B ? counts[b] : 0;
+        int tot;
+        const int incl = cpb_block_scan_incl(c, s_scan, &tot);
+        if (b < B) offsets[b] = s_carry + incl - c;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = s_carry - base;
+}

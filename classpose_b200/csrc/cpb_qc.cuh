@@ -1,0 +1,220 @@
+// Row (4): remove_bad_flow_masks -> flow_error -> masks_to_flows.
+//   k_centres : per label, the label pixel nearest to the label's mean position, ext
+//   k_diffuse : per label, float64 Jacobi heat diffusion from the centre, n_iter = 2*max(ext)
+//   k_flow_err: per label, gradient of T (raw, neighbours of other labels leak in), unit
+//               vectors, mean squared difference to dP/5, bad = err > threshold
+// One block per label, labels of a tile strided over gridDim.x, tile = blockIdx.y.
+#pragma once
+#include "cpb_common.cuh"
+
+#define CPB_QC_THREADS 128
+#define CPB_DIFF_SMEM_CELLS 2304   // (bbox_h+2)*(bbox_w+2) cells that fit the shared-memory path
+
+struct MinKey { double d; int idx; };
+
+CPB_DEVICE bool cpb_minkey_less(double d0, int i0, double d1, int i1) {
+    return d0 < d1 || (d0 == d1 && i0 < i1);
+}
+
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
+k_centres(const int* CPB_RESTRICT lab, int H, int W, LabelTables t) {
+    CPB_SHARED double s_d[CPB_QC_THREADS / 32];
+    CPB_SHARED int s_i[CPB_QC_THREADS / 32];
+    const int b = blockIdx.y, LC = t.LC, N = H * W;
+    const int lb = t.lbound[b];
+    const int* L = lab + (size_t)b * N;
+    for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
+        const size_t k = (size_t)b * LC + l;
+        const int c = t.cnt[k];
+        if (c <= 0) continue;   // block-uniform
+        const int y0 = t.ymin[k], x0 = t.xmin[k];
+        const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        // means of (coordinate relative to the bbox + 1), as the reference computes them
+        const double ymed = __ddiv_rn(__ll2double_rn((long long)t.sumy[k] - (long long)c * y0 + c), __int2double_rn(c));
+        const double xmed = __ddiv_rn(__ll2double_rn((long long)t.sumx[k] - (long long)c * x0 + c), __int2double_rn(c));
+        double bd = 1e300; int bi = CPB_IMAX;
+        for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+            const int ry = i / w, rx = i - ry * w;
+            if (L[(y0 + ry) * W + x0 + rx] == l) {
+                const double dx = __dsub_rn(__int2double_rn(rx + 1), xmed);
+                const double dy = __dsub_rn(__int2double_rn(ry + 1), ymed);
+                const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (cpb_minkey_less(d, i, bd, bi)) { bd = d; bi = i; }
+            }
+        }
+        for (int s = 16; s; s >>= 1) {
+            const double od = __shfl_xor_sync(CPB_FULL, bd, s);
+            const int oi = __shfl_xor_sync(CPB_FULL, bi, s);
+            if (cpb_minkey_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { s_d[threadIdx.x >> 5] = bd; s_i[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int q = 1; q < CPB_QC_THREADS / 32; q++)
+                if (cpb_minkey_less(s_d[q], s_i[q], bd, bi)) { bd = s_d[q]; bi = s_i[q]; }
+            const int ry = bi / w, rx = bi - ry * w;
+            t.cy[k] = y0 + ry; t.cx[k] = x0 + rx;
+            atomicMax(&t.niter[b], 2 * (h + w + 2));
+        }
+    }
+}
+
+// Neighbour order of the reference: self, (-1,0), (1,0), (0,-1), (0,1), (-1,-1), (-1,1), (1,-1), (1,1)
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
+k_diffuse(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
+          double* CPB_RESTRICT T2, int niter_override) {
+    CPB_DYN_SMEM(double, s_buf);   // 2 * CPB_DIFF_SMEM_CELLS doubles + CPB_DIFF_SMEM_CELLS bytes
+    const int b = blockIdx.y, LC = t.LC, N = H * W;
+    const int lb = t.lbound[b];
+    const int* L = lab + (size_t)b * N;
+    double* Tb = T + (size_t)b * N;
+    double* T2b = T2 + (size_t)b * N;
+    const int n_it = niter_override > 0 ? niter_override : t.niter[b];
+    for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
+        const size_t k = (size_t)b * LC + l;
+        if (t.cnt[k] <= 0) continue;
+        const int y0 = t.ymin[k], x0 = t.xmin[k];
+        const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        const int cy = t.cy[k], cx = t.cx[k];
+        const int hh = h + 2, ww = w + 2, cells = hh * ww;
+        if (cells <= CPB_DIFF_SMEM_CELLS) {
+            double* A = s_buf;
+            double* Bf = s_buf + CPB_DIFF_SMEM_CELLS;
+            unsigned char* mem = reinterpret_cast<unsigned char*>(s_buf + 2 * CPB_DIFF_SMEM_CELLS);
+            __syncthreads();
+            for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+                const int ry = i / ww - 1, rx = i % ww - 1;
+                const bool in = ry >= 0 && ry < h && rx >= 0 && rx < w && L[(y0 + ry) * W + x0 + rx] == l;
+                mem[i] = in ? 1 : 0;
+                A[i] = 0.0; Bf[i] = 0.0;
+            }
+            const int ci = (cy - y0 + 1) * ww + (cx - x0 + 1);
+            __syncthreads();
+            double* cur = A; double* nxt = Bf;
+            for (int it = 0; it < n_it; it++) {
+                for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+                    if (!mem[i]) continue;
+                    // T[centre] += 1 happens before the averaging step: fold it into the reads
+                    #define CPB_TV(j) (cur[(j)] + ((j) == ci ? 1.0 : 0.0))
+                    double s = CPB_TV(i);
+                    s = __dadd_rn(s, CPB_TV(i - ww));
+                    s = __dadd_rn(s, CPB_TV(i + ww));
+                    s = __dadd_rn(s, CPB_TV(i - 1));
+                    s = __dadd_rn(s, CPB_TV(i + 1));
+                    s = __dadd_rn(s, CPB_TV(i - ww - 1));
+                    s = __dadd_rn(s, CPB_TV(i - ww + 1));
+                    s = __dadd_rn(s, CPB_TV(i + ww - 1));
+                    s = __dadd_rn(s, CPB_TV(i + ww + 1));
+                    #undef CPB_TV
+                    nxt[i] = __ddiv_rn(s, 9.0);
+                }
+                __syncthreads();
+                double* tmp = cur; cur = nxt; nxt = tmp;
+            }
+            for (int i = threadIdx.x; i < cells; i += blockDim.x)
+                if (mem[i]) Tb[(y0 + i / ww - 1) * W + x0 + i % ww - 1] = cur[i];
+        } else {
+            // large instance: iterate in global memory (two full-tile float64 planes)
+            __syncthreads();
+            for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+                const int p = (y0 + i / w) * W + x0 + i % w;
+                if (L[p] == l) { Tb[p] = 0.0; T2b[p] = 0.0; }
+            }
+            __syncthreads();
+            double* cur = Tb; double* nxt = T2b;
+            const int cp = cy * W + cx;
+            for (int it = 0; it < n_it; it++) {
+                for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+                    const int y = y0 + i / w, x = x0 + i % w;
+                    const int p = y * W + x;
+                    if (L[p] != l) continue;
+                    double s = 0.0;
+                    const int oy[9] = {0, -1, 1, 0, 0, -1, -1, 1, 1};
+                    const int ox[9] = {0, 0, 0, -1, 1, -1, 1, -1, 1};
+                    for (int q = 0; q < 9; q++) {
+                        const int yy = y + oy[q], xx = x + ox[q];
+                        double v = 0.0;
+                        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                            const int pq = yy * W + xx;
+                            if (L[pq] == l) v = cur[pq] + (pq == cp ? 1.0 : 0.0);
+                        }
+                        s = q == 0 ? v : __dadd_rn(s, v);
+                    }
+                    nxt[p] = __ddiv_rn(s, 9.0);
+                }
+                __syncthreads();
+                double* tmp = cur; cur = nxt; nxt = tmp;
+            }
+            if (cur != Tb) {
+                for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+                    const int p = (y0 + i / w) * W + x0 + i % w;
+                    if (L[p] == l) Tb[p] = cur[p];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// T of a neighbouring pixel as the reference's padded array holds it: 0 off-tile and on
+// background, the (possibly foreign) instance's T otherwise.
+CPB_DEVICE double cpb_T_at(const double* CPB_RESTRICT Tb, const int* CPB_RESTRICT L, int H, int W, int y, int x) {
+    if (y < 0 || y >= H || x < 0 || x >= W) return 0.0;
+    const int p = y * W + x;
+    return L[p] > 0 ? Tb[p] : 0.0;
+}
+
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
+k_flow_err(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, LabelTables t,
+           const double* CPB_RESTRICT T, double threshold, double* CPB_RESTRICT mu_out) {
+    CPB_SHARED double s_ey[CPB_QC_THREADS / 32], s_ex[CPB_QC_THREADS / 32];
+    const int b = blockIdx.y, LC = t.LC, N = H * W;
+    const int lb = t.lbound[b];
+    const int* L = lab + (size_t)b * N;
+    const double* Tb = T + (size_t)b * N;
+    const float* dPy = dP ? dP + ((size_t)b * 2 + 0) * N : nullptr;
+    const float* dPx = dP ? dP + ((size_t)b * 2 + 1) * N : nullptr;
+    for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
+        const size_t k = (size_t)b * LC + l;
+        const int c = t.cnt[k];
+        if (c <= 0) continue;
+        const int y0 = t.ymin[k], x0 = t.xmin[k];
+        const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        double ey = 0.0, ex = 0.0;
+        for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+            const int y = y0 + i / w, x = x0 + i % w;
+            const int p = y * W + x;
+            if (L[p] != l) continue;
+            const double dy = __dsub_rn(cpb_T_at(Tb, L, H, W, y + 1, x), cpb_T_at(Tb, L, H, W, y - 1, x));
+            const double dx = __dsub_rn(cpb_T_at(Tb, L, H, W, y, x + 1), cpb_T_at(Tb, L, H, W, y, x - 1));
+            const double nrm = __dadd_rn(1e-60, __dsqrt_rn(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx))));
+            const double my = __ddiv_rn(dy, nrm), mx = __ddiv_rn(dx, nrm);
+            if (mu_out) {
+                mu_out[((size_t)b * 2 + 0) * N + p] = my;
+                mu_out[((size_t)b * 2 + 1) * N + p] = mx;
+            }
+            if (dP) {
+                const double ry = __dsub_rn(my, (double)__fdiv_rn(dPy[p], 5.0f));
+                const double rx = __dsub_rn(mx, (double)__fdiv_rn(dPx[p], 5.0f));
+                ey += __dmul_rn(ry, ry);
+                ex += __dmul_rn(rx, rx);
+            }
+        }
+        if (!dP) continue;
+        for (int s = 16; s; s >>= 1) {
+            ey += __shfl_xor_sync(CPB_FULL, ey, s);
+            ex += __shfl_xor_sync(CPB_FULL, ex, s);
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { s_ey[threadIdx.x >> 5] = ey; s_ex[threadIdx.x >> 5] = ex; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sy = 0.0, sx = 0.0;
+            for (int q = 0; q < CPB_QC_THREADS / 32; q++) { sy += s_ey[q]; sx += s_ex[q]; }
+            const double e = sy / (double)c + sx / (double)c;
+            t.err[k] = e;
+            t.flag[k] = e > threshold ? 1 : 0;
+        }
+    }
+}

@@ -1,0 +1,154 @@
+/*
+ * classpose_b200 -- C ABI of the B200-native Classpose post-network path.
+ *
+ * One shared library (libclasspose_b200.so), plain pointers and sizes, no torch types.
+ * Every *_device entry point takes DEVICE pointers, a caller-owned device workspace
+ * (size from cpb_workspace_bytes) and the caller's CUDA stream (cudaStream_t passed as
+ * void*; NULL = legacy default stream).  Calls are asynchronous on that stream, never
+ * synchronise the host, keep no global state and may be issued concurrently from
+ * several host threads as long as each call has its own workspace (the reference runs
+ * >= 2 inference threads per process: predict_wsi.py:728-797).
+ * The *_host entry points take HOST pointers and perform the H2D / D2H copies
+ * themselves (chunked, double-buffered on internal streams); they return when the
+ * outputs are in host memory.
+ *
+ * Return value: 0 on success, a negative CPB_E_* code on argument errors, or a
+ * positive cudaError_t if a launch/copy failed.  There is no CPU fallback.
+ *
+ * Each entry point cites the reference interface it stands in for.  The arithmetic of
+ * rows (2)-(5) lives in cellpose==4.0.8 (not vendored by the reference); citations for
+ * those are the reference's call sites plus SURVEY.md Appendix A.
+ *
+ * Label images are int32 [B,H,W], 0 = background, instance ids 1..n per tile (n in
+ * counts[b]).  Flow fields are float32 [B,2,H,W] (dY, dX) at network scale (5x unit
+ * vectors), cell probabilities float32 [B,H,W], class logits float32 [B,C,H,W].
+ */
+#ifndef CLASSPOSE_B200_H
+#define CLASSPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPB_ABI_VERSION 1
+
+#define CPB_E_ARG       (-1) /* bad shape / null pointer */
+#define CPB_E_WORKSPACE (-2) /* workspace too small */
+#define CPB_E_RANGE     (-3) /* B*H*W does not fit the 31-bit pixel index; split the batch */
+
+/* Parameters of dynamics.resize_and_compute_masks as called at
+ * /root/reference/src/classpose/models.py:149-159; defaults from models.py:490-498,751-752. */
+typedef struct cpb_params {
+    int32_t niter;              /* 200 */
+    float   cellprob_threshold; /* 0.0 */
+    double  flow_threshold;     /* 0.4; <= 0 disables the flow-error check */
+    int32_t min_size;           /* 15; <= 0 skips the size filters (holes are still filled) */
+    double  max_size_fraction;  /* 0.4 */
+    int32_t remove_border;      /* 0; 1 = also drop instances touching the tile border
+                                   (metrics/pq.py:65-92), applied last */
+    int32_t fill_holes;         /* 1 = resize_and_compute_masks contract; 0 = dynamics.compute_masks
+                                   contract with min_size=-1 (no hole fill / size filter) */
+} cpb_params;
+
+int  cpb_abi_version(void);
+/* label-table capacity (max label value + 1 a tile can produce) used by the fused path */
+int  cpb_label_capacity(int H, int W);
+/* bytes of device workspace needed by any *_device call on a [B,H,W] batch with C classes
+ * and label values <= lcap-1 (pass lcap = 0 for the fused-path default) */
+size_t cpb_workspace_bytes(int B, int H, int W, int C, int lcap);
+
+/* ---- fused path: dP, cellprob (, logits) -> masks (, per-cell class) --------------------
+ * Replaces: classpose.models.compute_masks 2-D branch (models.py:97-188, one plane per
+ * tile) + compute_class_masks (models.py:191-230) as called from ClassposeModel.eval
+ * (models.py:750-770).
+ * logits may be NULL (then cell_class / class_masks are not written).
+ * masks [B,H,W] int32, counts [B] int32 (instances per tile),
+ * cell_class [B,lcap] int32 (entry l = class of instance l, entry 0 = 0; only 0..counts[b]
+ * are meaningful), class_masks [B,H,W] uint8 or NULL. */
+int cpb_compute_masks_device(const float* dP, const float* cellprob, const float* logits,
+                             int B, int H, int W, int C, const cpb_params* prm,
+                             int32_t* masks, int32_t* counts, int32_t* cell_class,
+                             uint8_t* class_masks, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* Same, HOST buffers in / out (pageable or pinned).  tiles_per_chunk <= 0 picks a default.
+ * device = CUDA device ordinal.  This is the call the e2e benchmark times. */
+int cpb_compute_masks_host(const float* dP, const float* cellprob, const float* logits,
+                           int B, int H, int W, int C, const cpb_params* prm,
+                           int32_t* masks, int32_t* counts, int32_t* cell_class,
+                           uint8_t* class_masks, int tiles_per_chunk, int device);
+
+/* ---- stage entry points (each is one row of SURVEY.md section 8a) ------------------------ */
+
+/* (2) dynamics.follow_flows / steps_interp on dP*(cellprob>thr)/5 (SURVEY A.2-A.3;
+ * reached from models.py:149).  p_final [B,H,W] int32: (y<<16)|x of the truncated end
+ * point of every foreground pixel, -1 for background.  p_float (optional, may be NULL)
+ * [B,2,H,W] float32 un-truncated (y,x), undefined on background. */
+int cpb_follow_flows_device(const float* dP, const float* cellprob, int B, int H, int W,
+                            int niter, float cellprob_threshold, int32_t* p_final,
+                            float* p_float, void* workspace, size_t workspace_bytes, void* stream);
+
+/* (3) dynamics.get_masks_torch: end points -> seeds -> labels, big-mask
+ * removal, first-appearance renumbering. */
+int cpb_get_masks_device(const int32_t* p_final, int B, int H, int W, double max_size_fraction,
+                         int32_t* masks, int32_t* counts, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* (4a) dynamics.masks_to_flows: float64 heat diffusion from each instance's
+ * centre; mu [B,2,H,W] float64 unit vectors (0 on background).  lcap > max label value. */
+int cpb_masks_to_flows_device(const int32_t* masks, int B, int H, int W, int lcap, double* mu,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* (4) dynamics.remove_bad_flow_masks: zero instances whose mean squared
+ * difference between mask-derived flows and dP/5 exceeds `threshold`; no renumbering.
+ * flow_err (optional) [B,lcap] float64 receives the per-label error. */
+int cpb_remove_bad_flow_masks_device(int32_t* masks, const float* dP, int B, int H, int W,
+                                     int lcap, double threshold, double* flow_err,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* (5) utils.fill_holes_and_remove_small_masks (also models.py:172-174). */
+int cpb_fill_holes_and_remove_small_masks_device(int32_t* masks, int B, int H, int W, int lcap,
+                                                 int min_size, int32_t* counts, void* workspace,
+                                                 size_t workspace_bytes, void* stream);
+
+/* (6) compute_class_masks (models.py:191-230): per-pixel arg-max class, per-instance
+ * majority (ties -> lowest class, class 0 may win, label 0 -> class 0).
+ * cell_class [B,lcap] int32; class_masks [B,H,W] uint8 or NULL. */
+int cpb_class_vote_device(const int32_t* masks, const float* logits, int B, int H, int W, int C,
+                          int lcap, int32_t* cell_class, uint8_t* class_masks, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* (7) metrics.pq.remove_border_instances (pq.py:65-92).  masks [B,H,W,nch] int32, channel 0
+ * holds the instance ids, every channel is zeroed for border instances (nch = 1 for a plain
+ * label image).  In place, as the reference mutates its argument. */
+int cpb_remove_border_instances_device(int32_t* masks, int B, int H, int W, int nch, int lcap,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* (1) transforms.average_tiles (core.py:215,218-220) fused with
+ * unaugment_tiles / unaugment_class_tiles (core.py:207-214; transforms/transforms.py:4-21)
+ * and the crop of core.py:226-229.
+ * y [B,ntiles,nch,ly,lx] float32 network outputs per sub-tile; y0/x0 [ntiles] window origins;
+ * flip [ntiles] bit0 = tile was flipped in Y, bit1 = in X (0 when augment=False);
+ * negate_flow != 0: channel 0 changes sign on Y flips and channel 1 on X flips (flow maps);
+ * taper_y [ly], taper_x [lx] float64 1-D taper factors (the 2-D weight is their product);
+ * output yf [B,nch,Ly-cy0-cy1,Lx-cx0-cx1] float32 = blended map cropped by (cy0,cy1,cx0,cx1).
+ * geometry arrays and tapers are DEVICE pointers. */
+int cpb_average_tiles_device(const float* y, int B, int ntiles, int nch, int ly, int lx,
+                             const int32_t* y0, const int32_t* x0, const int32_t* flip,
+                             int negate_flow, const double* taper_y, const double* taper_x,
+                             int Ly, int Lx, int cy0, int cy1, int cx0, int cx1, float* yf,
+                             void* stream);
+
+/* (e) global label offsets: exclusive prefix sum of per-tile instance counts.
+ * offsets [B] int64 = base + sum(counts[0..b)); total [1] int64 = sum(counts).  `base` is the
+ * rank's offset obtained from the cross-GPU all-gather of totals (host side). */
+int cpb_label_offsets_device(const int32_t* counts, int B, int64_t base, int64_t* offsets,
+                             int64_t* total, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLASSPOSE_B200_H */
