@@ -37,6 +37,10 @@ SIGNATURES = {
     "cpb_label_capacity": (C.c_int, [_I, _I]),
     "cpb_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "cpb_compute_masks_device": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, _P, _Z, _P]),
+    "cpb_num_stages": (C.c_int, []),
+    "cpb_stage_name": (C.c_char_p, [_I]),
+    "cpb_compute_masks_profiled_device": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, _P, _Z, _P, _P]),
+    "cpb_debug_launch_count": (C.c_longlong, []),
     "cpb_compute_masks_host": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, _I, _I]),
     "cpb_follow_flows_device": (C.c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "cpb_get_masks_device": (C.c_int, [_P, _I, _I, _I, _D, _P, _P, _P, _Z, _P]),

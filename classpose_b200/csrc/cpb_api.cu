@@ -11,11 +11,47 @@
 #include "cpb_qc.cuh"
 #include "cpb_post.cuh"
 
+#include <atomic>
 #ifndef CPB_SIM
 #include <mutex>
 #endif
 
+static_assert(sizeof(cpb_params) == 40, "cpb_params layout is part of the ABI (python mirror: _abi.Params)");
+
 namespace {
+
+std::atomic<long long> g_launches{0};   // statistics only: kernels launched by this library
+#define CPB_LAUNCH_COUNTED(...) do { g_launches.fetch_add(1, std::memory_order_relaxed); CPB_LAUNCH(__VA_ARGS__); } while (0)
+
+// Optional per-stage timing of the fused path (cpb_compute_masks_profiled_device).
+enum Stage { S_PREP = 0, S_FOLLOW, S_SEEDS, S_LOOKUP, S_FINALIZE, S_MAP1, S_CENTRES, S_DIFFUSE, S_FLOWERR,
+             S_DROP, S_SIZE1, S_MAP2, S_FILL, S_MAP3, S_SIZE2, S_MAP4, S_BORDER, S_VOTE, S_COUNT };
+const char* kStageNames[S_COUNT] = {"prep_flow", "follow_flows", "seeds", "lookup", "gm_finalize", "map_stats_1",
+                                    "centres", "diffuse", "flow_err", "drop_bad_stats", "size_renumber_1",
+                                    "map_stats_2", "fill_holes", "map_stats_3", "size_renumber_2", "map_final",
+                                    "border", "vote"};
+struct Prof {
+#ifndef CPB_SIM
+    cudaEvent_t begin[S_COUNT], end[S_COUNT];
+#endif
+    bool used[S_COUNT];
+    cudaStream_t st;
+};
+inline void prof_begin(Prof* p, int s) {
+#ifndef CPB_SIM
+    if (p) { cudaEventRecord(p->begin[s], p->st); p->used[s] = true; }
+#endif
+}
+inline void prof_end(Prof* p, int s) {
+#ifndef CPB_SIM
+    if (p) cudaEventRecord(p->end[s], p->st);
+#endif
+}
+struct ProfScope {
+    Prof* p; int s;
+    ProfScope(Prof* p_, int s_) : p(p_), s(s_) { prof_begin(p, s); }
+    ~ProfScope() { prof_end(p, s); }
+};
 
 constexpr int kLabelBlocksPerTile = 24;   // per-label kernels: grid (kLabelBlocksPerTile, B)
 constexpr int kVoteSmemInts = 16 * 1024;  // 64 KB table for the class vote
@@ -48,6 +84,7 @@ struct Workspace {
     int* vote;           // [B*LC*C]
     LabelTables t;
     size_t bytes;
+    Prof* prof;          // optional stage timing
 };
 
 Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
@@ -113,22 +150,23 @@ int sm_count() { return 4; }
 // ---- stage launch sequences (all asynchronous on `st`) ---------------------------------------
 
 int run_init_tables(const Workspace& w, int B, cudaStream_t st) {
-    CPB_LAUNCH(k_init_tables, dim3(blocks_for(w.t.LC, 256), B), dim3(256), 0, st, w.t);
+    CPB_LAUNCH_COUNTED(k_init_tables, dim3(blocks_for(w.t.LC, 256), B), dim3(256), 0, st, w.t);
     CPB_CHECK_LAUNCH();
     return 0;
 }
 
 int run_set_lbound(const Workspace& w, int B, int v, cudaStream_t st) {
-    CPB_LAUNCH(k_fill_i32, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t.lbound, B, v);
+    CPB_LAUNCH_COUNTED(k_fill_i32, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t.lbound, B, v);
     CPB_CHECK_LAUNCH();
     return 0;
 }
 
 // map labels (remap / drop flags / hole keys) and optionally regather statistics
 int run_map_stats(const Workspace& w, int32_t* lab, int B, int H, int W, int nch, const int* map,
-                  const int* drop, const u64* holekey, bool stats, cudaStream_t st) {
+                  const int* drop, const u64* holekey, bool stats, cudaStream_t st, int stage = -1) {
+    ProfScope ps(stage >= 0 ? w.prof : nullptr, stage >= 0 ? stage : 0);
     if (stats) { int e = run_init_tables(w, B, st); if (e) return e; }
-    CPB_LAUNCH(k_map_stats, dim3(blocks_for((long long)B * H * W, 256)), dim3(256), 0, st, lab, B, H, W, nch,
+    CPB_LAUNCH_COUNTED(k_map_stats, dim3(blocks_for((long long)B * H * W, 256)), dim3(256), 0, st, lab, B, H, W, nch,
                map, drop, holekey, stats ? 1 : 0, w.t);
     CPB_CHECK_LAUNCH();
     return 0;
@@ -137,14 +175,17 @@ int run_map_stats(const Workspace& w, int32_t* lab, int B, int H, int W, int nch
 int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B, int H, int W, int niter,
                float thr, int32_t* pfinal, float* pfloat, int* hist, cudaStream_t st) {
     const long long BN = (long long)B * H * W;
+    prof_begin(w.prof, S_PREP);
     cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
     if (hist) cudaMemsetAsync(hist, 0, BN * sizeof(int), st);
     const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
-    CPB_LAUNCH(k_prep_flow, dim3(blocks_for(BN, 256)), dim3(256), 0, st, dP, cellprob, B, H, W, thr, sx, sy,
+    CPB_LAUNCH_COUNTED(k_prep_flow, dim3(blocks_for(BN, 256)), dim3(256), 0, st, dP, cellprob, B, H, W, thr, sx, sy,
                w.flow, pfinal, w.list, w.list_n);
     CPB_CHECK_LAUNCH();
+    prof_end(w.prof, S_PREP);
+    ProfScope ps(w.prof, S_FOLLOW);
     const unsigned grid = (unsigned)std::min<long long>(blocks_for(BN, 256), (long long)sm_count() * 8);
-    CPB_LAUNCH(k_follow, dim3(grid), dim3(256), 0, st, w.flow, w.list, w.list_n, H, W, niter, pfinal, pfloat, hist);
+    CPB_LAUNCH_COUNTED(k_follow, dim3(grid), dim3(256), 0, st, w.flow, w.list, w.list_n, H, W, niter, pfinal, pfloat, hist);
     CPB_CHECK_LAUNCH();
     return 0;
 }
@@ -153,13 +194,18 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
 int run_get_masks(const Workspace& w, const int32_t* pfinal, int B, int H, int W, double msf, int32_t* masks,
                   int32_t* counts, cudaStream_t st) {
     const long long BN = (long long)B * H * W;
+    prof_begin(w.prof, S_SEEDS);
     cudaMemsetAsync(w.M, 0, BN * sizeof(int), st);
-    CPB_LAUNCH(k_seeds, dim3(B), dim3(256), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.M, w.t.lbound);
+    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(256), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.M, w.t.lbound);
     CPB_CHECK_LAUNCH();
+    prof_end(w.prof, S_SEEDS);
+    prof_begin(w.prof, S_LOOKUP);
     int e = run_init_tables(w, B, st); if (e) return e;
-    CPB_LAUNCH(k_lookup, dim3(blocks_for(BN, 256)), dim3(256), 0, st, pfinal, w.M, B, H, W, masks, w.t);
+    CPB_LAUNCH_COUNTED(k_lookup, dim3(blocks_for(BN, 256)), dim3(256), 0, st, pfinal, w.M, B, H, W, masks, w.t);
     CPB_CHECK_LAUNCH();
-    CPB_LAUNCH(k_gm_finalize, dim3(B), dim3(256), 0, st, w.t, H, W, msf, w.skey, w.sidx, counts);
+    prof_end(w.prof, S_LOOKUP);
+    ProfScope ps(w.prof, S_FINALIZE);
+    CPB_LAUNCH_COUNTED(k_gm_finalize, dim3(B), dim3(256), 0, st, w.t, H, W, msf, w.skey, w.sidx, counts);
     CPB_CHECK_LAUNCH();
     return 0;   // caller applies w.t.remap
 }
@@ -169,12 +215,17 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
                 double* mu_out, cudaStream_t st) {
     cudaMemsetAsync(w.t.niter, 0, B * sizeof(int), st);
     const dim3 grid(kLabelBlocksPerTile, B);
-    CPB_LAUNCH(k_centres, grid, dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t);
+    prof_begin(w.prof, S_CENTRES);
+    CPB_LAUNCH_COUNTED(k_centres, grid, dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t);
     CPB_CHECK_LAUNCH();
+    prof_end(w.prof, S_CENTRES);
     const size_t smem = (size_t)CPB_DIFF_SMEM_CELLS * 17;
-    CPB_LAUNCH(k_diffuse, grid, dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0);
+    prof_begin(w.prof, S_DIFFUSE);
+    CPB_LAUNCH_COUNTED(k_diffuse, grid, dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0);
     CPB_CHECK_LAUNCH();
-    CPB_LAUNCH(k_flow_err, grid, dim3(CPB_QC_THREADS), 0, st, masks, dP, H, W, w.t, w.T, thr, mu_out);
+    prof_end(w.prof, S_DIFFUSE);
+    ProfScope ps(w.prof, S_FLOWERR);
+    CPB_LAUNCH_COUNTED(k_flow_err, grid, dim3(CPB_QC_THREADS), 0, st, masks, dP, H, W, w.t, w.T, thr, mu_out);
     CPB_CHECK_LAUNCH();
     return 0;
 }
@@ -186,18 +237,24 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
     int e;
     if (!have_stats) { e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, nullptr, true, st); if (e) return e; }
     const int mode = min_size > 0 ? 1 : 0;
-    CPB_LAUNCH(k_size_renumber, dim3(B), dim3(256), 0, st, w.t, H, W, min_size, mode, w.skey, w.sidx, (int*)nullptr);
+    prof_begin(w.prof, S_SIZE1);
+    CPB_LAUNCH_COUNTED(k_size_renumber, dim3(B), dim3(256), 0, st, w.t, H, W, min_size, mode, w.skey, w.sidx, (int*)nullptr);
     CPB_CHECK_LAUNCH();
-    e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, true, st); if (e) return e;
+    prof_end(w.prof, S_SIZE1);
+    e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, true, st, S_MAP2); if (e) return e;
+    prof_begin(w.prof, S_FILL);
     cudaMemsetAsync(w.holekey, 0, BN * sizeof(u64), st);
-    CPB_LAUNCH(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
+    CPB_LAUNCH_COUNTED(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
                masks, H, W, w.t, w.holekey, w.status);
     CPB_CHECK_LAUNCH();
-    e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, w.holekey, true, st); if (e) return e;
+    prof_end(w.prof, S_FILL);
+    e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, w.holekey, true, st, S_MAP3); if (e) return e;
     if (mode == 1) {
-        CPB_LAUNCH(k_size_renumber, dim3(B), dim3(256), 0, st, w.t, H, W, min_size, 1, w.skey, w.sidx, counts);
+        prof_begin(w.prof, S_SIZE2);
+        CPB_LAUNCH_COUNTED(k_size_renumber, dim3(B), dim3(256), 0, st, w.t, H, W, min_size, 1, w.skey, w.sidx, counts);
         CPB_CHECK_LAUNCH();
-        e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, false, st); if (e) return e;
+        prof_end(w.prof, S_SIZE2);
+        e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, false, st, S_MAP4); if (e) return e;
     } else if (counts) {
         cudaMemcpyAsync(counts, w.t.lbound, B * sizeof(int), cudaMemcpyDeviceToDevice, st);
     }
@@ -206,15 +263,17 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
 
 int run_vote(const Workspace& w, const int32_t* masks, const float* logits, int B, int H, int W, int C,
              int32_t* cell_class, uint8_t* class_masks, cudaStream_t st) {
-    CPB_LAUNCH(k_vote, dim3(B), dim3(512), kVoteSmemInts * 4, st, masks, logits, H, W, C, w.t.LC, w.t.lbound,
+    ProfScope ps(w.prof, S_VOTE);
+    CPB_LAUNCH_COUNTED(k_vote, dim3(B), dim3(512), kVoteSmemInts * 4, st, masks, logits, H, W, C, w.t.LC, w.t.lbound,
                kVoteSmemInts, w.vote, cell_class, class_masks);
     CPB_CHECK_LAUNCH();
     return 0;
 }
 
 int run_border(const Workspace& w, int32_t* masks, int B, int H, int W, int nch, cudaStream_t st) {
+    ProfScope ps(w.prof, S_BORDER);
     int e = run_init_tables(w, B, st); if (e) return e;
-    CPB_LAUNCH(k_border_flags, dim3(B), dim3(256), 0, st, masks, H, W, nch, w.t);
+    CPB_LAUNCH_COUNTED(k_border_flags, dim3(B), dim3(256), 0, st, masks, H, W, nch, w.t);
     CPB_CHECK_LAUNCH();
     return run_map_stats(w, masks, B, H, W, nch, nullptr, w.t.flag, nullptr, false, st);
 }
@@ -242,6 +301,7 @@ size_t cpb_workspace_bytes(int B, int H, int W, int C, int lcap) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);                                  \
     const uintptr_t wsa_ = (reinterpret_cast<uintptr_t>(workspace) + kAlign - 1) / kAlign * kAlign; \
     Workspace w = carve(reinterpret_cast<void*>(wsa_), B, H, W, (Cval), (lcapval));            \
+    w.prof = nullptr;            \
     if (w.bytes + (wsa_ - reinterpret_cast<uintptr_t>(workspace)) > workspace_bytes) return CPB_E_WORKSPACE;
 
 int cpb_follow_flows_device(const float* dP, const float* cellprob, int B, int H, int W, int niter,
@@ -270,7 +330,7 @@ int cpb_get_masks_device(const int32_t* p_final, int B, int H, int W, double max
     CPB_PROLOGUE(0, 0)
     const long long BN = (long long)B * H * W;
     cudaMemsetAsync(w.hist, 0, BN * sizeof(int), st);
-    CPB_LAUNCH(k_hist_from_pfinal, dim3(blocks_for(BN, 256)), dim3(256), 0, st, p_final, B, H, W, w.hist);
+    CPB_LAUNCH_COUNTED(k_hist_from_pfinal, dim3(blocks_for(BN, 256)), dim3(256), 0, st, p_final, B, H, W, w.hist);
     CPB_CHECK_LAUNCH();
     int e = run_get_masks(w, p_final, B, H, W, max_size_fraction, masks, counts, st); if (e) return e;
     return run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, false, st);
@@ -328,20 +388,24 @@ int cpb_remove_border_instances_device(int32_t* masks, int B, int H, int W, int 
     return run_border(w, masks, B, H, W, nch, st);
 }
 
-int cpb_compute_masks_device(const float* dP, const float* cellprob, const float* logits, int B, int H, int W,
+}  // extern "C"
+
+static int compute_masks_impl(const float* dP, const float* cellprob, const float* logits, int B, int H, int W,
                              int C, const cpb_params* prm, int32_t* masks, int32_t* counts, int32_t* cell_class,
-                             uint8_t* class_masks, void* workspace, size_t workspace_bytes, void* stream) {
+                             uint8_t* class_masks, void* workspace, size_t workspace_bytes, void* stream, Prof* prof) {
     if (!dP || !cellprob || !prm || !masks || !counts) return CPB_E_ARG;
     if (logits && (!cell_class || C < 1 || C > 255)) return CPB_E_ARG;
     if (prm->niter < 0) return CPB_E_ARG;
     CPB_PROLOGUE(logits ? C : 0, 0)
+    w.prof = prof;
+    if (prof) prof->st = st;
     int e;
     // (2) Euler integration + end-point histogram
     e = run_follow(w, dP, cellprob, B, H, W, prm->niter, prm->cellprob_threshold, w.pfinal, nullptr, w.hist, st);
     if (e) return e;
     // (3) seeds -> labels; apply the first-appearance remap while gathering label statistics
     e = run_get_masks(w, w.pfinal, B, H, W, prm->max_size_fraction, masks, counts, st); if (e) return e;
-    e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, true, st); if (e) return e;
+    e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, true, st, S_MAP1); if (e) return e;
     // (4) flow-error check; dropped labels become 0 in the pass that regathers statistics
     bool have_stats = true;
     if (prm->flow_threshold > 0.0) {
@@ -349,9 +413,9 @@ int cpb_compute_masks_device(const float* dP, const float* cellprob, const float
         if (prm->fill_holes) {
             // k_map_stats resets `flag` via init_tables before reading it, so copy the flags out first
             cudaMemcpyAsync(w.sidx, w.t.flag, (size_t)B * w.t.LC * sizeof(int), cudaMemcpyDeviceToDevice, st);
-            e = run_map_stats(w, masks, B, H, W, 1, nullptr, w.sidx, nullptr, true, st); if (e) return e;
+            e = run_map_stats(w, masks, B, H, W, 1, nullptr, w.sidx, nullptr, true, st, S_DROP); if (e) return e;
         } else {
-            e = run_map_stats(w, masks, B, H, W, 1, nullptr, w.t.flag, nullptr, false, st); if (e) return e;
+            e = run_map_stats(w, masks, B, H, W, 1, nullptr, w.t.flag, nullptr, false, st, S_DROP); if (e) return e;
             have_stats = false;
         }
     }
@@ -368,6 +432,44 @@ int cpb_compute_masks_device(const float* dP, const float* cellprob, const float
     return 0;
 }
 
+
+extern "C" {
+
+int cpb_compute_masks_device(const float* dP, const float* cellprob, const float* logits, int B, int H, int W,
+                             int C, const cpb_params* prm, int32_t* masks, int32_t* counts, int32_t* cell_class,
+                             uint8_t* class_masks, void* workspace, size_t workspace_bytes, void* stream) {
+    return compute_masks_impl(dP, cellprob, logits, B, H, W, C, prm, masks, counts, cell_class, class_masks, workspace,
+                              workspace_bytes, stream, nullptr);
+}
+
+int cpb_num_stages(void) { return S_COUNT; }
+const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames[i] : ""; }
+long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, const float* logits, int B, int H,
+                                      int W, int C, const cpb_params* prm, int32_t* masks, int32_t* counts,
+                                      int32_t* cell_class, uint8_t* class_masks, void* workspace,
+                                      size_t workspace_bytes, void* stream, float* stage_ms) {
+#ifdef CPB_SIM
+    (void)stage_ms;
+    return compute_masks_impl(dP, cellprob, logits, B, H, W, C, prm, masks, counts, cell_class, class_masks, workspace,
+                              workspace_bytes, stream, nullptr);
+#else
+    if (!stage_ms) return CPB_E_ARG;
+    Prof prof{};
+    for (int i = 0; i < S_COUNT; i++) { cudaEventCreate(&prof.begin[i]); cudaEventCreate(&prof.end[i]); prof.used[i] = false; }
+    int rc = compute_masks_impl(dP, cellprob, logits, B, H, W, C, prm, masks, counts, cell_class, class_masks,
+                                workspace, workspace_bytes, stream, &prof);
+    cudaError_t ce = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+    for (int i = 0; i < S_COUNT; i++) {
+        stage_ms[i] = 0.f;
+        if (rc == 0 && ce == cudaSuccess && prof.used[i]) cudaEventElapsedTime(&stage_ms[i], prof.begin[i], prof.end[i]);
+        cudaEventDestroy(prof.begin[i]); cudaEventDestroy(prof.end[i]);
+    }
+    return rc ? rc : (int)ce;
+#endif
+}
+
 int cpb_average_tiles_device(const float* y, int B, int ntiles, int nch, int ly, int lx, const int32_t* y0,
                              const int32_t* x0, const int32_t* flip, int negate_flow, const double* taper_y,
                              const double* taper_x, int Ly, int Lx, int cy0, int cy1, int cx0, int cx1, float* yf,
@@ -378,7 +480,7 @@ int cpb_average_tiles_device(const float* y, int B, int ntiles, int nch, int ly,
         return CPB_E_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long total = (long long)B * nch * oH * oW;
-    CPB_LAUNCH(k_average_tiles, dim3(blocks_for(total, 256)), dim3(256), 0, st, y, B, ntiles, nch, ly, lx, y0, x0,
+    CPB_LAUNCH_COUNTED(k_average_tiles, dim3(blocks_for(total, 256)), dim3(256), 0, st, y, B, ntiles, nch, ly, lx, y0, x0,
                flip, negate_flow, taper_y, taper_x, cy0, cx0, oH, oW, yf);
     CPB_CHECK_LAUNCH();
     return 0;
@@ -388,7 +490,7 @@ int cpb_label_offsets_device(const int32_t* counts, int B, int64_t base, int64_t
                              void* stream) {
     if (!counts || !offsets || B <= 0) return CPB_E_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CPB_LAUNCH(k_label_offsets, dim3(1), dim3(256), 0, st, counts, B, (long long)base,
+    CPB_LAUNCH_COUNTED(k_label_offsets, dim3(1), dim3(256), 0, st, counts, B, (long long)base,
                reinterpret_cast<long long*>(offsets), reinterpret_cast<long long*>(total));
     CPB_CHECK_LAUNCH();
     return 0;

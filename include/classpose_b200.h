@@ -74,6 +74,18 @@ int cpb_compute_masks_device(const float* dP, const float* cellprob, const float
                              uint8_t* class_masks, void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* Measurement aid: the same fused path with CUDA events around each stage; synchronises the stream
+ * and writes cpb_num_stages() device times in milliseconds to stage_ms (HOST pointer). */
+int cpb_num_stages(void);
+const char* cpb_stage_name(int i);
+int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, const float* logits,
+                                      int B, int H, int W, int C, const cpb_params* prm,
+                                      int32_t* masks, int32_t* counts, int32_t* cell_class,
+                                      uint8_t* class_masks, void* workspace, size_t workspace_bytes,
+                                      void* stream, float* stage_ms);
+/* number of kernels this library has launched in this process (statistics for the benchmark) */
+long long cpb_debug_launch_count(void);
+
 /* Same, HOST buffers in / out (pageable or pinned).  tiles_per_chunk <= 0 picks a default.
  * device = CUDA device ordinal.  This is the call the e2e benchmark times. */
 int cpb_compute_masks_host(const float* dP, const float* cellprob, const float* logits,

@@ -1,0 +1,336 @@
+"""Parity cases shared by the simulator tests (CPU, `-m "not gpu"`) and the GPU tests.
+
+Every case takes a backend `be` exposing the C-ABI call layer with numpy in / numpy out
+(tests/backends.py) and compares the kernels with the oracle on identical seeded inputs.
+Bars (BASELINE.json north_star): integer / label work bit-exact given identical inputs;
+follow_flows >= 99.9 % identical truncated end points (float32 Euler integration is compared
+with torch's CPU grid_sample, which itself differs from torch's CUDA grid_sample at this level);
+fused path F1 >= 0.995 at IoU 0.5, matched-cell class exact, cell-count delta <= 0.1 %.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from oracle import classpose_ref, dynamics, metrics, synth, transforms as otf, utils as outils
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+_tile_cache = {}
+
+
+def std_tile(seed, **kw):
+    key = (seed, tuple(sorted(kw.items())))
+    if key not in _tile_cache:
+        t = synth.make_tile(seed, **kw)
+        st = {}
+        t["masks_oracle"] = dynamics.resize_and_compute_masks(t["dP"], t["cellprob"], return_stages=st)
+        t["stages"] = st
+        _tile_cache[key] = t
+    return _tile_cache[key]
+
+
+def adv_tile():
+    if "adv" not in _tile_cache:
+        t = synth.make_adversarial_tile()
+        st = {}
+        t["masks_oracle"] = dynamics.resize_and_compute_masks(t["dP"], t["cellprob"], return_stages=st)
+        t["stages"] = st
+        _tile_cache["adv"] = t
+    return _tile_cache["adv"]
+
+
+def pack_pfinal(stages, H, W):
+    pf = np.full((H, W), -1, np.int32)
+    ys, xs = stages["inds"]
+    pf[ys, xs] = (stages["p_final"][0].astype(np.int32) << 16) | stages["p_final"][1].astype(np.int32)
+    return pf
+
+
+def c32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------ (2)
+def case_follow_flows(be):
+    tiles = [std_tile(0, H=128, W=128, n_grid=5), std_tile(1), adv_tile(), std_tile(2, H=96, W=160, n_grid=6)]
+    tot = same = 0
+    for t in tiles:
+        H, W = t["cellprob"].shape
+        pf, pfl = be.follow_flows(f32(t["dP"][None]), f32(t["cellprob"][None]), 200, 0.0, want_float=True)
+        st = t["stages"]
+        ys, xs = st["inds"]
+        assert (pf[0][t["cellprob"] <= 0] == -1).all()
+        py, px = pf[0][ys, xs] >> 16, pf[0][ys, xs] & 0xFFFF
+        eq = (py == st["p_final"][0]) & (px == st["p_final"][1])
+        tot += len(ys)
+        same += int(eq.sum())
+        # un-truncated positions: pixels orbiting a sink amplify float32 rounding differences, so the
+        # bound is loose (a tenth of a pixel); the truncated end points below are what get_masks consumes
+        d = np.maximum(np.abs(pfl[0, 0][ys, xs] - st["p_float"][0]), np.abs(pfl[0, 1][ys, xs] - st["p_float"][1]))
+        assert np.mean(d < 0.1) > 0.999 and np.median(d) < 1e-3
+    assert same / tot >= 0.999, f"identical truncated end points: {same}/{tot}"
+
+
+def case_follow_flows_few_iters_exact(be):
+    """With few steps rounding cannot amplify: end points must match the oracle exactly."""
+    t = std_tile(1)
+    st = {}
+    fg = t["cellprob"] > 0
+    p = dynamics.follow_flows(t["dP"] * fg / 5.0, np.nonzero(fg), 3).int().numpy()
+    pf, _ = be.follow_flows(f32(t["dP"][None]), f32(t["cellprob"][None]), 3, 0.0)
+    ys, xs = np.nonzero(fg)
+    eq = ((pf[0][ys, xs] >> 16) == p[0]) & ((pf[0][ys, xs] & 0xFFFF) == p[1])
+    assert eq.mean() > 0.9999
+
+
+# ------------------------------------------------------------------------------------ (3)
+def case_get_masks_exact(be):
+    for t in (std_tile(0, H=128, W=128, n_grid=5), std_tile(1), adv_tile(), std_tile(2, H=96, W=160, n_grid=6),
+              std_tile(5, H=128, W=128, n_grid=16, axes=(2.5, 3.5))):
+        H, W = t["cellprob"].shape
+        m, cnt = be.get_masks(pack_pfinal(t["stages"], H, W)[None], 0.4)
+        ref = t["stages"]["masks_get"]
+        np.testing.assert_array_equal(m[0], ref)
+        assert cnt[0] == ref.max()
+
+
+def case_get_masks_plateaus_and_ties(be):
+    """Hand-made end points: plateau bins (each is its own seed), equal-count seeds whose windows
+    overlap (later raster position wins), a seed at the tile corner, an over-sized label."""
+    H, W = 64, 80
+    rng = np.random.default_rng(7)
+    fg = np.ones((H, W), bool)
+    ys, xs = np.nonzero(fg)
+    targets = [(0, 0, 40), (10, 10, 30), (10, 11, 30), (10, 14, 30), (30, 30, 12), (30, 33, 12), (33, 30, 25),
+               (50, 70, 11), (63, 79, 60), (40, 8, 10), (20, 60, 2200)]
+    ty = np.concatenate([np.full(n, y) for y, x, n in targets])
+    tx = np.concatenate([np.full(n, x) for y, x, n in targets])
+    # halo of low counts (3) around some seeds so that regions actually grow and overlap
+    hy, hx = [], []
+    for y, x, n in targets[1:7]:
+        for dy in range(-3, 4):
+            for dx in range(-3, 4):
+                if (dy or dx) and 0 <= y + dy < H and 0 <= x + dx < W:
+                    hy += [y + dy] * 3
+                    hx += [x + dx] * 3
+    ty = np.concatenate([ty, np.array(hy)])
+    tx = np.concatenate([tx, np.array(hx)])
+    n = len(ys)
+    assert len(ty) <= n
+    rest = n - len(ty)
+    ty = np.concatenate([ty, rng.integers(0, H, rest)])
+    tx = np.concatenate([tx, rng.integers(0, W, rest)])
+    perm = rng.permutation(n)
+    p_final = np.stack([ty[perm], tx[perm]]).astype(np.int32)
+    ref = dynamics.get_masks(p_final, (ys, xs), (H, W), max_size_fraction=0.4)
+    pf = np.zeros((H, W), np.int32)
+    pf[ys, xs] = (p_final[0] << 16) | p_final[1]
+    m, cnt = be.get_masks(pf[None], 0.4)
+    np.testing.assert_array_equal(m[0], ref)
+    assert cnt[0] == ref.max() and ref.max() >= 5
+
+
+def case_get_masks_no_seeds(be):
+    H, W = 32, 48
+    pf = np.full((H, W), -1, np.int32)
+    ys, xs = np.mgrid[0:H, 0:W]
+    pf[:] = (ys.astype(np.int32) << 16) | xs.astype(np.int32)   # every pixel stays put: counts of 1, no seed
+    m, cnt = be.get_masks(pf[None], 0.4)
+    assert not m.any() and cnt[0] == 0
+
+
+# ------------------------------------------------------------------------------------ (4)
+def case_masks_to_flows_exact(be):
+    for lab in (std_tile(1)["labels"], synth.adversarial_labels(), std_tile(2, H=96, W=160, n_grid=6)["labels"]):
+        mu = be.masks_to_flows(c32(lab[None]), int(lab.max()) + 2)
+        ref = dynamics.masks_to_flows(lab)
+        assert np.abs(mu[0] - ref).max() <= 1e-12
+
+
+def corrupt_flows(t, every=4, seed=0):
+    """Replace the flows of every `every`-th planted cell by noise so that its flow error is large."""
+    rng = np.random.default_rng(seed)
+    dP = t["dP"].copy()
+    for l in range(1, int(t["labels"].max()) + 1, every):
+        m = t["labels"] == l
+        dP[:, m] = rng.normal(0, 3.0, size=(2, int(m.sum()))).astype(np.float32)
+    return dP
+
+
+def case_remove_bad_flow_masks_exact(be):
+    for t in (std_tile(1), std_tile(3), adv_tile()):
+        lab = t["labels"].astype(np.int32)
+        dP = corrupt_flows(t)
+        err_ref, _ = dynamics.flow_error(lab, dP)
+        ref = dynamics.remove_bad_flow_masks(lab.copy(), dP, 0.4)
+        out, err = be.remove_bad_flow_masks(c32(lab[None]).copy(), f32(dP[None]), int(lab.max()) + 2, 0.4, want_err=True)
+        n = len(err_ref)
+        assert np.abs(err[0, 1:n + 1] - err_ref).max() < 1e-9
+        assert (err_ref > 0.4).sum() >= 1
+        np.testing.assert_array_equal(out[0], ref)
+
+
+# ------------------------------------------------------------------------------------ (5)
+def nested_rings(H=96, W=96):
+    yy, xx = np.mgrid[0:H, 0:W]
+    r2 = (yy - 48) ** 2 + (xx - 48) ** 2
+    lab = np.zeros((H, W), np.int32)
+    lab[(r2 <= 44 ** 2) & (r2 > 38 ** 2)] = 3     # outer ring
+    lab[(r2 <= 30 ** 2) & (r2 > 24 ** 2)] = 1     # inner ring (lower id, processed first upstream)
+    lab[r2 <= 8 ** 2] = 2                          # core cell
+    lab[(yy - 10) ** 2 + (xx - 10) ** 2 <= 9] = 4  # outside everything, larger than min_size
+    lab[2:4, 80:83] = 5                            # tiny
+    return lab
+
+
+def case_fill_holes_exact(be):
+    labs = [synth.adversarial_labels(), nested_rings(), std_tile(1)["stages"]["masks_qc"].astype(np.int32)]
+    # non-contiguous labels with small ones: exercises the positional size filter upstream uses
+    q = nested_rings().copy()
+    q[q == 4] = 9
+    q[q == 5] = 6
+    q[60:62, 2:5] = 7
+    labs.append(q)
+    # all foreground, no background pixel at all
+    a = np.ones((40, 40), np.int32)
+    a[:, 20:] = 2
+    a[5:8, 5:8] = 3
+    a[30:32, 30:33] = 5
+    labs.append(a)
+    for lab in labs:
+        for min_size in (15, 0):
+            ref = outils.fill_holes_and_remove_small_masks(lab.copy(), min_size=min_size)
+            out, cnt = be.fill_holes_and_remove_small_masks(c32(lab[None]).copy(), int(lab.max()) + 2, min_size)
+            np.testing.assert_array_equal(out[0], ref, err_msg=f"min_size={min_size}")
+            if min_size > 0:
+                assert cnt[0] == ref.max()
+
+
+# ------------------------------------------------------------------------------------ (6)
+def case_class_vote_reference_vectors(be):
+    g = np.load(os.path.join(GOLDEN, "ref_class_vote.npz"))
+    for k in range(int(g["ncases"])):
+        masks, logits = g[f"masks{k}"], g[f"logits{k}"]
+        cc, cm = be.class_vote(c32(masks[None]), f32(logits[:, 0][None]), int(masks.max()) + 2, want_class_masks=True)
+        np.testing.assert_array_equal(cm[0].astype(np.int64), g[f"class_masks{k}"])
+    t = adv_tile()
+    m = t["masks_oracle"]
+    ref, _ = classpose_ref.compute_class_masks(m, t["logits"][:, None])
+    cc, cm = be.class_vote(c32(m[None]), f32(t["logits"][None]), int(m.max()) + 2, want_class_masks=True)
+    np.testing.assert_array_equal(cm[0], ref)
+    for l in range(1, int(m.max()) + 1):
+        assert cc[0, l] == ref[m == l][0]
+
+
+# ------------------------------------------------------------------------------------ (7)
+def case_border_reference_vectors(be):
+    g = np.load(os.path.join(GOLDEN, "ref_border.npz"))
+    for k in range(int(g["ncases"])):
+        a = g[f"in2d_{k}"]
+        out = be.remove_border_instances(c32(a[None]).copy(), int(a.max()) + 2, 1)
+        np.testing.assert_array_equal(out[0], g[f"out2d_{k}"])
+        a = g[f"in3d_{k}"]
+        out = be.remove_border_instances(c32(a[None]).copy(), int(a[..., 0].max()) + 2, a.shape[-1])
+        np.testing.assert_array_equal(out[0], g[f"out3d_{k}"])
+
+
+# ------------------------------------------------------------------------------------ (1)
+def case_average_tiles(be):
+    from classpose_b200 import transforms as btf
+    rng = np.random.default_rng(3)
+    for augment, nch in ((False, 3), (True, 3), (True, 5)):
+        Ly = Lx = 272
+        geo = btf.tile_geometry(Ly, Lx, 256, augment=augment, tile_overlap=0.1)
+        nt = geo["ny"] * geo["nx"]
+        y = rng.normal(size=(nt, nch, 256, 256)).astype(np.float32)
+        # oracle: un-augment (flows negate, logits do not), then average
+        y5 = y.reshape(geo["ny"], geo["nx"], nch, 256, 256).copy()
+        if augment:
+            y5 = otf.unaugment_tiles(y5) if nch == 3 else classpose_ref.unaugment_class_tiles(y5)
+        ysub = [[a, a + 256] for a in geo["y0"]]
+        xsub = [[a, a + 256] for a in geo["x0"]]
+        ref = otf.average_tiles(y5.reshape(nt, nch, 256, 256), ysub, xsub, Ly, Lx)
+        ty, tx = btf.taper_1d(256, 256)
+        out = be.average_tiles(y[None], geo["y0"], geo["x0"], geo["flip"], nch == 3 and augment, ty, tx, Ly, Lx,
+                               (0, 0, 0, 0))
+        np.testing.assert_allclose(out[0], ref, rtol=0, atol=1e-6)
+        assert np.mean(out[0] == ref) > 0.999
+        crop = (8, 8, 8, 8)
+        outc = be.average_tiles(y[None], geo["y0"], geo["x0"], geo["flip"], nch == 3 and augment, ty, tx, Ly, Lx, crop)
+        np.testing.assert_array_equal(outc[0], out[0][:, 8:-8, 8:-8])
+
+
+# ------------------------------------------------------------------------------------ fused
+def fused_compare(be, tiles, C, **kw):
+    B = len(tiles)
+    dP = f32(np.stack([t["dP"] for t in tiles]))
+    cp = f32(np.stack([t["cellprob"] for t in tiles]))
+    lg = f32(np.stack([t["logits"] for t in tiles]))
+    masks, counts, cell_class, class_masks = be.compute_masks(dP, cp, lg, want_class_masks=True, **kw)
+    tp = fp = fn = nref = nnew = 0
+    for b, t in enumerate(tiles):
+        ref = t["masks_oracle"] if not kw else dynamics.resize_and_compute_masks(t["dP"], t["cellprob"], **kw)
+        ref_cm, _ = classpose_ref.compute_class_masks(ref, t["logits"][:, None])
+        r = metrics.class_agreement(ref, ref_cm, masks[b], class_masks[b].astype(np.int64))
+        assert not r["class_mismatch"], f"class differs on matched cells {r['class_mismatch'][:5]}"
+        tp += r["tp"]; fp += r["fp"]; fn += r["fn"]; nref += r["n_true"]; nnew += r["n_pred"]
+        assert counts[b] == masks[b].max() == len(np.unique(masks[b])) - 1
+        for l in range(1, int(counts[b]) + 1):
+            assert cell_class[b, l] == class_masks[b][masks[b] == l][0]
+    f1 = 1.0 if (2 * tp + fp + fn) == 0 else 2 * tp / (2 * tp + fp + fn)
+    return f1, nref, nnew
+
+
+def case_fused_path(be):
+    tiles = [std_tile(s) for s in (1, 3, 4, 6)] + [adv_tile()]
+    f1, nref, nnew = fused_compare(be, tiles, 7)
+    assert f1 >= 0.995, f1
+    assert abs(nnew - nref) <= max(1, 0.001 * nref), (nref, nnew)
+
+
+def case_fused_path_other_shapes(be):
+    tiles = [std_tile(2, H=96, W=160, n_grid=6, C=5), std_tile(7, H=96, W=160, n_grid=6, C=5)]
+    f1, nref, nnew = fused_compare(be, tiles, 5)
+    assert f1 >= 0.995 and nnew == nref
+    dense = [std_tile(5, H=128, W=128, n_grid=16, axes=(2.5, 3.5), C=10)]
+    f1, nref, nnew = fused_compare(be, dense, 10)
+    assert f1 >= 0.99 and abs(nnew - nref) <= 1
+
+
+def case_fused_empty_and_params(be):
+    H = W = 64
+    dP = np.zeros((2, 2, H, W), np.float32)
+    cp = -np.ones((2, H, W), np.float32)
+    t = std_tile(0, H=128, W=128, n_grid=5)
+    masks, counts, cc, cm = be.compute_masks(dP, cp, None)
+    assert not masks.any() and not counts.any()
+    # flow check off / no min size / border removal: compare with the oracle under the same switches
+    one = [t]
+    for kw in (dict(flow_threshold=0.0), dict(min_size=0), dict(cellprob_threshold=1.5), dict(niter=50)):
+        f1, nref, nnew = fused_compare(be, one, 7, **kw)
+        assert f1 >= 0.99 and abs(nref - nnew) <= 1, kw
+    m, c, _, _ = be.compute_masks(f32(t["dP"][None]), f32(t["cellprob"][None]), None, remove_border=True)
+    ref = classpose_ref.remove_border_instances(t["masks_oracle"].astype(np.int32).copy())
+    r = metrics.match_instances(ref, m[0])
+    assert r["fp"] == 0 and r["fn"] == 0
+
+
+def case_label_offsets(be):
+    counts = np.array([3, 0, 7, 1, 250, 12] * 100, np.int32)
+    offs, total = be.label_offsets(counts, 1000)
+    ref = 1000 + np.cumsum(counts.astype(np.int64)) - counts
+    np.testing.assert_array_equal(offs, ref)
+    assert total[0] == counts.sum()
+
+
+ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_get_masks_exact,
+             case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
+             case_remove_bad_flow_masks_exact, case_fill_holes_exact, case_class_vote_reference_vectors,
+             case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
+             case_fused_empty_and_params, case_label_offsets]

@@ -1,0 +1,124 @@
+"""CPU-side checks: the CUDA library loads and exports every symbol the header declares, the host
+logic mirrors the reference's geometry, the hooks patch by attribute, and there is no CPU fallback."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import classpose_b200
+from classpose_b200 import _abi, _lib, distributed as cdist, hooks, transforms as btf
+from oracle import transforms as otf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    path = _lib.build()
+    lib = ctypes.CDLL(path)          # no GPU needed to load
+    header = open(os.path.join(ROOT, "include", "classpose_b200.h")).read()
+    names = set(re.findall(r"\b(cpb_[a-z_0-9]+)\s*\(", header))
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), n
+    assert names == set(_abi.SIGNATURES), names ^ set(_abi.SIGNATURES)
+    _abi.declare(lib)
+    assert lib.cpb_abi_version() == _abi.ABI_VERSION
+    assert lib.cpb_label_capacity(256, 256) == 256 * 256 // 11 + 2
+    assert lib.cpb_workspace_bytes(4, 256, 256, 7, 0) > 4 * 256 * 256 * 36
+
+
+def test_params_struct_layout_matches_header():
+    p = _abi.make_params()
+    assert (p.niter, p.min_size, p.fill_holes, p.remove_border) == (200, 15, 1, 0)
+    assert abs(p.flow_threshold - 0.4) < 1e-15 and abs(p.max_size_fraction - 0.4) < 1e-15
+    assert ctypes.sizeof(_abi.Params) == 40   # int,float,double,int,(pad),double,int,int; static_assert in cpb_api.cu
+    assert _abi.make_params(flow_threshold=None).flow_threshold == 0.0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the GPU-less behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(classpose_b200.ClassposeB200Error):
+        classpose_b200.get_engine()
+    from classpose_b200 import dynamics
+    with pytest.raises(classpose_b200.ClassposeB200Error):
+        dynamics.resize_and_compute_masks(np.zeros((2, 8, 8), np.float32), np.ones((8, 8), np.float32))
+    with pytest.raises(classpose_b200.ClassposeB200Error):
+        classpose_b200.compute_class_masks(np.ones((4, 4), np.int32), np.zeros((3, 1, 4, 4), np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "classpose_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inl")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "cusim" not in src or f == "cpb_platform.h", f
+
+
+@pytest.mark.parametrize("Ly,Lx,bsize,augment", [(272, 272, 256, False), (272, 272, 256, True), (528, 400, 256, False),
+                                                  (300, 1040, 256, True), (256, 256, 256, False), (200, 180, 224, True)])
+def test_tile_geometry_matches_make_tiles(Ly, Lx, bsize, augment):
+    img = np.zeros((1, Ly, Lx), np.float32)
+    IMG, ysub, xsub, Lyt, Lxt = otf.make_tiles(img, bsize=bsize, augment=augment, tile_overlap=0.1)
+    g = btf.tile_geometry(Ly, Lx, bsize, augment=augment, tile_overlap=0.1)
+    assert (g["Ly"], g["Lx"]) == (Lyt, Lxt)
+    assert list(g["y0"]) == [s[0] for s in ysub] and list(g["x0"]) == [s[0] for s in xsub]
+    assert (g["ly"], g["lx"]) == IMG.shape[-2:]
+    if augment:
+        codes = [otf._flip_code(j, i) for j in range(g["ny"]) for i in range(g["nx"])]
+        assert list(g["flip"]) == codes
+
+
+def test_taper_and_pad_match_oracle():
+    for ly, lx in ((256, 256), (224, 200), (300, 256)):
+        ty, tx = btf.taper_1d(ly, lx)
+        np.testing.assert_array_equal(np.outer(ty, tx), otf._taper_mask(ly, lx))
+    for L in ((256, 256), (225, 301), (100, 100)):
+        assert btf.get_pad_yx(*L, min_size=(256, 256)) == otf.get_pad_yx(*L, min_size=(256, 256))
+
+
+def test_hooks_patch_and_restore_by_attribute():
+    fake_models = types.ModuleType("classpose.models")
+    fake_models.compute_masks = "orig_a"
+    fake_models.compute_class_masks = "orig_c"
+    fake_dyn = types.ModuleType("cellpose.dynamics")
+    fake_dyn.resize_and_compute_masks = "orig_b"
+    fake_dyn.compute_masks = "orig_b2"
+    fake_tf = types.ModuleType("cellpose.transforms")
+    fake_tf.average_tiles = "orig_d"
+    mods = {"classpose.models": fake_models, "cellpose.dynamics": fake_dyn, "cellpose.transforms": fake_tf}
+    patched = hooks.install(mods)
+    assert {"classpose.models.compute_masks", "classpose.models.compute_class_masks",
+            "cellpose.dynamics.resize_and_compute_masks", "cellpose.transforms.average_tiles"} <= set(patched)
+    from classpose_b200 import dynamics, models
+    assert fake_models.compute_masks is models.compute_masks
+    assert fake_dyn.resize_and_compute_masks is dynamics.resize_and_compute_masks
+    hooks.uninstall()
+    assert fake_models.compute_masks == "orig_a" and fake_tf.average_tiles == "orig_d"
+
+
+def test_reference_signatures_are_honoured():
+    import inspect
+    from classpose_b200 import dynamics, models
+    sig = inspect.signature(models.compute_masks)
+    assert list(sig.parameters) == ["dP", "cellprob", "shape", "do_3D", "niter", "cellprob_threshold", "flow_threshold",
+                                    "min_size", "max_size_fraction", "stitch_threshold", "device"]
+    sig = inspect.signature(dynamics.resize_and_compute_masks)
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert d["niter"] == 200 and d["cellprob_threshold"] == 0.0 and d["flow_threshold"] == 0.4
+    assert d["min_size"] == 15 and d["max_size_fraction"] == 0.4 and d["resize"] is None
+    assert list(inspect.signature(models.compute_class_masks).parameters)[:2] == ["masks", "y_class"]
+
+
+def test_shard_ranges_cover_the_tile_list():
+    for n, w in ((244036, 8), (10, 3), (5, 8), (1024, 4)):
+        spans = [cdist.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,149 @@
+"""GPU tests of the reference-facing python boundary (hooks A-D): numpy in, numpy out, same return
+types as the reference, results against the oracle / the reference's golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from oracle import classpose_ref, dynamics as odyn, metrics, transforms as otf, utils as outils
+
+pytestmark = pytest.mark.gpu
+
+
+def test_native_library_is_loaded():
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    n0 = eng.launch_count()
+    eng.compute_masks_batch(np.zeros((1, 2, 32, 32), np.float32), np.ones((1, 32, 32), np.float32))
+    assert eng.launch_count() > n0
+    loaded = open("/proc/self/maps").read()
+    assert "libclasspose_b200.so" in loaded
+
+
+def test_hook_b_resize_and_compute_masks_numpy_contract():
+    from classpose_b200 import dynamics
+    t = pc.std_tile(1)
+    m = dynamics.resize_and_compute_masks(t["dP"], t["cellprob"], niter=200, cellprob_threshold=0.0,
+                                          flow_threshold=0.4, min_size=15, max_size_fraction=0.4, resize=None,
+                                          device=None)
+    assert isinstance(m, np.ndarray) and m.dtype == np.uint16 and m.shape == t["cellprob"].shape
+    r = metrics.match_instances(t["masks_oracle"], m)
+    assert r["f1"] >= 0.995
+    z = dynamics.resize_and_compute_masks(t["dP"], -np.abs(t["cellprob"]) - 1)
+    assert z.shape == m.shape and not z.any()
+    m2 = dynamics.compute_masks(t["dP"], t["cellprob"])      # min_size=-1: no fill / size filter
+    ref2 = odyn.compute_masks(t["dP"], t["cellprob"])
+    assert metrics.match_instances(ref2, m2)["f1"] >= 0.995
+
+
+def test_hook_a_models_compute_masks():
+    import torch
+    from classpose_b200 import models
+    tiles = [pc.std_tile(1), pc.std_tile(3)]
+    dP = np.stack([t["dP"] for t in tiles], 1)           # [2, nimg, H, W]
+    cp = np.stack([t["cellprob"] for t in tiles])
+    one = models.compute_masks(dP[:, :1], cp[:1], (1, 256, 256), False, 200, 0.0, 0.4, 15, 0.4, 0.0, torch.device("cpu"))
+    assert one.shape == (256, 256)
+    assert metrics.match_instances(tiles[0]["masks_oracle"], one)["f1"] >= 0.995
+    both = models.compute_masks(dP, cp, (2, 256, 256), False, 200, 0.0, 0.4, 15, 0.4, 0.0, torch.device("cuda"))
+    assert both.shape == (2, 256, 256)
+    np.testing.assert_array_equal(both[0], one)
+    with pytest.raises(NotImplementedError):
+        models.compute_masks(dP, cp, (2, 256, 256), True, 200, 0.0, 0.4, 15, 0.4, 0.0, None)
+
+
+def test_hook_c_compute_class_masks_reference_vectors(golden_dir):
+    from classpose_b200 import models
+    g = np.load(os.path.join(golden_dir, "ref_class_vote.npz"))
+    for k in range(int(g["ncases"])):
+        cm, uniq = models.compute_class_masks(g[f"masks{k}"].copy(), g[f"logits{k}"].copy())
+        assert cm.dtype == np.int64
+        np.testing.assert_array_equal(cm, g[f"class_masks{k}"])
+        np.testing.assert_array_equal(uniq, g[f"unique{k}"])
+    cm, uniq = models.compute_class_masks(np.zeros((8, 8), np.uint16), np.zeros((3, 1, 8, 8), np.float32))
+    assert not cm.any() and list(uniq) == [0]
+
+
+def test_hook_d_average_tiles_and_unaugment():
+    from classpose_b200 import transforms as btf
+    rng = np.random.default_rng(0)
+    img = rng.normal(size=(3, 272, 272)).astype(np.float32)
+    IMG, ysub, xsub, Ly, Lx = otf.make_tiles(img, bsize=256, augment=False)
+    y = IMG.reshape(-1, 3, 256, 256)
+    out = btf.average_tiles(y, ysub, xsub, Ly, Lx)
+    ref = otf.average_tiles(y, ysub, xsub, Ly, Lx)
+    assert out.dtype == np.float32 and out.shape == ref.shape
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-6)
+    y5 = rng.normal(size=(3, 3, 3, 64, 64)).astype(np.float32)
+    np.testing.assert_array_equal(btf.unaugment_tiles(y5.copy()), otf.unaugment_tiles(y5.copy()))
+    np.testing.assert_array_equal(btf.unaugment_class_tiles(y5.copy()), classpose_ref.unaugment_class_tiles(y5.copy()))
+
+
+def test_border_and_fill_wrappers(golden_dir):
+    from classpose_b200 import metrics as bmetrics, utils as butils
+    g = np.load(os.path.join(golden_dir, "ref_border.npz"))
+    for k in range(int(g["ncases"])):
+        for tag in ("2d", "3d"):
+            a = g[f"in{tag}_{k}"].copy()
+            out = bmetrics.remove_border_instances(a)
+            assert out is a
+            np.testing.assert_array_equal(out, g[f"out{tag}_{k}"])
+    lab = pc.nested_rings().astype(np.uint16)
+    np.testing.assert_array_equal(butils.fill_holes_and_remove_small_masks(lab.copy(), 15),
+                                  outils.fill_holes_and_remove_small_masks(lab.copy(), 15))
+
+
+def test_host_buffer_path_matches_device_path():
+    import torch
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    tiles = [pc.std_tile(s) for s in (1, 3, 4)]
+    dP = np.stack([t["dP"] for t in tiles]); cp = np.stack([t["cellprob"] for t in tiles])
+    lg = np.stack([t["logits"] for t in tiles])
+    md, cd, ccd, _ = eng.compute_masks_batch(dP, cp, lg)
+    mh, ch, cch, cmh = eng.compute_masks_host(dP, cp, lg, tiles_per_chunk=2, want_class_masks=True)
+    np.testing.assert_array_equal(mh.numpy(), md.cpu().numpy())
+    np.testing.assert_array_equal(ch.numpy(), cd.cpu().numpy())
+    for b in range(3):
+        n = int(ch[b])
+        np.testing.assert_array_equal(cch[b, :n + 1].numpy(), ccd[b, :n + 1].cpu().numpy())
+
+
+def test_concurrent_calls_from_two_threads():
+    """The reference runs two inference threads per process; calls must be re-entrant."""
+    import threading
+    import torch
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    tiles = [pc.std_tile(1), pc.std_tile(3)]
+    res = [None, None]
+
+    def work(i):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                m, c, _, _ = eng.compute_masks_batch(tiles[i]["dP"][None], tiles[i]["cellprob"][None])
+            s.synchronize()
+        res[i] = m[0].cpu().numpy()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for i in range(2):
+        assert metrics.match_instances(tiles[i]["masks_oracle"], res[i])["f1"] >= 0.995
+
+
+def test_device_synth_and_batch_consistency():
+    """Device-side generator + a batch of 64 tiles: every tile recovers its planted cells."""
+    import torch
+    from classpose_b200 import synth
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    d = synth.make_batch(64, 256, 256, 7, seed=5)
+    masks, counts, cc, _ = eng.compute_masks_batch(d["dP"], d["cellprob"], d["logits"])
+    torch.cuda.synchronize()
+    planted = torch.stack([(d["labels"][b].unique() > 0).sum() for b in range(64)])
+    assert (counts.cpu() - planted.cpu()).abs().float().mean() < 1.0
+    # oracle on two of them
+    for b in (0, 63):
+        ref = odyn.resize_and_compute_masks(d["dP"][b].cpu().numpy(), d["cellprob"][b].cpu().numpy())
+        assert metrics.match_instances(ref, masks[b].cpu().numpy())["f1"] >= 0.995
