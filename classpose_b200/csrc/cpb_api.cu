@@ -53,7 +53,8 @@ struct ProfScope {
     ~ProfScope() { prof_end(p, s); }
 };
 
-constexpr int kLabelBlocksPerTile = 24;   // per-label kernels: grid (kLabelBlocksPerTile, B)
+constexpr int kLabelBlocksPerTile = 24;
+constexpr int kWarpDiffuseBlocksPerTile = 8; // x CPB_DW_WARPS warps: labels of a tile in flight   // per-label kernels: grid (kLabelBlocksPerTile, B)
 constexpr int kVoteSmemInts = 16 * 1024;  // 64 KB table for the class vote
 constexpr size_t kAlign = 256;
 
@@ -93,7 +94,7 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     const int LC = lcap > 0 ? lcap : cpb_label_capacity(H, W);
     const size_t BL = (size_t)B * LC;
     Carver c{reinterpret_cast<char*>(base), 0};
-    w.flow = c.take<float2>(BN);
+    w.flow = c.take<float2>((size_t)B * (H + 2) * (W + 2));
     w.pfinal = c.take<int>(BN);
     w.hist = c.take<int>(BN);
     w.M = c.take<int>(BN);
@@ -179,7 +180,7 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
     if (hist) cudaMemsetAsync(hist, 0, BN * sizeof(int), st);
     const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
-    CPB_LAUNCH_COUNTED(k_prep_flow, dim3(blocks_for(BN, 256)), dim3(256), 0, st, dP, cellprob, B, H, W, thr, sx, sy,
+    CPB_LAUNCH_COUNTED(k_prep_flow, dim3(blocks_for((long long)B * (H + 2) * (W + 2), 256)), dim3(256), 0, st, dP, cellprob, B, H, W, thr, sx, sy,
                w.flow, pfinal, w.list, w.list_n);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_PREP);
@@ -221,7 +222,10 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
     prof_end(w.prof, S_CENTRES);
     const size_t smem = (size_t)CPB_DIFF_SMEM_CELLS * 17;
     prof_begin(w.prof, S_DIFFUSE);
-    CPB_LAUNCH_COUNTED(k_diffuse, grid, dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0);
+    CPB_LAUNCH_COUNTED(k_diffuse_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks, H, W,
+                       w.t, w.T, 0);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_diffuse, grid, dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0, 1);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_DIFFUSE);
     ProfScope ps(w.prof, S_FLOWERR);

@@ -6,60 +6,70 @@
 #pragma once
 #include "cpb_common.cuh"
 
-// k_prep_flow: one thread per pixel.
-//   flow[b][y][x] = ( dX*fg/5 * 2/(W-1) , dY*fg/5 * 2/(H-1) )   (x component first)
-//   p_final[b][y][x] = -1 on background
-//   foreground pixels are appended to `list` (global pixel index), block-contiguous.
+// The masked, scaled flow field is stored zero-padded by one pixel on every side, x component
+// first:  flow[b][y+1][x+1] = ( dX*fg/5 * 2/(W-1) , dY*fg/5 * 2/(H-1) ),  row pitch Wp = W+2.
+// Clamped positions sample taps in [-1, L], so all four bilinear taps are always inside the
+// padded array and grid_sample's zero padding costs no bounds checks (a zero tap adds v*w = 0).
+//
+// k_prep_flow: one thread per padded pixel.  Also writes p_final = -1 on background and appends
+// foreground pixels to `list` (global pixel index in the un-padded layout), block-contiguous.
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, int B, int H, int W,
             float thr, float sx, float sy, float2* CPB_RESTRICT flow, int* CPB_RESTRICT pfinal,
             unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n) {
     CPB_SHARED int s_scan[33];
     CPB_SHARED unsigned s_base;
-    const int N = H * W;
-    const long long total = (long long)B * N;
-    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = H * W, Wp = W + 2, Np = (H + 2) * Wp;
+    const long long total = (long long)B * Np;
+    const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool fg = false;
-    if (gi < total) {
-        const int b = (int)(gi / N);
-        const int r = (int)(gi - (long long)b * N);
-        const float cp = cellprob[gi];
-        fg = cp > thr;
-        const float m = fg ? 1.0f : 0.0f;
-        const float dy = dP[((size_t)b * 2 + 0) * N + r];
-        const float dx = dP[((size_t)b * 2 + 1) * N + r];
-        // (dP * fg) / 5.  then  *= 2/(L-1)   -- each a separately rounded float32 op
-        const float fy = __fmul_rn(__fdiv_rn(__fmul_rn(dy, m), 5.0f), sy);
-        const float fx = __fmul_rn(__fdiv_rn(__fmul_rn(dx, m), 5.0f), sx);
-        flow[gi] = make_float2(fx, fy);
-        if (!fg) pfinal[gi] = -1;
+    unsigned gi = 0;
+    if (gp < total) {
+        const int b = (int)(gp / Np);
+        const int rp = (int)(gp - (long long)b * Np);
+        const int yp = rp / Wp, xp = rp - yp * Wp;
+        float2 out = make_float2(0.f, 0.f);
+        if (yp >= 1 && yp <= H && xp >= 1 && xp <= W) {
+            const int r = (yp - 1) * W + (xp - 1);
+            gi = (unsigned)b * (unsigned)N + (unsigned)r;
+            const float cp = cellprob[gi];
+            fg = cp > thr;
+            const float m = fg ? 1.0f : 0.0f;
+            const float dy = dP[((size_t)b * 2 + 0) * N + r];
+            const float dx = dP[((size_t)b * 2 + 1) * N + r];
+            // (dP * fg) / 5.  then  *= 2/(L-1)   -- each a separately rounded float32 op
+            out.y = __fmul_rn(__fdiv_rn(__fmul_rn(dy, m), 5.0f), sy);
+            out.x = __fmul_rn(__fdiv_rn(__fmul_rn(dx, m), 5.0f), sx);
+            if (!fg) pfinal[gi] = -1;
+        }
+        flow[gp] = out;
     }
     int tot;
     const int incl = cpb_block_scan_incl(fg ? 1 : 0, s_scan, &tot);
     if (threadIdx.x == 0 && tot > 0) s_base = atomicAdd(list_n, (unsigned)tot);
     __syncthreads();
-    if (fg) list[s_base + incl - 1] = (unsigned)gi;
+    if (fg) list[s_base + incl - 1] = gi;
 }
 
 // One Euler step in normalised coordinates, arithmetic order as ATen's grid_sampler_2d.
-CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int H, int W, float fH, float fW,
-                               float& px, float& py) {
+// f points at pixel (0,0) of the padded tile; Wp is its row pitch.
+CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int Wp, float fH, float fW, float& px, float& py) {
     const float ix = ((px + 1.f) * fW - 1.f) / 2.f;
     const float iy = ((py + 1.f) * fH - 1.f) / 2.f;
     const float fx0 = floorf(ix), fy0 = floorf(iy);
-    const int x0 = (int)fx0, y0 = (int)fy0;
+    const int idx = (int)fy0 * Wp + (int)fx0;
     const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+    const float2* r0 = f + idx;      // f is an opaque per-thread pointer: one IMAD.WIDE
+    const float2* r1 = r0 + Wp;
+    const float2 vnw = __ldg(r0), vne = __ldg(r0 + 1), vsw = __ldg(r1), vse = __ldg(r1 + 1);
     const float wnw = (fx1 - ix) * (fy1 - iy);
     const float wne = (ix - fx0) * (fy1 - iy);
     const float wsw = (fx1 - ix) * (iy - fy0);
     const float wse = (ix - fx0) * (iy - fy0);
-    float ox = 0.f, oy = 0.f;
-    const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
-    const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
-    if (yin0 && xin0) { const float2 v = __ldg(&f[y0 * W + x0]);           ox += v.x * wnw; oy += v.y * wnw; }
-    if (yin0 && xin1) { const float2 v = __ldg(&f[y0 * W + x0 + 1]);       ox += v.x * wne; oy += v.y * wne; }
-    if (yin1 && xin0) { const float2 v = __ldg(&f[(y0 + 1) * W + x0]);     ox += v.x * wsw; oy += v.y * wsw; }
-    if (yin1 && xin1) { const float2 v = __ldg(&f[(y0 + 1) * W + x0 + 1]); ox += v.x * wse; oy += v.y * wse; }
+    float ox = vnw.x * wnw, oy = vnw.y * wnw;   // 0 + v*w
+    ox += vne.x * wne; oy += vne.y * wne;
+    ox += vsw.x * wsw; oy += vsw.y * wsw;
+    ox += vse.x * wse; oy += vse.y * wse;
     px = fminf(fmaxf(px + ox, -1.f), 1.f);
     py = fminf(fmaxf(py + oy, -1.f), 1.f);
 }
@@ -70,7 +80,7 @@ k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
          const unsigned* CPB_RESTRICT list_n, int H, int W, int niter,
          int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
     const unsigned total = *list_n;
-    const int N = H * W;
+    const int N = H * W, Wp = W + 2, Np = (H + 2) * Wp;
     const float fW = (float)W, fH = (float)H;
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
     const int lane = threadIdx.x & 31;
@@ -83,11 +93,14 @@ k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
         const int b = (int)(gi / (unsigned)N);
         const int r = (int)(gi - (unsigned)b * (unsigned)N);
         const int y = r / W, x = r - y * W;
-        const float2* f = flow + (size_t)b * N;
+        const float2* f = flow + (size_t)b * Np + Wp + 1;
+#ifndef CPB_SIM
+        asm volatile("" : "+l"(f));   // keep the tile base in a register pair (address = base + idx*8)
+#endif
         // pt = idx / (L-1) * 2 - 1
         float px = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, wm1), 2.f), 1.f);
         float py = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, hm1), 2.f), 1.f);
-        for (int t = 0; t < niter; t++) cpb_euler_step(f, H, W, fH, fW, px, py);
+        for (int t = 0; t < niter; t++) cpb_euler_step(f, Wp, fH, fW, px, py);
         // undo: (pt + 1) * 0.5 * (L-1)
         const float ex = __fmul_rn(__fmul_rn(__fadd_rn(px, 1.f), 0.5f), wm1);
         const float ey = __fmul_rn(__fmul_rn(__fadd_rn(py, 1.f), 0.5f), hm1);

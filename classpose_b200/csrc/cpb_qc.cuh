@@ -60,10 +60,121 @@ k_centres(const int* CPB_RESTRICT lab, int H, int W, LabelTables t) {
     }
 }
 
+// Exact x/9 in three ops instead of the ~25-instruction IEEE division sequence: with r = RN(1/9) and
+// q = RN(x*r), the residual x - 9q is exact in one FMA and RN(q + rem*r) is the correctly rounded
+// quotient (Markstein); checked against true division on 6e8 random operands.  Outside
+// the safe exponent range fall back to the real division.
+CPB_DEVICE double cpb_div9(double x) {
+    const double ax = fabs(x);
+    if (ax < 1e-280 || ax > 1e280) return __ddiv_rn(x, 9.0);
+    const double r = 1.0 / 9.0;
+    const double q = __dmul_rn(x, r);
+    const double rem = __fma_rn(-9.0, q, x);
+    return __fma_rn(rem, r, q);
+}
+
+#define CPB_DW_WARPS 4         // labels in flight per block (one warp each)
+#define CPB_DW_CELLS 676       // per-warp tile incl. 1-cell halo: 26 x 26  (bbox up to 24 x 24)
+#define CPB_DW_PAD 8           // strips may read past the last row
+#define CPB_DW_STRIP 8
+#define CPB_DW_MAXS 3          // strips per lane
+
+CPB_DEVICE bool cpb_diffuse_is_small(int h, int w) {
+    return (h + 2) * (w + 2) <= CPB_DW_CELLS && h * ((w + CPB_DW_STRIP - 1) / CPB_DW_STRIP) <= 32 * CPB_DW_MAXS;
+}
+
+// k_diffuse_warp: one WARP per label for labels whose halo'd bbox fits CPB_DW_CELLS (nuclei-sized).
+// The label's T lives in shared memory (double-buffered); every lane owns up to CPB_DW_MAXS
+// horizontal strips of 8 cells, loads the 3 x 10 neighbourhood of a strip once and sums the nine
+// neighbours of each cell in the reference's order.  Only __syncwarp() between iterations.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, 4)
+k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
+               int niter_override) {
+    CPB_SHARED double s_T[CPB_DW_WARPS][2][CPB_DW_CELLS + CPB_DW_PAD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, LC = t.LC, N = H * W;
+    const int lb = t.lbound[b];
+    const int* L = lab + (size_t)b * N;
+    double* Tb = T + (size_t)b * N;
+    const int n_it = niter_override > 0 ? niter_override : t.niter[b];
+    double* A = s_T[warp][0];
+    double* Bf = s_T[warp][1];
+    for (int l = 1 + blockIdx.x * CPB_DW_WARPS + warp; l <= lb; l += gridDim.x * CPB_DW_WARPS) {
+        const size_t k = (size_t)b * LC + l;
+        if (t.cnt[k] <= 0) continue;      // warp-uniform
+        const int y0 = t.ymin[k], x0 = t.xmin[k];
+        const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        if (!cpb_diffuse_is_small(h, w)) continue;
+        const int ww = w + 2, cells = (h + 2) * ww;
+        const int spr = (w + CPB_DW_STRIP - 1) / CPB_DW_STRIP, ns = h * spr;
+        __syncwarp();
+        for (int i = lane; i < cells + CPB_DW_PAD; i += 32) { A[i] = 0.0; Bf[i] = 0.0; }
+        // strips owned by this lane: base index of the strip's first cell and its member mask
+        int sbase[CPB_DW_MAXS]; unsigned smask[CPB_DW_MAXS];
+        #pragma unroll
+        for (int q = 0; q < CPB_DW_MAXS; q++) {
+            const int s = lane + 32 * q;
+            sbase[q] = 0; smask[q] = 0;
+            if (s < ns) {
+                const int r = s / spr, c0 = (s - r * spr) * CPB_DW_STRIP;
+                sbase[q] = (r + 1) * ww + c0 + 1;
+                unsigned m = 0;
+                for (int c = 0; c < CPB_DW_STRIP && c0 + c < w; c++)
+                    if (L[(y0 + r) * W + x0 + c0 + c] == l) m |= 1u << c;
+                smask[q] = m;
+            }
+        }
+        const int ci = (t.cy[k] - y0 + 1) * ww + (t.cx[k] - x0 + 1);
+        __syncwarp();
+        double* cur = A; double* nxt = Bf;
+        for (int it = 0; it < n_it; it++) {
+            if (lane == 0) cur[ci] += 1.0;
+            __syncwarp();
+            #pragma unroll
+            for (int q = 0; q < CPB_DW_MAXS; q++) {
+                const unsigned m = smask[q];
+                if (m == 0) continue;
+                const double* pm = cur + sbase[q] - 1;        // cell left of the strip, middle row
+                const double* pu = pm - ww;
+                const double* pd = pm + ww;
+                double u[CPB_DW_STRIP + 2], c[CPB_DW_STRIP + 2], d[CPB_DW_STRIP + 2];
+                #pragma unroll
+                for (int j = 0; j < CPB_DW_STRIP + 2; j++) { u[j] = pu[j]; c[j] = pm[j]; d[j] = pd[j]; }
+                #pragma unroll
+                for (int j = 0; j < CPB_DW_STRIP; j++) {
+                    // self, up, down, left, right, up-left, up-right, down-left, down-right
+                    double sum = __dadd_rn(c[j + 1], u[j + 1]);
+                    sum = __dadd_rn(sum, d[j + 1]);
+                    sum = __dadd_rn(sum, c[j]);
+                    sum = __dadd_rn(sum, c[j + 2]);
+                    sum = __dadd_rn(sum, u[j]);
+                    sum = __dadd_rn(sum, u[j + 2]);
+                    sum = __dadd_rn(sum, d[j]);
+                    sum = __dadd_rn(sum, d[j + 2]);
+                    if (m >> j & 1) nxt[sbase[q] + j] = cpb_div9(sum);
+                }
+            }
+            __syncwarp();
+            double* tmp = cur; cur = nxt; nxt = tmp;
+        }
+        #pragma unroll
+        for (int q = 0; q < CPB_DW_MAXS; q++) {
+            unsigned m = smask[q];
+            const int i0 = sbase[q];
+            while (m) {
+                const int j = __ffs((int)m) - 1;
+                m &= m - 1;
+                const int i = i0 + j;
+                Tb[(y0 + i / ww - 1) * W + x0 + i % ww - 1] = cur[i];
+            }
+        }
+    }
+}
+
 // Neighbour order of the reference: self, (-1,0), (1,0), (0,-1), (0,1), (-1,-1), (-1,1), (1,-1), (1,1)
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
 k_diffuse(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
-          double* CPB_RESTRICT T2, int niter_override) {
+          double* CPB_RESTRICT T2, int niter_override, int skip_small) {
     CPB_DYN_SMEM(double, s_buf);   // 2 * CPB_DIFF_SMEM_CELLS doubles + CPB_DIFF_SMEM_CELLS bytes
     const int b = blockIdx.y, LC = t.LC, N = H * W;
     const int lb = t.lbound[b];
@@ -76,6 +187,7 @@ k_diffuse(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_
         if (t.cnt[k] <= 0) continue;
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        if (skip_small && cpb_diffuse_is_small(h, w)) continue;
         const int cy = t.cy[k], cx = t.cx[k];
         const int hh = h + 2, ww = w + 2, cells = hh * ww;
         if (cells <= CPB_DIFF_SMEM_CELLS) {
@@ -107,7 +219,7 @@ k_diffuse(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_
                     s = __dadd_rn(s, CPB_TV(i + ww - 1));
                     s = __dadd_rn(s, CPB_TV(i + ww + 1));
                     #undef CPB_TV
-                    nxt[i] = __ddiv_rn(s, 9.0);
+                    nxt[i] = cpb_div9(s);
                 }
                 __syncthreads();
                 double* tmp = cur; cur = nxt; nxt = tmp;
@@ -141,7 +253,7 @@ k_diffuse(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_
                         }
                         s = q == 0 ? v : __dadd_rn(s, v);
                     }
-                    nxt[p] = __ddiv_rn(s, 9.0);
+                    nxt[p] = cpb_div9(s);
                 }
                 __syncthreads();
                 double* tmp = cur; cur = nxt; nxt = tmp;

@@ -357,6 +357,7 @@ inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline int __float2int_rz(float f) { return (int)f; }
 inline float __int2float_rn(int i) { return (float)i; }
 inline double __int2double_rn(int i) { return (double)i; }
