@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -69,6 +69,11 @@ class ClockSampler:
                 self.rows.append([c.strip() for c in line.split(",")])
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
 
     def stop(self):
         if self.proc is None:
@@ -206,14 +211,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()
     for _ in range(max(3, args.warmup)):
         out = step()
     barrier()
     n_cells_step = int(out[1].sum().item())
-    launches0 = eng.launch_count()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.rows.clear()          # keep only samples taken during the timed region
+    launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -327,7 +335,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--tiles", type=int, default=1024, help="tiles per GPU per step")
     ap.add_argument("--chunk", type=int, default=128, help="tiles per chunk of the host-buffer call")

@@ -74,100 +74,75 @@ CPB_DEVICE double cpb_div9(double x) {
 }
 
 #define CPB_DW_WARPS 4         // labels in flight per block (one warp each)
-#define CPB_DW_CELLS 676       // per-warp tile incl. 1-cell halo: 26 x 26  (bbox up to 24 x 24)
-#define CPB_DW_PAD 8           // strips may read past the last row
-#define CPB_DW_STRIP 8
-#define CPB_DW_MAXS 3          // strips per lane
+#define CPB_DC_MAX 32          // register path: bbox up to 32 x 32
 
-CPB_DEVICE bool cpb_diffuse_is_small(int h, int w) {
-    return (h + 2) * (w + 2) <= CPB_DW_CELLS && h * ((w + CPB_DW_STRIP - 1) / CPB_DW_STRIP) <= 32 * CPB_DW_MAXS;
-}
+CPB_DEVICE bool cpb_diffuse_is_small(int h, int w) { return h <= CPB_DC_MAX && w <= CPB_DC_MAX; }
 
-// k_diffuse_warp: one WARP per label for labels whose halo'd bbox fits CPB_DW_CELLS (nuclei-sized).
-// The label's T lives in shared memory (double-buffered); every lane owns up to CPB_DW_MAXS
-// horizontal strips of 8 cells, loads the 3 x 10 neighbourhood of a strip once and sums the nine
-// neighbours of each cell in the reference's order.  Only __syncwarp() between iterations.
-CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, 4)
+// k_diffuse_warp: one WARP per label for labels whose bbox fits 32 x 32 (nuclei-sized), entirely in
+// registers: lane j owns column j of the bbox (one float64 per row, rows fully unrolled); vertical
+// neighbours are the lane's own registers, horizontal and diagonal ones arrive by warp shuffle.
+// No shared memory, no barriers; the nine neighbours are summed in the reference's order.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, 3)
 k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                int niter_override) {
-    CPB_SHARED double s_T[CPB_DW_WARPS][2][CPB_DW_CELLS + CPB_DW_PAD];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y, LC = t.LC, N = H * W;
     const int lb = t.lbound[b];
     const int* L = lab + (size_t)b * N;
     double* Tb = T + (size_t)b * N;
     const int n_it = niter_override > 0 ? niter_override : t.niter[b];
-    double* A = s_T[warp][0];
-    double* Bf = s_T[warp][1];
     for (int l = 1 + blockIdx.x * CPB_DW_WARPS + warp; l <= lb; l += gridDim.x * CPB_DW_WARPS) {
         const size_t k = (size_t)b * LC + l;
         if (t.cnt[k] <= 0) continue;      // warp-uniform
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         if (!cpb_diffuse_is_small(h, w)) continue;
-        const int ww = w + 2, cells = (h + 2) * ww;
-        const int spr = (w + CPB_DW_STRIP - 1) / CPB_DW_STRIP, ns = h * spr;
-        __syncwarp();
-        for (int i = lane; i < cells + CPB_DW_PAD; i += 32) { A[i] = 0.0; Bf[i] = 0.0; }
-        // strips owned by this lane: base index of the strip's first cell and its member mask
-        int sbase[CPB_DW_MAXS]; unsigned smask[CPB_DW_MAXS];
+        unsigned member = 0;               // bit r: pixel (y0+r, x0+lane) belongs to the label
+        if (lane < w)
+            for (int r = 0; r < h; r++)
+                if (L[(y0 + r) * W + x0 + lane] == l) member |= 1u << r;
+        const int cr = t.cy[k] - y0;
+        const double inc = (lane == t.cx[k] - x0) ? 1.0 : 0.0;
+        double Tc[CPB_DC_MAX];
         #pragma unroll
-        for (int q = 0; q < CPB_DW_MAXS; q++) {
-            const int s = lane + 32 * q;
-            sbase[q] = 0; smask[q] = 0;
-            if (s < ns) {
-                const int r = s / spr, c0 = (s - r * spr) * CPB_DW_STRIP;
-                sbase[q] = (r + 1) * ww + c0 + 1;
-                unsigned m = 0;
-                for (int c = 0; c < CPB_DW_STRIP && c0 + c < w; c++)
-                    if (L[(y0 + r) * W + x0 + c0 + c] == l) m |= 1u << c;
-                smask[q] = m;
-            }
-        }
-        const int ci = (t.cy[k] - y0 + 1) * ww + (t.cx[k] - x0 + 1);
-        __syncwarp();
-        double* cur = A; double* nxt = Bf;
+        for (int r = 0; r < CPB_DC_MAX; r++) Tc[r] = 0.0;
         for (int it = 0; it < n_it; it++) {
-            if (lane == 0) cur[ci] += 1.0;
-            __syncwarp();
+            double upT = 0.0, upL = 0.0, upR = 0.0;
+            double curT = Tc[0];
+            if (cr == 0) curT = __dadd_rn(curT, inc);          // T[centre] += 1 before averaging
+            double curL = __shfl_up_sync(CPB_FULL, curT, 1), curR = __shfl_down_sync(CPB_FULL, curT, 1);
+            if (lane == 0) curL = 0.0;
+            if (lane == 31) curR = 0.0;
             #pragma unroll
-            for (int q = 0; q < CPB_DW_MAXS; q++) {
-                const unsigned m = smask[q];
-                if (m == 0) continue;
-                const double* pm = cur + sbase[q] - 1;        // cell left of the strip, middle row
-                const double* pu = pm - ww;
-                const double* pd = pm + ww;
-                double u[CPB_DW_STRIP + 2], c[CPB_DW_STRIP + 2], d[CPB_DW_STRIP + 2];
-                #pragma unroll
-                for (int j = 0; j < CPB_DW_STRIP + 2; j++) { u[j] = pu[j]; c[j] = pm[j]; d[j] = pd[j]; }
-                #pragma unroll
-                for (int j = 0; j < CPB_DW_STRIP; j++) {
+            for (int r = 0; r < CPB_DC_MAX; r++) {
+                if (r < h) {                                    // warp-uniform
+                    double dnT = 0.0, dnL = 0.0, dnR = 0.0;
+                    if (r + 1 < CPB_DC_MAX && r + 1 < h) {
+                        dnT = Tc[r + 1 < CPB_DC_MAX ? r + 1 : r];
+                        if (cr == r + 1) dnT = __dadd_rn(dnT, inc);
+                        dnL = __shfl_up_sync(CPB_FULL, dnT, 1);
+                        dnR = __shfl_down_sync(CPB_FULL, dnT, 1);
+                        if (lane == 0) dnL = 0.0;
+                        if (lane == 31) dnR = 0.0;
+                    }
                     // self, up, down, left, right, up-left, up-right, down-left, down-right
-                    double sum = __dadd_rn(c[j + 1], u[j + 1]);
-                    sum = __dadd_rn(sum, d[j + 1]);
-                    sum = __dadd_rn(sum, c[j]);
-                    sum = __dadd_rn(sum, c[j + 2]);
-                    sum = __dadd_rn(sum, u[j]);
-                    sum = __dadd_rn(sum, u[j + 2]);
-                    sum = __dadd_rn(sum, d[j]);
-                    sum = __dadd_rn(sum, d[j + 2]);
-                    if (m >> j & 1) nxt[sbase[q] + j] = cpb_div9(sum);
+                    double sum = __dadd_rn(curT, upT);
+                    sum = __dadd_rn(sum, dnT);
+                    sum = __dadd_rn(sum, curL);
+                    sum = __dadd_rn(sum, curR);
+                    sum = __dadd_rn(sum, upL);
+                    sum = __dadd_rn(sum, upR);
+                    sum = __dadd_rn(sum, dnL);
+                    sum = __dadd_rn(sum, dnR);
+                    Tc[r] = (member >> r & 1) ? cpb_div9(sum) : 0.0;
+                    upT = curT; upL = curL; upR = curR;
+                    curT = dnT; curL = dnL; curR = dnR;
                 }
             }
-            __syncwarp();
-            double* tmp = cur; cur = nxt; nxt = tmp;
         }
         #pragma unroll
-        for (int q = 0; q < CPB_DW_MAXS; q++) {
-            unsigned m = smask[q];
-            const int i0 = sbase[q];
-            while (m) {
-                const int j = __ffs((int)m) - 1;
-                m &= m - 1;
-                const int i = i0 + j;
-                Tb[(y0 + i / ww - 1) * W + x0 + i % ww - 1] = cur[i];
-            }
-        }
+        for (int r = 0; r < CPB_DC_MAX; r++)
+            if (r < h && (member >> r & 1)) Tb[(y0 + r) * W + x0 + lane] = Tc[r];
     }
 }
 
