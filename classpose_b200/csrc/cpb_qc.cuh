@@ -73,76 +73,80 @@ CPB_DEVICE double cpb_div9(double x) {
     return __fma_rn(rem, r, q);
 }
 
+// Branch-free variant for operands known to stay far from the subnormal / overflow range (the warp
+// kernel: inside a 32 x 32 bbox T is 0 or within [9^-64, n_iter]).
+CPB_DEVICE double cpb_div9_fast(double x) {
+    const double r = 1.0 / 9.0;
+    const double q = __dmul_rn(x, r);
+    const double rem = __fma_rn(-9.0, q, x);
+    return __fma_rn(rem, r, q);
+}
+
 #define CPB_DW_WARPS 4         // labels in flight per block (one warp each)
-#define CPB_DC_MAX 32          // register path: bbox up to 32 x 32
+#define CPB_DC_MAX 32          // warp path: bbox up to 32 x 32
+#define CPB_DC_PITCH 34        // + one halo column on each side
 
 CPB_DEVICE bool cpb_diffuse_is_small(int h, int w) { return h <= CPB_DC_MAX && w <= CPB_DC_MAX; }
 
-// k_diffuse_warp: one WARP per label for labels whose bbox fits 32 x 32 (nuclei-sized), entirely in
-// registers: lane j owns column j of the bbox (one float64 per row, rows fully unrolled); vertical
-// neighbours are the lane's own registers, horizontal and diagonal ones arrive by warp shuffle.
-// No shared memory, no barriers; the nine neighbours are summed in the reference's order.
-CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, 3)
+// k_diffuse_warp: one WARP per label for labels whose bbox fits 32 x 32 (nuclei-sized).
+// The label's T lives in a per-warp shared-memory tile with a zero halo; lane j owns column j and
+// walks down the rows with a 3 x 3 sliding window in registers: three conflict-free row loads per
+// step, nine neighbours summed in the reference's order, in-place Jacobi update (row r is written
+// only after every lane holds rows r and r+1 in registers).  No block barriers.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, 6)
 k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                int niter_override) {
+    CPB_SHARED double s_T[CPB_DW_WARPS][(CPB_DC_MAX + 2) * CPB_DC_PITCH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y, LC = t.LC, N = H * W;
     const int lb = t.lbound[b];
     const int* L = lab + (size_t)b * N;
     double* Tb = T + (size_t)b * N;
     const int n_it = niter_override > 0 ? niter_override : t.niter[b];
+    double* S = s_T[warp];
     for (int l = 1 + blockIdx.x * CPB_DW_WARPS + warp; l <= lb; l += gridDim.x * CPB_DW_WARPS) {
         const size_t k = (size_t)b * LC + l;
         if (t.cnt[k] <= 0) continue;      // warp-uniform
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         if (!cpb_diffuse_is_small(h, w)) continue;
+        __syncwarp();
+        for (int i = lane; i < (h + 2) * CPB_DC_PITCH; i += 32) S[i] = 0.0;
         unsigned member = 0;               // bit r: pixel (y0+r, x0+lane) belongs to the label
         if (lane < w)
             for (int r = 0; r < h; r++)
                 if (L[(y0 + r) * W + x0 + lane] == l) member |= 1u << r;
-        const int cr = t.cy[k] - y0;
-        const double inc = (lane == t.cx[k] - x0) ? 1.0 : 0.0;
-        double Tc[CPB_DC_MAX];
-        #pragma unroll
-        for (int r = 0; r < CPB_DC_MAX; r++) Tc[r] = 0.0;
+        const int ci = (t.cy[k] - y0 + 1) * CPB_DC_PITCH + (t.cx[k] - x0 + 1);
+        const double* p = S + lane;        // p[0], p[1], p[2] = columns j-1, j, j+1 of the halo row
+        double* own = S + CPB_DC_PITCH + lane + 1;
+        __syncwarp();
         for (int it = 0; it < n_it; it++) {
-            double upT = 0.0, upL = 0.0, upR = 0.0;
-            double curT = Tc[0];
-            if (cr == 0) curT = __dadd_rn(curT, inc);          // T[centre] += 1 before averaging
-            double curL = __shfl_up_sync(CPB_FULL, curT, 1), curR = __shfl_down_sync(CPB_FULL, curT, 1);
-            if (lane == 0) curL = 0.0;
-            if (lane == 31) curR = 0.0;
-            #pragma unroll
-            for (int r = 0; r < CPB_DC_MAX; r++) {
-                if (r < h) {                                    // warp-uniform
-                    double dnT = 0.0, dnL = 0.0, dnR = 0.0;
-                    if (r + 1 < CPB_DC_MAX && r + 1 < h) {
-                        dnT = Tc[r + 1 < CPB_DC_MAX ? r + 1 : r];
-                        if (cr == r + 1) dnT = __dadd_rn(dnT, inc);
-                        dnL = __shfl_up_sync(CPB_FULL, dnT, 1);
-                        dnR = __shfl_down_sync(CPB_FULL, dnT, 1);
-                        if (lane == 0) dnL = 0.0;
-                        if (lane == 31) dnR = 0.0;
-                    }
-                    // self, up, down, left, right, up-left, up-right, down-left, down-right
-                    double sum = __dadd_rn(curT, upT);
-                    sum = __dadd_rn(sum, dnT);
-                    sum = __dadd_rn(sum, curL);
-                    sum = __dadd_rn(sum, curR);
-                    sum = __dadd_rn(sum, upL);
-                    sum = __dadd_rn(sum, upR);
-                    sum = __dadd_rn(sum, dnL);
-                    sum = __dadd_rn(sum, dnR);
-                    Tc[r] = (member >> r & 1) ? cpb_div9(sum) : 0.0;
-                    upT = curT; upL = curL; upR = curR;
-                    curT = dnT; curL = dnL; curR = dnR;
-                }
+            if (lane == 0) S[ci] += 1.0;   // T[centre] += 1 before averaging
+            __syncwarp();
+            double uL = p[0], uC = p[1], uR = p[2];
+            double cL = p[CPB_DC_PITCH], cC = p[CPB_DC_PITCH + 1], cR = p[CPB_DC_PITCH + 2];
+            for (int r = 0; r < h; r++) {
+                const double* q = p + (r + 2) * CPB_DC_PITCH;
+                const double dL = q[0], dC = q[1], dR = q[2];
+                // self, up, down, left, right, up-left, up-right, down-left, down-right
+                double sum = __dadd_rn(cC, uC);
+                sum = __dadd_rn(sum, dC);
+                sum = __dadd_rn(sum, cL);
+                sum = __dadd_rn(sum, cR);
+                sum = __dadd_rn(sum, uL);
+                sum = __dadd_rn(sum, uR);
+                sum = __dadd_rn(sum, dL);
+                sum = __dadd_rn(sum, dR);
+                const double v = cpb_div9_fast(sum);
+                __syncwarp();              // all lanes hold rows r and r+1 before row r is overwritten
+                if (member >> r & 1) own[r * CPB_DC_PITCH] = v;
+                uL = cL; uC = cC; uR = cR;
+                cL = dL; cC = dC; cR = dR;
             }
+            __syncwarp();
         }
-        #pragma unroll
-        for (int r = 0; r < CPB_DC_MAX; r++)
-            if (r < h && (member >> r & 1)) Tb[(y0 + r) * W + x0 + lane] = Tc[r];
+        for (int r = 0; r < h; r++)
+            if (member >> r & 1) Tb[(y0 + r) * W + x0 + lane] = own[r * CPB_DC_PITCH];
     }
 }
 
