@@ -37,6 +37,15 @@ WORKLOAD = "conic config: batch of 1024 synthetic 256x256 tiles (C=7), compute_m
 PARAMS = dict(niter=200, cellprob_threshold=0.0, flow_threshold=0.4, min_size=15, max_size_fraction=0.4)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ----------------------------------------------------------------------------------------------
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -172,7 +181,7 @@ def run_reference(args):
                          "sample": f"{sample} tiles of the workload per step, one process per core"},
         "e2e": {"value": value, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -326,10 +335,19 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "stages_ms": stages,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _protect_stdout():
+    """Libraries (NCCL prints its version) may write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the duration of the run and return a file object on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -342,6 +360,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global _REAL_STDOUT
+    _REAL_STDOUT = _protect_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

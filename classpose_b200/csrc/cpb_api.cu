@@ -10,6 +10,7 @@
 #include "cpb_tables.cuh"
 #include "cpb_qc.cuh"
 #include "cpb_post.cuh"
+#include "cpb_fused.cuh"
 
 #include <atomic>
 #ifndef CPB_SIM
@@ -26,9 +27,10 @@ std::atomic<long long> g_launches{0};   // statistics only: kernels launched by 
 // Optional per-stage timing of the fused path (cpb_compute_masks_profiled_device).
 enum Stage { S_PREP = 0, S_FOLLOW, S_SEEDS, S_LOOKUP, S_FINALIZE, S_MAP1, S_CENTRES, S_DIFFUSE, S_FLOWERR,
              S_DROP, S_SIZE1, S_MAP2, S_FILL, S_MAP3, S_SIZE2, S_MAP4, S_BORDER, S_VOTE, S_COUNT };
+// (S_MAP1, S_DROP, S_MAP2 are only used by the stage-by-stage entry points; the fused path has no such passes)
 const char* kStageNames[S_COUNT] = {"prep_flow", "follow_flows", "seeds", "lookup", "gm_finalize", "map_stats_1",
-                                    "centres", "diffuse", "flow_err", "drop_bad_stats", "size_renumber_1",
-                                    "map_stats_2", "fill_holes", "map_stats_3", "size_renumber_2", "map_final",
+                                    "centres", "diffuse", "flow_err", "drop_bad_stats", "size_filter_1",
+                                    "map_stats_2", "fill_holes", "recount_hole_tiles", "size_filter_2", "final_map",
                                     "border", "vote"};
 struct Prof {
 #ifndef CPB_SIM
@@ -82,6 +84,8 @@ struct Workspace {
     int* status;
     u64* skey;           // [B*LC]
     int* sidx;           // [B*LC]
+    int* sinv;           // [B*LC]
+    int* alive;          // [B*LC]
     int* vote;           // [B*LC*C]
     LabelTables t;
     size_t bytes;
@@ -106,13 +110,15 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     w.status = reinterpret_cast<int*>(w.list_n) + 1;
     w.skey = c.take<u64>(BL);
     w.sidx = c.take<int>(BL);
+    w.sinv = c.take<int>(BL);
+    w.alive = c.take<int>(BL);
     w.vote = c.take<int>(C > 0 ? BL * C : 0);
     LabelTables& t = w.t;
     t.LC = LC;
     t.cnt = c.take<int>(BL); t.first = c.take<int>(BL);
     t.ymin = c.take<int>(BL); t.ymax = c.take<int>(BL); t.xmin = c.take<int>(BL); t.xmax = c.take<int>(BL);
     t.sumy = c.take<u64>(BL); t.sumx = c.take<u64>(BL);
-    t.remap = c.take<int>(BL); t.flag = c.take<int>(BL);
+    t.remap = c.take<int>(BL); t.flag = c.take<int>(BL); t.alive = nullptr;
     t.cy = c.take<int>(BL); t.cx = c.take<int>(BL);
     t.err = c.take<double>(BL);
     t.lbound = c.take<int>(B); t.nlab = c.take<int>(B); t.niter = c.take<int>(B); t.misc = c.take<int>(B);
@@ -206,7 +212,7 @@ int run_get_masks(const Workspace& w, const int32_t* pfinal, int B, int H, int W
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_LOOKUP);
     ProfScope ps(w.prof, S_FINALIZE);
-    CPB_LAUNCH_COUNTED(k_gm_finalize, dim3(B), dim3(256), 0, st, w.t, H, W, msf, w.skey, w.sidx, counts);
+    CPB_LAUNCH_COUNTED(k_gm_finalize, dim3(B), dim3(256), 0, st, w.t, H, W, msf, w.skey, w.sidx, counts, 0);
     CPB_CHECK_LAUNCH();
     return 0;   // caller applies w.t.remap
 }
@@ -404,31 +410,77 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     w.prof = prof;
     if (prof) prof->st = st;
     int e;
+    const long long BN = (long long)B * H * W;
     // (2) Euler integration + end-point histogram
     e = run_follow(w, dP, cellprob, B, H, W, prm->niter, prm->cellprob_threshold, w.pfinal, nullptr, w.hist, st);
     if (e) return e;
-    // (3) seeds -> labels; apply the first-appearance remap while gathering label statistics
-    e = run_get_masks(w, w.pfinal, B, H, W, prm->max_size_fraction, masks, counts, st); if (e) return e;
-    e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, true, st, S_MAP1); if (e) return e;
-    // (4) flow-error check; dropped labels become 0 in the pass that regathers statistics
-    bool have_stats = true;
+    // (3) seeds -> raw labels (seed order + 1) and their statistics; ids after get_masks live in t.remap
+    prof_begin(w.prof, S_SEEDS);
+    cudaMemsetAsync(w.M, 0, BN * sizeof(int), st);
+    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(256), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.M, w.t.lbound);
+    CPB_CHECK_LAUNCH();
+    prof_end(w.prof, S_SEEDS);
+    prof_begin(w.prof, S_LOOKUP);
+    e = run_init_tables(w, B, st); if (e) return e;
+    cudaMemsetAsync(masks, 0, BN * sizeof(int), st);
+    cudaMemsetAsync(w.t.misc, 0, B * sizeof(int), st);
+    {
+        const unsigned grid = (unsigned)std::min<long long>(blocks_for(BN, 256), (long long)sm_count() * 8);
+        CPB_LAUNCH_COUNTED(k_lookup_list, dim3(grid), dim3(256), 0, st, w.list, w.list_n, w.pfinal, w.M, H, W, masks, w.t);
+        CPB_CHECK_LAUNCH();
+    }
+    prof_end(w.prof, S_LOOKUP);
+    w.t.alive = w.alive;
+    prof_begin(w.prof, S_FINALIZE);
+    CPB_LAUNCH_COUNTED(k_gm_finalize, dim3(B), dim3(256), 0, st, w.t, H, W, prm->max_size_fraction, w.skey, w.sidx,
+                       (int*)nullptr, 1);
+    CPB_CHECK_LAUNCH();
+    prof_end(w.prof, S_FINALIZE);
+    // (4) flow-error check on the raw labels; bad labels are only flagged
     if (prm->flow_threshold > 0.0) {
         e = run_flow_qc(w, masks, dP, B, H, W, prm->flow_threshold, nullptr, st); if (e) return e;
-        if (prm->fill_holes) {
-            // k_map_stats resets `flag` via init_tables before reading it, so copy the flags out first
-            cudaMemcpyAsync(w.sidx, w.t.flag, (size_t)B * w.t.LC * sizeof(int), cudaMemcpyDeviceToDevice, st);
-            e = run_map_stats(w, masks, B, H, W, 1, nullptr, w.sidx, nullptr, true, st, S_DROP); if (e) return e;
-        } else {
-            e = run_map_stats(w, masks, B, H, W, 1, nullptr, w.t.flag, nullptr, false, st, S_DROP); if (e) return e;
-            have_stats = false;
-        }
     }
-    // (5) hole fill + size filters
+    // (5) size filter / hole fill / size filter as table operations, one final pixel pass
     if (prm->fill_holes) {
-        e = run_fill_small(w, masks, B, H, W, prm->min_size, counts, have_stats, st); if (e) return e;
+        prof_begin(w.prof, S_SIZE1);
+        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(256), 0, st, w.t, H, W, prm->min_size, 1, (const int*)nullptr,
+                           w.skey, w.sidx, w.sinv);
+        CPB_CHECK_LAUNCH();
+        prof_end(w.prof, S_SIZE1);
+        prof_begin(w.prof, S_FILL);
+        cudaMemsetAsync(w.holekey, 0, BN * sizeof(u64), st);
+        CPB_LAUNCH_COUNTED(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
+                           masks, H, W, w.t, w.holekey, w.status);
+        CPB_CHECK_LAUNCH();
+        prof_end(w.prof, S_FILL);
+        prof_begin(w.prof, S_MAP3);
+        CPB_LAUNCH_COUNTED(k_reset_counts, dim3(blocks_for(w.t.LC, 256), B), dim3(256), 0, st, w.t);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_recount, dim3(blocks_for(BN, 256)), dim3(256), 0, st, masks, w.holekey, B, H, W, w.t);
+        CPB_CHECK_LAUNCH();
+        prof_end(w.prof, S_MAP3);
+        prof_begin(w.prof, S_SIZE2);
+        // second filter on every tile: besides holes, labels that survived the positional first filter are
+        // caught here (labels are contiguous again, so position == value)
+        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(256), 0, st, w.t, H, W, prm->min_size, 1, (const int*)nullptr,
+                           w.skey, w.sidx, w.sinv);
+        CPB_CHECK_LAUNCH();
+        prof_end(w.prof, S_SIZE2);
     } else {
-        cudaMemcpyAsync(counts, w.t.lbound, B * sizeof(int), cudaMemcpyDeviceToDevice, st);
+        prof_begin(w.prof, S_SIZE1);
+        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(256), 0, st, w.t, H, W, 0, 2, (const int*)nullptr, w.skey, w.sidx,
+                           w.sinv);
+        CPB_CHECK_LAUNCH();
+        prof_end(w.prof, S_SIZE1);
     }
+    prof_begin(w.prof, S_MAP4);
+    CPB_LAUNCH_COUNTED(k_final, dim3(blocks_for(BN, 256)), dim3(256), 0, st, masks,
+                       prm->fill_holes ? (const u64*)w.holekey : (const u64*)nullptr, B, H, W, w.t, counts);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_finish_bounds, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t, B);
+    CPB_CHECK_LAUNCH();
+    prof_end(w.prof, S_MAP4);
+    w.t.alive = nullptr;
     // (7) optional border-instance removal (labels are not renumbered afterwards, as in the reference)
     if (prm->remove_border) { e = run_border(w, masks, B, H, W, 1, st); if (e) return e; }
     // (6) class vote

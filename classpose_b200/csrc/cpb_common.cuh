@@ -16,6 +16,7 @@ struct LabelTables {
     u64* sumy; u64* sumx;                          // coordinate sums
     int* remap;      // label -> new label (0 = dropped)
     int* flag;       // scratch flags (bad flow / removed-by-position / border)
+    int* alive;      // fused path: label still exists (NULL = every label with cnt > 0)
     int* cy; int* cx;                              // diffusion centre
     double* err;     // flow error
     int* lbound;     // [B] highest label value that may be present in the tile
@@ -25,6 +26,10 @@ struct LabelTables {
 };
 
 CPB_DEVICE int cpb_lane() { return threadIdx.x & 31; }
+
+CPB_DEVICE bool cpb_label_live(const LabelTables& t, size_t k) {
+    return t.cnt[k] > 0 && (t.alive == nullptr || t.alive[k] != 0);
+}
 
 // Block-wide inclusive scan of one int per thread (blockDim.x multiple of 32, <= 1024).
 // `warp_tot` must point to >= 33 ints of shared memory.  Returns inclusive prefix;

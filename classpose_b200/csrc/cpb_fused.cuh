@@ -1,0 +1,173 @@
+// Fused path only: the label image keeps the RAW labels (seed order + 1) from the lookup until the
+// final pass; every renumbering / removal between get_masks and the output is carried by per-tile
+// tables (remap = current id of a raw label, alive), so pixels are touched by three passes only:
+// lookup (statistics), recount (tiles that had a hole filled) and final.
+#pragma once
+#include "cpb_common.cuh"
+#include "cpb_masks.cuh"
+
+// k_lookup_list: grid-stride over the compacted foreground list (full warps).  raw label = painted
+// label at the pixel's end point; statistics of the raw labels go to the tables.  `lab` must be
+// zeroed beforehand (background stays 0).
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_lookup_list(const unsigned* CPB_RESTRICT list, const unsigned* CPB_RESTRICT list_n,
+              const int* CPB_RESTRICT pfinal, const int* CPB_RESTRICT M, int H, int W,
+              int* CPB_RESTRICT lab, LabelTables t) {
+    const unsigned total = *list_n;
+    const int N = H * W;
+    for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {
+        const unsigned i = i0 + threadIdx.x;
+        int l = 0, b = 0, r = 0, y = 0, x = 0;
+        if (i < total) {
+            const unsigned gi = list[i];
+            b = (int)(gi / (unsigned)N);
+            r = (int)(gi - (unsigned)b * (unsigned)N);
+            const int pf = pfinal[gi];
+            l = M[(size_t)b * N + (pf >> 16) * W + (pf & 0xffff)];
+            lab[gi] = l;
+            y = r / W; x = r - y * W;
+        }
+        cpb_stats_accum(t, b, l, r, y, x);
+    }
+}
+
+// k_fuse_size: one block per tile.  Table form of "drop flagged labels, size filter, renumber":
+//   present(l) = alive[l] && !flag[l] && cnt[l] > 0        (flag = bad flow, set by k_flow_err)
+//   mode 2: no hole fill / size filter requested: remap = present ? current id : 0, nothing renumbered
+//   otherwise: position of a present label = rank of its CURRENT id (remap) among present labels; when
+//   min_size > 0 every present label with cnt < min_size removes the label whose current id equals that
+//   position (upstream indexes by position, see k_size_renumber); survivors get new ids 1..n in order of
+//   first appearance.  Writes remap, alive, nlab.  Tiles with only_if[b] == 0 are skipped when only_if != NULL.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_fuse_size(LabelTables t, int H, int W, int min_size, int mode, const int* CPB_RESTRICT only_if,
+            u64* CPB_RESTRICT scratch_key, int* CPB_RESTRICT scratch_idx, int* CPB_RESTRICT scratch_inv) {
+    CPB_SHARED int s_n, s_fg;
+    CPB_SHARED u64 s_keys[CPB_RANK_CHUNK];
+    const int b = blockIdx.x;
+    if (only_if && only_if[b] == 0) return;
+    const int LC = t.LC;
+    const int lb = t.lbound[b];
+    const int* cnt = t.cnt + (size_t)b * LC;
+    const int* first = t.first + (size_t)b * LC;
+    int* remap = t.remap + (size_t)b * LC;
+    int* flag = t.flag + (size_t)b * LC;
+    int* alive = t.alive + (size_t)b * LC;
+    u64* keys = scratch_key + (size_t)b * LC;
+    int* rank = scratch_idx + (size_t)b * LC;
+    int* inv = scratch_inv + (size_t)b * LC;     // current id -> raw label
+    const int n_cur = t.nlab[b];
+    if (mode == 2) {
+        for (int l = threadIdx.x; l <= lb; l += blockDim.x) {
+            const bool pres = l >= 1 && alive[l] && !flag[l] && cnt[l] > 0;
+            if (!pres) { remap[l] = 0; alive[l] = 0; }
+        }
+        return;
+    }
+    if (threadIdx.x == 0) { s_n = 0; s_fg = 0; }
+    __syncthreads();
+    int part = 0;
+    for (int l = 1 + threadIdx.x; l <= lb; l += blockDim.x) {
+        const bool pres = alive[l] && !flag[l] && cnt[l] > 0;
+        if (pres) {
+            part += cnt[l];
+            const int k = atomicAdd(&s_n, 1);
+            keys[k] = ((u64)(unsigned)remap[l] << 32) | (unsigned)l;
+        }
+        if (alive[l]) inv[remap[l]] = l;
+    }
+    for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(CPB_FULL, part, d);
+    if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_fg, part);
+    __syncthreads();
+    const int n = s_n;
+    const int has_bg = (s_fg < H * W) ? 1 : 0;
+    if (min_size > 0) {
+        cpb_block_rank(keys, n, rank, s_keys);          // rank[k] = 1-based position among present labels
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const int l = (int)(keys[k] & 0xffffffffu);
+            if (cnt[l] < min_size) {
+                const int victim = rank[k] - (has_bg ? 0 : 1);
+                if (victim >= 1 && victim <= n_cur) flag[inv[victim]] = 1;
+            }
+        }
+        __syncthreads();
+    }
+    // survivors, ordered by first appearance
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int l = threadIdx.x; l <= lb; l += blockDim.x) {
+        const bool pres = l >= 1 && alive[l] && !flag[l] && cnt[l] > 0;
+        if (pres) {
+            const int k = atomicAdd(&s_n, 1);
+            keys[k] = ((u64)(unsigned)first[l] << 32) | (unsigned)l;
+        } else {
+            remap[l] = 0; alive[l] = 0;
+        }
+    }
+    __syncthreads();
+    const int n2 = s_n;
+    cpb_block_rank(keys, n2, rank, s_keys);
+    for (int k = threadIdx.x; k < n2; k += blockDim.x) remap[(int)(keys[k] & 0xffffffffu)] = rank[k];
+    if (threadIdx.x == 0) t.nlab[b] = n2;
+}
+
+// k_recount: pixel pass over the tiles in which a hole was filled (t.misc[b] != 0): recompute count and
+// first appearance of every live label on the image with the hole proposals applied.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_recount(const int* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, int B, int H, int W, LabelTables t) {
+    const int N = H * W;
+    const long long total = (long long)B * N;
+    const long long base = (long long)blockIdx.x * blockDim.x;
+    if (base >= total) return;
+    const long long gi = base + threadIdx.x;
+    int l = 0, b = 0, r = 0, y = 0, x = 0;
+    if (gi < total) {
+        b = (int)(gi / N);
+        if (t.misc[b] != 0) {
+            r = (int)(gi - (long long)b * N);
+            const u64 hk = holekey[gi];
+            l = hk ? (int)(hk & 0xffffffffu) : lab[gi];
+            if (l > 0 && t.alive[(size_t)b * t.LC + l] == 0) l = 0;
+            y = r / W; x = r - y * W;
+        }
+    }
+    if (__ballot_sync(CPB_FULL, l > 0) == 0) return;
+    cpb_stats_accum(t, b, l, r, y, x);
+}
+
+// grid (ceil(LC/256), B): reset count / first of the tiles that need a recount
+CPB_KERNEL k_reset_counts(LabelTables t) {
+    const int b = blockIdx.y;
+    if (t.misc[b] == 0) return;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > t.lbound[b] || l >= t.LC) return;
+    const size_t k = (size_t)b * t.LC + l;
+    t.cnt[k] = 0; t.first[k] = CPB_IMAX;
+}
+
+// k_final: raw label (or hole proposal) -> final id, in place; also publishes the per-tile counts.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_final(int* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, int B, int H, int W, LabelTables t,
+        int* CPB_RESTRICT counts_out) {
+    const int N = H * W;
+    const long long total = (long long)B * N;
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= total) return;
+    const int b = (int)(gi / N);
+    int l = lab[gi];
+    if (holekey && t.misc[b] != 0) {
+        const u64 hk = holekey[gi];
+        if (hk) l = (int)(hk & 0xffffffffu);
+    }
+    const int out = l > 0 ? t.remap[(size_t)b * t.LC + l] : 0;
+    if (out != l) lab[gi] = out;
+    if (gi - (long long)b * N == 0) {
+        const int n = t.nlab[b];
+        if (counts_out) counts_out[b] = n;
+    }
+}
+
+// after k_final the image holds ids 1..nlab: shrink the label bound accordingly (vote, border)
+CPB_KERNEL k_finish_bounds(LabelTables t, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) t.lbound[b] = t.nlab[b];
+}

@@ -125,7 +125,7 @@ k_lookup(const int* CPB_RESTRICT pfinal, const int* CPB_RESTRICT M, int B, int H
 // renumber the rest 1..n in order of first appearance.
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_gm_finalize(LabelTables t, int H, int W, double max_size_fraction, u64* CPB_RESTRICT scratch_key,
-              int* CPB_RESTRICT scratch_idx, int* CPB_RESTRICT counts_out) {
+              int* CPB_RESTRICT scratch_idx, int* CPB_RESTRICT counts_out, int keep_raw) {
     CPB_SHARED int s_n;
     CPB_SHARED u64 s_keys[CPB_RANK_CHUNK];
     const int b = blockIdx.x;
@@ -141,9 +141,11 @@ k_gm_finalize(LabelTables t, int H, int W, double max_size_fraction, u64* CPB_RE
     __syncthreads();
     for (int l = threadIdx.x; l <= lb; l += blockDim.x) {
         remap[l] = 0;
+        if (keep_raw) t.alive[(size_t)b * LC + l] = 0;
         if (l >= 1) {
             const int c = cnt[l];
             if (c > 0 && !((double)c > big)) {
+                if (keep_raw) t.alive[(size_t)b * LC + l] = 1;
                 const int k = atomicAdd(&s_n, 1);
                 keys[k] = ((u64)(unsigned)first[l] << 32) | (unsigned)l;
             }
@@ -155,7 +157,7 @@ k_gm_finalize(LabelTables t, int H, int W, double max_size_fraction, u64* CPB_RE
     for (int k = threadIdx.x; k < n; k += blockDim.x) remap[(int)(keys[k] & 0xffffffffu)] = rank[k];
     if (threadIdx.x == 0) {
         t.nlab[b] = n;
-        t.lbound[b] = n;   // labels are 1..n after the remap is applied
+        if (!keep_raw) t.lbound[b] = n;   // labels are 1..n after the remap is applied
         if (counts_out) counts_out[b] = n;
     }
 }

@@ -14,7 +14,7 @@
 #define CPB_SHARED static thread_local
 #define CPB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(cusim::dyn_smem())
 #define CPB_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    cusim::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+    cusim::launch(#kernel, (grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
 #define CPB_RESTRICT
 #define CPB_LAUNCH_BOUNDS(t, b)
 #else

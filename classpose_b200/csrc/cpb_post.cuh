@@ -24,7 +24,7 @@ k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_
     unsigned* rc = s_bits + CPB_FILL_WORDS;
     for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
         const size_t k = (size_t)b * LC + l;
-        if (t.cnt[k] <= 0) continue;
+        if (!cpb_label_live(t, k)) continue;
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         if (h < 3 || w < 3) continue;
@@ -78,6 +78,7 @@ k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_
         for (int i = threadIdx.x; i < h * wpr; i += blockDim.x) {
             unsigned hole = fr[i] & ~rc[i];
             const int r = i / wpr, j = i - r * wpr;
+            if (hole) t.misc[b] = 1;     // tile has at least one filled hole
             while (hole) {
                 const int c = __ffs((int)hole) - 1;
                 hole &= hole - 1;

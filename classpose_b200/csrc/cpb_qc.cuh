@@ -26,7 +26,7 @@ k_centres(const int* CPB_RESTRICT lab, int H, int W, LabelTables t) {
     for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
         const size_t k = (size_t)b * LC + l;
         const int c = t.cnt[k];
-        if (c <= 0) continue;   // block-uniform
+        if (!cpb_label_live(t, k)) continue;   // block-uniform
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         // means of (coordinate relative to the bbox + 1), as the reference computes them
@@ -106,7 +106,7 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
     double* S = s_T[warp];
     for (int l = 1 + blockIdx.x * CPB_DW_WARPS + warp; l <= lb; l += gridDim.x * CPB_DW_WARPS) {
         const size_t k = (size_t)b * LC + l;
-        if (t.cnt[k] <= 0) continue;      // warp-uniform
+        if (!cpb_label_live(t, k)) continue;      // warp-uniform
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         if (!cpb_diffuse_is_small(h, w)) continue;
@@ -163,7 +163,7 @@ k_diffuse(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_
     const int n_it = niter_override > 0 ? niter_override : t.niter[b];
     for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
         const size_t k = (size_t)b * LC + l;
-        if (t.cnt[k] <= 0) continue;
+        if (!cpb_label_live(t, k)) continue;
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         if (skip_small && cpb_diffuse_is_small(h, w)) continue;
@@ -250,10 +250,12 @@ k_diffuse(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_
 
 // T of a neighbouring pixel as the reference's padded array holds it: 0 off-tile and on
 // background, the (possibly foreign) instance's T otherwise.
-CPB_DEVICE double cpb_T_at(const double* CPB_RESTRICT Tb, const int* CPB_RESTRICT L, int H, int W, int y, int x) {
+CPB_DEVICE double cpb_T_at(const double* CPB_RESTRICT Tb, const int* CPB_RESTRICT L, const int* CPB_RESTRICT alive,
+                           int H, int W, int y, int x) {
     if (y < 0 || y >= H || x < 0 || x >= W) return 0.0;
     const int p = y * W + x;
-    return L[p] > 0 ? Tb[p] : 0.0;
+    const int l = L[p];
+    return (l > 0 && (alive == nullptr || alive[l] != 0)) ? Tb[p] : 0.0;
 }
 
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
@@ -264,12 +266,13 @@ k_flow_err(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int
     const int lb = t.lbound[b];
     const int* L = lab + (size_t)b * N;
     const double* Tb = T + (size_t)b * N;
+    const int* alive = t.alive ? t.alive + (size_t)b * LC : nullptr;
     const float* dPy = dP ? dP + ((size_t)b * 2 + 0) * N : nullptr;
     const float* dPx = dP ? dP + ((size_t)b * 2 + 1) * N : nullptr;
     for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
         const size_t k = (size_t)b * LC + l;
         const int c = t.cnt[k];
-        if (c <= 0) continue;
+        if (!cpb_label_live(t, k)) continue;
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         double ey = 0.0, ex = 0.0;
@@ -277,8 +280,8 @@ k_flow_err(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int
             const int y = y0 + i / w, x = x0 + i % w;
             const int p = y * W + x;
             if (L[p] != l) continue;
-            const double dy = __dsub_rn(cpb_T_at(Tb, L, H, W, y + 1, x), cpb_T_at(Tb, L, H, W, y - 1, x));
-            const double dx = __dsub_rn(cpb_T_at(Tb, L, H, W, y, x + 1), cpb_T_at(Tb, L, H, W, y, x - 1));
+            const double dy = __dsub_rn(cpb_T_at(Tb, L, alive, H, W, y + 1, x), cpb_T_at(Tb, L, alive, H, W, y - 1, x));
+            const double dx = __dsub_rn(cpb_T_at(Tb, L, alive, H, W, y, x + 1), cpb_T_at(Tb, L, alive, H, W, y, x - 1));
             const double nrm = __dadd_rn(1e-60, __dsqrt_rn(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx))));
             const double my = __ddiv_rn(dy, nrm), mx = __ddiv_rn(dx, nrm);
             if (mu_out) {

@@ -321,6 +321,27 @@ def case_fused_empty_and_params(be):
     assert r["fp"] == 0 and r["fn"] == 0
 
 
+def case_fused_qc_then_positional_size_filter(be):
+    """Fused path where the flow check removes labels first, so the later size filter (which upstream
+    indexes by POSITION in the sorted unique list) removes labels other than the small ones."""
+    t = dict(std_tile(8))
+    t["dP"] = corrupt_flows(t, every=5, seed=3)
+    kw = dict(min_size=150)
+    st = {}
+    ref = dynamics.resize_and_compute_masks(t["dP"], t["cellprob"], return_stages=st, **kw)
+    qc = st["masks_qc"]
+    assert len(np.unique(qc)) - 1 < qc.max(), "flow check must have removed labels"
+    # what a by-label ("intended") size filter would have produced differs from upstream's by-position one
+    ids, cnt = np.unique(qc[qc > 0], return_counts=True)
+    intended = np.isin(qc, ids[cnt >= 150])
+    assert (intended != (ref > 0)).any(), "scenario does not exercise the positional quirk"
+    masks, counts, _, _ = be.compute_masks(f32(t["dP"][None]), f32(t["cellprob"][None]), None, **kw)
+    r = metrics.match_instances(ref, masks[0])
+    assert r["fp"] == 0 and r["fn"] == 0 and r["f1"] == 1.0, {k: v for k, v in r.items() if k != "pairs"}
+    assert counts[0] == ref.max()
+    assert ((masks[0] > 0) == (ref > 0)).mean() > 0.9995
+
+
 def case_label_offsets(be):
     counts = np.array([3, 0, 7, 1, 250, 12] * 100, np.int32)
     offs, total = be.label_offsets(counts, 1000)
@@ -333,4 +354,4 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_get_mask
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
              case_remove_bad_flow_masks_exact, case_fill_holes_exact, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
-             case_fused_empty_and_params, case_label_offsets]
+             case_fused_empty_and_params, case_fused_qc_then_positional_size_filter, case_label_offsets]

@@ -89,6 +89,7 @@ constexpr int kMaxThreads = 1024;
 
 struct WarpState {
     uint64_t slot[32];
+    uint32_t want[32];          // mask of the collective each arrived lane is waiting in
     uint32_t arrived = 0, left = 0;
 };
 
@@ -98,6 +99,8 @@ struct Worker {
     void* fiber_sp[kMaxThreads];
     bool done[kMaxThreads];
     dim3 tid[kMaxThreads];
+    const char* wait_what[kMaxThreads];
+    unsigned wait_mask[kMaxThreads];
     int cur = 0, nthreads = 0, live = 0;
     int bar_arrived = 0;
     unsigned bar_gen = 0;
@@ -148,6 +151,8 @@ inline void fiber_main() {
     abort();
 }
 
+inline const char*& tl_kernel_name();
+
 inline void run_block(Worker* w) {
     const int n = w->nthreads;
     for (int i = 0; i < n; i++) {
@@ -173,12 +178,18 @@ inline void run_block(Worker* w) {
             cusim_switch(&w->sched_sp, w->fiber_sp[i]);
         }
         if (w->live > 0 && w->progress == before) {
-            fprintf(stderr, "cusim: deadlock in block (%u,%u,%u): %d live threads, %d at barrier\n",
+            fprintf(stderr, "cusim: deadlock in %s block (%u,%u,%u): %d live threads, %d at barrier\n", tl_kernel_name(),
                     w->bid.x, w->bid.y, w->bid.z, w->live, w->bar_arrived);
+            for (int i = 0; i < n; i++)
+                if (!w->done[i]) fprintf(stderr, "  thread %d: %s mask=%08x  warp arrived=%08x left=%08x\n", i,
+                                         w->wait_what[i] ? w->wait_what[i] : "?", w->wait_mask[i],
+                                         w->warps[i >> 5].arrived, w->warps[i >> 5].left);
             abort();
         }
     }
 }
+
+inline const char*& tl_kernel_name() { static const char* n = "?"; return n; }
 
 inline int num_workers() {
     static int n = [] {
@@ -190,7 +201,8 @@ inline int num_workers() {
 }
 
 template <class F>
-inline void launch(dim3 grid, dim3 block, size_t smem, F f) {
+inline void launch(const char* name, dim3 grid, dim3 block, size_t smem, F f) {
+    tl_kernel_name() = name;
     std::function<void()> body = f;
     const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
     const int nthreads = (int)(block.x * block.y * block.z);
@@ -234,12 +246,23 @@ inline R warp_collective(unsigned mask, uint64_t v, Fn fn) {
     unsigned bit = 1u << lane;
     if (!(mask & bit)) { fprintf(stderr, "cusim: lane %d not in mask %08x\n", lane, mask); abort(); }
     for (int l = 0; l < nl; l++)
-        if ((mask >> l & 1) && w->done[(t & ~31) + l]) { fprintf(stderr, "cusim: mask names exited lane\n"); abort(); }
+        if ((mask >> l & 1) && w->done[(t & ~31) + l]) { fprintf(stderr, "cusim: mask %08x names exited lane %d in %s (thread %d)\n", mask, l, tl_kernel_name(), t); abort(); }
+    w->wait_what[t] = "drain"; w->wait_mask[t] = mask;
     while (ws.arrived & bit) yield();  // previous collective of this lane not drained yet
     ws.slot[lane] = v;
+    ws.want[lane] = mask;
     ws.arrived |= bit;
     w->progress++;
-    while ((ws.arrived & mask) != mask) yield();
+    w->wait_what[t] = "arrive";
+    // complete when every lane of the mask has arrived *in this same collective* (lanes of a warp can be
+    // inside different collectives at the same time, e.g. some in a subset reduce, others already waiting
+    // in the next full-warp ballot)
+    auto complete = [&]() {
+        if ((ws.arrived & mask) != mask) return false;
+        for (int l2 = 0; l2 < 32; l2++) if ((mask >> l2 & 1) && ws.want[l2] != mask) return false;
+        return true;
+    };
+    while (!complete()) yield();
     R r = fn(ws.slot, mask, lane);
     ws.left |= bit;
     if ((ws.left & mask) == mask) { ws.arrived &= ~mask; ws.left &= ~mask; w->progress++; }
@@ -256,6 +279,7 @@ inline void __syncthreads() {
     unsigned gen = w->bar_gen;
     w->bar_arrived++;
     if (w->bar_arrived >= w->live) { w->bar_arrived = 0; w->bar_gen++; w->progress++; return; }
+    w->wait_what[w->cur] = "barrier";
     while (w->bar_gen == gen) cusim::yield();
 }
 inline void __syncwarp(unsigned mask = 0xffffffffu) {
