@@ -57,7 +57,8 @@ struct ProfScope {
 
 constexpr int kLabelBlocksPerTile = 24;
 constexpr int kWarpDiffuseBlocksPerTile = 8; // x CPB_DW_WARPS warps: labels of a tile in flight   // per-label kernels: grid (kLabelBlocksPerTile, B)
-constexpr int kVoteSmemInts = 16 * 1024;  // 64 KB table for the class vote
+constexpr int kVoteSmemInts = 6 * 1024;   // 24 KB (instance, class) table per tile: 4 blocks of 512 threads per SM;
+                                          // tiles with more than 6144/C labels use the global table
 constexpr size_t kAlign = 256;
 
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
@@ -98,7 +99,7 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     const int LC = lcap > 0 ? lcap : cpb_label_capacity(H, W);
     const size_t BL = (size_t)B * LC;
     Carver c{reinterpret_cast<char*>(base), 0};
-    w.flow = c.take<float2>((size_t)B * (H + 2) * (W + 2));
+    w.flow = c.take<float2>((size_t)B * (H + 2) * (W + 2 * CPB_FLOW_PADX));
     w.pfinal = c.take<int>(BN);
     w.hist = c.take<int>(BN);
     w.M = c.take<int>(BN);
@@ -186,8 +187,16 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
     if (hist) cudaMemsetAsync(hist, 0, BN * sizeof(int), st);
     const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
-    CPB_LAUNCH_COUNTED(k_prep_flow, dim3(blocks_for((long long)B * (H + 2) * (W + 2), 256)), dim3(256), 0, st, dP, cellprob, B, H, W, thr, sx, sy,
-               w.flow, pfinal, w.list, w.list_n);
+    const bool vec4 = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(dP) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(cellprob) % 16 == 0) && (reinterpret_cast<uintptr_t>(pfinal) % 16 == 0);
+    if (vec4) {
+        CPB_LAUNCH_COUNTED(k_prep_flow_v4, dim3(blocks_for((long long)B * (H + 2) * (W / 4), 256)), dim3(256), 0, st,
+                           reinterpret_cast<const float4*>(dP), reinterpret_cast<const float4*>(cellprob), B, H, W, thr, sx,
+                           sy, reinterpret_cast<float4*>(w.flow), reinterpret_cast<int4*>(pfinal), w.list, w.list_n);
+    } else {
+        CPB_LAUNCH_COUNTED(k_prep_flow, dim3(blocks_for((long long)B * (H + 2) * (W + 2 * CPB_FLOW_PADX), 256)), dim3(256),
+                           0, st, dP, cellprob, B, H, W, thr, sx, sy, w.flow, pfinal, w.list, w.list_n);
+    }
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_PREP);
     ProfScope ps(w.prof, S_FOLLOW);
@@ -223,7 +232,7 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
     cudaMemsetAsync(w.t.niter, 0, B * sizeof(int), st);
     const dim3 grid(kLabelBlocksPerTile, B);
     prof_begin(w.prof, S_CENTRES);
-    CPB_LAUNCH_COUNTED(k_centres, grid, dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t);
+    CPB_LAUNCH_COUNTED(k_centres, grid, dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t, 1);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_CENTRES);
     const size_t smem = (size_t)CPB_DIFF_SMEM_CELLS * 17;
@@ -235,7 +244,10 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_DIFFUSE);
     ProfScope ps(w.prof, S_FLOWERR);
-    CPB_LAUNCH_COUNTED(k_flow_err, grid, dim3(CPB_QC_THREADS), 0, st, masks, dP, H, W, w.t, w.T, thr, mu_out);
+    CPB_LAUNCH_COUNTED(k_flow_err_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(128), 0, st, masks, dP, H, W, w.t, w.T,
+                       thr, mu_out);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_flow_err, grid, dim3(CPB_QC_THREADS), 0, st, masks, dP, H, W, w.t, w.T, thr, mu_out, 1);
     CPB_CHECK_LAUNCH();
     return 0;
 }
@@ -254,8 +266,10 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
     e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, true, st, S_MAP2); if (e) return e;
     prof_begin(w.prof, S_FILL);
     cudaMemsetAsync(w.holekey, 0, BN * sizeof(u64), st);
+    CPB_LAUNCH_COUNTED(k_fill_holes_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(128), 0, st, masks, H, W, w.t, w.holekey);
+    CPB_CHECK_LAUNCH();
     CPB_LAUNCH_COUNTED(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
-               masks, H, W, w.t, w.holekey, w.status);
+               masks, H, W, w.t, w.holekey, w.status, 1);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_FILL);
     e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, w.holekey, true, st, S_MAP3); if (e) return e;
@@ -449,8 +463,11 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         prof_end(w.prof, S_SIZE1);
         prof_begin(w.prof, S_FILL);
         cudaMemsetAsync(w.holekey, 0, BN * sizeof(u64), st);
+        CPB_LAUNCH_COUNTED(k_fill_holes_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(128), 0, st, masks, H, W, w.t,
+                           w.holekey);
+        CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
-                           masks, H, W, w.t, w.holekey, w.status);
+                           masks, H, W, w.t, w.holekey, w.status, 1);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_FILL);
         prof_begin(w.prof, S_MAP3);

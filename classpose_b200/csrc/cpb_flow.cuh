@@ -6,12 +6,21 @@
 #pragma once
 #include "cpb_common.cuh"
 
-// The masked, scaled flow field is stored zero-padded by one pixel on every side, x component
-// first:  flow[b][y+1][x+1] = ( dX*fg/5 * 2/(W-1) , dY*fg/5 * 2/(H-1) ),  row pitch Wp = W+2.
-// Clamped positions sample taps in [-1, L], so all four bilinear taps are always inside the
-// padded array and grid_sample's zero padding costs no bounds checks (a zero tap adds v*w = 0).
-//
-// k_prep_flow: one thread per padded pixel.  Also writes p_final = -1 on background and appends
+// The masked, scaled flow field is stored zero-padded (one row above / below, CPB_FLOW_PADX columns left /
+// right), x component first:
+//   flow[b][y+1][x+PADX] = ( dX*fg/5 * 2/(W-1) , dY*fg/5 * 2/(H-1) ),  row pitch Wp = W + 2*PADX.
+// Clamped positions sample taps in [-1, L], so all four bilinear taps are always inside the padded array and
+// grid_sample's zero padding costs no bounds checks (a zero tap adds v*w = 0).  PADX = 2 keeps the interior
+// of every row 16-byte aligned for the vectorised writer.
+#define CPB_FLOW_PADX 2
+
+CPB_DEVICE float2 cpb_scaled_flow(float dy, float dx, bool fg, float sx, float sy) {
+    // (dP * fg) / 5.  then  *= 2/(L-1)   -- each a separately rounded float32 op
+    const float m = fg ? 1.0f : 0.0f;
+    return make_float2(__fmul_rn(__fdiv_rn(__fmul_rn(dx, m), 5.0f), sx), __fmul_rn(__fdiv_rn(__fmul_rn(dy, m), 5.0f), sy));
+}
+
+// k_prep_flow: one thread per padded pixel (any W).  Also writes p_final = -1 on background and appends
 // foreground pixels to `list` (global pixel index in the un-padded layout), block-contiguous.
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, int B, int H, int W,
@@ -19,7 +28,7 @@ k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, in
             unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n) {
     CPB_SHARED int s_scan[33];
     CPB_SHARED unsigned s_base;
-    const int N = H * W, Wp = W + 2, Np = (H + 2) * Wp;
+    const int N = H * W, Wp = W + 2 * CPB_FLOW_PADX, Np = (H + 2) * Wp;
     const long long total = (long long)B * Np;
     const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool fg = false;
@@ -29,17 +38,11 @@ k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, in
         const int rp = (int)(gp - (long long)b * Np);
         const int yp = rp / Wp, xp = rp - yp * Wp;
         float2 out = make_float2(0.f, 0.f);
-        if (yp >= 1 && yp <= H && xp >= 1 && xp <= W) {
-            const int r = (yp - 1) * W + (xp - 1);
+        if (yp >= 1 && yp <= H && xp >= CPB_FLOW_PADX && xp < W + CPB_FLOW_PADX) {
+            const int r = (yp - 1) * W + (xp - CPB_FLOW_PADX);
             gi = (unsigned)b * (unsigned)N + (unsigned)r;
-            const float cp = cellprob[gi];
-            fg = cp > thr;
-            const float m = fg ? 1.0f : 0.0f;
-            const float dy = dP[((size_t)b * 2 + 0) * N + r];
-            const float dx = dP[((size_t)b * 2 + 1) * N + r];
-            // (dP * fg) / 5.  then  *= 2/(L-1)   -- each a separately rounded float32 op
-            out.y = __fmul_rn(__fdiv_rn(__fmul_rn(dy, m), 5.0f), sy);
-            out.x = __fmul_rn(__fdiv_rn(__fmul_rn(dx, m), 5.0f), sx);
+            fg = cellprob[gi] > thr;
+            out = cpb_scaled_flow(dP[((size_t)b * 2 + 0) * N + r], dP[((size_t)b * 2 + 1) * N + r], fg, sx, sy);
             if (!fg) pfinal[gi] = -1;
         }
         flow[gp] = out;
@@ -49,6 +52,59 @@ k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, in
     if (threadIdx.x == 0 && tot > 0) s_base = atomicAdd(list_n, (unsigned)tot);
     __syncthreads();
     if (fg) list[s_base + incl - 1] = gi;
+}
+
+// k_prep_flow_v4: W % 4 == 0.  One thread per group of 4 pixels of a padded row (rows -1 and H are the zero
+// rows): three 128-bit loads, two 128-bit flow stores, one 128-bit p_final store.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_prep_flow_v4(const float4* CPB_RESTRICT dP, const float4* CPB_RESTRICT cellprob, int B, int H, int W,
+               float thr, float sx, float sy, float4* CPB_RESTRICT flow, int4* CPB_RESTRICT pfinal,
+               unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n) {
+    CPB_SHARED int s_scan[33];
+    CPB_SHARED unsigned s_base;
+    const int W4 = W >> 2, N4 = (H * W) >> 2;
+    const int Wp4 = (W + 2 * CPB_FLOW_PADX) >> 1;           // row pitch in float4 (2 pixels each)
+    const long long total = (long long)B * (H + 2) * W4;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int nfg = 0;
+    unsigned gi0 = 0;
+    bool f0 = false, f1 = false, f2 = false, f3 = false;
+    if (g < total) {
+        const int b = (int)(g / ((long long)(H + 2) * W4));
+        const int rem = (int)(g - (long long)b * (H + 2) * W4);
+        const int yp = rem / W4, xg = rem - yp * W4;
+        float4* row = flow + ((size_t)b * (H + 2) + yp) * Wp4;
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+        if (yp >= 1 && yp <= H) {
+            const int y = yp - 1;
+            const int q = y * W4 + xg;                          // float4 index inside the tile plane
+            const float4 cp = cellprob[(size_t)b * N4 + q];
+            const float4 dy = dP[((size_t)b * 2 + 0) * N4 + q];
+            const float4 dx = dP[((size_t)b * 2 + 1) * N4 + q];
+            f0 = cp.x > thr; f1 = cp.y > thr; f2 = cp.z > thr; f3 = cp.w > thr;
+            const float2 a0 = cpb_scaled_flow(dy.x, dx.x, f0, sx, sy), a1 = cpb_scaled_flow(dy.y, dx.y, f1, sx, sy);
+            const float2 a2 = cpb_scaled_flow(dy.z, dx.z, f2, sx, sy), a3 = cpb_scaled_flow(dy.w, dx.w, f3, sx, sy);
+            o0 = make_float4(a0.x, a0.y, a1.x, a1.y);
+            o1 = make_float4(a2.x, a2.y, a3.x, a3.y);
+            gi0 = (unsigned)b * (unsigned)(H * W) + (unsigned)(q << 2);
+            pfinal[(size_t)b * N4 + q] = make_int4(f0 ? 0 : -1, f1 ? 0 : -1, f2 ? 0 : -1, f3 ? 0 : -1);
+            nfg = (int)f0 + (int)f1 + (int)f2 + (int)f3;
+        }
+        row[1 + 2 * xg] = o0;                                   // pixels 4xg, 4xg+1  (padded x = 4xg + 2)
+        row[2 + 2 * xg] = o1;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xg == 0) row[0] = z;                                // left pad (2 px)
+        if (xg == W4 - 1) row[Wp4 - 1] = z;                     // right pad (2 px)
+    }
+    int tot;
+    const int incl = cpb_block_scan_incl(nfg, s_scan, &tot);
+    if (threadIdx.x == 0 && tot > 0) s_base = atomicAdd(list_n, (unsigned)tot);
+    __syncthreads();
+    unsigned o = s_base + (unsigned)(incl - nfg);
+    if (f0) list[o++] = gi0;
+    if (f1) list[o++] = gi0 + 1;
+    if (f2) list[o++] = gi0 + 2;
+    if (f3) list[o++] = gi0 + 3;
 }
 
 // One Euler step in normalised coordinates, arithmetic order as ATen's grid_sampler_2d.
@@ -80,7 +136,7 @@ k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
          const unsigned* CPB_RESTRICT list_n, int H, int W, int niter,
          int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
     const unsigned total = *list_n;
-    const int N = H * W, Wp = W + 2, Np = (H + 2) * Wp;
+    const int N = H * W, Wp = W + 2 * CPB_FLOW_PADX, Np = (H + 2) * Wp;
     const float fW = (float)W, fH = (float)H;
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
     const int lane = threadIdx.x & 31;
@@ -93,7 +149,7 @@ k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
         const int b = (int)(gi / (unsigned)N);
         const int r = (int)(gi - (unsigned)b * (unsigned)N);
         const int y = r / W, x = r - y * W;
-        const float2* f = flow + (size_t)b * Np + Wp + 1;
+        const float2* f = flow + (size_t)b * Np + Wp + CPB_FLOW_PADX;
 #ifndef CPB_SIM
         asm volatile("" : "+l"(f));   // keep the tile base in a register pair (address = base + idx*8)
 #endif

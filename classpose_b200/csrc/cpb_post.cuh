@@ -13,7 +13,7 @@
 // outermost instance -- the one the reference's sequential loop ends with -- wins.
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FILL_THREADS, 3)
 k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_RESTRICT holekey,
-             int* CPB_RESTRICT status) {
+             int* CPB_RESTRICT status, int skip_small) {
     CPB_DYN_SMEM(unsigned, s_bits);     // free[CPB_FILL_WORDS] | reach[CPB_FILL_WORDS]
     CPB_SHARED int s_changed;
     const int b = blockIdx.y, LC = t.LC, N = H * W;
@@ -28,6 +28,7 @@ k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         if (h < 3 || w < 3) continue;
+        if (skip_small && h <= 32 && w <= 32) continue;     // handled by k_fill_holes_warp
         const int wpr = (w + 31) >> 5;
         if (h * wpr > CPB_FILL_WORDS) { if (threadIdx.x == 0) atomicOr(status, 1); continue; }
         __syncthreads();
@@ -88,10 +89,58 @@ k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_
     }
 }
 
+// k_fill_holes_warp: the same hole detection for bboxes up to 32 x 32, one WARP per label and no shared
+// memory: lane r holds row r of the crop as a 32-bit mask; the border flood runs on warp shuffles.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(128, 8)
+k_fill_holes_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_RESTRICT holekey) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int b = blockIdx.y, LC = t.LC, N = H * W;
+    const int lb = t.lbound[b];
+    const int* L = lab + (size_t)b * N;
+    u64* HK = holekey + (size_t)b * N;
+    for (int l = 1 + blockIdx.x * nw + warp; l <= lb; l += gridDim.x * nw) {
+        const size_t k = (size_t)b * LC + l;
+        if (!cpb_label_live(t, k)) continue;
+        const int y0 = t.ymin[k], x0 = t.xmin[k];
+        const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        if (h < 3 || w < 3 || h > 32 || w > 32) continue;
+        unsigned fr = 0;                       // row `lane`: bit c = pixel (lane, c) is not l
+        for (int r = 0; r < h; r++) {
+            const bool notl = lane < w && L[(y0 + r) * W + x0 + lane] != l;
+            const unsigned m = __ballot_sync(CPB_FULL, notl);
+            if (lane == r) fr = m;
+        }
+        unsigned rc = (lane == 0 || lane == h - 1) ? fr : (fr & (1u | (1u << (w - 1))));
+        if (lane >= h) rc = 0;
+        for (;;) {
+            unsigned up = __shfl_up_sync(CPB_FULL, rc, 1), dn = __shfl_down_sync(CPB_FULL, rc, 1);
+            if (lane == 0) up = 0;
+            if (lane == 31) dn = 0;
+            unsigned n = (rc | up | dn) & fr;
+            for (;;) {
+                const unsigned m = (n | (n << 1) | (n >> 1)) & fr;
+                if (m == n) break;
+                n = m;
+            }
+            const bool ch = n != rc;
+            rc = n;
+            if (!__any_sync(CPB_FULL, ch)) break;
+        }
+        unsigned hole = fr & ~rc;
+        if (hole) t.misc[b] = 1;
+        const u64 prio = (u64)((unsigned)(h * w)) << 32;
+        while (hole) {
+            const int c = __ffs((int)hole) - 1;
+            hole &= hole - 1;
+            atomicMax(&HK[(y0 + lane) * W + x0 + c], prio | (unsigned)l);
+        }
+    }
+}
+
 // k_vote: one block per tile.  Per-pixel arg-max over the C logits (first maximum wins),
 // histogram (instance, class) in shared memory, per-instance arg-max (first maximum wins).
 // Falls back to a global table when (lbound+1)*C ints exceed the shared-memory budget.
-CPB_KERNEL CPB_LAUNCH_BOUNDS(512, 2)
+CPB_KERNEL CPB_LAUNCH_BOUNDS(512, 4)
 k_vote(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT logits, int H, int W, int C, int LC,
        const int* CPB_RESTRICT lbound, int smem_ints, int* CPB_RESTRICT gtable,
        int* CPB_RESTRICT cell_class, unsigned char* CPB_RESTRICT class_masks) {

@@ -17,7 +17,7 @@ CPB_DEVICE bool cpb_minkey_less(double d0, int i0, double d1, int i1) {
 }
 
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
-k_centres(const int* CPB_RESTRICT lab, int H, int W, LabelTables t) {
+k_centres(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, int skip_small) {
     CPB_SHARED double s_d[CPB_QC_THREADS / 32];
     CPB_SHARED int s_i[CPB_QC_THREADS / 32];
     const int b = blockIdx.y, LC = t.LC, N = H * W;
@@ -29,6 +29,10 @@ k_centres(const int* CPB_RESTRICT lab, int H, int W, LabelTables t) {
         if (!cpb_label_live(t, k)) continue;   // block-uniform
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        if (skip_small && h <= 32 && w <= 32) {     // centre computed by the warp kernel itself
+            if (threadIdx.x == 0) atomicMax(&t.niter[b], 2 * (h + w + 2));
+            continue;
+        }
         // means of (coordinate relative to the bbox + 1), as the reference computes them
         const double ymed = __ddiv_rn(__ll2double_rn((long long)t.sumy[k] - (long long)c * y0 + c), __int2double_rn(c));
         const double xmed = __ddiv_rn(__ll2double_rn((long long)t.sumx[k] - (long long)c * x0 + c), __int2double_rn(c));
@@ -116,32 +120,77 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
         if (lane < w)
             for (int r = 0; r < h; r++)
                 if (L[(y0 + r) * W + x0 + lane] == l) member |= 1u << r;
-        const int ci = (t.cy[k] - y0 + 1) * CPB_DC_PITCH + (t.cx[k] - x0 + 1);
+        // centre = member pixel nearest to the mean of (bbox-relative coordinate + 1); first in raster order on ties
+        int ci;
+        {
+            const int c = t.cnt[k];
+            const double ymed = __ddiv_rn(__ll2double_rn((long long)t.sumy[k] - (long long)c * y0 + c), __int2double_rn(c));
+            const double xmed = __ddiv_rn(__ll2double_rn((long long)t.sumx[k] - (long long)c * x0 + c), __int2double_rn(c));
+            const double dx = __dsub_rn(__int2double_rn(lane + 1), xmed);
+            const double dx2 = __dmul_rn(dx, dx);
+            double bd = 1e300; int bi = CPB_IMAX;
+            for (int r = 0; r < h; r++) {
+                if (member >> r & 1) {
+                    const double dy = __dsub_rn(__int2double_rn(r + 1), ymed);
+                    const double d = __dadd_rn(dx2, __dmul_rn(dy, dy));
+                    const int idx = r * w + lane;
+                    if (cpb_minkey_less(d, idx, bd, bi)) { bd = d; bi = idx; }
+                }
+            }
+            for (int sft = 16; sft; sft >>= 1) {
+                const double od = __shfl_xor_sync(CPB_FULL, bd, sft);
+                const int oi = __shfl_xor_sync(CPB_FULL, bi, sft);
+                if (cpb_minkey_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+            }
+            const int cr = bi / w, cc = bi - cr * w;
+            if (lane == 0) { t.cy[k] = y0 + cr; t.cx[k] = x0 + cc; }
+            ci = (cr + 1) * CPB_DC_PITCH + (cc + 1);
+        }
         const double* p = S + lane;        // p[0], p[1], p[2] = columns j-1, j, j+1 of the halo row
         double* own = S + CPB_DC_PITCH + lane + 1;
         __syncwarp();
+        // Two independent row streams per lane (top half / bottom half of the bbox) double the number of
+        // independent float64 chains in flight.  Stream A walks rows [0, hh), stream B rows [hh, h).
+        // In-place Jacobi stays exact: A's last step needs the OLD row hh, which B overwrites in its first
+        // step, so B's initial centre row is kept as A's final "down" row.
+        const int hh = (h + 1) >> 1, hb = h - hh;     // hb <= hh
         for (int it = 0; it < n_it; it++) {
             if (lane == 0) S[ci] += 1.0;   // T[centre] += 1 before averaging
             __syncwarp();
-            double uL = p[0], uC = p[1], uR = p[2];
-            double cL = p[CPB_DC_PITCH], cC = p[CPB_DC_PITCH + 1], cR = p[CPB_DC_PITCH + 2];
-            for (int r = 0; r < h; r++) {
-                const double* q = p + (r + 2) * CPB_DC_PITCH;
-                const double dL = q[0], dC = q[1], dR = q[2];
+            const double* pa = p;                              // halo row above row 0
+            const double* pb = p + hh * CPB_DC_PITCH;          // row hh-1 (row above stream B's first row)
+            double auL = pa[0], auC = pa[1], auR = pa[2];
+            double acL = pa[CPB_DC_PITCH], acC = pa[CPB_DC_PITCH + 1], acR = pa[CPB_DC_PITCH + 2];
+            double buL = pb[0], buC = pb[1], buR = pb[2];
+            double bcL = pb[CPB_DC_PITCH], bcC = pb[CPB_DC_PITCH + 1], bcR = pb[CPB_DC_PITCH + 2];
+            const double zL = bcL, zC = bcC, zR = bcR;         // old row hh = A's last "down" row
+            for (int r = 0; r < hh; r++) {
+                double adL, adC, adR;
+                if (r + 1 < hh) {
+                    const double* q = pa + (r + 2) * CPB_DC_PITCH;
+                    adL = q[0]; adC = q[1]; adR = q[2];
+                } else { adL = zL; adC = zC; adR = zR; }
+                const bool bon = r < hb;                       // warp-uniform
+                double bdL = 0.0, bdC = 0.0, bdR = 0.0;
+                if (bon) {
+                    const double* q = pb + (r + 2) * CPB_DC_PITCH;
+                    bdL = q[0]; bdC = q[1]; bdR = q[2];
+                }
                 // self, up, down, left, right, up-left, up-right, down-left, down-right
-                double sum = __dadd_rn(cC, uC);
-                sum = __dadd_rn(sum, dC);
-                sum = __dadd_rn(sum, cL);
-                sum = __dadd_rn(sum, cR);
-                sum = __dadd_rn(sum, uL);
-                sum = __dadd_rn(sum, uR);
-                sum = __dadd_rn(sum, dL);
-                sum = __dadd_rn(sum, dR);
-                const double v = cpb_div9_fast(sum);
-                __syncwarp();              // all lanes hold rows r and r+1 before row r is overwritten
-                if (member >> r & 1) own[r * CPB_DC_PITCH] = v;
-                uL = cL; uC = cC; uR = cR;
-                cL = dL; cC = dC; cR = dR;
+                double sa = __dadd_rn(acC, auC), sb = __dadd_rn(bcC, buC);
+                sa = __dadd_rn(sa, adC); sb = __dadd_rn(sb, bdC);
+                sa = __dadd_rn(sa, acL); sb = __dadd_rn(sb, bcL);
+                sa = __dadd_rn(sa, acR); sb = __dadd_rn(sb, bcR);
+                sa = __dadd_rn(sa, auL); sb = __dadd_rn(sb, buL);
+                sa = __dadd_rn(sa, auR); sb = __dadd_rn(sb, buR);
+                sa = __dadd_rn(sa, adL); sb = __dadd_rn(sb, bdL);
+                sa = __dadd_rn(sa, adR); sb = __dadd_rn(sb, bdR);
+                const double va = cpb_div9_fast(sa), vb = cpb_div9_fast(sb);
+                __syncwarp();              // every lane holds the rows it still needs before they are overwritten
+                if (member >> r & 1) own[r * CPB_DC_PITCH] = va;
+                if (bon && (member >> (hh + r) & 1)) own[(hh + r) * CPB_DC_PITCH] = vb;
+                auL = acL; auC = acC; auR = acR; acL = adL; acC = adC; acR = adR;
+                buL = bcL; buC = bcC; buR = bcR; bcL = bdL; bcC = bdC; bcR = bdR;
             }
             __syncwarp();
         }
@@ -260,7 +309,7 @@ CPB_DEVICE double cpb_T_at(const double* CPB_RESTRICT Tb, const int* CPB_RESTRIC
 
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
 k_flow_err(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, LabelTables t,
-           const double* CPB_RESTRICT T, double threshold, double* CPB_RESTRICT mu_out) {
+           const double* CPB_RESTRICT T, double threshold, double* CPB_RESTRICT mu_out, int skip_small) {
     CPB_SHARED double s_ey[CPB_QC_THREADS / 32], s_ex[CPB_QC_THREADS / 32];
     const int b = blockIdx.y, LC = t.LC, N = H * W;
     const int lb = t.lbound[b];
@@ -275,6 +324,7 @@ k_flow_err(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int
         if (!cpb_label_live(t, k)) continue;
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        if (skip_small && w <= 32) continue;       // handled by k_flow_err_warp
         double ey = 0.0, ex = 0.0;
         for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
             const int y = y0 + i / w, x = x0 + i % w;
@@ -307,6 +357,62 @@ k_flow_err(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int
             double sy = 0.0, sx = 0.0;
             for (int q = 0; q < CPB_QC_THREADS / 32; q++) { sy += s_ey[q]; sx += s_ex[q]; }
             const double e = sy / (double)c + sx / (double)c;
+            t.err[k] = e;
+            t.flag[k] = e > threshold ? 1 : 0;
+        }
+    }
+}
+
+// k_flow_err_warp: the same per-label flow error, one WARP per label for bboxes up to 32 px wide
+// (lane = column, loop over rows, coalesced row reads).
+CPB_KERNEL CPB_LAUNCH_BOUNDS(128, 8)
+k_flow_err_warp(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, LabelTables t,
+                const double* CPB_RESTRICT T, double threshold, double* CPB_RESTRICT mu_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int b = blockIdx.y, LC = t.LC, N = H * W;
+    const int lb = t.lbound[b];
+    const int* L = lab + (size_t)b * N;
+    const double* Tb = T + (size_t)b * N;
+    const int* alive = t.alive ? t.alive + (size_t)b * LC : nullptr;
+    const float* dPy = dP ? dP + ((size_t)b * 2 + 0) * N : nullptr;
+    const float* dPx = dP ? dP + ((size_t)b * 2 + 1) * N : nullptr;
+    for (int l = 1 + blockIdx.x * nw + warp; l <= lb; l += gridDim.x * nw) {
+        const size_t k = (size_t)b * LC + l;
+        const int c = t.cnt[k];
+        if (!cpb_label_live(t, k)) continue;
+        const int y0 = t.ymin[k], x0 = t.xmin[k];
+        const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        if (w > 32) continue;
+        double ey = 0.0, ex = 0.0;
+        const int x = x0 + lane;
+        if (lane < w) {
+            for (int r = 0; r < h; r++) {
+                const int y = y0 + r;
+                const int p = y * W + x;
+                if (L[p] != l) continue;
+                const double dy = __dsub_rn(cpb_T_at(Tb, L, alive, H, W, y + 1, x), cpb_T_at(Tb, L, alive, H, W, y - 1, x));
+                const double dx = __dsub_rn(cpb_T_at(Tb, L, alive, H, W, y, x + 1), cpb_T_at(Tb, L, alive, H, W, y, x - 1));
+                const double nrm = __dadd_rn(1e-60, __dsqrt_rn(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx))));
+                const double my = __ddiv_rn(dy, nrm), mx = __ddiv_rn(dx, nrm);
+                if (mu_out) {
+                    mu_out[((size_t)b * 2 + 0) * N + p] = my;
+                    mu_out[((size_t)b * 2 + 1) * N + p] = mx;
+                }
+                if (dP) {
+                    const double ry = __dsub_rn(my, (double)__fdiv_rn(dPy[p], 5.0f));
+                    const double rx = __dsub_rn(mx, (double)__fdiv_rn(dPx[p], 5.0f));
+                    ey += __dmul_rn(ry, ry);
+                    ex += __dmul_rn(rx, rx);
+                }
+            }
+        }
+        if (!dP) continue;
+        for (int sft = 16; sft; sft >>= 1) {
+            ey += __shfl_xor_sync(CPB_FULL, ey, sft);
+            ex += __shfl_xor_sync(CPB_FULL, ex, sft);
+        }
+        if (lane == 0) {
+            const double e = ey / (double)c + ex / (double)c;
             t.err[k] = e;
             t.flag[k] = e > threshold ? 1 : 0;
         }

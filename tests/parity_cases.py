@@ -303,6 +303,18 @@ def case_fused_path_other_shapes(be):
     assert f1 >= 0.99 and abs(nnew - nref) <= 1
 
 
+def case_fused_odd_width(be):
+    """W not a multiple of 4 (scalar prep kernel, unaligned rows) and a non-multiple-of-32 tile."""
+    tiles = [std_tile(9, H=70, W=57, n_grid=3, C=3), std_tile(10, H=70, W=57, n_grid=3, C=3)]
+    for t in tiles:
+        pf, _ = be.follow_flows(f32(t["dP"][None]), f32(t["cellprob"][None]), 200, 0.0)
+        ys, xs = t["stages"]["inds"]
+        eq = ((pf[0][ys, xs] >> 16) == t["stages"]["p_final"][0]) & ((pf[0][ys, xs] & 0xFFFF) == t["stages"]["p_final"][1])
+        assert eq.mean() >= 0.99     # a sink sitting on an integer boundary flips truncation for its pixels
+    f1, nref, nnew = fused_compare(be, tiles, 3)
+    assert f1 >= 0.99 and nnew == nref
+
+
 def case_fused_empty_and_params(be):
     H = W = 64
     dP = np.zeros((2, 2, H, W), np.float32)
@@ -354,4 +366,5 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_get_mask
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
              case_remove_bad_flow_masks_exact, case_fill_holes_exact, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
-             case_fused_empty_and_params, case_fused_qc_then_positional_size_filter, case_label_offsets]
+             case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
+             case_label_offsets]
