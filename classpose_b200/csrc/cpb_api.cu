@@ -244,10 +244,7 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_DIFFUSE);
     ProfScope ps(w.prof, S_FLOWERR);
-    CPB_LAUNCH_COUNTED(k_flow_err_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(128), 0, st, masks, dP, H, W, w.t, w.T,
-                       thr, mu_out);
-    CPB_CHECK_LAUNCH();
-    CPB_LAUNCH_COUNTED(k_flow_err, grid, dim3(CPB_QC_THREADS), 0, st, masks, dP, H, W, w.t, w.T, thr, mu_out, 1);
+    CPB_LAUNCH_COUNTED(k_flow_err, grid, dim3(CPB_QC_THREADS), 0, st, masks, dP, H, W, w.t, w.T, thr, mu_out, 0);
     CPB_CHECK_LAUNCH();
     return 0;
 }

@@ -10,6 +10,13 @@
 #define CPB_QC_THREADS 128
 #define CPB_DIFF_SMEM_CELLS 2304   // (bbox_h+2)*(bbox_w+2) cells that fit the shared-memory path
 
+#define CPB_DW_WARPS 4         // warp path: labels in flight per block (one warp each)
+#define CPB_DC_MAXH 30         // warp path: bbox up to 30 rows x 32 columns (6 blocks of 4 warps fit one SM)
+#define CPB_DC_MAXW 32
+#define CPB_DC_PITCH 34        // + one halo column on each side
+
+CPB_DEVICE bool cpb_diffuse_is_small(int h, int w) { return h <= CPB_DC_MAXH && w <= CPB_DC_MAXW; }
+
 struct MinKey { double d; int idx; };
 
 CPB_DEVICE bool cpb_minkey_less(double d0, int i0, double d1, int i1) {
@@ -29,7 +36,7 @@ k_centres(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, int skip_sma
         if (!cpb_label_live(t, k)) continue;   // block-uniform
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
-        if (skip_small && h <= 32 && w <= 32) {     // centre computed by the warp kernel itself
+        if (skip_small && cpb_diffuse_is_small(h, w)) {     // centre computed by the warp kernel itself
             if (threadIdx.x == 0) atomicMax(&t.niter[b], 2 * (h + w + 2));
             continue;
         }
@@ -86,11 +93,6 @@ CPB_DEVICE double cpb_div9_fast(double x) {
     return __fma_rn(rem, r, q);
 }
 
-#define CPB_DW_WARPS 4         // labels in flight per block (one warp each)
-#define CPB_DC_MAX 32          // warp path: bbox up to 32 x 32
-#define CPB_DC_PITCH 34        // + one halo column on each side
-
-CPB_DEVICE bool cpb_diffuse_is_small(int h, int w) { return h <= CPB_DC_MAX && w <= CPB_DC_MAX; }
 
 // k_diffuse_warp: one WARP per label for labels whose bbox fits 32 x 32 (nuclei-sized).
 // The label's T lives in a per-warp shared-memory tile with a zero halo; lane j owns column j and
@@ -100,7 +102,7 @@ CPB_DEVICE bool cpb_diffuse_is_small(int h, int w) { return h <= CPB_DC_MAX && w
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, 6)
 k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                int niter_override) {
-    CPB_SHARED double s_T[CPB_DW_WARPS][(CPB_DC_MAX + 2) * CPB_DC_PITCH];
+    CPB_SHARED double s_T[CPB_DW_WARPS][(CPB_DC_MAXH + 3) * CPB_DC_PITCH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y, LC = t.LC, N = H * W;
     const int lb = t.lbound[b];
@@ -115,7 +117,7 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         if (!cpb_diffuse_is_small(h, w)) continue;
         __syncwarp();
-        for (int i = lane; i < (h + 2) * CPB_DC_PITCH; i += 32) S[i] = 0.0;
+        for (int i = lane; i < (h + 3) * CPB_DC_PITCH; i += 32) S[i] = 0.0;
         unsigned member = 0;               // bit r: pixel (y0+r, x0+lane) belongs to the label
         if (lane < w)
             for (int r = 0; r < h; r++)
@@ -149,48 +151,32 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
         const double* p = S + lane;        // p[0], p[1], p[2] = columns j-1, j, j+1 of the halo row
         double* own = S + CPB_DC_PITCH + lane + 1;
         __syncwarp();
-        // Two independent row streams per lane (top half / bottom half of the bbox) double the number of
-        // independent float64 chains in flight.  Stream A walks rows [0, hh), stream B rows [hh, h).
-        // In-place Jacobi stays exact: A's last step needs the OLD row hh, which B overwrites in its first
-        // step, so B's initial centre row is kept as A's final "down" row.
-        const int hh = (h + 1) >> 1, hb = h - hh;     // hb <= hh
+        // Two rows per step: rows r and r+1 are independent given the old rows r-1 .. r+2, so both nine-term
+        // chains are in flight together and one __syncwarp() covers both in-place stores.
         for (int it = 0; it < n_it; it++) {
             if (lane == 0) S[ci] += 1.0;   // T[centre] += 1 before averaging
             __syncwarp();
-            const double* pa = p;                              // halo row above row 0
-            const double* pb = p + hh * CPB_DC_PITCH;          // row hh-1 (row above stream B's first row)
-            double auL = pa[0], auC = pa[1], auR = pa[2];
-            double acL = pa[CPB_DC_PITCH], acC = pa[CPB_DC_PITCH + 1], acR = pa[CPB_DC_PITCH + 2];
-            double buL = pb[0], buC = pb[1], buR = pb[2];
-            double bcL = pb[CPB_DC_PITCH], bcC = pb[CPB_DC_PITCH + 1], bcR = pb[CPB_DC_PITCH + 2];
-            const double zL = bcL, zC = bcC, zR = bcR;         // old row hh = A's last "down" row
-            for (int r = 0; r < hh; r++) {
-                double adL, adC, adR;
-                if (r + 1 < hh) {
-                    const double* q = pa + (r + 2) * CPB_DC_PITCH;
-                    adL = q[0]; adC = q[1]; adR = q[2];
-                } else { adL = zL; adC = zC; adR = zR; }
-                const bool bon = r < hb;                       // warp-uniform
-                double bdL = 0.0, bdC = 0.0, bdR = 0.0;
-                if (bon) {
-                    const double* q = pb + (r + 2) * CPB_DC_PITCH;
-                    bdL = q[0]; bdC = q[1]; bdR = q[2];
-                }
+            double uL = p[0], uC = p[1], uR = p[2];
+            double cL = p[CPB_DC_PITCH], cC = p[CPB_DC_PITCH + 1], cR = p[CPB_DC_PITCH + 2];
+            for (int r = 0; r < h; r += 2) {
+                const double* q = p + (r + 2) * CPB_DC_PITCH;
+                const double dL = q[0], dC = q[1], dR = q[2];                                   // row r+1
+                const double eL = q[CPB_DC_PITCH], eC = q[CPB_DC_PITCH + 1], eR = q[CPB_DC_PITCH + 2];   // row r+2
                 // self, up, down, left, right, up-left, up-right, down-left, down-right
-                double sa = __dadd_rn(acC, auC), sb = __dadd_rn(bcC, buC);
-                sa = __dadd_rn(sa, adC); sb = __dadd_rn(sb, bdC);
-                sa = __dadd_rn(sa, acL); sb = __dadd_rn(sb, bcL);
-                sa = __dadd_rn(sa, acR); sb = __dadd_rn(sb, bcR);
-                sa = __dadd_rn(sa, auL); sb = __dadd_rn(sb, buL);
-                sa = __dadd_rn(sa, auR); sb = __dadd_rn(sb, buR);
-                sa = __dadd_rn(sa, adL); sb = __dadd_rn(sb, bdL);
-                sa = __dadd_rn(sa, adR); sb = __dadd_rn(sb, bdR);
-                const double va = cpb_div9_fast(sa), vb = cpb_div9_fast(sb);
-                __syncwarp();              // every lane holds the rows it still needs before they are overwritten
-                if (member >> r & 1) own[r * CPB_DC_PITCH] = va;
-                if (bon && (member >> (hh + r) & 1)) own[(hh + r) * CPB_DC_PITCH] = vb;
-                auL = acL; auC = acC; auR = acR; acL = adL; acC = adC; acR = adR;
-                buL = bcL; buC = bcC; buR = bcR; bcL = bdL; bcC = bdC; bcR = bdR;
+                double s0 = __dadd_rn(cC, uC), s1 = __dadd_rn(dC, cC);
+                s0 = __dadd_rn(s0, dC); s1 = __dadd_rn(s1, eC);
+                s0 = __dadd_rn(s0, cL); s1 = __dadd_rn(s1, dL);
+                s0 = __dadd_rn(s0, cR); s1 = __dadd_rn(s1, dR);
+                s0 = __dadd_rn(s0, uL); s1 = __dadd_rn(s1, cL);
+                s0 = __dadd_rn(s0, uR); s1 = __dadd_rn(s1, cR);
+                s0 = __dadd_rn(s0, dL); s1 = __dadd_rn(s1, eL);
+                s0 = __dadd_rn(s0, dR); s1 = __dadd_rn(s1, eR);
+                const double v0 = cpb_div9_fast(s0), v1 = cpb_div9_fast(s1);
+                __syncwarp();              // every lane holds rows r .. r+2 before rows r, r+1 are overwritten
+                if (member >> r & 1) own[r * CPB_DC_PITCH] = v0;
+                if (r + 1 < h && (member >> (r + 1) & 1)) own[(r + 1) * CPB_DC_PITCH] = v1;
+                uL = dL; uC = dC; uR = dR;
+                cL = eL; cC = eC; cR = eR;
             }
             __syncwarp();
         }
