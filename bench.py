@@ -36,6 +36,20 @@ C = 7
 WORKLOAD = "conic config: batch of 1024 synthetic 256x256 tiles (C=7), compute_masks + class vote (BASELINE configs[1])"
 PARAMS = dict(niter=200, cellprob_threshold=0.0, flow_threshold=0.4, min_size=15, max_size_fraction=0.4)
 
+# Additional BASELINE.json configs (not the driver's bench line; run with --workload):
+#   wsi   configs[2]: synthetic 40x WSI 100k x 100k px, tile 256 / overlap 0.1 -> 494^2 = 244,036 tiles, puma (C=10),
+#                     tiles sharded over the ranks, cyclic pool of 1024 distinct resident tiles per rank
+#   tta   configs[3]: monusac (C=5) with --tta: 9 flipped sub-tile maps per padded 272^2 tile blended before dynamics
+#   dense configs[4]: 512^2 tiles, ~2k cells per tile, flow check on
+EXTRA = {
+    "wsi": dict(H=256, W=256, C=10, tiles=1024, n_grid=10, axes=(5.0, 9.0), total_tiles=244036,
+                name="synthetic 40x WSI 100k x 100k px, tile 256 overlap 0.1 (244,036 tiles), puma C=10 (BASELINE configs[2])"),
+    "tta": dict(H=256, W=256, C=5, tiles=256, n_grid=10, axes=(5.0, 9.0),
+                name="monusac C=5 with TTA: 9 sub-tile maps per padded 272^2 tile blended, then dynamics (BASELINE configs[3])"),
+    "dense": dict(H=512, W=512, C=7, tiles=128, n_grid=45, axes=(3.5, 5.0),
+                  name="dense nuclei stress: 512x512 tiles, ~2k cells per tile, flow check on (BASELINE configs[4])"),
+}
+
 
 _REAL_STDOUT = None
 
@@ -341,6 +355,119 @@ def run_ours(args):
     return 0
 
 
+def run_extra(args):
+    """BASELINE configs[2..4]; same timing rules as the main arm (CUDA events, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from classpose_b200 import distributed as cdist, synth, transforms as btf
+    from classpose_b200.engine import get_engine
+    eng = get_engine(dev)
+    cfg = EXTRA[args.workload]
+    Hh, Ww, Cc, B = cfg["H"], cfg["W"], cfg["C"], (args.tiles if args.tiles != 1024 or args.workload == "wsi" else cfg["tiles"])
+    data = synth.make_batch(B, Hh, Ww, Cc, n_grid=cfg["n_grid"], axes=cfg["axes"], seed=99 + 7919 * rank, device=dev,
+                            chunk=min(64, B))
+    dP, cellprob, logits = data["dP"], data["cellprob"], data["logits"]
+    extra = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "tta":
+        # what run_net holds after the network when augment=True: 9 flipped sub-tile maps of the padded tile
+        pad = btf.get_pad_yx(Hh, Ww, min_size=(256, 256))
+        Ly, Lx = Hh + pad[0] + pad[1], Ww + pad[2] + pad[3]
+        geo = btf.tile_geometry(Ly, Lx, 256, augment=True)
+        full = torch.zeros((B, 3 + Cc, Ly, Lx), device=dev)
+        full[:, 0:2, pad[0]:pad[0] + Hh, pad[2]:pad[2] + Ww] = dP
+        full[:, 2, pad[0]:pad[0] + Hh, pad[2]:pad[2] + Ww] = cellprob
+        full[:, 3:, pad[0]:pad[0] + Hh, pad[2]:pad[2] + Ww] = logits
+        nt = len(geo["y0"])
+        sub = torch.empty((B, nt, 3 + Cc, 256, 256), device=dev)
+        for j in range(nt):
+            t = full[:, :, geo["y0"][j]:geo["y0"][j] + 256, geo["x0"][j]:geo["x0"][j] + 256].clone()
+            f = int(geo["flip"][j])
+            if f & 1:
+                t = t.flip(2); t[:, 0] *= -1          # the network sees a Y-flipped tile: dY changes sign
+            if f & 2:
+                t = t.flip(3); t[:, 1] *= -1
+            sub[:, j] = t
+        y_flow = sub[:, :, :3].contiguous()
+        y_cls = sub[:, :, 3:].contiguous()
+        del sub, full
+        ty, tx = btf.taper_1d(256, 256)
+        g = {k: torch.from_numpy(geo[k]).to(dev) for k in ("y0", "x0", "flip")}
+        tyd, txd = torch.from_numpy(ty).to(dev), torch.from_numpy(tx).to(dev)
+
+        def step():
+            yf = eng.calls.average_tiles(y_flow, g["y0"], g["x0"], g["flip"], True, tyd, txd, Ly, Lx, pad)
+            yc = eng.calls.average_tiles(y_cls, g["y0"], g["x0"], g["flip"], False, tyd, txd, Ly, Lx, pad)
+            return eng.compute_masks_batch(yf[:, :2].contiguous(), yf[:, 2].contiguous(), yc, **PARAMS)
+        out = step()
+        ref = eng.compute_masks_batch(dP, cellprob, logits, **PARAMS)
+        extra["blend_max_abs_err_vs_unblended"] = float((eng.calls.average_tiles(
+            y_flow, g["y0"], g["x0"], g["flip"], True, tyd, txd, Ly, Lx, pad)[:, :2] - dP).abs().max().item())
+        extra["cells_vs_unblended"] = [int(out[1].sum().item()), int(ref[1].sum().item())]
+        nbatches = 1
+    else:
+        def step():
+            return eng.compute_masks_batch(dP, cellprob, logits, **PARAMS)
+        nbatches = 1
+        if args.workload == "wsi":
+            a, b_ = cdist.shard_range(cfg["total_tiles"], rank, world)
+            nbatches = -(-(b_ - a) // B)
+            extra["tiles_this_rank"] = b_ - a
+
+    for _ in range(max(3, args.warmup)):
+        out = step()
+    barrier()
+    cells_step = int(out[1].sum().item())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = args.steps if args.workload != "wsi" else nbatches
+    barrier()
+    ev0.record()
+    total_cells = torch.zeros((), dtype=torch.int64, device=dev)
+    for _ in range(steps):
+        out = step()
+        total_cells += out[1].sum()
+    if world > 1:      # the one exchange: per-rank instance totals -> global label offsets
+        base = cdist.rank_base_offset(total_cells.reshape(1))
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        c = total_cells.clone()
+        dist.all_reduce(c)
+        total_cells = c
+    if rank == 0:
+        if args.workload == "wsi":
+            tiles_done = cfg["total_tiles"]
+            extra["slide_seconds"] = ms * 1e-3
+            extra["note"] = "each rank loops over its shard in batches of %d tiles drawn cyclically from %d resident tiles" % (B, B)
+        else:
+            tiles_done = world * B * steps
+        emit({"metric": "tiles_per_sec", "value": tiles_done / (ms * 1e-3), "unit": "tiles/s", "n_gpus": world,
+              "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": ms / steps, "higher_is_better": True,
+              "scaling": "strong" if args.workload == "wsi" else "weak", "vs_baseline": None, "dtype": "f32",
+              "data": "synthetic", "cells_per_sec": float(total_cells.item()) / (ms * 1e-3),
+              "cells_per_tile": cells_step / B,
+              "config": {"workload": cfg["name"], "tiles_per_batch": B, "tile": [Hh, Ww], "classes": Cc, **PARAMS}, **extra})
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def _protect_stdout():
     """Libraries (NCCL prints its version) may write to fd 1; the contract is ONE JSON line on stdout.
     Point fd 1 at stderr for the duration of the run and return a file object on the real stdout."""
@@ -359,11 +486,14 @@ def main():
     ap.add_argument("--chunk", type=int, default=128, help="tiles per chunk of the host-buffer call")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="conic1024", choices=["conic1024", "wsi", "tta", "dense"])
     args = ap.parse_args()
     global _REAL_STDOUT
     _REAL_STDOUT = _protect_stdout()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "conic1024":
+        return run_extra(args)
     return run_ours(args)
 
 
