@@ -407,9 +407,11 @@ def run_extra(args):
         g = {k: torch.from_numpy(geo[k]).to(dev) for k in ("y0", "x0", "flip")}
         tyd, txd = torch.from_numpy(ty).to(dev), torch.from_numpy(tx).to(dev)
 
+        x4, cover = btf.tile_cover(geo["y0"], geo["x0"], 256, 256, Ly, Lx)
+
         def step():
-            yf = eng.calls.average_tiles(y_flow, g["y0"], g["x0"], g["flip"], True, tyd, txd, Ly, Lx, pad)
-            yc = eng.calls.average_tiles(y_cls, g["y0"], g["x0"], g["flip"], False, tyd, txd, Ly, Lx, pad)
+            yf = eng.calls.average_tiles(y_flow, g["y0"], g["x0"], g["flip"], True, tyd, txd, Ly, Lx, pad, x4, cover)
+            yc = eng.calls.average_tiles(y_cls, g["y0"], g["x0"], g["flip"], False, tyd, txd, Ly, Lx, pad, x4, cover)
             return eng.compute_masks_batch(yf[:, :2].contiguous(), yf[:, 2].contiguous(), yc, **PARAMS)
         out = step()
         ref = eng.compute_masks_batch(dP, cellprob, logits, **PARAMS)

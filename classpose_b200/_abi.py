@@ -50,6 +50,7 @@ SIGNATURES = {
     "cpb_class_vote_device": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "cpb_remove_border_instances_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "cpb_average_tiles_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "cpb_average_tiles_ex_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     "cpb_label_offsets_device": (C.c_int, [_P, _I, _L, _P, _P, _P]),
 }
 

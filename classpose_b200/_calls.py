@@ -123,15 +123,18 @@ class Calls:
         self.mem.keep_alive(ws, masks)
         return masks
 
-    def average_tiles(self, y, y0, x0, flip, negate_flow, taper_y, taper_x, Ly, Lx, crop=(0, 0, 0, 0)):
+    def average_tiles(self, y, y0, x0, flip, negate_flow, taper_y, taper_x, Ly, Lx, crop=(0, 0, 0, 0),
+                      x0_multiple_of_4=False, max_cover=0):
+        """x0_multiple_of_4 / max_cover: host-side knowledge of the window geometry (see tile_cover) that
+        enables the 128-bit kernel; leave at the defaults when unknown."""
         B, ntiles, nch, ly, lx = y.shape
         cy0, cy1, cx0, cx1 = crop
         yf = self.mem.empty((B, nch, Ly - cy0 - cy1, Lx - cx0 - cx1), "float32")
-        rc = self.lib.cpb_average_tiles_device(self._p(y), B, ntiles, nch, ly, lx, self._p(y0), self._p(x0),
-                                               self._p(flip), 1 if negate_flow else 0, self._p(taper_y),
-                                               self._p(taper_x), int(Ly), int(Lx), cy0, cy1, cx0, cx1, self._p(yf),
-                                               self.stream())
-        check(rc, "cpb_average_tiles_device")
+        rc = self.lib.cpb_average_tiles_ex_device(self._p(y), B, ntiles, nch, ly, lx, self._p(y0), self._p(x0),
+                                                  self._p(flip), 1 if negate_flow else 0, self._p(taper_y),
+                                                  self._p(taper_x), int(Ly), int(Lx), cy0, cy1, cx0, cx1, self._p(yf),
+                                                  1 if x0_multiple_of_4 else 0, int(max_cover), self.stream())
+        check(rc, "cpb_average_tiles_ex_device")
         self.mem.keep_alive(y, y0, x0, flip, taper_y, taper_x)
         return yf
 

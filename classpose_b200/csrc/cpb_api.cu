@@ -544,14 +544,35 @@ int cpb_average_tiles_device(const float* y, int B, int ntiles, int nch, int ly,
                              const int32_t* x0, const int32_t* flip, int negate_flow, const double* taper_y,
                              const double* taper_x, int Ly, int Lx, int cy0, int cy1, int cx0, int cx1, float* yf,
                              void* stream) {
+    return cpb_average_tiles_ex_device(y, B, ntiles, nch, ly, lx, y0, x0, flip, negate_flow, taper_y, taper_x, Ly, Lx,
+                                       cy0, cy1, cx0, cx1, yf, 0, 0, stream);
+}
+
+int cpb_average_tiles_ex_device(const float* y, int B, int ntiles, int nch, int ly, int lx, const int32_t* y0,
+                                const int32_t* x0, const int32_t* flip, int negate_flow, const double* taper_y,
+                                const double* taper_x, int Ly, int Lx, int cy0, int cy1, int cx0, int cx1, float* yf,
+                                int x0_multiple_of_4, int max_cover, void* stream) {
     if (!y || !y0 || !x0 || !flip || !taper_y || !taper_x || !yf) return CPB_E_ARG;
     const int oH = Ly - cy0 - cy1, oW = Lx - cx0 - cx1;
     if (B <= 0 || ntiles <= 0 || nch <= 0 || ly <= 0 || lx <= 0 || oH <= 0 || oW <= 0 || cy0 < 0 || cx0 < 0)
         return CPB_E_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const long long total = (long long)B * nch * oH * oW;
-    CPB_LAUNCH_COUNTED(k_average_tiles, dim3(blocks_for(total, 256)), dim3(256), 0, st, y, B, ntiles, nch, ly, lx, y0, x0,
-               flip, negate_flow, taper_y, taper_x, cy0, cx0, oH, oW, yf);
+    // vector path: the host vouches for the tile geometry (device arrays are not read back here)
+    (void)max_cover;
+    const bool vec4 = x0_multiple_of_4 && nch <= 16 && (lx % 4 == 0) && (cx0 % 4 == 0) && (oW % 4 == 0) &&
+                      (reinterpret_cast<uintptr_t>(y) % 16 == 0) && (reinterpret_cast<uintptr_t>(yf) % 16 == 0);
+    if (vec4) {
+        const dim3 grid4(blocks_for((long long)B * oH * (oW / 4), 256));
+#define CPB_BLEND_ARGS y, B, ntiles, nch, ly, lx, y0, x0, flip, negate_flow, taper_y, taper_x, cy0, cx0, oH, oW, yf
+        if (nch <= 4)      { CPB_LAUNCH_COUNTED(k_average_tiles_v4<4>, grid4, dim3(256), 0, st, CPB_BLEND_ARGS); }
+        else if (nch <= 8) { CPB_LAUNCH_COUNTED(k_average_tiles_v4<8>, grid4, dim3(256), 0, st, CPB_BLEND_ARGS); }
+        else               { CPB_LAUNCH_COUNTED(k_average_tiles_v4<16>, grid4, dim3(256), 0, st, CPB_BLEND_ARGS); }
+#undef CPB_BLEND_ARGS
+    } else {
+        const long long total = (long long)B * nch * oH * oW;
+        CPB_LAUNCH_COUNTED(k_average_tiles, dim3(blocks_for(total, 256)), dim3(256), 0, st, y, B, ntiles, nch, ly, lx, y0,
+                           x0, flip, negate_flow, taper_y, taper_x, cy0, cx0, oH, oW, yf);
+    }
     CPB_CHECK_LAUNCH();
     return 0;
 }

@@ -237,6 +237,81 @@ k_average_tiles(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly,
     yf[gi] = (float)__ddiv_rn((double)acc, navg);
 }
 
+// k_average_tiles_v4: same arithmetic, one thread per 4 consecutive output pixels of one row and ALL channels
+// (NCH >= nch accumulators of 4 floats live in registers).  Requires lx, crop offset, output width and every
+// tile origin x0 to be multiples of 4, so that the four pixels are covered by exactly the same tiles and map
+// to one aligned float4 of each tile (reversed when the tile is X-flipped).  Tiles are visited in tile order,
+// the taper weights of a tile are formed once and reused for every channel.
+template <int NCH>
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, (NCH > 8 ? 1 : 2))
+k_average_tiles_v4(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly, int lx,
+                   const int* CPB_RESTRICT ty0, const int* CPB_RESTRICT tx0, const int* CPB_RESTRICT flip,
+                   int negate_flow, const double* CPB_RESTRICT taper_y, const double* CPB_RESTRICT taper_x,
+                   int cy0, int cx0, int oH, int oW, float* CPB_RESTRICT yf) {
+    const int oW4 = oW >> 2;
+    const long long total = (long long)B * oH * oW4;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const int X4 = (int)(g % oW4);
+    const int Y = (int)((g / oW4) % oH);
+    const int b = (int)(g / ((long long)oW4 * oH));
+    const int gy = Y + cy0, gx = X4 * 4 + cx0;
+    float acc[NCH][4];
+    #pragma unroll
+    for (int ch = 0; ch < NCH; ch++) { acc[ch][0] = 0.f; acc[ch][1] = 0.f; acc[ch][2] = 0.f; acc[ch][3] = 0.f; }
+    double navg[4] = {0.0, 0.0, 0.0, 0.0};
+    const size_t plane = (size_t)ly * lx;
+    for (int j = 0; j < ntiles; j++) {
+        const int ry = gy - ty0[j], rx = gx - tx0[j];
+        if (ry < 0 || ry >= ly || rx < 0 || rx >= lx) continue;
+        const int f = flip[j];
+        const int sy = (f & 1) ? ly - 1 - ry : ry;
+        const int sx = (f & 2) ? lx - 4 - rx : rx;           // first of the 4 source pixels (reversed if flipped)
+        const float* src = y + ((size_t)b * ntiles + j) * nch * plane + (size_t)sy * lx + sx;
+        const double wy = taper_y[ry];
+        double wgt[4];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            wgt[k] = __dmul_rn(wy, taper_x[rx + k]);
+            navg[k] = __dadd_rn(navg[k], wgt[k]);
+        }
+        constexpr int G = NCH < 8 ? NCH : 8;                 // channels loaded together
+        #pragma unroll
+        for (int c0 = 0; c0 < NCH; c0 += G) {
+            float4 v4[G];
+            #pragma unroll
+            for (int q = 0; q < G; q++)
+                if (c0 + q < nch) v4[q] = *reinterpret_cast<const float4*>(src + (c0 + q) * plane);
+            #pragma unroll
+            for (int q = 0; q < G; q++) {
+                const int ch = c0 + q;
+                if (ch < nch) {
+                    float v[4];
+                    if (f & 2) { v[0] = v4[q].w; v[1] = v4[q].z; v[2] = v4[q].y; v[3] = v4[q].x; }
+                    else       { v[0] = v4[q].x; v[1] = v4[q].y; v[2] = v4[q].z; v[3] = v4[q].w; }
+                    const bool neg = negate_flow && ((ch == 0 && (f & 1)) || (ch == 1 && (f & 2)));
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float vv = neg ? -v[k] : v[k];
+                        acc[ch][k] = (float)__dadd_rn((double)acc[ch][k], __dmul_rn((double)vv, wgt[k]));
+                    }
+                }
+            }
+        }
+    }
+    #pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+        if (ch < nch) {
+            float4 o;
+            o.x = (float)__ddiv_rn((double)acc[ch][0], navg[0]);
+            o.y = (float)__ddiv_rn((double)acc[ch][1], navg[1]);
+            o.z = (float)__ddiv_rn((double)acc[ch][2], navg[2]);
+            o.w = (float)__ddiv_rn((double)acc[ch][3], navg[3]);
+            *reinterpret_cast<float4*>(yf + (((size_t)b * nch + ch) * oH + Y) * oW + X4 * 4) = o;
+        }
+    }
+}
+
 // k_label_offsets: single block; offsets[b] = base + sum(counts[0..b)), total = sum(counts).
 CPB_KERNEL k_label_offsets(const int* CPB_RESTRICT counts, int B, long long base,
                            long long* CPB_RESTRICT offsets, long long* CPB_RESTRICT total) {

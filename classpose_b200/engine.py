@@ -148,12 +148,13 @@ class Engine:
         with torch.cuda.device(self.device):
             return self.calls.remove_border_instances(self._dev(masks, torch.int32).clone(), lcap, nch)
 
-    def average_tiles(self, y, y0, x0, flip, negate_flow, taper_y, taper_x, Ly, Lx, crop=(0, 0, 0, 0)):
+    def average_tiles(self, y, y0, x0, flip, negate_flow, taper_y, taper_x, Ly, Lx, crop=(0, 0, 0, 0),
+                      x0_multiple_of_4=False, max_cover=0):
         with torch.cuda.device(self.device):
             return self.calls.average_tiles(self._dev(y, torch.float32), self._dev(y0, torch.int32),
                                             self._dev(x0, torch.int32), self._dev(flip, torch.int32), negate_flow,
                                             self._dev(taper_y, torch.float64), self._dev(taper_x, torch.float64),
-                                            Ly, Lx, crop)
+                                            Ly, Lx, crop, x0_multiple_of_4, max_cover)
 
     def label_offsets(self, counts, base=0):
         with torch.cuda.device(self.device):

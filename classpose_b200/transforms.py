@@ -71,6 +71,16 @@ def taper_1d(ly, lx, sig=7.5):
     return np.ascontiguousarray(ty), np.ascontiguousarray(tx)
 
 
+def tile_cover(y0, x0, ly, lx, Ly, Lx):
+    """Host-side facts about a window layout that let the blend use its 128-bit kernel:
+    (every x0 is a multiple of 4, maximum number of windows covering one pixel)."""
+    y0, x0 = np.asarray(y0, np.int64), np.asarray(x0, np.int64)
+    cover = np.zeros((int(Ly), int(Lx)), np.int32)
+    for a, b in zip(y0, x0):
+        cover[a:a + ly, b:b + lx] += 1
+    return bool((x0 % 4 == 0).all()), int(cover.max())
+
+
 def blend_tiles(y, y0, x0, Ly, Lx, flip=None, negate_flow=False, crop=(0, 0, 0, 0), device=None):
     """Batched blend: y [B,ntiles,nch,ly,lx] (numpy or CUDA tensor) -> [B,nch,Ly-crop,Lx-crop].
     `flip`/`negate_flow` fuse unaugment_tiles (flows) or unaugment_class_tiles (logits)."""
@@ -78,8 +88,9 @@ def blend_tiles(y, y0, x0, Ly, Lx, flip=None, negate_flow=False, crop=(0, 0, 0, 
     B, ntiles, nch, ly, lx = y.shape
     ty, tx = taper_1d(ly, lx)
     flip = np.zeros(ntiles, np.int32) if flip is None else np.asarray(flip, np.int32)
+    x4, cover = tile_cover(y0, x0, ly, lx, Ly, Lx)
     out = eng.average_tiles(y, np.asarray(y0, np.int32), np.asarray(x0, np.int32), flip, negate_flow, ty, tx,
-                            int(Ly), int(Lx), tuple(int(c) for c in crop))
+                            int(Ly), int(Lx), tuple(int(c) for c in crop), x0_multiple_of_4=x4, max_cover=cover)
     return out if (isinstance(y, torch.Tensor) and y.is_cuda) else out.cpu().numpy()
 
 

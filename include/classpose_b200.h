@@ -154,6 +154,15 @@ int cpb_average_tiles_device(const float* y, int B, int ntiles, int nch, int ly,
                              int Ly, int Lx, int cy0, int cy1, int cx0, int cx1, float* yf,
                              void* stream);
 
+/* Same, with a host-side promise that enables the 128-bit path: every window origin x0[j] is a multiple of 4
+ * (x0_multiple_of_4 != 0; device arrays are not read back by the library).  max_cover (maximum number of
+ * windows over one pixel) is informational.  Pass 0, 0 when unknown. */
+int cpb_average_tiles_ex_device(const float* y, int B, int ntiles, int nch, int ly, int lx,
+                                const int32_t* y0, const int32_t* x0, const int32_t* flip,
+                                int negate_flow, const double* taper_y, const double* taper_x,
+                                int Ly, int Lx, int cy0, int cy1, int cx0, int cx1, float* yf,
+                                int x0_multiple_of_4, int max_cover, void* stream);
+
 /* (e) global label offsets: exclusive prefix sum of per-tile instance counts.
  * offsets [B] int64 = base + sum(counts[0..b)); total [1] int64 = sum(counts).  `base` is the
  * rank's offset obtained from the cross-GPU all-gather of totals (host side). */

@@ -49,11 +49,13 @@ class _Base:
     def remove_border_instances(self, masks, lcap, nch=1):
         return _np(self._calls().remove_border_instances(self._in(masks), lcap, nch))
 
-    def average_tiles(self, y, y0, x0, flip, negate, ty, tx, Ly, Lx, crop=(0, 0, 0, 0)):
+    def average_tiles(self, y, y0, x0, flip, negate, ty, tx, Ly, Lx, crop=(0, 0, 0, 0), vector=True):
+        from classpose_b200.transforms import tile_cover
+        x4, cover = tile_cover(y0, x0, y.shape[-2], y.shape[-1], Ly, Lx) if vector else (False, 0)
         return _np(self._calls().average_tiles(self._in(y), self._in(np.asarray(y0, np.int32)),
                                                self._in(np.asarray(x0, np.int32)), self._in(np.asarray(flip, np.int32)),
                                                negate, self._in(np.asarray(ty, np.float64)),
-                                               self._in(np.asarray(tx, np.float64)), Ly, Lx, crop))
+                                               self._in(np.asarray(tx, np.float64)), Ly, Lx, crop, x4, cover))
 
     def compute_masks(self, dP, cp, logits=None, want_class_masks=False, **kw):
         from classpose_b200._abi import make_params

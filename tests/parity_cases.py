@@ -264,6 +264,26 @@ def case_average_tiles(be):
         crop = (8, 8, 8, 8)
         outc = be.average_tiles(y[None], geo["y0"], geo["x0"], geo["flip"], nch == 3 and augment, ty, tx, Ly, Lx, crop)
         np.testing.assert_array_equal(outc[0], out[0][:, 8:-8, 8:-8])
+        # the scalar kernel (no geometry promises) gives bit-identical results to the 128-bit one
+        outs = be.average_tiles(y[None], geo["y0"], geo["x0"], geo["flip"], nch == 3 and augment, ty, tx, Ly, Lx, crop,
+                                vector=False)
+        np.testing.assert_array_equal(outs, outc)
+    # odd geometry: origins not multiples of 4 -> scalar path only
+    y = rng.normal(size=(2, 3, 2, 30, 50)).astype(np.float32)
+    y0, x0 = np.array([0, 7, 11]), np.array([0, 9, 3])
+    ty, tx = np.linspace(0.2, 1, 30), np.linspace(0.3, 1, 50)
+    ref = np.zeros((2, 2, 41, 59), np.float32)
+    for b in range(2):
+        Navg = np.zeros((41, 59)); yf = np.zeros((2, 41, 59), np.float32); m = np.outer(ty, tx)
+        for j in range(3):
+            yf[:, y0[j]:y0[j] + 30, x0[j]:x0[j] + 50] += y[b, j] * m
+            Navg[y0[j]:y0[j] + 30, x0[j]:x0[j] + 50] += m
+        with np.errstate(invalid="ignore", divide="ignore"):
+            yf /= Navg
+        ref[b] = yf
+    out = be.average_tiles(y, y0, x0, np.zeros(3, np.int32), False, ty, tx, 41, 59, (0, 0, 0, 0))
+    cov = np.isfinite(ref)
+    np.testing.assert_allclose(out[cov], ref[cov], rtol=0, atol=1e-6)
 
 
 # ------------------------------------------------------------------------------------ fused

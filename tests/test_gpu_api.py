@@ -147,3 +147,38 @@ def test_device_synth_and_batch_consistency():
     for b in (0, 63):
         ref = odyn.resize_and_compute_masks(d["dP"][b].cpu().numpy(), d["cellprob"][b].cpu().numpy())
         assert metrics.match_instances(ref, masks[b].cpu().numpy())["f1"] >= 0.995
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] size (1024 conic tiles): size-independent properties of the result.
+    labels contiguous 1..counts[b]; every instance within [min_size, 0.4*N]; classes in range; a tile gives the
+    bit-identical result alone and inside the batch; the run is deterministic; hole fill is idempotent."""
+    import torch
+    from classpose_b200 import synth
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    B, H, W, C = 1024, 256, 256, 7
+    d = synth.make_batch(B, H, W, C, seed=77)
+    masks, counts, cc, _ = eng.compute_masks_batch(d["dP"], d["cellprob"], d["logits"])
+    masks2, counts2, cc2, _ = eng.compute_masks_batch(d["dP"], d["cellprob"], d["logits"])
+    assert torch.equal(masks, masks2) and torch.equal(counts, counts2) and torch.equal(cc, cc2)
+    LC = eng.label_capacity(H, W)
+    key = (torch.arange(B, device=masks.device).view(B, 1, 1) * LC + masks).reshape(-1).long()
+    area = torch.bincount(key, minlength=B * LC).view(B, LC)
+    present = area[:, 1:] > 0
+    assert torch.equal(present.sum(1).int(), counts)                       # no gaps, no extra labels
+    assert torch.equal(masks.view(B, -1).max(1).values.int(), counts)
+    lab_area = area[:, 1:][present]
+    assert int(lab_area.min()) >= 15 and int(lab_area.max()) <= 0.4 * H * W
+    idx = torch.arange(LC, device=masks.device).view(1, LC)
+    live = (idx >= 1) & (idx <= counts.view(B, 1))
+    assert int(cc[live].min()) >= 0 and int(cc[live].max()) < C
+    assert int(counts.sum()) > 80 * B                                      # ~90 planted cells per tile
+    for b in (0, 517, 1023):
+        m1, c1, k1, _ = eng.compute_masks_batch(d["dP"][b:b + 1], d["cellprob"][b:b + 1], d["logits"][b:b + 1])
+        assert torch.equal(m1[0], masks[b]) and int(c1[0]) == int(counts[b])
+        assert torch.equal(k1[0, :int(c1[0]) + 1], cc[b, :int(c1[0]) + 1])
+    again, cnt_again = eng.fill_holes_and_remove_small_masks(masks[:64], LC, 15)
+    assert torch.equal(again, masks[:64]) and torch.equal(cnt_again, counts[:64])
+    offs, total = eng.label_offsets(counts, 0)
+    assert int(total[0]) == int(counts.sum()) and int(offs[-1]) == int(counts[:-1].sum())
