@@ -311,11 +311,25 @@ def run_ours(args):
     }
     dom = max(stages, key=stages.get)
     peak, peak_src = load_peaks()
+    # DRAM traffic of the dominant kernel: from the committed ncu capture of this same workload (per launch)
+    traffic, traffic_src = None, None
+    kern = {"follow_flows": "k_follow", "diffuse": "k_diffuse_warp", "vote": "k_vote", "prep_flow": "k_prep_flow_v4"}.get(dom)
+    try:
+        import glob
+        tj = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "traffic.json")))[-1]
+        tdata = json.load(open(tj))
+        if kern in tdata["kernels"] and tdata.get("tiles_per_launch") == B:
+            k_ = tdata["kernels"][kern]
+            traffic = k_["dram_read_bytes"] + k_["dram_write_bytes"]
+            traffic_src = os.path.relpath(tj, ROOT)
+    except Exception:
+        pass
     dom_bytes = stage_bytes.get(dom, (16 + 4 * C) * N) * B
     achieved = dom_bytes / (stages[dom] * 1e-3) / 1e9
     whole_bytes = (16 + 4 * C) * N * B
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
                 "kernel_ms": stages[dom], "kernel_share_of_step": stages[dom] / sum(stages.values()),
                 "whole_path_achieved_GBs": whole_bytes / (ms_step * 1e-3) / 1e9,
                 "whole_path_frac": whole_bytes / (ms_step * 1e-3) / 1e9 / peak,
