@@ -13,6 +13,7 @@
 #include "cpb_fused.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #ifndef CPB_SIM
 #include <mutex>
 #endif
@@ -153,6 +154,15 @@ void ensure_attributes() {}
 int sm_count() { return 4; }
 #endif
 
+// CPB_FOLLOW_MERGE=0 selects the plain kernel (A/B measurements); results are bit-identical either way
+std::atomic<int> g_follow_merge{-1};     // -1: take CPB_FOLLOW_MERGE from the environment
+bool follow_merge_enabled() {
+    const int v = g_follow_merge.load(std::memory_order_relaxed);
+    if (v >= 0) return v != 0;
+    static const bool on = [] { const char* e = getenv("CPB_FOLLOW_MERGE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 #define CPB_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
 // ---- stage launch sequences (all asynchronous on `st`) ---------------------------------------
@@ -201,7 +211,14 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     prof_end(w.prof, S_PREP);
     ProfScope ps(w.prof, S_FOLLOW);
     const unsigned grid = (unsigned)std::min<long long>(blocks_for(BN, 256), (long long)sm_count() * 8);
-    CPB_LAUNCH_COUNTED(k_follow, dim3(grid), dim3(256), 0, st, w.flow, w.list, w.list_n, H, W, niter, pfinal, pfloat, hist);
+    if (follow_merge_enabled() && niter >= 32 && B < (1 << 28)) {
+        // merge points at a quarter and a half of the integration (48 and 96 of 200 steps)
+        CPB_LAUNCH_COUNTED(k_follow_merge, dim3(grid), dim3(CPB_FM_THREADS), 0, st, w.flow, w.list, w.list_n, H, W, niter,
+                           (niter * 6) / 25, (niter * 12) / 25, pfinal, pfloat, hist);
+    } else {
+        CPB_LAUNCH_COUNTED(k_follow, dim3(grid), dim3(256), 0, st, w.flow, w.list, w.list_n, H, W, niter, pfinal, pfloat,
+                           hist);
+    }
     CPB_CHECK_LAUNCH();
     return 0;
 }
@@ -514,6 +531,7 @@ int cpb_compute_masks_device(const float* dP, const float* cellprob, const float
 
 int cpb_num_stages(void) { return S_COUNT; }
 const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames[i] : ""; }
+void cpb_debug_set_follow_merge(int mode) { g_follow_merge.store(mode, std::memory_order_relaxed); }
 long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, const float* logits, int B, int H,

@@ -63,6 +63,9 @@ class _Base:
         out = self._calls().compute_masks(self._in(dP), self._in(cp), self._in(logits), prm, want_class_masks)
         return tuple(_np(o) for o in out)
 
+    def set_follow_merge(self, mode):
+        self._calls().lib.cpb_debug_set_follow_merge(int(mode))
+
     def label_offsets(self, counts, base=0):
         a, b = self._calls().label_offsets(self._in(counts), base)
         return _np(a), _np(b)

@@ -89,6 +89,27 @@ def case_follow_flows_few_iters_exact(be):
     assert eq.mean() > 0.9999
 
 
+def case_follow_flows_merge_is_exact(be):
+    """Trajectory merging must not change a single bit: compare with the plain kernel on batches whose list
+    chunks span several tiles, and on many tiny tiles (more than 4 tiles per chunk -> merging is bypassed)."""
+    tiles = [std_tile(s) for s in (1, 3, 4)]
+    dP = f32(np.stack([t["dP"] for t in tiles])); cp = f32(np.stack([t["cellprob"] for t in tiles]))
+    rng = np.random.default_rng(5)
+    small_dP = f32(rng.normal(0, 2.0, size=(96, 2, 16, 16))); small_cp = f32(rng.normal(-1.0, 1.0, size=(96, 16, 16)))
+    try:
+        for a, b in ((dP, cp), (small_dP, small_cp)):
+            be.set_follow_merge(0)
+            p0, f0 = be.follow_flows(a, b, 200, 0.0, want_float=True)
+            be.set_follow_merge(1)
+            p1, f1 = be.follow_flows(a, b, 200, 0.0, want_float=True)
+            np.testing.assert_array_equal(p0, p1)
+            fg = b > 0
+            np.testing.assert_array_equal(f0[:, 0][fg], f1[:, 0][fg])
+            np.testing.assert_array_equal(f0[:, 1][fg], f1[:, 1][fg])
+    finally:
+        be.set_follow_merge(-1)
+
+
 # ------------------------------------------------------------------------------------ (3)
 def case_get_masks_exact(be):
     for t in (std_tile(0, H=128, W=128, n_grid=5), std_tile(1), adv_tile(), std_tile(2, H=96, W=160, n_grid=6),
@@ -382,7 +403,7 @@ def case_label_offsets(be):
     assert total[0] == counts.sum()
 
 
-ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_get_masks_exact,
+ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_flows_merge_is_exact, case_get_masks_exact,
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
              case_remove_bad_flow_masks_exact, case_fill_holes_exact, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
