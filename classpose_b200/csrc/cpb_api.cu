@@ -210,7 +210,7 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_PREP);
     ProfScope ps(w.prof, S_FOLLOW);
-    const unsigned grid = (unsigned)std::min<long long>(blocks_for(BN, 256), (long long)sm_count() * 8);
+    const unsigned grid = (unsigned)std::min<long long>(blocks_for(BN, 256), (long long)sm_count() * 16);
     if (follow_merge_enabled() && niter >= 32 && B < (1 << 28)) {
         // merge points at a quarter and a half of the integration (48 and 96 of 200 steps)
         CPB_LAUNCH_COUNTED(k_follow_merge, dim3(grid), dim3(CPB_FM_THREADS), 0, st, w.flow, w.list, w.list_n, H, W, niter,

@@ -131,7 +131,10 @@ CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int Wp, float fH, f
 }
 
 // k_follow: grid-stride over the compacted foreground list, one pixel per thread.
-CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+#ifndef CPB_F_MINBLOCKS
+#define CPB_F_MINBLOCKS 4
+#endif
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, CPB_F_MINBLOCKS)
 k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
          const unsigned* CPB_RESTRICT list_n, int H, int W, int niter,
          int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
@@ -224,7 +227,10 @@ CPB_DEVICE int cpb_block_merge(u64 key, int nact, bool unique, u64* s_keys, int*
     return unique ? incl - 1 : s_own[slot];
 }
 
-CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FM_THREADS, 4)
+#ifndef CPB_FM_MINBLOCKS
+#define CPB_FM_MINBLOCKS 8
+#endif
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FM_THREADS, CPB_FM_MINBLOCKS)
 k_follow_merge(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
                const unsigned* CPB_RESTRICT list_n, int H, int W, int niter, int m1, int m2,
                int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
