@@ -228,7 +228,7 @@ CPB_DEVICE int cpb_block_merge(u64 key, int nact, bool unique, u64* s_keys, int*
 }
 
 #ifndef CPB_FM_MINBLOCKS
-#define CPB_FM_MINBLOCKS 8
+#define CPB_FM_MINBLOCKS 6
 #endif
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FM_THREADS, CPB_FM_MINBLOCKS)
 k_follow_merge(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
