@@ -52,6 +52,7 @@ SIGNATURES = {
     "cpb_remove_border_instances_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "cpb_average_tiles_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "cpb_average_tiles_ex_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "cpb_cell_contours_device": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _Z, _P]),
     "cpb_label_offsets_device": (C.c_int, [_P, _I, _L, _P, _P, _P]),
 }
 

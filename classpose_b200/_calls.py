@@ -138,6 +138,23 @@ class Calls:
         self.mem.keep_alive(y, y0, x0, flip, taper_y, taper_x)
         return yf
 
+    def cell_contours(self, masks, lcap, points_cap=None):
+        """PostProcessor features per label: dict(npoints, offsets, total, points, feat, perimeter, valid)."""
+        B, H, W = masks.shape
+        cap = int(points_cap) if points_cap else max(1024, B * H * W // 8)
+        out = dict(npoints=self.mem.zeros((B, lcap), "int32"), offsets=self.mem.zeros((B, lcap), "int64"),
+                   total=self.mem.zeros((1,), "int64"), points=self.mem.empty((cap, 2), "int16"),
+                   feat=self.mem.zeros((B, lcap, 8), "int64"), perimeter=self.mem.zeros((B, lcap), "float64"),
+                   valid=self.mem.zeros((B, lcap), "int32"))
+        ws, n = self._ws(B, H, W, 0, lcap)
+        rc = self.lib.cpb_cell_contours_device(self._p(masks), B, H, W, int(lcap), self._p(out["npoints"]),
+                                               self._p(out["offsets"]), self._p(out["total"]), self._p(out["points"]), cap,
+                                               self._p(out["feat"]), self._p(out["perimeter"]), self._p(out["valid"]),
+                                               self._p(ws), n, self.stream())
+        check(rc, "cpb_cell_contours_device")
+        self.mem.keep_alive(ws, masks)
+        return out
+
     def label_offsets(self, counts, base=0):
         B = counts.shape[0]
         offsets = self.mem.empty((B,), "int64")

@@ -11,6 +11,7 @@
 #include "cpb_qc.cuh"
 #include "cpb_post.cuh"
 #include "cpb_fused.cuh"
+#include "cpb_contour.cuh"
 
 #include <atomic>
 #include <cstdlib>
@@ -556,6 +557,36 @@ int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, co
     }
     return rc ? rc : (int)ce;
 #endif
+}
+
+int cpb_cell_contours_device(const int32_t* masks, int B, int H, int W, int lcap, int32_t* npoints, int64_t* offsets,
+                             int64_t* total, int16_t* points, int64_t points_cap, int64_t* feat, double* perimeter,
+                             int32_t* valid, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!masks || !npoints || !offsets || !total || !points || !feat || !perimeter || !valid || lcap < 2 || points_cap < 0)
+        return CPB_E_ARG;
+    CPB_PROLOGUE(0, lcap)
+    const long long BN = (long long)B * H * W;
+    int e = run_set_lbound(w, B, lcap - 1, st); if (e) return e;
+    e = run_map_stats(w, const_cast<int32_t*>(masks), B, H, W, 1, nullptr, nullptr, nullptr, true, st); if (e) return e;
+    cudaMemsetAsync(w.M, 0, BN * sizeof(int), st);                       // border marks
+    const dim3 grid(4, B);
+    long long* tile_base = reinterpret_cast<long long*>(w.skey);
+    CPB_LAUNCH_COUNTED(k_contours, grid, dim3(128), 0, st, masks, H, W, w.t, w.M, npoints, reinterpret_cast<long long*>(feat),
+                       perimeter, w.sidx, (const long long*)nullptr, (short*)nullptr, (long long)0, (int*)nullptr);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_contour_tile_sums, dim3(B), dim3(256), 0, st, npoints, w.t, w.t.misc);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_label_offsets, dim3(1), dim3(256), 0, st, w.t.misc, B, (long long)0, tile_base,
+                       reinterpret_cast<long long*>(total));
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_contour_offsets, dim3(B), dim3(256), 0, st, npoints, w.t, tile_base,
+                       reinterpret_cast<long long*>(offsets));
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_contours, grid, dim3(128), 0, st, masks, H, W, w.t, w.M, npoints, reinterpret_cast<long long*>(feat),
+                       perimeter, w.sidx, reinterpret_cast<const long long*>(offsets), reinterpret_cast<short*>(points),
+                       (long long)points_cap, valid);
+    CPB_CHECK_LAUNCH();
+    return 0;
 }
 
 int cpb_average_tiles_device(const float* y, int B, int ntiles, int nch, int ly, int lx, const int32_t* y0,

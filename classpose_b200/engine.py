@@ -17,7 +17,7 @@ from . import _lib
 from ._abi import ClassposeB200Error, check, make_params
 from ._calls import Calls
 
-_DT = {"int32": torch.int32, "uint8": torch.uint8, "float32": torch.float32, "float64": torch.float64,
+_DT = {"int32": torch.int32, "int16": torch.int16, "uint8": torch.uint8, "float32": torch.float32, "float64": torch.float64,
        "int64": torch.int64}
 
 
@@ -155,6 +155,10 @@ class Engine:
                                             self._dev(x0, torch.int32), self._dev(flip, torch.int32), negate_flow,
                                             self._dev(taper_y, torch.float64), self._dev(taper_x, torch.float64),
                                             Ly, Lx, crop, x0_multiple_of_4, max_cover)
+
+    def cell_contours(self, masks, lcap, points_cap=None):
+        with torch.cuda.device(self.device):
+            return self.calls.cell_contours(self._dev(masks, torch.int32), lcap, points_cap)
 
     def label_offsets(self, counts, base=0):
         with torch.cuda.device(self.device):

@@ -166,6 +166,24 @@ int cpb_average_tiles_ex_device(const float* y, int B, int ntiles, int nch, int 
                                 int Ly, int Lx, int cy0, int cy1, int cx0, int cx1, float* yf,
                                 int x0_multiple_of_4, int max_cover, void* stream);
 
+/* ---- next row N1: PostProcessor features on the device --------------------------------------------
+ * Replaces the per-cell host loop of PostProcessor.__call__ (predict_wsi.py:595-656): ndimage.find_objects,
+ * cv2.findContours(cell_mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE)[0] and the shapely polygon measures.
+ * For every label l of every tile (index [b*lcap + l]):
+ *   npoints   int32   points of contours[0], identical to cv2's list (0 if the label is absent)
+ *   offsets   int64   start of the label's points in `points` (exclusive scan in (tile, label) order)
+ *   points    int16   [points_cap][2] (x, y) in tile pixels; total[0] = points needed -- if it exceeds
+ *                     points_cap the labels that do not fit are left unwritten (valid = 0), call again
+ *   feat      int64   [..][8] pixel area, ymin, ymax, xmin, xmax, A2, Sx, Sy with the exact integer polygon sums:
+ *                     area = |A2|/2, centroid = (Sx, Sy) / (3*A2)
+ *   perimeter float64 polygon length in tile pixels
+ *   valid     int32   ring has >= 4 points, non-zero area and neither touches nor crosses itself
+ * Slide coordinates are an affine map on the host: p*scale + tile_origin (area*scale^2, perimeter*scale). */
+int cpb_cell_contours_device(const int32_t* masks, int B, int H, int W, int lcap, int32_t* npoints,
+                             int64_t* offsets, int64_t* total, int16_t* points, int64_t points_cap,
+                             int64_t* feat, double* perimeter, int32_t* valid, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* (e) global label offsets: exclusive prefix sum of per-tile instance counts.
  * offsets [B] int64 = base + sum(counts[0..b)); total [1] int64 = sum(counts).  `base` is the
  * rank's offset obtained from the cross-GPU all-gather of totals (host side). */

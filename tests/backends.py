@@ -63,6 +63,10 @@ class _Base:
         out = self._calls().compute_masks(self._in(dP), self._in(cp), self._in(logits), prm, want_class_masks)
         return tuple(_np(o) for o in out)
 
+    def cell_contours(self, masks, lcap, points_cap=None):
+        out = self._calls().cell_contours(self._in(masks), lcap, points_cap)
+        return {k: _np(v) for k, v in out.items()}
+
     def set_follow_merge(self, mode):
         self._calls().lib.cpb_debug_set_follow_merge(int(mode))
 

@@ -395,6 +395,114 @@ def case_fused_qc_then_positional_size_filter(be):
     assert ((masks[0] > 0) == (ref > 0)).mean() > 0.9995
 
 
+def contour_test_labels():
+    """Label images with blobs, thin lines, necks, diagonal chains, multi-component labels, border cells."""
+    rng = np.random.default_rng(11)
+    H, W = 96, 128
+    yy, xx = np.mgrid[0:H, 0:W]
+    lab = np.zeros((H, W), np.int32)
+    k = 0
+    for _ in range(40):                       # random ellipses (overlaps overwrite -> odd shapes, split labels)
+        cy, cx, a, b, th = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(1, 9), rng.uniform(1, 9), rng.uniform(0, 3.2)
+        u = ((xx - cx) * np.cos(th) + (yy - cy) * np.sin(th)) / a
+        v = (-(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)) / b
+        k += 1
+        lab[u * u + v * v <= 1] = k
+    k += 1; lab[5, 10:30] = k                 # horizontal 1-px line
+    k += 1; lab[10:30, 3] = k                 # vertical line
+    k += 1
+    for i in range(12): lab[40 + i, 60 + i] = k   # diagonal chain
+    k += 1; lab[70:74, 20:24] = k; lab[74, 23] = k; lab[75:79, 23:27] = k   # two squares joined by a neck
+    k += 1; lab[60:63, 100:103] = k; lab[66:69, 106:109] = k; lab[80, 90] = k   # three components, one label
+    k += 1; lab[0:3, 50:55] = k               # touches the top border
+    k += 1; lab[H - 1, W - 4:W] = k           # bottom-right corner line
+    k += 1; lab[30, 100] = k                  # single pixel
+    k += 1; lab[20:25, 110:115] = k; lab[22, 112] = 0   # ring with a hole (outer border only)
+    noise = rng.uniform(size=(H, W)) < 0.03   # salt noise creates ragged borders
+    lab[noise] = 0
+    return lab
+
+
+def case_cell_contours_match_cv2(be):
+    """Next row N1: contours[0] of cv2.findContours(cell_mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) -- the very call
+    the reference's PostProcessor makes (predict_wsi.py:614-618) -- plus bbox / area / polygon measures."""
+    import cv2
+    from scipy.ndimage import find_objects
+    labs = [contour_test_labels(), adv_tile()["masks_oracle"].astype(np.int32), std_tile(1)["masks_oracle"].astype(np.int32)]
+    for lab in labs:
+        H, W = lab.shape
+        lcap = int(lab.max()) + 2
+        out = be.cell_contours(c32(lab[None]), lcap)
+        total = 0
+        for l, slc in enumerate(find_objects(lab), start=1):
+            if slc is None:
+                assert out["npoints"][0, l] == 0
+                continue
+            ys, xs = slc
+            cell = lab[ys, xs] == l
+            cs = cv2.findContours(np.uint8(cell), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]
+            ref = cs[0][:, 0] + np.array([xs.start, ys.start])
+            n, off = int(out["npoints"][0, l]), int(out["offsets"][0, l])
+            assert off == total
+            total += n
+            np.testing.assert_array_equal(out["points"][off:off + n], ref, err_msg=f"label {l}")
+            f = out["feat"][0, l]
+            assert f[0] == cell.sum() and (f[1], f[2] + 1, f[3], f[4] + 1) == (ys.start, ys.stop, xs.start, xs.stop)
+            # polygon measures of the closed ring (shoelace), as shapely computes them
+            x, y = ref[:, 0].astype(np.float64), ref[:, 1].astype(np.float64)
+            xn, yn = np.roll(x, -1), np.roll(y, -1)
+            cross = x * yn - xn * y
+            assert f[5] == int(round(cross.sum()))
+            if len(ref) >= 2:
+                np.testing.assert_allclose(out["perimeter"][0, l], np.hypot(xn - x, yn - y).sum(), rtol=1e-12)
+            if f[5] != 0:
+                cx = ((x + xn) * cross).sum() / (3 * cross.sum()); cy = ((y + yn) * cross).sum() / (3 * cross.sum())
+                np.testing.assert_allclose([f[6] / (3 * f[5]), f[7] / (3 * f[5])], [cx, cy], rtol=1e-12)
+            # validity: brute-force restatement of "ring neither touches nor crosses itself"
+            assert bool(out["valid"][0, l]) == ring_is_simple(ref), f"label {l}: {ref.tolist()}"
+        assert int(out["total"][0]) == total
+    # a points buffer that is too small reports the needed total and writes only what fits
+    lab = labs[0]
+    small = be.cell_contours(c32(lab[None]), int(lab.max()) + 2, points_cap=1024)
+    full = be.cell_contours(c32(lab[None]), int(lab.max()) + 2)
+    assert small["total"][0] == full["total"][0]
+
+
+def ring_is_simple(pts):
+    """Brute-force polygon validity on integer points: >= 4 points, non-zero area, no self contact."""
+    n = len(pts)
+    if n < 4:
+        return False
+    P = [tuple(int(v) for v in p) for p in pts]
+    a2 = sum(P[i][0] * P[(i + 1) % n][1] - P[(i + 1) % n][0] * P[i][1] for i in range(n))
+    if a2 == 0:
+        return False
+
+    def orient(a, b, c):
+        v = (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0])
+        return (v > 0) - (v < 0)
+
+    def on(a, b, p):
+        return min(a[0], b[0]) <= p[0] <= max(a[0], b[0]) and min(a[1], b[1]) <= p[1] <= max(a[1], b[1])
+
+    def touch(a, b, c, d):
+        o1, o2, o3, o4 = orient(a, b, c), orient(a, b, d), orient(c, d, a), orient(c, d, b)
+        if o1 != o2 and o3 != o4:
+            return True
+        return (o1 == 0 and on(a, b, c)) or (o2 == 0 and on(a, b, d)) or (o3 == 0 and on(c, d, a)) or (o4 == 0 and on(c, d, b))
+
+    for i in range(n):
+        a, b, c = P[i], P[(i + 1) % n], P[(i + 2) % n]
+        if orient(a, b, c) == 0 and (b[0] - a[0]) * (c[0] - b[0]) + (b[1] - a[1]) * (c[1] - b[1]) < 0:
+            return False
+        for j in range(i + 2, n):
+            if i == 0 and j == n - 1:
+                continue
+            if touch(a, b, P[j], P[(j + 1) % n]):
+                return False
+    return True
+
+
 def case_label_offsets(be):
     counts = np.array([3, 0, 7, 1, 250, 12] * 100, np.int32)
     offs, total = be.label_offsets(counts, 1000)
@@ -408,4 +516,4 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_f
              case_remove_bad_flow_masks_exact, case_fill_holes_exact, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
              case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
-             case_label_offsets]
+             case_cell_contours_match_cv2, case_label_offsets]

@@ -182,3 +182,47 @@ def test_full_size_batch_properties():
     assert torch.equal(again, masks[:64]) and torch.equal(cnt_again, counts[:64])
     offs, total = eng.label_offsets(counts, 0)
     assert int(total[0]) == int(counts.sum()) and int(offs[-1]) == int(counts[:-1].sum())
+
+
+def test_postprocessor_cells_match_reference_loop():
+    """Next row N1: the device cell table against the reference PostProcessor loop restated with its own library
+    calls (find_objects + cv2.findContours; shapely is absent, its measures are the shoelace formulas)."""
+    import cv2
+    from scipy.ndimage import find_objects
+    from classpose_b200 import postprocess
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    tiles = [pc.std_tile(1), pc.adv_tile()]
+    dP = np.stack([t["dP"] for t in tiles]); cp = np.stack([t["cellprob"] for t in tiles])
+    lg = np.stack([t["logits"] for t in tiles])
+    masks, counts, cc, _ = eng.compute_masks_batch(dP, cp, lg)
+    table = postprocess.cell_table(masks, counts)
+    coords, scale = [(1000, 2000), (1256, 2000)], 1.136
+    cells, n_invalid = postprocess.cells_as_reference_dicts(table, cc.cpu().numpy(), coords, scale,
+                                                            labels=[f"c{i}" for i in range(7)])
+    mh = masks.cpu().numpy()
+    for b in range(2):
+        ref_cells = []
+        for l, slc in enumerate(find_objects(mh[b]), start=1):
+            if slc is None:
+                continue
+            ys, xs = slc
+            cell = mh[b][ys, xs] == l
+            cs = cv2.findContours(np.uint8(cell), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]
+            pts = (cs[0][:, 0] + np.array([xs.start, ys.start])) * scale + np.array(coords[b])
+            if pts.shape[0] < 4 or not pc.ring_is_simple(cs[0][:, 0]):
+                continue
+            x, y = pts[:, 0], pts[:, 1]
+            xn, yn = np.roll(x, -1), np.roll(y, -1)
+            cr = x * yn - xn * y
+            ref_cells.append(dict(coords=pts.tolist() + [pts[0].tolist()], area=abs(cr.sum()) / 2,
+                                  perimeter=np.hypot(xn - x, yn - y).sum(),
+                                  centroid=[((x + xn) * cr).sum() / (3 * cr.sum()), ((y + yn) * cr).sum() / (3 * cr.sum())],
+                                  class_int=int(cc[b, l]) - 1))
+        assert len(ref_cells) == len(cells[b]) > 0
+        for r, c in zip(ref_cells, cells[b]):
+            np.testing.assert_allclose(c["coords"], r["coords"], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(c["area"], r["area"], rtol=1e-9)
+            np.testing.assert_allclose(c["perimeter"], r["perimeter"], rtol=1e-9)
+            np.testing.assert_allclose(c["centroid"], np.round(r["centroid"], 2), atol=0.011)
+            assert c["class_int"] == r["class_int"]
