@@ -226,3 +226,43 @@ def test_postprocessor_cells_match_reference_loop():
             np.testing.assert_allclose(c["perimeter"], r["perimeter"], rtol=1e-9)
             np.testing.assert_allclose(c["centroid"], np.round(r["centroid"], 2), atol=0.011)
             assert c["class_int"] == r["class_int"]
+
+
+def test_device_resident_eval_tail_matches_host_path():
+    """Next row N3: network sub-tile outputs on the GPU -> blend -> masks -> classes without leaving the device,
+    against the reference's host sequence (unaugment, average_tiles, crop, dynamics, class vote) on the oracle."""
+    import torch
+    from classpose_b200 import core
+    t = pc.std_tile(4)
+    C = t["logits"].shape[0]
+    for augment in (False, True):
+        pads, geo = core.tile_layout(256, 256, 256, augment=augment)
+        Ly, Lx = geo["Ly"], geo["Lx"]
+        full = np.zeros((C + 3, Ly, Lx), np.float32)
+        full[:C, pads[0]:pads[0] + 256, pads[2]:pads[2] + 256] = t["logits"]
+        full[C:C + 2, pads[0]:pads[0] + 256, pads[2]:pads[2] + 256] = t["dP"]
+        full[C + 2, pads[0]:pads[0] + 256, pads[2]:pads[2] + 256] = t["cellprob"]
+        # what the network would emit per sub-tile: flipped inputs give flipped outputs with dY / dX sign changes
+        tiles = np.zeros((len(geo["y0"]), C + 3, 256, 256), np.float32)
+        for j, (y0, x0, f) in enumerate(zip(geo["y0"], geo["x0"], geo["flip"])):
+            s = full[:, y0:y0 + 256, x0:x0 + 256].copy()
+            if f & 1:
+                s = s[:, ::-1]; s[C] *= -1
+            if f & 2:
+                s = s[:, :, ::-1]; s[C + 1] *= -1
+            tiles[j] = s
+        # reference host sequence
+        ysub = [[a, a + 256] for a in geo["y0"]]; xsub = [[a, a + 256] for a in geo["x0"]]
+        yfl = tiles[:, C:].reshape(geo["ny"], geo["nx"], 3, 256, 256).copy()
+        ycl = tiles[:, :C].reshape(geo["ny"], geo["nx"], C, 256, 256).copy()
+        if augment:
+            yfl = otf.unaugment_tiles(yfl); ycl = classpose_ref.unaugment_class_tiles(ycl)
+        yf = otf.average_tiles(yfl.reshape(-1, 3, 256, 256), ysub, xsub, Ly, Lx)[:, pads[0]:Ly - pads[1], pads[2]:Lx - pads[3]]
+        yc = otf.average_tiles(ycl.reshape(-1, C, 256, 256), ysub, xsub, Ly, Lx)[:, pads[0]:Ly - pads[1], pads[2]:Lx - pads[3]]
+        ref = odyn.resize_and_compute_masks(yf[:2], yf[2])
+        ref_cm, _ = classpose_ref.compute_class_masks(ref, yc[:, None])
+        masks, counts, cc, cm, dP, cellprob = core.eval_tail(torch.from_numpy(tiles[None]).cuda(), C, pads, geo,
+                                                              augment=augment, want_class_masks=True)
+        np.testing.assert_allclose(dP[0].cpu().numpy(), yf[:2], rtol=0, atol=1e-6)
+        r = metrics.class_agreement(ref, ref_cm, masks[0].cpu().numpy(), cm[0].cpu().numpy().astype(np.int64))
+        assert r["f1"] >= 0.995 and not r["class_mismatch"] and r["n_pred"] == r["n_true"]
