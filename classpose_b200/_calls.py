@@ -155,6 +155,18 @@ class Calls:
         self.mem.keep_alive(ws, masks)
         return out
 
+    def dedup_cells(self, cx, cy, size, max_dist=7.5, want_group=False):
+        n = int(cx.shape[0])
+        keep = self.mem.zeros((max(n, 1),), "int32")
+        group = self.mem.zeros((max(n, 1),), "int32") if want_group else None
+        nb = int(self.lib.cpb_dedup_workspace_bytes(n))
+        ws = self.mem.empty((nb,), "uint8")
+        rc = self.lib.cpb_dedup_cells_device(self._p(cx), self._p(cy), self._p(size), n, float(max_dist), self._p(keep),
+                                             self._p(group), self._p(ws), nb, self.stream())
+        check(rc, "cpb_dedup_cells_device")
+        self.mem.keep_alive(ws, cx, cy, size)
+        return keep[:n], (group[:n] if want_group else None)
+
     def label_offsets(self, counts, base=0):
         B = counts.shape[0]
         offsets = self.mem.empty((B,), "int64")

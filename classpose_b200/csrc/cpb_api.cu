@@ -12,6 +12,7 @@
 #include "cpb_post.cuh"
 #include "cpb_fused.cuh"
 #include "cpb_contour.cuh"
+#include "cpb_dedup.cuh"
 
 #include <atomic>
 #include <cstdlib>
@@ -557,6 +558,47 @@ int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, co
     }
     return rc ? rc : (int)ce;
 #endif
+}
+
+static unsigned dedup_table_size(long long n) {
+    unsigned m = 1024;
+    while ((long long)m < 2 * n && m < (1u << 30)) m <<= 1;
+    return m;
+}
+
+size_t cpb_dedup_workspace_bytes(int64_t n) {
+    if (n <= 0) return kAlign;
+    Carver c{nullptr, 0};
+    c.take<int>(dedup_table_size(n)); c.take<int>(n); c.take<int>(n); c.take<u64>(n); c.take<int>(n);
+    return c.off + kAlign;
+}
+
+int cpb_dedup_cells_device(const double* cx, const double* cy, const double* size, int64_t n, double max_dist,
+                           int32_t* keep, int32_t* group, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n == 0) return 0;
+    if (!cx || !cy || !size || !keep || !workspace || n < 0 || n >= (1LL << 31) || !(max_dist > 0.0)) return CPB_E_ARG;
+    if (workspace_bytes < cpb_dedup_workspace_bytes(n)) return CPB_E_WORKSPACE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const uintptr_t wsa = (reinterpret_cast<uintptr_t>(workspace) + kAlign - 1) / kAlign * kAlign;
+    Carver c{reinterpret_cast<char*>(wsa), 0};
+    const unsigned M = dedup_table_size(n);
+    int* head = c.take<int>(M); int* next = c.take<int>(n); int* parent = c.take<int>(n);
+    u64* best_size = c.take<u64>(n); int* best_idx = c.take<int>(n);
+    cudaMemsetAsync(head, 0xff, (size_t)M * sizeof(int), st);
+    const dim3 grid(blocks_for(n, 256));
+    const double inv_cell = 1.0 / max_dist;
+    CPB_LAUNCH_COUNTED(k_dedup_insert, grid, dim3(256), 0, st, cx, cy, (long long)n, inv_cell, M - 1, head, next, parent,
+                       best_size, best_idx);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_dedup_link, grid, dim3(256), 0, st, cx, cy, (long long)n, inv_cell, max_dist * max_dist, M - 1,
+                       (const int*)head, (const int*)next, parent);
+    CPB_CHECK_LAUNCH();
+    for (int phase = 0; phase < 3; phase++) {
+        CPB_LAUNCH_COUNTED(k_dedup_select, grid, dim3(256), 0, st, size, (long long)n, parent, best_size, best_idx, phase,
+                           keep, group);
+        CPB_CHECK_LAUNCH();
+    }
+    return 0;
 }
 
 int cpb_cell_contours_device(const int32_t* masks, int B, int H, int W, int lcap, int32_t* npoints, int64_t* offsets,

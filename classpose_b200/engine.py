@@ -160,6 +160,11 @@ class Engine:
         with torch.cuda.device(self.device):
             return self.calls.cell_contours(self._dev(masks, torch.int32), lcap, points_cap)
 
+    def dedup_cells(self, cx, cy, size, max_dist=7.5, want_group=False):
+        with torch.cuda.device(self.device):
+            return self.calls.dedup_cells(self._dev(cx, torch.float64), self._dev(cy, torch.float64),
+                                          self._dev(size, torch.float64), max_dist, want_group)
+
     def label_offsets(self, counts, base=0):
         with torch.cuda.device(self.device):
             return self.calls.label_offsets(self._dev(counts, torch.int32), base)

@@ -184,6 +184,15 @@ int cpb_cell_contours_device(const int32_t* masks, int B, int H, int W, int lcap
                              int64_t* feat, double* perimeter, int32_t* valid, void* workspace,
                              size_t workspace_bytes, void* stream);
 
+/* ---- next row N2: overlap de-duplication across tiles -------------------------------------------------
+ * Replaces deduplicate() (predict_wsi.py:896-965): cells whose centroids are within max_dist (7.5) of each other
+ * are grouped (connected components of that relation) and only the largest cell of a group is kept (ties: lowest
+ * index).  cx, cy, size: float64 [n] device arrays in slide coordinates; keep int32 [n] (1 = survives);
+ * group (optional) int32 [n] = representative index of the cell's group. */
+size_t cpb_dedup_workspace_bytes(int64_t n);
+int cpb_dedup_cells_device(const double* cx, const double* cy, const double* size, int64_t n, double max_dist,
+                           int32_t* keep, int32_t* group, void* workspace, size_t workspace_bytes, void* stream);
+
 /* (e) global label offsets: exclusive prefix sum of per-tile instance counts.
  * offsets [B] int64 = base + sum(counts[0..b)); total [1] int64 = sum(counts).  `base` is the
  * rank's offset obtained from the cross-GPU all-gather of totals (host side). */

@@ -67,6 +67,11 @@ class _Base:
         out = self._calls().cell_contours(self._in(masks), lcap, points_cap)
         return {k: _np(v) for k, v in out.items()}
 
+    def dedup_cells(self, cx, cy, size, max_dist=7.5, want_group=False):
+        a, b = self._calls().dedup_cells(self._in(np.asarray(cx, np.float64)), self._in(np.asarray(cy, np.float64)),
+                                         self._in(np.asarray(size, np.float64)), max_dist, want_group)
+        return _np(a), _np(b)
+
     def set_follow_merge(self, mode):
         self._calls().lib.cpb_debug_set_follow_merge(int(mode))
 

@@ -503,6 +503,45 @@ def ring_is_simple(pts):
     return True
 
 
+def overlap_duplicates(seed=0, n_cells=3000, extent=4000.0):
+    """Cells of a slide seen by overlapping tiles: every cell appears 1-4 times with sub-pixel centroid jitter and
+    slightly different areas (what the 64-px tile overlap of predict_wsi produces); cells are >= 16 px apart."""
+    rng = np.random.default_rng(seed)
+    g = int(extent // 16)
+    pick = rng.choice(g * g, size=n_cells, replace=False)
+    base = np.stack([(pick % g) * 16.0 + rng.uniform(2, 6, n_cells), (pick // g) * 16.0 + rng.uniform(2, 6, n_cells)], 1)
+    copies = rng.choice([1, 1, 1, 2, 2, 4], size=n_cells)
+    centers = np.concatenate([base[i] + rng.normal(0, 0.4, size=(c, 2)) for i, c in enumerate(copies)])
+    sizes = np.concatenate([rng.uniform(80, 300) + rng.uniform(-5, 5, size=c) for c in copies])
+    perm = rng.permutation(len(sizes))
+    return centers[perm], sizes[perm]
+
+
+def case_dedup_overlapping_tiles(be):
+    """Next row N2: duplicates from tile overlaps (pairs / cliques): identical to the reference's greedy grouping."""
+    from oracle import dedup as odedup
+    for seed in (0, 1):
+        centers, sizes = overlap_duplicates(seed)
+        ref = odedup.reference_greedy(centers, sizes, 7.5)
+        keep, group = be.dedup_cells(centers[:, 0], centers[:, 1], sizes, 7.5, want_group=True)
+        np.testing.assert_array_equal(keep.astype(bool), ref)
+        assert ref.sum() == 3000 and len(np.unique(group)) == 3000
+    # the reference's order dependence only shows on chains: any visiting order of the pairs gives the same answer here
+    pairs = odedup.query_pairs(centers, 7.5)
+    np.testing.assert_array_equal(odedup.reference_greedy(centers, sizes, 7.5, pairs[::-1]), ref)
+
+
+def case_dedup_random_points_components(be):
+    """Dense random points (chains and clusters): the device result is the connected-components rule exactly."""
+    from oracle import dedup as odedup
+    rng = np.random.default_rng(4)
+    for n, extent in ((2000, 300.0), (5000, 2000.0), (1, 10.0), (2, 1.0)):
+        centers = rng.uniform(0, extent, size=(n, 2)) - extent / 3      # negative coordinates too
+        sizes = rng.integers(10, 60, size=n).astype(np.float64)          # many ties -> lowest index must win
+        keep, _ = be.dedup_cells(centers[:, 0], centers[:, 1], sizes, 7.5)
+        np.testing.assert_array_equal(keep.astype(bool), odedup.components_keep_largest(centers, sizes, 7.5))
+
+
 def case_label_offsets(be):
     counts = np.array([3, 0, 7, 1, 250, 12] * 100, np.int32)
     offs, total = be.label_offsets(counts, 1000)
@@ -516,4 +555,5 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_f
              case_remove_bad_flow_masks_exact, case_fill_holes_exact, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
              case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
-             case_cell_contours_match_cv2, case_label_offsets]
+             case_cell_contours_match_cv2, case_dedup_overlapping_tiles, case_dedup_random_points_components,
+             case_label_offsets]

@@ -266,3 +266,18 @@ def test_device_resident_eval_tail_matches_host_path():
         np.testing.assert_allclose(dP[0].cpu().numpy(), yf[:2], rtol=0, atol=1e-6)
         r = metrics.class_agreement(ref, ref_cm, masks[0].cpu().numpy(), cm[0].cpu().numpy().astype(np.int64))
         assert r["f1"] >= 0.995 and not r["class_mismatch"] and r["n_pred"] == r["n_true"]
+
+
+def test_dedup_feature_list_signature():
+    """Next row N2: same call shape as the reference's deduplicate(features, max_dist)."""
+    from classpose_b200 import dedup
+    from oracle import dedup as odedup
+    centers, sizes = pc.overlap_duplicates(3, n_cells=500, extent=1500.0)
+    feats = [{"id": i, "properties": {"measurements": [{"name": "area", "value": float(s)},
+                                                       {"name": "centroidX", "value": float(c[0])},
+                                                       {"name": "centroidY", "value": float(c[1])}]}}
+             for i, (c, s) in enumerate(zip(centers, sizes))]
+    out = dedup.deduplicate(feats)
+    ref = odedup.reference_greedy(centers, sizes, 7.5)
+    assert [f["id"] for f in out] == list(np.nonzero(ref)[0])
+    assert dedup.deduplicate([]) == []
