@@ -507,8 +507,13 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         prof_end(w.prof, S_SIZE1);
     }
     prof_begin(w.prof, S_MAP4);
-    CPB_LAUNCH_COUNTED(k_final, dim3(blocks_for(BN, 256)), dim3(256), 0, st, masks,
-                       prm->fill_holes ? (const u64*)w.holekey : (const u64*)nullptr, B, H, W, w.t, counts);
+    if ((H * W) % 4 == 0 && reinterpret_cast<uintptr_t>(masks) % 16 == 0) {
+        CPB_LAUNCH_COUNTED(k_final_v4, dim3(blocks_for(BN / 4, 256)), dim3(256), 0, st, reinterpret_cast<int4*>(masks),
+                           prm->fill_holes ? (const u64*)w.holekey : (const u64*)nullptr, B, H, W, w.t, counts);
+    } else {
+        CPB_LAUNCH_COUNTED(k_final, dim3(blocks_for(BN, 256)), dim3(256), 0, st, masks,
+                           prm->fill_holes ? (const u64*)w.holekey : (const u64*)nullptr, B, H, W, w.t, counts);
+    }
     CPB_CHECK_LAUNCH();
     CPB_LAUNCH_COUNTED(k_finish_bounds, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t, B);
     CPB_CHECK_LAUNCH();

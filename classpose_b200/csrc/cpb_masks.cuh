@@ -52,9 +52,23 @@ k_seeds(const int* CPB_RESTRICT hist, int H, int W, int LC, u64* CPB_RESTRICT se
     int* Mb = M + (size_t)b * N;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    for (int p = threadIdx.x; p < N; p += blockDim.x) {
-        const int v = h[p];
-        if (v > CPB_SEED_MIN) {
+    // the histogram is almost everywhere 0: scan it with 128-bit loads when the tile allows
+    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
+    const int nq = vec ? N / 4 : N;
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        int vals[4];
+        int nv = 1;
+        if (vec) {
+            const int4 v4 = *reinterpret_cast<const int4*>(h + 4 * q);
+            vals[0] = v4.x; vals[1] = v4.y; vals[2] = v4.z; vals[3] = v4.w; nv = 4;
+            if (max(max(v4.x, v4.y), max(v4.z, v4.w)) <= CPB_SEED_MIN) continue;
+        } else {
+            vals[0] = h[q];
+        }
+        for (int e = 0; e < nv; e++) {
+            const int v = vals[e];
+            if (v <= CPB_SEED_MIN) continue;
+            const int p = vec ? 4 * q + e : q;
             const int y = p / W, x = p - y * W;
             bool ismax = true;
             for (int dy = -2; dy <= 2 && ismax; dy++)

@@ -94,94 +94,126 @@ CPB_DEVICE double cpb_div9_fast(double x) {
 }
 
 
-// k_diffuse_warp: one WARP per label for labels whose bbox fits 32 x 32 (nuclei-sized).
-// The label's T lives in a per-warp shared-memory tile with a zero halo; lane j owns column j and
-// walks down the rows with a 3 x 3 sliding window in registers: three conflict-free row loads per
-// step, nine neighbours summed in the reference's order, in-place Jacobi update (row r is written
-// only after every lane holds rows r and r+1 in registers).  No block barriers.
+// k_diffuse_warp: one WARP per label -- or per PAIR of labels -- for labels whose bbox fits 30 x 32 (nuclei-sized).
+// The label's T lives in a per-warp shared-memory tile with a zero halo; lane j owns column j and walks down the
+// rows with a 3 x 3 sliding window in registers: conflict-free row loads, nine neighbours summed in the
+// reference's order, in-place Jacobi update (a row is written only after every lane holds the rows it still
+// needs), two rows per step.  The kernel is bound by the float64 pipe and its cost is (rows x 11 warp
+// instructions) whatever the number of busy lanes, so two consecutive labels whose widths fit side by side
+// (wA + 1 + wB <= 32, a zero column between them) share one pass: same arithmetic per label, half the issue slots.
+struct DiffSub { int l; size_t k; int y0, x0, h, w, coff; };
+
+CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTables& t, double* CPB_RESTRICT Tb,
+                                double* S, const DiffSub& A, const DiffSub& B, bool has_b, int n_it) {
+    const int lane = threadIdx.x & 31;
+    const bool inA = lane < A.w;
+    const bool inB = has_b && lane >= B.coff && lane < B.coff + B.w;
+    const DiffSub& my = inB ? B : A;
+    const bool mine = inA || inB;
+    const int col = lane - my.coff;
+    const int hj = has_b ? max(A.h, B.h) : A.h;
+    __syncwarp();
+    for (int i = lane; i < (hj + 3) * CPB_DC_PITCH; i += 32) S[i] = 0.0;
+    unsigned member = 0;               // bit r: pixel (y0+r, x0+col) belongs to this lane's label
+    if (mine)
+        for (int r = 0; r < my.h; r++)
+            if (L[(my.y0 + r) * W + my.x0 + col] == my.l) member |= 1u << r;
+    // centres: member pixel nearest to the mean of (bbox-relative coordinate + 1); first in raster order on ties
+    int ci[2] = {0, 0};
+    for (int q = 0; q < (has_b ? 2 : 1); q++) {
+        const DiffSub& sub = q ? B : A;
+        const bool in = q ? inB : inA;
+        const int c = t.cnt[sub.k];
+        const double ymed = __ddiv_rn(__ll2double_rn((long long)t.sumy[sub.k] - (long long)c * sub.y0 + c), __int2double_rn(c));
+        const double xmed = __ddiv_rn(__ll2double_rn((long long)t.sumx[sub.k] - (long long)c * sub.x0 + c), __int2double_rn(c));
+        const double dx = __dsub_rn(__int2double_rn(col + 1), xmed);
+        const double dx2 = __dmul_rn(dx, dx);
+        double bd = 1e300; int bi = CPB_IMAX;
+        if (in)
+            for (int r = 0; r < sub.h; r++) {
+                if (member >> r & 1) {
+                    const double dy = __dsub_rn(__int2double_rn(r + 1), ymed);
+                    const double d = __dadd_rn(dx2, __dmul_rn(dy, dy));
+                    const int idx = r * sub.w + col;
+                    if (cpb_minkey_less(d, idx, bd, bi)) { bd = d; bi = idx; }
+                }
+            }
+        for (int sft = 16; sft; sft >>= 1) {
+            const double od = __shfl_xor_sync(CPB_FULL, bd, sft);
+            const int oi = __shfl_xor_sync(CPB_FULL, bi, sft);
+            if (cpb_minkey_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+        }
+        const int cr = bi / sub.w, cc = bi - cr * sub.w;
+        if (lane == 0) { t.cy[sub.k] = sub.y0 + cr; t.cx[sub.k] = sub.x0 + cc; }
+        ci[q] = (cr + 1) * CPB_DC_PITCH + (sub.coff + cc + 1);
+    }
+    const double* p = S + lane;        // p[0], p[1], p[2] = columns j-1, j, j+1 of the halo row
+    double* own = S + CPB_DC_PITCH + lane + 1;
+    __syncwarp();
+    for (int it = 0; it < n_it; it++) {
+        if (lane == 0) { S[ci[0]] += 1.0; if (has_b) S[ci[1]] += 1.0; }   // T[centre] += 1 before averaging
+        __syncwarp();
+        double uL = p[0], uC = p[1], uR = p[2];
+        double cL = p[CPB_DC_PITCH], cC = p[CPB_DC_PITCH + 1], cR = p[CPB_DC_PITCH + 2];
+        for (int r = 0; r < hj; r += 2) {
+            const double* q = p + (r + 2) * CPB_DC_PITCH;
+            const double dL = q[0], dC = q[1], dR = q[2];                                   // row r+1
+            const double eL = q[CPB_DC_PITCH], eC = q[CPB_DC_PITCH + 1], eR = q[CPB_DC_PITCH + 2];   // row r+2
+            // self, up, down, left, right, up-left, up-right, down-left, down-right
+            double s0 = __dadd_rn(cC, uC), s1 = __dadd_rn(dC, cC);
+            s0 = __dadd_rn(s0, dC); s1 = __dadd_rn(s1, eC);
+            s0 = __dadd_rn(s0, cL); s1 = __dadd_rn(s1, dL);
+            s0 = __dadd_rn(s0, cR); s1 = __dadd_rn(s1, dR);
+            s0 = __dadd_rn(s0, uL); s1 = __dadd_rn(s1, cL);
+            s0 = __dadd_rn(s0, uR); s1 = __dadd_rn(s1, cR);
+            s0 = __dadd_rn(s0, dL); s1 = __dadd_rn(s1, eL);
+            s0 = __dadd_rn(s0, dR); s1 = __dadd_rn(s1, eR);
+            const double v0 = cpb_div9_fast(s0), v1 = cpb_div9_fast(s1);
+            __syncwarp();              // every lane holds rows r .. r+2 before rows r, r+1 are overwritten
+            if (member >> r & 1) own[r * CPB_DC_PITCH] = v0;
+            if (member >> (r + 1) & 1) own[(r + 1) * CPB_DC_PITCH] = v1;
+            uL = dL; uC = dC; uR = dR;
+            cL = eL; cC = eC; cR = eR;
+        }
+        __syncwarp();
+    }
+    if (mine)
+        for (int r = 0; r < my.h; r++)
+            if (member >> r & 1) Tb[(my.y0 + r) * W + my.x0 + col] = own[r * CPB_DC_PITCH];
+}
+
+CPB_DEVICE bool cpb_diffuse_load_sub(const LabelTables& t, int b, int l, int lb, DiffSub& s) {
+    if (l > lb) return false;
+    s.l = l; s.k = (size_t)b * t.LC + l; s.coff = 0;
+    if (!cpb_label_live(t, s.k)) return false;
+    s.y0 = t.ymin[s.k]; s.x0 = t.xmin[s.k];
+    s.h = t.ymax[s.k] - s.y0 + 1; s.w = t.xmax[s.k] - s.x0 + 1;
+    return cpb_diffuse_is_small(s.h, s.w);
+}
+
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, 6)
 k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                int niter_override) {
     CPB_SHARED double s_T[CPB_DW_WARPS][(CPB_DC_MAXH + 3) * CPB_DC_PITCH];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y, LC = t.LC, N = H * W;
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, N = H * W;
     const int lb = t.lbound[b];
     const int* L = lab + (size_t)b * N;
     double* Tb = T + (size_t)b * N;
     const int n_it = niter_override > 0 ? niter_override : t.niter[b];
     double* S = s_T[warp];
-    for (int l = 1 + blockIdx.x * CPB_DW_WARPS + warp; l <= lb; l += gridDim.x * CPB_DW_WARPS) {
-        const size_t k = (size_t)b * LC + l;
-        if (!cpb_label_live(t, k)) continue;      // warp-uniform
-        const int y0 = t.ymin[k], x0 = t.xmin[k];
-        const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
-        if (!cpb_diffuse_is_small(h, w)) continue;
-        __syncwarp();
-        for (int i = lane; i < (h + 3) * CPB_DC_PITCH; i += 32) S[i] = 0.0;
-        unsigned member = 0;               // bit r: pixel (y0+r, x0+lane) belongs to the label
-        if (lane < w)
-            for (int r = 0; r < h; r++)
-                if (L[(y0 + r) * W + x0 + lane] == l) member |= 1u << r;
-        // centre = member pixel nearest to the mean of (bbox-relative coordinate + 1); first in raster order on ties
-        int ci;
-        {
-            const int c = t.cnt[k];
-            const double ymed = __ddiv_rn(__ll2double_rn((long long)t.sumy[k] - (long long)c * y0 + c), __int2double_rn(c));
-            const double xmed = __ddiv_rn(__ll2double_rn((long long)t.sumx[k] - (long long)c * x0 + c), __int2double_rn(c));
-            const double dx = __dsub_rn(__int2double_rn(lane + 1), xmed);
-            const double dx2 = __dmul_rn(dx, dx);
-            double bd = 1e300; int bi = CPB_IMAX;
-            for (int r = 0; r < h; r++) {
-                if (member >> r & 1) {
-                    const double dy = __dsub_rn(__int2double_rn(r + 1), ymed);
-                    const double d = __dadd_rn(dx2, __dmul_rn(dy, dy));
-                    const int idx = r * w + lane;
-                    if (cpb_minkey_less(d, idx, bd, bi)) { bd = d; bi = idx; }
-                }
-            }
-            for (int sft = 16; sft; sft >>= 1) {
-                const double od = __shfl_xor_sync(CPB_FULL, bd, sft);
-                const int oi = __shfl_xor_sync(CPB_FULL, bi, sft);
-                if (cpb_minkey_less(od, oi, bd, bi)) { bd = od; bi = oi; }
-            }
-            const int cr = bi / w, cc = bi - cr * w;
-            if (lane == 0) { t.cy[k] = y0 + cr; t.cx[k] = x0 + cc; }
-            ci = (cr + 1) * CPB_DC_PITCH + (cc + 1);
+    // work item = pair of consecutive labels (2i+1, 2i+2); everything below is warp-uniform
+    for (int wi = blockIdx.x * CPB_DW_WARPS + warp; 2 * wi + 1 <= lb; wi += gridDim.x * CPB_DW_WARPS) {
+        DiffSub A, B;
+        const bool okA = cpb_diffuse_load_sub(t, b, 2 * wi + 1, lb, A);
+        const bool okB = cpb_diffuse_load_sub(t, b, 2 * wi + 2, lb, B);
+        if (okA && okB && A.w + 1 + B.w <= CPB_DC_MAXW) {
+            B.coff = A.w + 1;
+            cpb_diffuse_job(L, W, t, Tb, S, A, B, true, n_it);
+        } else {
+            if (okA) cpb_diffuse_job(L, W, t, Tb, S, A, A, false, n_it);
+            if (okB) cpb_diffuse_job(L, W, t, Tb, S, B, B, false, n_it);
         }
-        const double* p = S + lane;        // p[0], p[1], p[2] = columns j-1, j, j+1 of the halo row
-        double* own = S + CPB_DC_PITCH + lane + 1;
-        __syncwarp();
-        // Two rows per step: rows r and r+1 are independent given the old rows r-1 .. r+2, so both nine-term
-        // chains are in flight together and one __syncwarp() covers both in-place stores.
-        for (int it = 0; it < n_it; it++) {
-            if (lane == 0) S[ci] += 1.0;   // T[centre] += 1 before averaging
-            __syncwarp();
-            double uL = p[0], uC = p[1], uR = p[2];
-            double cL = p[CPB_DC_PITCH], cC = p[CPB_DC_PITCH + 1], cR = p[CPB_DC_PITCH + 2];
-            for (int r = 0; r < h; r += 2) {
-                const double* q = p + (r + 2) * CPB_DC_PITCH;
-                const double dL = q[0], dC = q[1], dR = q[2];                                   // row r+1
-                const double eL = q[CPB_DC_PITCH], eC = q[CPB_DC_PITCH + 1], eR = q[CPB_DC_PITCH + 2];   // row r+2
-                // self, up, down, left, right, up-left, up-right, down-left, down-right
-                double s0 = __dadd_rn(cC, uC), s1 = __dadd_rn(dC, cC);
-                s0 = __dadd_rn(s0, dC); s1 = __dadd_rn(s1, eC);
-                s0 = __dadd_rn(s0, cL); s1 = __dadd_rn(s1, dL);
-                s0 = __dadd_rn(s0, cR); s1 = __dadd_rn(s1, dR);
-                s0 = __dadd_rn(s0, uL); s1 = __dadd_rn(s1, cL);
-                s0 = __dadd_rn(s0, uR); s1 = __dadd_rn(s1, cR);
-                s0 = __dadd_rn(s0, dL); s1 = __dadd_rn(s1, eL);
-                s0 = __dadd_rn(s0, dR); s1 = __dadd_rn(s1, eR);
-                const double v0 = cpb_div9_fast(s0), v1 = cpb_div9_fast(s1);
-                __syncwarp();              // every lane holds rows r .. r+2 before rows r, r+1 are overwritten
-                if (member >> r & 1) own[r * CPB_DC_PITCH] = v0;
-                if (r + 1 < h && (member >> (r + 1) & 1)) own[(r + 1) * CPB_DC_PITCH] = v1;
-                uL = dL; uC = dC; uR = dR;
-                cL = eL; cC = eC; cR = eR;
-            }
-            __syncwarp();
-        }
-        for (int r = 0; r < h; r++)
-            if (member >> r & 1) Tb[(y0 + r) * W + x0 + lane] = own[r * CPB_DC_PITCH];
     }
 }
 
