@@ -487,9 +487,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_FILL);
         prof_begin(w.prof, S_MAP3);
-        CPB_LAUNCH_COUNTED(k_reset_counts, dim3(blocks_for(w.t.LC, 256), B), dim3(256), 0, st, w.t);
-        CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED(k_recount, dim3(blocks_for(BN, 256)), dim3(256), 0, st, masks, w.holekey, B, H, W, w.t);
+        CPB_LAUNCH_COUNTED(k_recount, dim3(B), dim3(1024), 0, st, masks, w.holekey, H, W, w.t);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_MAP3);
         prof_begin(w.prof, S_SIZE2);

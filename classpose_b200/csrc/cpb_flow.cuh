@@ -110,10 +110,13 @@ k_prep_flow_v4(const float4* CPB_RESTRICT dP, const float4* CPB_RESTRICT cellpro
 // One Euler step in normalised coordinates, arithmetic order as ATen's grid_sampler_2d.
 // f points at pixel (0,0) of the padded tile; Wp is its row pitch.
 CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int Wp, float fH, float fW, float& px, float& py) {
-    const float ix = ((px + 1.f) * fW - 1.f) / 2.f;
-    const float iy = ((py + 1.f) * fH - 1.f) / 2.f;
+    // ATen: ix = ((x + 1) * W - 1) / 2, which nvcc contracts to fma(x + 1, W, -1) * 0.5.  Scaling by 0.5 commutes
+    // with rounding, so fma(x + 1, W/2, -0.5) is the same float with one instruction less (fH, fW arrive halved).
+    const float ix = fmaf(px + 1.f, fW, -0.5f);
+    const float iy = fmaf(py + 1.f, fH, -0.5f);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
-    const int idx = (int)fy0 * Wp + (int)fx0;
+    // tap index from the (integer-valued, < 2^24) floats: one conversion instead of two
+    const int idx = (int)fmaf(fy0, (float)Wp, fx0);
     const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
     const float2* r0 = f + idx;      // f is an opaque per-thread pointer: one IMAD.WIDE
     const float2* r1 = r0 + Wp;
@@ -140,7 +143,7 @@ k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
          int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
     const unsigned total = *list_n;
     const int N = H * W, Wp = W + 2 * CPB_FLOW_PADX, Np = (H + 2) * Wp;
-    const float fW = (float)W, fH = (float)H;
+    const float fW = 0.5f * (float)W, fH = 0.5f * (float)H;      // halved: see cpb_euler_step
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
     const int lane = threadIdx.x & 31;
     for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {
@@ -242,7 +245,7 @@ k_follow_merge(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT lis
     CPB_SHARED int s_scan[33];
     const unsigned total = *list_n;
     const int N = H * W, Wp = W + 2 * CPB_FLOW_PADX, Np = (H + 2) * Wp;
-    const float fW = (float)W, fH = (float)H;
+    const float fW = 0.5f * (float)W, fH = 0.5f * (float)H;      // halved: see cpb_euler_step
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
     const int t = threadIdx.x, lane = t & 31;
     for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {

@@ -110,38 +110,28 @@ k_fuse_size(LabelTables t, int H, int W, int min_size, int mode, const int* CPB_
     if (threadIdx.x == 0) t.nlab[b] = n2;
 }
 
-// k_recount: pixel pass over the tiles in which a hole was filled (t.misc[b] != 0): recompute count and
-// first appearance of every live label on the image with the hole proposals applied.
-CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
-k_recount(const int* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, int B, int H, int W, LabelTables t) {
-    const int N = H * W;
-    const long long total = (long long)B * N;
-    const long long base = (long long)blockIdx.x * blockDim.x;
-    if (base >= total) return;
-    const long long gi = base + threadIdx.x;
-    int l = 0, b = 0, r = 0, y = 0, x = 0;
-    if (gi < total) {
-        b = (int)(gi / N);
-        if (t.misc[b] != 0) {
-            r = (int)(gi - (long long)b * N);
-            const u64 hk = holekey[gi];
-            l = hk ? (int)(hk & 0xffffffffu) : lab[gi];
-            if (l > 0 && t.alive[(size_t)b * t.LC + l] == 0) l = 0;
+// k_recount: one block per tile, only tiles in which a hole was filled (t.misc[b] != 0) do any work: reset count /
+// first appearance of the tile's labels and recompute them on the image with the hole proposals applied.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(1024, 1)
+k_recount(const int* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, int H, int W, LabelTables t) {
+    const int b = blockIdx.x;
+    if (t.misc[b] == 0) return;
+    const int N = H * W, LC = t.LC, lb = t.lbound[b];
+    for (int l = threadIdx.x; l <= lb; l += blockDim.x) { t.cnt[(size_t)b * LC + l] = 0; t.first[(size_t)b * LC + l] = CPB_IMAX; }
+    __syncthreads();
+    const int* L = lab + (size_t)b * N;
+    const u64* HK = holekey + (size_t)b * N;
+    for (int r0 = 0; r0 < N; r0 += blockDim.x) {
+        const int r = r0 + threadIdx.x;
+        int l = 0, y = 0, x = 0;
+        if (r < N) {
+            const u64 hk = HK[r];
+            l = hk ? (int)(hk & 0xffffffffu) : L[r];
+            if (l > 0 && t.alive[(size_t)b * LC + l] == 0) l = 0;
             y = r / W; x = r - y * W;
         }
+        cpb_stats_accum(t, b, l, r, y, x);
     }
-    if (__ballot_sync(CPB_FULL, l > 0) == 0) return;
-    cpb_stats_accum(t, b, l, r, y, x);
-}
-
-// grid (ceil(LC/256), B): reset count / first of the tiles that need a recount
-CPB_KERNEL k_reset_counts(LabelTables t) {
-    const int b = blockIdx.y;
-    if (t.misc[b] == 0) return;
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l > t.lbound[b] || l >= t.LC) return;
-    const size_t k = (size_t)b * t.LC + l;
-    t.cnt[k] = 0; t.first[k] = CPB_IMAX;
 }
 
 // k_final: raw label (or hole proposal) -> final id, in place; also publishes the per-tile counts.
