@@ -202,9 +202,12 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     const bool vec4 = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(dP) % 16 == 0) &&
                       (reinterpret_cast<uintptr_t>(cellprob) % 16 == 0) && (reinterpret_cast<uintptr_t>(pfinal) % 16 == 0);
     if (vec4) {
-        CPB_LAUNCH_COUNTED(k_prep_flow_v4, dim3(blocks_for((long long)B * (H + 2) * (W / 4), 256)), dim3(256), 0, st,
+        const int patch = (W % 64 == 0) ? 1 : 0;
+        const long long nblk = patch ? (long long)B * ((H + 2 + 15) / 16) * (W / 64)
+                                     : (long long)blocks_for((long long)B * (H + 2) * (W / 4), 256);
+        CPB_LAUNCH_COUNTED(k_prep_flow_v4, dim3((unsigned)nblk), dim3(256), 0, st,
                            reinterpret_cast<const float4*>(dP), reinterpret_cast<const float4*>(cellprob), B, H, W, thr, sx,
-                           sy, reinterpret_cast<float4*>(w.flow), reinterpret_cast<int4*>(pfinal), w.list, w.list_n);
+                           sy, reinterpret_cast<float4*>(w.flow), reinterpret_cast<int4*>(pfinal), w.list, w.list_n, patch);
     } else {
         CPB_LAUNCH_COUNTED(k_prep_flow, dim3(blocks_for((long long)B * (H + 2) * (W + 2 * CPB_FLOW_PADX), 256)), dim3(256),
                            0, st, dP, cellprob, B, H, W, thr, sx, sy, w.flow, pfinal, w.list, w.list_n);

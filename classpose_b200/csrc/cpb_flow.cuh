@@ -59,20 +59,36 @@ k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, in
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_prep_flow_v4(const float4* CPB_RESTRICT dP, const float4* CPB_RESTRICT cellprob, int B, int H, int W,
                float thr, float sx, float sy, float4* CPB_RESTRICT flow, int4* CPB_RESTRICT pfinal,
-               unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n) {
+               unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n, int patch) {
     CPB_SHARED int s_scan[33];
     CPB_SHARED unsigned s_base;
     const int W4 = W >> 2, N4 = (H * W) >> 2;
     const int Wp4 = (W + 2 * CPB_FLOW_PADX) >> 1;           // row pitch in float4 (2 pixels each)
-    const long long total = (long long)B * (H + 2) * W4;
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // thread -> (tile b, padded row yp, group of 4 pixels xg).  patch != 0 (W % 64 == 0): a block covers a
+    // 16-row x 64-pixel patch, so that its foreground pixels -- one contiguous run of the list -- are whole
+    // cells rather than 4-row slices (k_follow_merge merges trajectories within such a run).
+    int b, yp, xg;
+    bool in;
+    if (patch) {
+        const int pbx = W4 >> 4, pby = (H + 2 + 15) >> 4;
+        const int blk = blockIdx.x;
+        b = blk / (pbx * pby);
+        const int rem = blk - b * (pbx * pby);
+        yp = (rem / pbx) * 16 + (threadIdx.x >> 4);
+        xg = (rem % pbx) * 16 + (threadIdx.x & 15);
+        in = b < B && yp < H + 2;
+    } else {
+        const long long total = (long long)B * (H + 2) * W4;
+        const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        in = g < total;
+        b = (int)(g / ((long long)(H + 2) * W4));
+        const int rem = (int)(g - (long long)b * (H + 2) * W4);
+        yp = rem / W4; xg = rem - yp * W4;
+    }
     int nfg = 0;
     unsigned gi0 = 0;
     bool f0 = false, f1 = false, f2 = false, f3 = false;
-    if (g < total) {
-        const int b = (int)(g / ((long long)(H + 2) * W4));
-        const int rem = (int)(g - (long long)b * (H + 2) * W4);
-        const int yp = rem / W4, xg = rem - yp * W4;
+    if (in) {
         float4* row = flow + ((size_t)b * (H + 2) + yp) * Wp4;
         float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
         if (yp >= 1 && yp <= H) {
