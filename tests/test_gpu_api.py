@@ -281,3 +281,34 @@ def test_dedup_feature_list_signature():
     ref = odedup.reference_greedy(centers, sizes, 7.5)
     assert [f["id"] for f in out] == list(np.nonzero(ref)[0])
     assert dedup.deduplicate([]) == []
+
+
+def test_dense_512_tile_against_oracle():
+    """BASELINE configs[4] shape: one 512x512 tile with ~1.8k small nuclei, all stages on, against the oracle."""
+    from classpose_b200.engine import get_engine
+    from oracle import synth as osynth
+    eng = get_engine()
+    t = osynth.make_tile(21, H=512, W=512, C=7, n_grid=45, axes=(3.5, 5.0))
+    ref = odyn.resize_and_compute_masks(t["dP"], t["cellprob"])
+    ref_cm, _ = classpose_ref.compute_class_masks(ref, t["logits"][:, None])
+    masks, counts, cc, cm = eng.compute_masks_batch(t["dP"][None], t["cellprob"][None], t["logits"][None],
+                                                    want_class_masks=True)
+    r = metrics.class_agreement(ref, ref_cm, masks[0].cpu().numpy(), cm[0].cpu().numpy().astype(np.int64))
+    assert r["n_true"] > 1500
+    assert r["f1"] >= 0.995 and not r["class_mismatch"], {k: v for k, v in r.items() if k not in ("pairs",)}
+    assert abs(r["n_pred"] - r["n_true"]) <= max(1, 0.001 * r["n_true"])
+
+
+def test_large_and_rectangular_tiles_run():
+    """Shapes beyond the benchmark: 1024x768 (large labels take the block-level diffusion / hole-fill paths)."""
+    import torch
+    from classpose_b200 import synth
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    d = synth.make_batch(2, 768, 1024, 5, n_grid=8, axes=(20.0, 40.0), seed=9)       # nuclei up to 80 px across
+    masks, counts, cc, _ = eng.compute_masks_batch(d["dP"], d["cellprob"], d["logits"])
+    torch.cuda.synchronize()
+    planted = torch.stack([(d["labels"][b].unique() > 0).sum() for b in range(2)]).cpu()
+    assert (counts.cpu() - planted).abs().max() <= 2
+    ref = odyn.resize_and_compute_masks(d["dP"][0].cpu().numpy(), d["cellprob"][0].cpu().numpy())
+    assert metrics.match_instances(ref, masks[0].cpu().numpy())["f1"] >= 0.99
