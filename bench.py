@@ -338,7 +338,7 @@ def run_ours(args):
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample of the same workload
     cores = os.cpu_count() or 1
-    sample = min(B, max(32, 2 * cores), 128)
+    sample = min(B, max(64, 8 * cores), 256)      # ~10-30 s of CPU work
     cpu = None
     if not args.no_cpu_baseline:
         tiles = [(dP[i].cpu().numpy(), cellprob[i].cpu().numpy(), logits[i].cpu().numpy()) for i in range(sample)]
