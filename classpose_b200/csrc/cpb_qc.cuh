@@ -319,10 +319,14 @@ k_diffuse(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_
 // background, the (possibly foreign) instance's T otherwise.
 CPB_DEVICE double cpb_T_at(const double* CPB_RESTRICT Tb, const int* CPB_RESTRICT L, const int* CPB_RESTRICT alive,
                            int H, int W, int y, int x) {
-    if (y < 0 || y >= H || x < 0 || x >= W) return 0.0;
-    const int p = y * W + x;
+    // branch-free: the label and T loads are issued unconditionally at a clamped address so that the four
+    // neighbour fetches of a pixel overlap; T of a non-label pixel is never written and is discarded here
+    const bool inb = y >= 0 && y < H && x >= 0 && x < W;
+    const int p = min(max(y, 0), H - 1) * W + min(max(x, 0), W - 1);
     const int l = L[p];
-    return (l > 0 && (alive == nullptr || alive[l] != 0)) ? Tb[p] : 0.0;
+    const double v = Tb[p];
+    const bool live = l > 0 && (alive == nullptr || alive[l] != 0);
+    return (inb && live) ? v : 0.0;
 }
 
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
