@@ -62,6 +62,7 @@ constexpr int kLabelBlocksPerTile = 24;
 constexpr int kWarpDiffuseBlocksPerTile = 8; // x CPB_DW_WARPS warps: labels of a tile in flight   // per-label kernels: grid (kLabelBlocksPerTile, B)
 constexpr int kVoteSmemInts = 6 * 1024;   // 24 KB (instance, class) table per tile: 4 blocks of 512 threads per SM;
                                           // tiles with more than 6144/C labels use the global table
+constexpr int kVoteSmemIntsMax = 24 * 1024; // 96 KB
 constexpr size_t kAlign = 256;
 
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
@@ -138,12 +139,15 @@ int check_geom(int B, int H, int W) {
 
 inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
 
+// per-tile table kernels (seed ranking, renumbering): one block per tile; big tiles can hold thousands of labels
+inline unsigned table_threads(int H, int W) { return (long long)H * W > 256 * 256 ? 1024u : 256u; }
+
 #ifndef CPB_SIM
 void ensure_attributes() {
     static std::once_flag once;
     std::call_once(once, [] {
         cudaFuncSetAttribute(k_fill_holes, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CPB_FILL_WORDS * 4);
-        cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, kVoteSmemInts * 4);
+        cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, kVoteSmemIntsMax * 4);
     });
 }
 int sm_count() {
@@ -234,7 +238,7 @@ int run_get_masks(const Workspace& w, const int32_t* pfinal, int B, int H, int W
     const long long BN = (long long)B * H * W;
     prof_begin(w.prof, S_SEEDS);
     cudaMemsetAsync(w.M, 0, BN * sizeof(int), st);
-    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(256), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.M, w.t.lbound);
+    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(table_threads(H, W)), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.M, w.t.lbound);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_SEEDS);
     prof_begin(w.prof, S_LOOKUP);
@@ -243,7 +247,7 @@ int run_get_masks(const Workspace& w, const int32_t* pfinal, int B, int H, int W
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_LOOKUP);
     ProfScope ps(w.prof, S_FINALIZE);
-    CPB_LAUNCH_COUNTED(k_gm_finalize, dim3(B), dim3(256), 0, st, w.t, H, W, msf, w.skey, w.sidx, counts, 0);
+    CPB_LAUNCH_COUNTED(k_gm_finalize, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, msf, w.skey, w.sidx, counts, 0);
     CPB_CHECK_LAUNCH();
     return 0;   // caller applies w.t.remap
 }
@@ -279,7 +283,7 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
     if (!have_stats) { e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, nullptr, true, st); if (e) return e; }
     const int mode = min_size > 0 ? 1 : 0;
     prof_begin(w.prof, S_SIZE1);
-    CPB_LAUNCH_COUNTED(k_size_renumber, dim3(B), dim3(256), 0, st, w.t, H, W, min_size, mode, w.skey, w.sidx, (int*)nullptr);
+    CPB_LAUNCH_COUNTED(k_size_renumber, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, min_size, mode, w.skey, w.sidx, (int*)nullptr);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_SIZE1);
     e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, true, st, S_MAP2); if (e) return e;
@@ -294,7 +298,7 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
     e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, w.holekey, true, st, S_MAP3); if (e) return e;
     if (mode == 1) {
         prof_begin(w.prof, S_SIZE2);
-        CPB_LAUNCH_COUNTED(k_size_renumber, dim3(B), dim3(256), 0, st, w.t, H, W, min_size, 1, w.skey, w.sidx, counts);
+        CPB_LAUNCH_COUNTED(k_size_renumber, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, min_size, 1, w.skey, w.sidx, counts);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_SIZE2);
         e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, false, st, S_MAP4); if (e) return e;
@@ -307,8 +311,10 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
 int run_vote(const Workspace& w, const int32_t* masks, const float* logits, int B, int H, int W, int C,
              int32_t* cell_class, uint8_t* class_masks, cudaStream_t st) {
     ProfScope ps(w.prof, S_VOTE);
-    CPB_LAUNCH_COUNTED(k_vote, dim3(B), dim3(512), kVoteSmemInts * 4, st, masks, logits, H, W, C, w.t.LC, w.t.lbound,
-               kVoteSmemInts, w.vote, cell_class, class_masks);
+    // (instance, class) table in shared memory: 24 KB for nuclei-scale tiles, up to 96 KB on big tiles
+    const int smem_ints = (int)std::min<long long>(std::max<long long>((long long)H * W / 16, kVoteSmemInts), kVoteSmemIntsMax);
+    CPB_LAUNCH_COUNTED(k_vote, dim3(B), dim3(512), smem_ints * 4, st, masks, logits, H, W, C, w.t.LC, w.t.lbound,
+               smem_ints, w.vote, cell_class, class_masks);
     CPB_CHECK_LAUNCH();
     return 0;
 }
@@ -450,7 +456,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     // (3) seeds -> raw labels (seed order + 1) and their statistics; ids after get_masks live in t.remap
     prof_begin(w.prof, S_SEEDS);
     cudaMemsetAsync(w.M, 0, BN * sizeof(int), st);
-    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(256), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.M, w.t.lbound);
+    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(table_threads(H, W)), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.M, w.t.lbound);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_SEEDS);
     prof_begin(w.prof, S_LOOKUP);
@@ -465,7 +471,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     prof_end(w.prof, S_LOOKUP);
     w.t.alive = w.alive;
     prof_begin(w.prof, S_FINALIZE);
-    CPB_LAUNCH_COUNTED(k_gm_finalize, dim3(B), dim3(256), 0, st, w.t, H, W, prm->max_size_fraction, w.skey, w.sidx,
+    CPB_LAUNCH_COUNTED(k_gm_finalize, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, prm->max_size_fraction, w.skey, w.sidx,
                        (int*)nullptr, 1);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_FINALIZE);
@@ -476,7 +482,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     // (5) size filter / hole fill / size filter as table operations, one final pixel pass
     if (prm->fill_holes) {
         prof_begin(w.prof, S_SIZE1);
-        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(256), 0, st, w.t, H, W, prm->min_size, 1, (const int*)nullptr,
+        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, prm->min_size, 1, (const int*)nullptr,
                            w.skey, w.sidx, w.sinv);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_SIZE1);
@@ -496,13 +502,13 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         prof_begin(w.prof, S_SIZE2);
         // second filter on every tile: besides holes, labels that survived the positional first filter are
         // caught here (labels are contiguous again, so position == value)
-        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(256), 0, st, w.t, H, W, prm->min_size, 1, (const int*)nullptr,
+        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, prm->min_size, 1, (const int*)nullptr,
                            w.skey, w.sidx, w.sinv);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_SIZE2);
     } else {
         prof_begin(w.prof, S_SIZE1);
-        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(256), 0, st, w.t, H, W, 0, 2, (const int*)nullptr, w.skey, w.sidx,
+        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, 0, 2, (const int*)nullptr, w.skey, w.sidx,
                            w.sinv);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_SIZE1);

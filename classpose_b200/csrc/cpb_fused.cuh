@@ -38,7 +38,7 @@ k_lookup_list(const unsigned* CPB_RESTRICT list, const unsigned* CPB_RESTRICT li
 //   min_size > 0 every present label with cnt < min_size removes the label whose current id equals that
 //   position (upstream indexes by position, see k_size_renumber); survivors get new ids 1..n in order of
 //   first appearance.  Writes remap, alive, nlab.  Tiles with only_if[b] == 0 are skipped when only_if != NULL.
-CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+CPB_KERNEL CPB_LAUNCH_BOUNDS(1024, 1)
 k_fuse_size(LabelTables t, int H, int W, int min_size, int mode, const int* CPB_RESTRICT only_if,
             u64* CPB_RESTRICT scratch_key, int* CPB_RESTRICT scratch_idx, int* CPB_RESTRICT scratch_inv) {
     CPB_SHARED int s_n, s_fg;

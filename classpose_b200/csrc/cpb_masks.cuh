@@ -39,7 +39,7 @@ CPB_DEVICE int cpb_hist_at(const int* CPB_RESTRICT h, int H, int W, int y, int x
 //  2. order: ascending count, ties by raster position (stable sort of a raster-ordered list)
 //  3. each seed grows inside its 11x11 window: 5 x { 3x3 dilation ; &= h > 2 }
 //  4. paint label = order+1; later (larger) labels overwrite -> atomicMax
-CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+CPB_KERNEL CPB_LAUNCH_BOUNDS(1024, 1)
 k_seeds(const int* CPB_RESTRICT hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
         int* CPB_RESTRICT seed_lab, int* CPB_RESTRICT M, int* CPB_RESTRICT nseeds) {
     CPB_SHARED int s_n;
@@ -137,7 +137,7 @@ k_lookup(const int* CPB_RESTRICT pfinal, const int* CPB_RESTRICT M, int B, int H
 
 // k_gm_finalize: one block per tile.  Drop labels larger than max_size_fraction of the tile,
 // renumber the rest 1..n in order of first appearance.
-CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+CPB_KERNEL CPB_LAUNCH_BOUNDS(1024, 1)
 k_gm_finalize(LabelTables t, int H, int W, double max_size_fraction, u64* CPB_RESTRICT scratch_key,
               int* CPB_RESTRICT scratch_idx, int* CPB_RESTRICT counts_out, int keep_raw) {
     CPB_SHARED int s_n;

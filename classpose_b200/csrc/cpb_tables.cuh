@@ -62,7 +62,7 @@ k_map_stats(int* CPB_RESTRICT lab, int B, int H, int W, int nch, const int* CPB_
 //   mode 0:  compact labels in increasing value order (the `j` counter of the fill loop).
 // Produces remap (old -> new), nlab, lbound(new) and -- permuted to the new ids -- the
 // bbox tables the hole fill needs (nbbox = 4 arrays [B][LC], may be NULL).
-CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+CPB_KERNEL CPB_LAUNCH_BOUNDS(1024, 1)
 k_size_renumber(LabelTables t, int H, int W, int min_size, int mode, u64* CPB_RESTRICT scratch_key,
                 int* CPB_RESTRICT scratch_idx, int* CPB_RESTRICT counts_out) {
     CPB_SHARED int s_scan[33];
