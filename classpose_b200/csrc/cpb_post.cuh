@@ -242,8 +242,14 @@ k_average_tiles(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly,
 // tile origin x0 to be multiples of 4, so that the four pixels are covered by exactly the same tiles and map
 // to one aligned float4 of each tile (reversed when the tile is X-flipped).  Tiles are visited in tile order,
 // the taper weights of a tile are formed once and reused for every channel.
+#ifndef CPB_BLEND_MINB
+#define CPB_BLEND_MINB 2
+#endif
+#ifndef CPB_BLEND_UNROLL
+#define CPB_BLEND_UNROLL 1
+#endif
 template <int NCH>
-CPB_KERNEL CPB_LAUNCH_BOUNDS(256, (NCH > 8 ? 1 : 2))
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, (NCH > 8 ? 1 : CPB_BLEND_MINB))
 k_average_tiles_v4(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly, int lx,
                    const int* CPB_RESTRICT ty0, const int* CPB_RESTRICT tx0, const int* CPB_RESTRICT flip,
                    int negate_flow, const double* CPB_RESTRICT taper_y, const double* CPB_RESTRICT taper_x,
@@ -261,6 +267,7 @@ k_average_tiles_v4(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int 
     for (int ch = 0; ch < NCH; ch++) { acc[ch][0] = 0.f; acc[ch][1] = 0.f; acc[ch][2] = 0.f; acc[ch][3] = 0.f; }
     double navg[4] = {0.0, 0.0, 0.0, 0.0};
     const size_t plane = (size_t)ly * lx;
+    #pragma unroll CPB_BLEND_UNROLL
     for (int j = 0; j < ntiles; j++) {
         const int ry = gy - ty0[j], rx = gx - tx0[j];
         if (ry < 0 || ry >= ly || rx < 0 || rx >= lx) continue;
