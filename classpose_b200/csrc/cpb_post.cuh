@@ -245,9 +245,6 @@ k_average_tiles(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly,
 #ifndef CPB_BLEND_MINB
 #define CPB_BLEND_MINB 2
 #endif
-#ifndef CPB_BLEND_UNROLL
-#define CPB_BLEND_UNROLL 1
-#endif
 template <int NCH>
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, (NCH > 8 ? 1 : CPB_BLEND_MINB))
 k_average_tiles_v4(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly, int lx,
@@ -267,7 +264,6 @@ k_average_tiles_v4(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int 
     for (int ch = 0; ch < NCH; ch++) { acc[ch][0] = 0.f; acc[ch][1] = 0.f; acc[ch][2] = 0.f; acc[ch][3] = 0.f; }
     double navg[4] = {0.0, 0.0, 0.0, 0.0};
     const size_t plane = (size_t)ly * lx;
-    #pragma unroll CPB_BLEND_UNROLL
     for (int j = 0; j < ntiles; j++) {
         const int ry = gy - ty0[j], rx = gx - tx0[j];
         if (ry < 0 || ry >= ly || rx < 0 || rx >= lx) continue;
