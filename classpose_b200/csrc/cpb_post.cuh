@@ -242,11 +242,9 @@ k_average_tiles(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly,
 // tile origin x0 to be multiples of 4, so that the four pixels are covered by exactly the same tiles and map
 // to one aligned float4 of each tile (reversed when the tile is X-flipped).  Tiles are visited in tile order,
 // the taper weights of a tile are formed once and reused for every channel.
-#ifndef CPB_BLEND_MINB
-#define CPB_BLEND_MINB 2
-#endif
+// blocks per SM measured on B200: 4 accumulator channels -> 4 blocks (4.0 TB/s), 8 -> 2 blocks (3.7 TB/s), 16 -> 1
 template <int NCH>
-CPB_KERNEL CPB_LAUNCH_BOUNDS(256, (NCH > 8 ? 1 : CPB_BLEND_MINB))
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, (NCH > 8 ? 1 : (NCH > 4 ? 2 : 4)))
 k_average_tiles_v4(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly, int lx,
                    const int* CPB_RESTRICT ty0, const int* CPB_RESTRICT tx0, const int* CPB_RESTRICT flip,
                    int negate_flow, const double* CPB_RESTRICT taper_y, const double* CPB_RESTRICT taper_x,
