@@ -55,6 +55,7 @@ SIGNATURES = {
     "cpb_cell_contours_device": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _Z, _P]),
     "cpb_dedup_workspace_bytes": (_Z, [_L]),
     "cpb_dedup_cells_device": (C.c_int, [_P, _P, _P, _L, _D, _P, _P, _P, _Z, _P]),
+    "cpb_prepare_tiles_device": (C.c_int, [_P, _I, _I, _I, _I, _D, _D, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "cpb_label_offsets_device": (C.c_int, [_P, _I, _L, _P, _P, _P]),
 }
 

@@ -167,6 +167,20 @@ class Calls:
         self.mem.keep_alive(ws, cx, cy, size)
         return keep[:n], (group[:n] if want_group else None)
 
+    def prepare_tiles(self, img, pads, y0, x0, flip, ly, lx, lower=1.0, upper=99.0):
+        """img [B,H,W,C] float32 -> (tiles [B,ntiles,C,ly,lx], lowhigh [B,C,2], code [B,C])."""
+        B, H, W, Cc = img.shape
+        nt = int(y0.shape[0])
+        tiles = self.mem.empty((B, nt, Cc, ly, lx), "float32")
+        lowhigh = self.mem.empty((B, Cc, 2), "float32")
+        code = self.mem.empty((B, Cc), "int32")
+        rc = self.lib.cpb_prepare_tiles_device(self._p(img), B, H, W, Cc, float(lower), float(upper), int(pads[0]),
+                                               int(pads[2]), nt, int(ly), int(lx), self._p(y0), self._p(x0), self._p(flip),
+                                               self._p(tiles), self._p(lowhigh), self._p(code), self.stream())
+        check(rc, "cpb_prepare_tiles_device")
+        self.mem.keep_alive(img, y0, x0, flip)
+        return tiles, lowhigh, code
+
     def label_offsets(self, counts, base=0):
         B = counts.shape[0]
         offsets = self.mem.empty((B,), "int64")

@@ -48,3 +48,18 @@ def eval_tail(y_tiles, nclasses, pads, geo, augment=False, device=None, want_cla
     masks, counts, cell_class, class_masks = eng.compute_masks_batch(dP, cellprob, yc, want_class_masks=want_class_masks,
                                                                      **params)
     return masks, counts, cell_class, class_masks, dP, cellprob
+
+
+def prepare_tiles(imgs, bsize=256, augment=False, tile_overlap=0.1, device=None):
+    """Next row N4: what happens to an image before the network (models.py:641-666 normalize_img with its defaults,
+    core.py:129-178 pad + make_tiles with the parity flips), on the device.
+    imgs: [B, Ly, Lx, nchan] (or [Ly, Lx, nchan]) float32 / uint8, numpy or CUDA tensor.
+    Returns (tiles [B, ntiles, nchan, ly, lx] CUDA float32, pads, geometry)."""
+    eng = get_engine(device if not (isinstance(imgs, torch.Tensor) and imgs.is_cuda) else imgs.device)
+    x = eng._dev(imgs, torch.float32)
+    if x.dim() == 3:
+        x = x.unsqueeze(0)
+    B, Ly0, Lx0, nchan = x.shape
+    pads, geo = tile_layout(Ly0, Lx0, bsize, augment=augment, tile_overlap=tile_overlap)
+    tiles, lowhigh, code = eng.prepare_tiles(x.contiguous(), pads, geo["y0"], geo["x0"], geo["flip"], geo["ly"], geo["lx"])
+    return tiles, pads, geo

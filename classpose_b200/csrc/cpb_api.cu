@@ -13,6 +13,7 @@
 #include "cpb_fused.cuh"
 #include "cpb_contour.cuh"
 #include "cpb_dedup.cuh"
+#include "cpb_prep.cuh"
 
 #include <atomic>
 #include <cstdlib>
@@ -570,6 +571,22 @@ int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, co
     }
     return rc ? rc : (int)ce;
 #endif
+}
+
+int cpb_prepare_tiles_device(const float* img, int B, int H, int W, int C, double lower, double upper, int pad_y,
+                             int pad_x, int ntiles, int ly, int lx, const int32_t* y0, const int32_t* x0,
+                             const int32_t* flip, float* tiles, float* lowhigh, int32_t* code, void* stream) {
+    if (!img || !y0 || !x0 || !flip || !tiles || !lowhigh || !code || B <= 0 || H <= 0 || W <= 0 || C <= 0 || ntiles <= 0 ||
+        ly <= 0 || lx <= 0 || !(lower >= 0.0 && upper <= 100.0 && lower <= upper))
+        return CPB_E_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CPB_LAUNCH_COUNTED(k_percentiles, dim3(B * C), dim3(1024), 0, st, img, H, W, C, lower, upper, lowhigh, code);
+    CPB_CHECK_LAUNCH();
+    const long long total = (long long)B * ntiles * C * ly * lx;
+    CPB_LAUNCH_COUNTED(k_make_tiles, dim3(blocks_for(total, 256)), dim3(256), 0, st, img, B, H, W, C, pad_y, pad_x, ntiles, ly,
+                       lx, y0, x0, flip, (const float*)lowhigh, (const int*)code, tiles);
+    CPB_CHECK_LAUNCH();
+    return 0;
 }
 
 static unsigned dedup_table_size(long long n) {

@@ -165,6 +165,11 @@ class Engine:
             return self.calls.dedup_cells(self._dev(cx, torch.float64), self._dev(cy, torch.float64),
                                           self._dev(size, torch.float64), max_dist, want_group)
 
+    def prepare_tiles(self, img, pads, y0, x0, flip, ly, lx, lower=1.0, upper=99.0):
+        with torch.cuda.device(self.device):
+            return self.calls.prepare_tiles(self._dev(img, torch.float32), pads, self._dev(y0, torch.int32),
+                                            self._dev(x0, torch.int32), self._dev(flip, torch.int32), ly, lx, lower, upper)
+
     def label_offsets(self, counts, base=0):
         with torch.cuda.device(self.device):
             return self.calls.label_offsets(self._dev(counts, torch.int32), base)

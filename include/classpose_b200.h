@@ -193,6 +193,18 @@ size_t cpb_dedup_workspace_bytes(int64_t n);
 int cpb_dedup_cells_device(const double* cx, const double* cy, const double* size, int64_t n, double max_dist,
                            int32_t* keep, int32_t* group, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- next row N4: tile preparation in front of the network ----------------------------------------------
+ * Replaces transforms.normalize_img with its defaults (models.py:641-666: per channel (x - p1) / (p99 - p1) with
+ * numpy's linear percentiles; a constant channel is left as is, a channel with p99 - p1 <= 1e-3 becomes 0) followed
+ * by np.pad and transforms.make_tiles with the parity flips (core.py:129-178).
+ * img [B,H,W,C] float32 channels-last; (pad_y, pad_x) = leading pads of get_pad_yx; windows y0/x0/flip [ntiles] as in
+ * cpb_average_tiles_device (coordinates in the padded image); tiles [B,ntiles,C,ly,lx] float32 out;
+ * lowhigh [B,C,2] float32 out = (p_lower, p_upper - p_lower); code [B,C] int32 out (1 normalised, 2 zeroed, 0 left). */
+int cpb_prepare_tiles_device(const float* img, int B, int H, int W, int C, double lower, double upper,
+                             int pad_y, int pad_x, int ntiles, int ly, int lx, const int32_t* y0,
+                             const int32_t* x0, const int32_t* flip, float* tiles, float* lowhigh,
+                             int32_t* code, void* stream);
+
 /* (e) global label offsets: exclusive prefix sum of per-tile instance counts.
  * offsets [B] int64 = base + sum(counts[0..b)); total [1] int64 = sum(counts).  `base` is the
  * rank's offset obtained from the cross-GPU all-gather of totals (host side). */

@@ -114,3 +114,37 @@ def average_tiles(y, ysub, xsub, Ly, Lx):
         Navg[ysub[j][0]:ysub[j][1], xsub[j][0]:xsub[j][1]] += mask
     yf /= Navg
     return yf
+
+
+# ---- tile preparation in front of the network --------------------------------------
+def normalize99(Y, lower=1, upper=99):
+    """cellpose.transforms.normalize99 (no down-sampling branch: a tile is far below 224**3 values)."""
+    X = Y.astype("float32").copy()
+    x01 = np.percentile(X, lower)
+    x99 = np.percentile(X, upper)
+    if x99 - x01 > 1e-3:
+        X -= x01
+        X /= (x99 - x01)
+    else:
+        X[:] = 0
+    return X
+
+
+def normalize_img(img, percentile=(1.0, 99.0)):
+    """cellpose.transforms.normalize_img with its defaults as Classpose calls it (models.py:641-666):
+    per channel (last axis) normalize99 over the whole image; constant channels are left untouched."""
+    img_norm = img.astype(np.float32).copy()
+    for c in range(img_norm.shape[-1]):
+        if np.ptp(img_norm[..., c]) > 0.0:
+            img_norm[..., c] = normalize99(img_norm[..., c], lower=percentile[0], upper=percentile[1])
+    return img_norm
+
+
+def prepare_tiles(img, bsize=256, augment=False, tile_overlap=0.1):
+    """One [Ly, Lx, nchan] image -> the network input run_net builds (core.py:129-178):
+    normalise, pad to the /16 grid, cut (and flip) the sub-tiles.  Returns (IMG [ntiles, nchan, ly, lx], ysub, xsub, pads)."""
+    x = normalize_img(img)
+    pads = get_pad_yx(x.shape[0], x.shape[1], min_size=(bsize, bsize))
+    imgb = np.pad(x.transpose(2, 0, 1), np.array([[0, 0], [pads[0], pads[1]], [pads[2], pads[3]]]), mode="constant")
+    IMG, ysub, xsub, Ly, Lx = make_tiles(imgb, bsize=bsize, augment=augment, tile_overlap=tile_overlap)
+    return IMG.reshape(-1, imgb.shape[0], IMG.shape[-2], IMG.shape[-1]), ysub, xsub, pads

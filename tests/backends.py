@@ -72,6 +72,12 @@ class _Base:
                                          self._in(np.asarray(size, np.float64)), max_dist, want_group)
         return _np(a), _np(b)
 
+    def prepare_tiles(self, img, pads, y0, x0, flip, ly, lx, lower=1.0, upper=99.0):
+        out = self._calls().prepare_tiles(self._in(img), pads, self._in(np.asarray(y0, np.int32)),
+                                          self._in(np.asarray(x0, np.int32)), self._in(np.asarray(flip, np.int32)), ly, lx,
+                                          lower, upper)
+        return tuple(_np(o) for o in out)
+
     def set_follow_merge(self, mode):
         self._calls().lib.cpb_debug_set_follow_merge(int(mode))
 

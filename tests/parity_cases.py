@@ -542,6 +542,37 @@ def case_dedup_random_points_components(be):
         np.testing.assert_array_equal(keep.astype(bool), odedup.components_keep_largest(centers, sizes, 7.5))
 
 
+def case_prepare_tiles(be):
+    """Next row N4: percentile normalisation + pad + make_tiles (with TTA flips) against numpy's own percentile."""
+    from classpose_b200 import transforms as btf
+    rng = np.random.default_rng(8)
+    imgs = []
+    a = rng.integers(0, 256, size=(256, 256, 3)).astype(np.float32)            # uint8-valued RGB tile
+    a[..., 2] = 137.0                                                          # constant channel: left untouched
+    imgs.append(a)
+    b = rng.normal(120, 40, size=(225, 225, 3)).astype(np.float32)             # 225-px WSI read (puma, 0.22 mpp)
+    b[..., 1] = 5.0 + 1e-4 * rng.uniform(size=(225, 225))                      # p99 - p1 <= 1e-3: zeroed
+    imgs.append(b)
+    imgs.append((rng.gamma(2.0, 30.0, size=(300, 280, 2))).astype(np.float32))  # larger than bsize: 2x2 tiles
+    for img in imgs:
+        for augment in (False, True):
+            ref, ysub, xsub, pads = otf.prepare_tiles(img, 256, augment=augment)
+            H, W, C = img.shape
+            geo = btf.tile_geometry(H + pads[0] + pads[1], W + pads[2] + pads[3], 256, augment=augment)
+            tiles, lowhigh, code = be.prepare_tiles(f32(img[None]), pads, geo["y0"], geo["x0"], geo["flip"], geo["ly"], geo["lx"])
+            assert tiles.shape[1:] == ref.shape
+            for c in range(C):
+                ch = img[..., c]
+                if np.ptp(ch) > 0:
+                    lo, hi = np.percentile(ch, 1), np.percentile(ch, 99)
+                    assert lowhigh[0, c, 0] == np.float32(lo), (lowhigh[0, c, 0], lo)
+                    assert lowhigh[0, c, 1] == np.float32(hi) - np.float32(lo)
+                    assert code[0, c] == (1 if np.float32(hi) - np.float32(lo) > 1e-3 else 2)
+                else:
+                    assert code[0, c] == 0
+            np.testing.assert_array_equal(tiles[0], ref)
+
+
 def case_label_offsets(be):
     counts = np.array([3, 0, 7, 1, 250, 12] * 100, np.int32)
     offs, total = be.label_offsets(counts, 1000)
@@ -555,5 +586,5 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_f
              case_remove_bad_flow_masks_exact, case_fill_holes_exact, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
              case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
-             case_cell_contours_match_cv2, case_dedup_overlapping_tiles, case_dedup_random_points_components,
+             case_cell_contours_match_cv2, case_prepare_tiles, case_dedup_overlapping_tiles, case_dedup_random_points_components,
              case_label_offsets]

@@ -312,3 +312,16 @@ def test_large_and_rectangular_tiles_run():
     assert (counts.cpu() - planted).abs().max() <= 2
     ref = odyn.resize_and_compute_masks(d["dP"][0].cpu().numpy(), d["cellprob"][0].cpu().numpy())
     assert metrics.match_instances(ref, masks[0].cpu().numpy())["f1"] >= 0.99
+
+
+def test_prepare_tiles_host_mirror():
+    """Next row N4 through the python mirror: uint8 RGB tile -> network input tiles, against the numpy sequence."""
+    from classpose_b200 import core
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, size=(2, 225, 225, 3)).astype(np.uint8)
+    for augment in (False, True):
+        tiles, pads, geo = core.prepare_tiles(img, 256, augment=augment)
+        for b in range(2):
+            ref, ysub, xsub, rpads = otf.prepare_tiles(img[b].astype(np.float32), 256, augment=augment)
+            assert tuple(rpads) == tuple(pads)
+            np.testing.assert_array_equal(tiles[b].cpu().numpy(), ref)
