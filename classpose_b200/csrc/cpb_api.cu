@@ -162,14 +162,6 @@ int sm_count() { return 4; }
 #endif
 
 // CPB_FOLLOW_MERGE=0 selects the plain kernel (A/B measurements); results are bit-identical either way
-std::atomic<int> g_diffuse_exact{-1};     // 1 (default): nine-term sum in the reference's order, bit-identical to the oracle;
-                                          // -1: CPB_DIFFUSE_FAST=1 in the environment selects the separable order
-bool diffuse_exact() {
-    const int v = g_diffuse_exact.load(std::memory_order_relaxed);
-    if (v >= 0) return v != 0;
-    static const bool fast = [] { const char* e = getenv("CPB_DIFFUSE_FAST"); return e && e[0] == '1'; }();
-    return !fast;
-}
 std::atomic<int> g_follow_merge{-1};     // -1: take CPB_FOLLOW_MERGE from the environment
 bool follow_merge_enabled() {
     const int v = g_follow_merge.load(std::memory_order_relaxed);
@@ -272,13 +264,8 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
     prof_end(w.prof, S_CENTRES);
     const size_t smem = (size_t)CPB_DIFF_SMEM_CELLS * 17;
     prof_begin(w.prof, S_DIFFUSE);
-    if (diffuse_exact()) {
-        CPB_LAUNCH_COUNTED(k_diffuse_warp<false>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                           H, W, w.t, w.T, 0);
-    } else {
-        CPB_LAUNCH_COUNTED(k_diffuse_warp<true>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                           H, W, w.t, w.T, 0);
-    }
+    CPB_LAUNCH_COUNTED(k_diffuse_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks, H, W,
+                       w.t, w.T, 0);
     CPB_CHECK_LAUNCH();
     CPB_LAUNCH_COUNTED(k_diffuse, grid, dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0, 1);
     CPB_CHECK_LAUNCH();
@@ -559,7 +546,6 @@ int cpb_compute_masks_device(const float* dP, const float* cellprob, const float
 
 int cpb_num_stages(void) { return S_COUNT; }
 const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames[i] : ""; }
-void cpb_debug_set_diffuse_exact(int on) { g_diffuse_exact.store(on ? 1 : 0, std::memory_order_relaxed); }
 void cpb_debug_set_follow_merge(int mode) { g_follow_merge.store(mode, std::memory_order_relaxed); }
 long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

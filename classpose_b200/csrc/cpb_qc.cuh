@@ -103,16 +103,6 @@ CPB_DEVICE double cpb_div9_fast(double x) {
 // (wA + 1 + wB <= 32, a zero column between them) share one pass: same arithmetic per label, half the issue slots.
 struct DiffSub { int l; size_t k; int y0, x0, h, w, coff; };
 
-// SEP = false: the nine neighbours are added in the reference's order (self, up, down, left, right, then the four
-//   diagonals) -- bit-identical to the oracle.
-// SEP = true : separable order, (row above) + (this row) + (row below) with each row summed left + centre + right once
-//   and reused by three rows: 7 instead of 11 float64 instructions per cell.  The same nine values are added, only
-//   the association differs; the diffusion field agrees to ~1e-15 relative and 99.9 % of the unit flows to 1e-13.
-//   NOT the default: where the oracle's gradient is exactly 0 by symmetry (centre pixel of a symmetric cell) a
-//   1e-17 asymmetry is normalised to a unit vector, which moves the flow error of a small cell by up to 1/area --
-//   enough to flip a decision next to the threshold.  Opt-in through cpb_debug_set_diffuse_exact(0) (-0.8 ms per
-//   1024 conic tiles).
-template <bool SEP>
 CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTables& t, double* CPB_RESTRICT Tb,
                                 double* S, const DiffSub& A, const DiffSub& B, bool has_b, int n_it) {
     const int lane = threadIdx.x & 31;
@@ -163,21 +153,6 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
     for (int it = 0; it < n_it; it++) {
         if (lane == 0) { S[ci[0]] += 1.0; if (has_b) S[ci[1]] += 1.0; }   // T[centre] += 1 before averaging
         __syncwarp();
-        if (SEP) {
-            double sU = __dadd_rn(__dadd_rn(p[0], p[1]), p[2]);                                     // halo row: 0
-            double sC = __dadd_rn(__dadd_rn(p[CPB_DC_PITCH], p[CPB_DC_PITCH + 1]), p[CPB_DC_PITCH + 2]);
-            for (int r = 0; r < hj; r += 2) {
-                const double* q = p + (r + 2) * CPB_DC_PITCH;
-                const double sD = __dadd_rn(__dadd_rn(q[0], q[1]), q[2]);                               // row r+1
-                const double sE = __dadd_rn(__dadd_rn(q[CPB_DC_PITCH], q[CPB_DC_PITCH + 1]), q[CPB_DC_PITCH + 2]);   // row r+2
-                const double v0 = cpb_div9_fast(__dadd_rn(__dadd_rn(sU, sC), sD));
-                const double v1 = cpb_div9_fast(__dadd_rn(__dadd_rn(sC, sD), sE));
-                __syncwarp();
-                if (member >> r & 1) own[r * CPB_DC_PITCH] = v0;
-                if (member >> (r + 1) & 1) own[(r + 1) * CPB_DC_PITCH] = v1;
-                sU = sD; sC = sE;
-            }
-        } else {
         double uL = p[0], uC = p[1], uR = p[2];
         double cL = p[CPB_DC_PITCH], cC = p[CPB_DC_PITCH + 1], cR = p[CPB_DC_PITCH + 2];
         for (int r = 0; r < hj; r += 2) {
@@ -200,7 +175,6 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
             uL = dL; uC = dC; uR = dR;
             cL = eL; cC = eC; cR = eR;
         }
-        }
         __syncwarp();
     }
     if (mine)
@@ -217,7 +191,6 @@ CPB_DEVICE bool cpb_diffuse_load_sub(const LabelTables& t, int b, int l, int lb,
     return cpb_diffuse_is_small(s.h, s.w);
 }
 
-template <bool SEP>
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, 6)
 k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                int niter_override) {
@@ -236,10 +209,10 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
         const bool okB = cpb_diffuse_load_sub(t, b, 2 * wi + 2, lb, B);
         if (okA && okB && A.w + 1 + B.w <= CPB_DC_MAXW) {
             B.coff = A.w + 1;
-            cpb_diffuse_job<SEP>(L, W, t, Tb, S, A, B, true, n_it);
+            cpb_diffuse_job(L, W, t, Tb, S, A, B, true, n_it);
         } else {
-            if (okA) cpb_diffuse_job<SEP>(L, W, t, Tb, S, A, A, false, n_it);
-            if (okB) cpb_diffuse_job<SEP>(L, W, t, Tb, S, B, B, false, n_it);
+            if (okA) cpb_diffuse_job(L, W, t, Tb, S, A, A, false, n_it);
+            if (okB) cpb_diffuse_job(L, W, t, Tb, S, B, B, false, n_it);
         }
     }
 }

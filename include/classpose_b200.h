@@ -83,11 +83,6 @@ int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, co
                                       int32_t* masks, int32_t* counts, int32_t* cell_class,
                                       uint8_t* class_masks, void* workspace, size_t workspace_bytes,
                                       void* stream, float* stage_ms);
-/* heat diffusion of masks_to_flows: 1 (default) = the nine neighbours are added in the reference's order
- * (bit-identical to the oracle); 0 = separable summation order (7 instead of 11 float64 instructions per cell).
- * The two differ by float64 rounding only, but unit vectors of exactly-zero gradients (symmetric cells) are
- * ill-conditioned, so the fast order can move a small cell's flow error -- hence opt-in. */
-void cpb_debug_set_diffuse_exact(int on);
 /* follow_flows variant: 1 = trajectory merging (default), 0 = plain kernel, -1 = CPB_FOLLOW_MERGE from the
  * environment.  Both give bit-identical results; the switch exists for A/B measurements and tests. */
 void cpb_debug_set_follow_merge(int mode);

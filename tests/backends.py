@@ -78,9 +78,6 @@ class _Base:
                                           lower, upper)
         return tuple(_np(o) for o in out)
 
-    def set_diffuse_exact(self, on):
-        self._calls().lib.cpb_debug_set_diffuse_exact(int(on))
-
     def set_follow_merge(self, mode):
         self._calls().lib.cpb_debug_set_follow_merge(int(mode))
 
