@@ -67,18 +67,28 @@ class Engine:
         return self.calls.label_capacity(H, W)
 
     # -- fused path ------------------------------------------------------------------------
+    MAX_PIXELS_PER_CALL = 2 ** 31 - 2 ** 24      # one device call indexes pixels with 31 bits (CPB_E_RANGE)
+
     def compute_masks_batch(self, dP, cellprob, logits=None, niter=200, cellprob_threshold=0.0,
                             flow_threshold=0.4, min_size=15, max_size_fraction=0.4, remove_border=False,
-                            fill_holes=True, want_class_masks=False):
+                            fill_holes=True, want_class_masks=False, max_pixels_per_call=None):
         """dP [B,2,H,W], cellprob [B,H,W], logits [B,C,H,W] (float32, CUDA or numpy)
-        -> masks int32 [B,H,W], counts int32 [B], cell_class int32 [B,LC] | None, class_masks uint8 | None."""
+        -> masks int32 [B,H,W], counts int32 [B], cell_class int32 [B,LC] | None, class_masks uint8 | None.
+        Batches beyond the 31-bit pixel index of one device call are processed in slices."""
         with torch.cuda.device(self.device):
             dP = self._dev(dP, torch.float32)
             cellprob = self._dev(cellprob, torch.float32)
             logits = self._dev(logits, torch.float32)
             prm = make_params(niter, cellprob_threshold, flow_threshold, min_size, max_size_fraction,
                               remove_border, fill_holes)
-            return self.calls.compute_masks(dP, cellprob, logits, prm, want_class_masks)
+            B, _, H, W = dP.shape
+            per = max(1, (max_pixels_per_call or self.MAX_PIXELS_PER_CALL) // (H * W))
+            if B <= per:
+                return self.calls.compute_masks(dP, cellprob, logits, prm, want_class_masks)
+            parts = [self.calls.compute_masks(dP[i:i + per], cellprob[i:i + per],
+                                              None if logits is None else logits[i:i + per], prm, want_class_masks)
+                     for i in range(0, B, per)]
+            return tuple(None if parts[0][k] is None else torch.cat([p[k] for p in parts]) for k in range(4))
 
     def compute_masks_host(self, dP, cellprob, logits=None, niter=200, cellprob_threshold=0.0, flow_threshold=0.4,
                            min_size=15, max_size_fraction=0.4, remove_border=False, fill_holes=True,

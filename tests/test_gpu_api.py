@@ -325,3 +325,16 @@ def test_prepare_tiles_host_mirror():
             ref, ysub, xsub, rpads = otf.prepare_tiles(img[b].astype(np.float32), 256, augment=augment)
             assert tuple(rpads) == tuple(pads)
             np.testing.assert_array_equal(tiles[b].cpu().numpy(), ref)
+
+
+def test_batch_slicing_beyond_the_pixel_index_limit():
+    """Engine slices batches that exceed one device call's 31-bit pixel index (forced here with a small limit)."""
+    import torch
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    tiles = [pc.std_tile(s) for s in (1, 3, 4, 6)]
+    dP = np.stack([t["dP"] for t in tiles]); cp = np.stack([t["cellprob"] for t in tiles]); lg = np.stack([t["logits"] for t in tiles])
+    a = eng.compute_masks_batch(dP, cp, lg, want_class_masks=True)
+    b = eng.compute_masks_batch(dP, cp, lg, want_class_masks=True, max_pixels_per_call=256 * 256 + 5)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
