@@ -46,7 +46,7 @@ EXTRA = {
                 name="synthetic 40x WSI 100k x 100k px, tile 256 overlap 0.1 (244,036 tiles), puma C=10 (BASELINE configs[2])"),
     "tta": dict(H=256, W=256, C=5, tiles=256, n_grid=10, axes=(5.0, 9.0),
                 name="monusac C=5 with TTA: 9 sub-tile maps per padded 272^2 tile blended, then dynamics (BASELINE configs[3])"),
-    "dense": dict(H=512, W=512, C=7, tiles=128, n_grid=45, axes=(3.5, 5.0),
+    "dense": dict(H=512, W=512, C=7, tiles=256, n_grid=45, axes=(3.5, 5.0),
                   name="dense nuclei stress: 512x512 tiles, ~2k cells per tile, flow check on (BASELINE configs[4])"),
 }
 
@@ -313,7 +313,7 @@ def run_ours(args):
     peak, peak_src = load_peaks()
     # DRAM traffic of the dominant kernel: from the committed ncu capture of this same workload (per launch)
     traffic, traffic_src = None, None
-    kern = {"follow_flows": "k_follow", "diffuse": "k_diffuse_warp", "vote": "k_vote", "prep_flow": "k_prep_flow_v4"}.get(dom)
+    kern = {"follow_flows": "k_follow_merge", "diffuse": "k_diffuse_warp", "vote": "k_vote", "prep_flow": "k_prep_flow_v4"}.get(dom)
     try:
         import glob
         tj = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "traffic.json")))[-1]
