@@ -264,8 +264,11 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
     prof_end(w.prof, S_CENTRES);
     const size_t smem = (size_t)CPB_DIFF_SMEM_CELLS * 17;
     prof_begin(w.prof, S_DIFFUSE);
-    CPB_LAUNCH_COUNTED(k_diffuse_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks, H, W,
-                       w.t, w.T, 0);
+    CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MIDH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
+                       H, W, w.t, w.T, 0);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MAXH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
+                       H, W, w.t, w.T, 0);
     CPB_CHECK_LAUNCH();
     CPB_LAUNCH_COUNTED(k_diffuse, grid, dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0, 1);
     CPB_CHECK_LAUNCH();

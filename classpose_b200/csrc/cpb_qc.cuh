@@ -11,7 +11,8 @@
 #define CPB_DIFF_SMEM_CELLS 2304   // (bbox_h+2)*(bbox_w+2) cells that fit the shared-memory path
 
 #define CPB_DW_WARPS 4         // warp path: labels in flight per block (one warp each)
-#define CPB_DC_MAXH 30         // warp path: bbox up to 30 rows x 32 columns (6 blocks of 4 warps fit one SM)
+#define CPB_DC_MAXH 30         // warp path: bbox up to 30 rows x 32 columns
+#define CPB_DC_MIDH 22         // ... in two size classes (<= 22 rows: 8 blocks of 4 warps per SM; <= 30 rows: 6)
 #define CPB_DC_MAXW 32
 #define CPB_DC_PITCH 34        // + one halo column on each side
 
@@ -182,19 +183,23 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
             if (member >> r & 1) Tb[(my.y0 + r) * W + my.x0 + col] = own[r * CPB_DC_PITCH];
 }
 
+// a label belongs to the kernel instance whose row capacity is the smallest that holds it
+template <int MAXH>
 CPB_DEVICE bool cpb_diffuse_load_sub(const LabelTables& t, int b, int l, int lb, DiffSub& s) {
     if (l > lb) return false;
     s.l = l; s.k = (size_t)b * t.LC + l; s.coff = 0;
     if (!cpb_label_live(t, s.k)) return false;
     s.y0 = t.ymin[s.k]; s.x0 = t.xmin[s.k];
     s.h = t.ymax[s.k] - s.y0 + 1; s.w = t.xmax[s.k] - s.x0 + 1;
-    return cpb_diffuse_is_small(s.h, s.w);
+    if (!cpb_diffuse_is_small(s.h, s.w)) return false;
+    return MAXH == CPB_DC_MIDH ? s.h <= CPB_DC_MIDH : s.h > CPB_DC_MIDH;
 }
 
-CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, 6)
+template <int MAXH>
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
 k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                int niter_override) {
-    CPB_SHARED double s_T[CPB_DW_WARPS][(CPB_DC_MAXH + 3) * CPB_DC_PITCH];
+    CPB_SHARED double s_T[CPB_DW_WARPS][(MAXH + 3) * CPB_DC_PITCH];
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.y, N = H * W;
     const int lb = t.lbound[b];
@@ -205,8 +210,8 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
     // work item = pair of consecutive labels (2i+1, 2i+2); everything below is warp-uniform
     for (int wi = blockIdx.x * CPB_DW_WARPS + warp; 2 * wi + 1 <= lb; wi += gridDim.x * CPB_DW_WARPS) {
         DiffSub A, B;
-        const bool okA = cpb_diffuse_load_sub(t, b, 2 * wi + 1, lb, A);
-        const bool okB = cpb_diffuse_load_sub(t, b, 2 * wi + 2, lb, B);
+        const bool okA = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 1, lb, A);
+        const bool okB = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 2, lb, B);
         if (okA && okB && A.w + 1 + B.w <= CPB_DC_MAXW) {
             B.coff = A.w + 1;
             cpb_diffuse_job(L, W, t, Tb, S, A, B, true, n_it);
