@@ -93,6 +93,7 @@ struct Workspace {
     int* sinv;           // [B*LC]
     int* alive;          // [B*LC]
     int* vote;           // [B*LC*C]
+    int* jobs;           // [B+1] diffusion job offsets, then 2 queue counters
     LabelTables t;
     size_t bytes;
     Prof* prof;          // optional stage timing
@@ -119,6 +120,7 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     w.sinv = c.take<int>(BL);
     w.alive = c.take<int>(BL);
     w.vote = c.take<int>(C > 0 ? BL * C : 0);
+    w.jobs = c.take<int>((size_t)B + 1 + 2);
     LabelTables& t = w.t;
     t.LC = LC;
     t.cnt = c.take<int>(BL); t.first = c.take<int>(BL);
@@ -161,12 +163,45 @@ void ensure_attributes() {}
 int sm_count() { return 4; }
 #endif
 
-// CPB_FOLLOW_MERGE=0 selects the plain kernel (A/B measurements); results are bit-identical either way
+// follow_flows variant: 2 = trajectory pool with many merge points (default), 1 = two merge points per 256-pixel
+// chunk, 0 = plain kernel; CPB_FOLLOW_MERGE in the environment or cpb_debug_set_follow_merge (A/B measurements
+// and tests).  Results are bit-identical in every mode.
 std::atomic<int> g_follow_merge{-1};     // -1: take CPB_FOLLOW_MERGE from the environment
-bool follow_merge_enabled() {
+int follow_merge_mode() {
     const int v = g_follow_merge.load(std::memory_order_relaxed);
-    if (v >= 0) return v != 0;
-    static const bool on = [] { const char* e = getenv("CPB_FOLLOW_MERGE"); return !(e && e[0] == '0'); }();
+    if (v >= 0) return v;
+    static const int env = [] { const char* e = getenv("CPB_FOLLOW_MERGE"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }();
+    return env;
+}
+
+// merge points of k_follow_pool for `niter` Euler steps: dense where the live count falls fastest (steps 24..64
+// of 200 on nuclei), sparse in the tail; CPB_FOLLOW_SCHEDULE="a,b,c" (step numbers) overrides for experiments
+FollowSchedule follow_schedule(int niter) {
+    static const int kPer200[] = {24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160};
+    FollowSchedule s{};
+    static const char* env = getenv("CPB_FOLLOW_SCHEDULE");
+    int last = 0;
+    if (env && env[0]) {
+        const char* p = env;
+        while (*p && s.n < CPB_FP_MAXMERGE) {
+            char* q = nullptr;
+            const long v = strtol(p, &q, 10);
+            if (q == p) break;
+            if (v > last && v < niter) { s.at[s.n++] = (int)v; last = (int)v; }
+            p = (*q == ',') ? q + 1 : q;
+        }
+        return s;
+    }
+    for (int v : kPer200) {
+        const int a = (int)((long long)v * niter / 200);
+        if (a > last && a < niter && s.n < CPB_FP_MAXMERGE) { s.at[s.n++] = a; last = a; }
+    }
+    return s;
+}
+
+// CPB_DIFFUSE_QUEUE=0 selects the static (block, warp) -> label map (A/B measurements); same results
+bool diffuse_queue_enabled() {
+    static const bool on = [] { const char* e = getenv("CPB_DIFFUSE_QUEUE"); return !(e && e[0] == '0'); }();
     return on;
 }
 
@@ -221,7 +256,17 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     prof_end(w.prof, S_PREP);
     ProfScope ps(w.prof, S_FOLLOW);
     const unsigned grid = (unsigned)std::min<long long>(blocks_for(BN, 256), (long long)sm_count() * 16);
-    if (follow_merge_enabled() && niter >= 32 && B < (1 << 28)) {
+    const int mode = follow_merge_mode();
+    if (mode == 2 && niter >= 32) {
+        // one block per chunk of the list (blocks past the end of the list exit at once)
+#ifdef CPB_SIM
+        const unsigned pgrid = (unsigned)std::min<long long>(blocks_for(BN, CPB_FP_POOL), 8);
+#else
+        const unsigned pgrid = blocks_for(BN, CPB_FP_POOL);
+#endif
+        CPB_LAUNCH_COUNTED(k_follow_pool, dim3(pgrid), dim3(CPB_FP_THREADS), 0, st, w.flow, w.list, w.list_n, H, W, niter,
+                           follow_schedule(niter), pfinal, pfloat, hist);
+    } else if (mode >= 1 && niter >= 32 && B < (1 << 28)) {
         // merge points at a quarter and a half of the integration (48 and 96 of 200 steps)
         CPB_LAUNCH_COUNTED(k_follow_merge, dim3(grid), dim3(CPB_FM_THREADS), 0, st, w.flow, w.list, w.list_n, H, W, niter,
                            (niter * 6) / 25, (niter * 12) / 25, pfinal, pfloat, hist);
@@ -264,12 +309,24 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
     prof_end(w.prof, S_CENTRES);
     const size_t smem = (size_t)CPB_DIFF_SMEM_CELLS * 17;
     prof_begin(w.prof, S_DIFFUSE);
-    CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MIDH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                       H, W, w.t, w.T, 0);
-    CPB_CHECK_LAUNCH();
-    CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MAXH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                       H, W, w.t, w.T, 0);
-    CPB_CHECK_LAUNCH();
+    if (diffuse_queue_enabled()) {
+        // persistent warps pulling label pairs from one queue per size class (see k_diffuse_jobs)
+        CPB_LAUNCH_COUNTED(k_diffuse_jobs, dim3(1), dim3(1024), 0, st, w.t.lbound, B, w.jobs, w.jobs + B + 1);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_diffuse_warp_q<CPB_DC_MIDH>, dim3(sm_count() * 8), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
+                           w.t, w.T, 0, w.jobs, w.jobs + B + 1);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_diffuse_warp_q<CPB_DC_MAXH>, dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
+                           w.t, w.T, 0, w.jobs, w.jobs + B + 2);
+        CPB_CHECK_LAUNCH();
+    } else {
+        CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MIDH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
+                           H, W, w.t, w.T, 0);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MAXH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
+                           H, W, w.t, w.T, 0);
+        CPB_CHECK_LAUNCH();
+    }
     CPB_LAUNCH_COUNTED(k_diffuse, grid, dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0, 1);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_DIFFUSE);

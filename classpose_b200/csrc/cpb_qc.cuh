@@ -222,6 +222,66 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
     }
 }
 
+// ---- dynamic job queue for the warp kernel --------------------------------------------------------------
+// Labels differ in height and tiles in n_iter, so a static (block, warp) -> label map leaves half of the
+// resident warps idle while the slowest warp of each block finishes.  k_diffuse_jobs numbers the label pairs of
+// the whole batch (exclusive scan of ceil(lbound/2) over tiles); persistent warps of k_diffuse_warp_q then pull
+// pair after pair from one atomic counter, so every resident warp stays busy until the queue is empty.
+CPB_KERNEL k_diffuse_jobs(const int* CPB_RESTRICT lbound, int B, int* CPB_RESTRICT joboff, int* CPB_RESTRICT counters) {
+    CPB_SHARED int s_scan[33];
+    CPB_SHARED int s_base;
+    if (threadIdx.x == 0) { s_base = 0; counters[0] = 0; counters[1] = 0; }
+    __syncthreads();
+    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+        const int b = b0 + threadIdx.x;
+        const int n = b < B ? (lbound[b] + 1) / 2 : 0;
+        int tot;
+        const int incl = cpb_block_scan_incl(n, s_scan, &tot);
+        if (b < B) joboff[b] = s_base + incl - n;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) joboff[B] = s_base;
+}
+
+template <int MAXH>
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
+k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t, double* CPB_RESTRICT T,
+                 int niter_override, const int* CPB_RESTRICT joboff, int* CPB_RESTRICT counter) {
+    CPB_SHARED double s_T[CPB_DW_WARPS][(MAXH + 3) * CPB_DC_PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = H * W;
+    const int total = joboff[B];
+    double* S = s_T[warp];
+    for (;;) {
+        int j = 0;
+        if (lane == 0) j = atomicAdd(counter, 1);
+        j = __shfl_sync(CPB_FULL, j, 0);
+        if (j >= total) break;
+        int lo = 0, hi = B;                       // joboff[lo] <= j < joboff[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (joboff[mid] <= j) lo = mid; else hi = mid;
+        }
+        const int b = lo, wi = j - joboff[lo];
+        const int lb = t.lbound[b];
+        const int* L = lab + (size_t)b * N;
+        double* Tb = T + (size_t)b * N;
+        const int n_it = niter_override > 0 ? niter_override : t.niter[b];
+        DiffSub A, Bs;
+        const bool okA = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 1, lb, A);
+        const bool okB = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 2, lb, Bs);
+        if (okA && okB && A.w + 1 + Bs.w <= CPB_DC_MAXW) {
+            Bs.coff = A.w + 1;
+            cpb_diffuse_job(L, W, t, Tb, S, A, Bs, true, n_it);
+        } else {
+            if (okA) cpb_diffuse_job(L, W, t, Tb, S, A, A, false, n_it);
+            if (okB) cpb_diffuse_job(L, W, t, Tb, S, Bs, Bs, false, n_it);
+        }
+    }
+}
+
 // Neighbour order of the reference: self, (-1,0), (1,0), (0,-1), (0,1), (-1,-1), (-1,1), (1,-1), (1,1)
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
 k_diffuse(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,

@@ -83,8 +83,9 @@ int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, co
                                       int32_t* masks, int32_t* counts, int32_t* cell_class,
                                       uint8_t* class_masks, void* workspace, size_t workspace_bytes,
                                       void* stream, float* stage_ms);
-/* follow_flows variant: 1 = trajectory merging (default), 0 = plain kernel, -1 = CPB_FOLLOW_MERGE from the
- * environment.  Both give bit-identical results; the switch exists for A/B measurements and tests. */
+/* follow_flows variant: 2 = trajectory pool with many merge points (default), 1 = two merge points per chunk,
+ * 0 = plain kernel, -1 = CPB_FOLLOW_MERGE from the environment.  All give bit-identical results; the switch
+ * exists for A/B measurements and tests. */
 void cpb_debug_set_follow_merge(int mode);
 /* number of kernels this library has launched in this process (statistics for the benchmark) */
 long long cpb_debug_launch_count(void);

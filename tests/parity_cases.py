@@ -100,12 +100,13 @@ def case_follow_flows_merge_is_exact(be):
         for a, b in ((dP, cp), (small_dP, small_cp)):
             be.set_follow_merge(0)
             p0, f0 = be.follow_flows(a, b, 200, 0.0, want_float=True)
-            be.set_follow_merge(1)
-            p1, f1 = be.follow_flows(a, b, 200, 0.0, want_float=True)
-            np.testing.assert_array_equal(p0, p1)
             fg = b > 0
-            np.testing.assert_array_equal(f0[:, 0][fg], f1[:, 0][fg])
-            np.testing.assert_array_equal(f0[:, 1][fg], f1[:, 1][fg])
+            for mode in (1, 2):       # two merge points per 256-pixel chunk; trajectory pool
+                be.set_follow_merge(mode)
+                p1, f1 = be.follow_flows(a, b, 200, 0.0, want_float=True)
+                np.testing.assert_array_equal(p0, p1)
+                np.testing.assert_array_equal(f0[:, 0][fg], f1[:, 0][fg])
+                np.testing.assert_array_equal(f0[:, 1][fg], f1[:, 1][fg])
     finally:
         be.set_follow_merge(-1)
 
