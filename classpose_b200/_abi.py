@@ -42,6 +42,7 @@ SIGNATURES = {
     "cpb_compute_masks_profiled_device": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, _P, _Z, _P, _P]),
     "cpb_debug_launch_count": (C.c_longlong, []),
     "cpb_debug_set_follow_merge": (None, [_I]),
+    "cpb_debug_set_switch": (None, [_I, _I]),
     "cpb_compute_masks_host": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, _I, _I]),
     "cpb_follow_flows_device": (C.c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "cpb_get_masks_device": (C.c_int, [_P, _I, _I, _I, _D, _P, _P, _P, _Z, _P]),

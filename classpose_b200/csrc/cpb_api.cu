@@ -129,6 +129,7 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     t.remap = c.take<int>(BL); t.flag = c.take<int>(BL); t.alive = nullptr;
     t.cy = c.take<int>(BL); t.cx = c.take<int>(BL);
     t.err = c.take<double>(BL);
+    t.done = c.take<int>(BL);
     t.lbound = c.take<int>(B); t.nlab = c.take<int>(B); t.niter = c.take<int>(B); t.misc = c.take<int>(B);
     w.bytes = c.off;
     return w;
@@ -174,10 +175,11 @@ int follow_merge_mode() {
     return env;
 }
 
-// merge points of k_follow_pool for `niter` Euler steps: dense where the live count falls fastest (steps 24..64
-// of 200 on nuclei), sparse in the tail; CPB_FOLLOW_SCHEDULE="a,b,c" (step numbers) overrides for experiments
+// merge points of k_follow_pool for `niter` Euler steps.  A merge costs about as much as three Euler steps of the
+// whole chunk, so six points where the live count falls fastest beat eleven (measured on B200: 2.59 ms vs 2.89 ms per
+// 1024 conic tiles; 16 points: 3.19 ms); CPB_FOLLOW_SCHEDULE="a,b,c" (step numbers) overrides for experiments
 FollowSchedule follow_schedule(int niter) {
-    static const int kPer200[] = {24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160};
+    static const int kPer200[] = {28, 40, 56, 72, 96, 128};
     FollowSchedule s{};
     static const char* env = getenv("CPB_FOLLOW_SCHEDULE");
     int last = 0;
@@ -199,11 +201,22 @@ FollowSchedule follow_schedule(int niter) {
     return s;
 }
 
-// CPB_DIFFUSE_QUEUE=0 selects the static (block, warp) -> label map (A/B measurements); same results
-bool diffuse_queue_enabled() {
-    static const bool on = [] { const char* e = getenv("CPB_DIFFUSE_QUEUE"); return !(e && e[0] == '0'); }();
-    return on;
+// A/B switches (environment at first use, or cpb_debug_set_switch): every setting gives the same results.
+//   CPB_DIFFUSE_QUEUE=0  static (block, warp) -> label map instead of the job queue
+//   CPB_QC_FUSED=0       every label's flow error from T in global memory (k_flow_err) instead of the diffusion tile
+//   CPB_VOTE_FUSED=0     class vote as its own pass over the finished label image
+std::atomic<int> g_switch[4] = {{-1}, {-1}, {-1}, {-1}};
+bool switch_on(int which, const char* env_name) {
+    int v = g_switch[which].load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv(env_name);
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
+bool diffuse_queue_enabled() { return switch_on(CPB_SWITCH_DIFFUSE_QUEUE, "CPB_DIFFUSE_QUEUE"); }
+bool qc_fused_enabled() { return switch_on(CPB_SWITCH_QC_FUSED, "CPB_QC_FUSED"); }
+bool vote_fused_enabled() { return switch_on(CPB_SWITCH_VOTE_FUSED, "CPB_VOTE_FUSED"); }
 
 #define CPB_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
@@ -264,8 +277,13 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
 #else
         const unsigned pgrid = blocks_for(BN, CPB_FP_POOL);
 #endif
-        CPB_LAUNCH_COUNTED(k_follow_pool, dim3(pgrid), dim3(CPB_FP_THREADS), 0, st, w.flow, w.list, w.list_n, H, W, niter,
-                           follow_schedule(niter), pfinal, pfloat, hist);
+        if (W == 256) {       // the WSI tile width: row pitch as an immediate
+            CPB_LAUNCH_COUNTED(k_follow_pool<256 + 2 * CPB_FLOW_PADX>, dim3(pgrid), dim3(CPB_FP_THREADS), 0, st, w.flow, w.list,
+                               w.list_n, H, W, niter, follow_schedule(niter), pfinal, pfloat, hist);
+        } else {
+            CPB_LAUNCH_COUNTED(k_follow_pool<0>, dim3(pgrid), dim3(CPB_FP_THREADS), 0, st, w.flow, w.list, w.list_n, H, W, niter,
+                               follow_schedule(niter), pfinal, pfloat, hist);
+        }
     } else if (mode >= 1 && niter >= 32 && B < (1 << 28)) {
         // merge points at a quarter and a half of the integration (48 and 96 of 200 steps)
         CPB_LAUNCH_COUNTED(k_follow_merge, dim3(grid), dim3(CPB_FM_THREADS), 0, st, w.flow, w.list, w.list_n, H, W, niter,
@@ -309,22 +327,24 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
     prof_end(w.prof, S_CENTRES);
     const size_t smem = (size_t)CPB_DIFF_SMEM_CELLS * 17;
     prof_begin(w.prof, S_DIFFUSE);
+    // labels that touch no other live label get their flow error inside the diffusion warp (no T round trip)
+    const float* qc_dP = (dP && !mu_out && qc_fused_enabled()) ? dP : nullptr;
     if (diffuse_queue_enabled()) {
         // persistent warps pulling label pairs from one queue per size class (see k_diffuse_jobs)
         CPB_LAUNCH_COUNTED(k_diffuse_jobs, dim3(1), dim3(1024), 0, st, w.t.lbound, B, w.jobs, w.jobs + B + 1);
         CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED(k_diffuse_warp_q<CPB_DC_MIDH>, dim3(sm_count() * 8), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                           w.t, w.T, 0, w.jobs, w.jobs + B + 1);
+                           w.t, w.T, 0, w.jobs, w.jobs + B + 1, qc_dP, thr);
         CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED(k_diffuse_warp_q<CPB_DC_MAXH>, dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                           w.t, w.T, 0, w.jobs, w.jobs + B + 2);
+                           w.t, w.T, 0, w.jobs, w.jobs + B + 2, qc_dP, thr);
         CPB_CHECK_LAUNCH();
     } else {
         CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MIDH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                           H, W, w.t, w.T, 0);
+                           H, W, w.t, w.T, 0, qc_dP, thr);
         CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MAXH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                           H, W, w.t, w.T, 0);
+                           H, W, w.t, w.T, 0, qc_dP, thr);
         CPB_CHECK_LAUNCH();
     }
     CPB_LAUNCH_COUNTED(k_diffuse, grid, dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0, 1);
@@ -574,6 +594,27 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_SIZE1);
     }
+    // (6) the class vote rides on the final pass unless something between the two changes the labels (border
+    // removal) or the per-pixel class image is wanted (it needs the finished per-instance classes)
+    const bool vote_fused = logits && !class_masks && !prm->remove_border && vote_fused_enabled() && (H * W) % 4 == 0 &&
+                            reinterpret_cast<uintptr_t>(masks) % 16 == 0 && reinterpret_cast<uintptr_t>(logits) % 16 == 0;
+    if (vote_fused) {
+        prof_begin(w.prof, S_MAP4);
+        CPB_LAUNCH_COUNTED(k_vote_zero, dim3(B), dim3(256), 0, st, w.t, C, w.vote);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_final_vote_v4, dim3(blocks_for(BN / 4, 256)), dim3(256), 0, st, reinterpret_cast<int4*>(masks),
+                           prm->fill_holes ? (const u64*)w.holekey : (const u64*)nullptr,
+                           reinterpret_cast<const float4*>(logits), B, H, W, C, w.t, counts, w.vote);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_finish_bounds, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t, B);
+        CPB_CHECK_LAUNCH();
+        prof_end(w.prof, S_MAP4);
+        w.t.alive = nullptr;
+        ProfScope ps(w.prof, S_VOTE);
+        CPB_LAUNCH_COUNTED(k_vote_finish, dim3(B), dim3(256), 0, st, w.t, C, (const int*)w.vote, cell_class);
+        CPB_CHECK_LAUNCH();
+        return 0;
+    }
     prof_begin(w.prof, S_MAP4);
     if ((H * W) % 4 == 0 && reinterpret_cast<uintptr_t>(masks) % 16 == 0) {
         CPB_LAUNCH_COUNTED(k_final_v4, dim3(blocks_for(BN / 4, 256)), dim3(256), 0, st, reinterpret_cast<int4*>(masks),
@@ -607,6 +648,10 @@ int cpb_compute_masks_device(const float* dP, const float* cellprob, const float
 int cpb_num_stages(void) { return S_COUNT; }
 const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames[i] : ""; }
 void cpb_debug_set_follow_merge(int mode) { g_follow_merge.store(mode, std::memory_order_relaxed); }
+void cpb_debug_set_switch(int which, int value) {
+    if (which == CPB_SWITCH_FOLLOW_MERGE) g_follow_merge.store(value, std::memory_order_relaxed);
+    else if (which > 0 && which < 4) g_switch[which].store(value, std::memory_order_relaxed);
+}
 long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, const float* logits, int B, int H,

@@ -19,6 +19,7 @@ struct LabelTables {
     int* alive;      // fused path: label still exists (NULL = every label with cnt > 0)
     int* cy; int* cx;                              // diffusion centre
     double* err;     // flow error
+    int* done;       // flow error already computed by the diffusion warp (label touches no other live label)
     int* lbound;     // [B] highest label value that may be present in the tile
     int* nlab;       // [B] number of instances after the last renumbering
     int* niter;      // [B] diffusion iterations (2 * max ext)

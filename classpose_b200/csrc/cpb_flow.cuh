@@ -125,7 +125,10 @@ k_prep_flow_v4(const float4* CPB_RESTRICT dP, const float4* CPB_RESTRICT cellpro
 
 // One Euler step in normalised coordinates, arithmetic order as ATen's grid_sampler_2d.
 // f points at pixel (0,0) of the padded tile; Wp is its row pitch.
-CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int Wp, float fH, float fW, float& px, float& py) {
+// WP > 0: row pitch known at compile time (both tap rows are addressed off one base register).
+template <int WP>
+CPB_DEVICE void cpb_euler_step_t(const float2* CPB_RESTRICT f, int Wp_rt, float fH, float fW, float& px, float& py) {
+    const int Wp = WP > 0 ? WP : Wp_rt;
     // ATen: ix = ((x + 1) * W - 1) / 2, which nvcc contracts to fma(x + 1, W, -1) * 0.5.  Scaling by 0.5 commutes
     // with rounding, so fma(x + 1, W/2, -0.5) is the same float with one instruction less (fH, fW arrive halved).
     const float ix = fmaf(px + 1.f, fW, -0.5f);
@@ -147,6 +150,9 @@ CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int Wp, float fH, f
     ox += vse.x * wse; oy += vse.y * wse;
     px = fminf(fmaxf(px + ox, -1.f), 1.f);
     py = fminf(fmaxf(py + oy, -1.f), 1.f);
+}
+CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int Wp, float fH, float fW, float& px, float& py) {
+    cpb_euler_step_t<0>(f, Wp, fH, fW, px, py);
 }
 
 // k_follow: grid-stride over the compacted foreground list, one pixel per thread.
@@ -374,7 +380,7 @@ k_follow_merge(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT lis
 // bitwise-equal (tile, x, y) are found through a hash of trajectory INDICES (32-bit CAS on the slot, full key
 // compared in the pool, so the key may be as wide as it likes), survivors are compacted and every pixel's
 // trajectory index is redirected.  On the synthetic conic tiles the live count falls to 72 % at step 30, 46 % at
-// step 50, 23 % at step 100 and 16 % at step 200, so 11 merge points leave ~45 % of the Euler steps of the
+// step 50, 23 % at step 100 and 16 % at step 200, so six merge points leave ~46 % of the Euler steps of the
 // plain kernel (two merge points over 256 pixels: ~60 %).  Which duplicate survives depends on the CAS race, but
 // duplicates hold the same bits, so the output is bit-identical to k_follow.
 #define CPB_FP_THREADS 256
@@ -388,6 +394,7 @@ struct FollowSchedule { int n; int at[CPB_FP_MAXMERGE]; };   // merge points (st
 #ifndef CPB_FP_MINBLOCKS
 #define CPB_FP_MINBLOCKS 6
 #endif
+template <int WP>
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FP_THREADS, CPB_FP_MINBLOCKS)
 k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
               const unsigned* CPB_RESTRICT list_n, int H, int W, int niter, FollowSchedule sch,
@@ -433,13 +440,15 @@ k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list
 #ifndef CPB_SIM
                 asm volatile("" : "+l"(f));
 #endif
-                for (int s = step; s < until; s++) cpb_euler_step(f, Wp, fH, fW, p.x, p.y);
+                for (int s = step; s < until; s++) cpb_euler_step_t<WP>(f, Wp, fH, fW, p.x, p.y);
                 s_pos[i] = p;
             }
             step = until;
             if (m == sch.n) break;
             // ---- merge: thread t owns trajectories [t*per, t*per + per)
-            for (int i = t; i < CPB_FP_SLOTS; i += CPB_FP_THREADS) s_slot[i] = -1;
+            // table of the smallest power of two >= 2n slots (load factor <= 1/2)
+            const int smask = n <= 32 ? 63 : min(CPB_FP_SLOTS, 1 << (33 - __clz(n - 1))) - 1;
+            for (int i = t; i <= smask; i += CPB_FP_THREADS) s_slot[i] = -1;
             __syncthreads();                                  // positions written, table cleared
             const int per = (n + CPB_FP_THREADS - 1) / CPB_FP_THREADS;   // <= CPB_FP_PER
             int rep[CPB_FP_PER];                              // -1: owner, else the trajectory it duplicates
@@ -456,13 +465,13 @@ k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list
                     mp[k] = p; mt[k] = tl;
                     const unsigned ux = __float_as_uint(p.x), uy = __float_as_uint(p.y);
                     unsigned h = (ux * 0x9E3779B1u) ^ (uy * 0x85EBCA77u) ^ ((unsigned)tl * 0xC2B2AE3Du);
-                    h = (h ^ (h >> 15)) & (CPB_FP_SLOTS - 1);
+                    h = (h ^ (h >> 15)) & smask;
                     for (;;) {
                         const int old = atomicCAS(&s_slot[h], -1, i);
                         if (old == -1) { rep[k] = -1; owners++; break; }
                         const float2 q = s_pos[old];
                         if (__float_as_uint(q.x) == ux && __float_as_uint(q.y) == uy && s_tile[old] == tl) { rep[k] = old; break; }
-                        h = (h + 1) & (CPB_FP_SLOTS - 1);
+                        h = (h + 1) & smask;
                     }
                 }
             }

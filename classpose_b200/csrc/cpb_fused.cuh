@@ -183,6 +183,98 @@ k_final_v4(int4* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, int B, int H
     if (g - (long long)b * N4 == 0 && counts_out) counts_out[b] = t.nlab[b];
 }
 
+// ---- class vote folded into the final pass ------------------------------------------------------------
+// The final pass already visits every pixel with its final id in registers, so the per-pixel arg-max over the
+// C logits (first maximum wins) and the (instance, class) histogram ride along: the label image is not read a
+// second time and the logits are streamed by the whole grid with 128-bit loads instead of one block per tile.
+// Histogram in global memory (L2 atomics, aggregated per thread and per warp), rows 0..nlab of each tile zeroed
+// by k_vote_zero; k_vote_finish takes the per-instance arg-max (first maximum wins).
+CPB_KERNEL k_vote_zero(LabelTables t, int C, int* CPB_RESTRICT vote) {
+    const int b = blockIdx.x;
+    int* tab = vote + (size_t)b * t.LC * C;
+    const int need = (t.nlab[b] + 1) * C;
+    for (int i = threadIdx.x; i < need; i += blockDim.x) tab[i] = 0;
+}
+
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_final_vote_v4(int4* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, const float4* CPB_RESTRICT logits, int B, int H,
+                int W, int C, LabelTables t, int* CPB_RESTRICT counts_out, int* CPB_RESTRICT vote) {
+    const int N4 = (H * W) >> 2;
+    const long long total = (long long)B * N4;
+    const long long g0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = g0 < total;
+    const long long g = valid ? g0 : total - 1;
+    const int b = (int)(g / N4);
+    const int q = (int)(g - (long long)b * N4);
+    const int* remap = t.remap + (size_t)b * t.LC;
+    const int4 v = lab[g];
+    int l[4] = {v.x, v.y, v.z, v.w};
+    if (holekey && t.misc[b] != 0) {
+        #pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const u64 hk = holekey[g * 4 + e];
+            if (hk) l[e] = (int)(hk & 0xffffffffu);
+        }
+    }
+    int o[4];
+    #pragma unroll
+    for (int e = 0; e < 4; e++) o[e] = l[e] > 0 ? remap[l[e]] : 0;
+    if (valid && (o[0] != v.x || o[1] != v.y || o[2] != v.z || o[3] != v.w)) lab[g] = make_int4(o[0], o[1], o[2], o[3]);
+    if (valid && q == 0 && counts_out) counts_out[b] = t.nlab[b];
+    int key[4] = {-1, -1, -1, -1}, cnt[4] = {1, 1, 1, 1};
+    if (valid && (o[0] | o[1] | o[2] | o[3]) != 0) {
+        const float4* G = logits + (size_t)b * C * N4 + q;
+        float4 best = G[0];
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        #pragma unroll 4
+        for (int c = 1; c < C; c++) {
+            const float4 x = G[(size_t)c * N4];
+            if (x.x > best.x) { best.x = x.x; a0 = c; }
+            if (x.y > best.y) { best.y = x.y; a1 = c; }
+            if (x.z > best.z) { best.z = x.z; a2 = c; }
+            if (x.w > best.w) { best.w = x.w; a3 = c; }
+        }
+        const int arg[4] = {a0, a1, a2, a3};
+        #pragma unroll
+        for (int e = 0; e < 4; e++) if (o[e] > 0) key[e] = o[e] * C + arg[e];
+        // the four pixels of a thread mostly agree: fold equal keys into the first of them
+        #pragma unroll
+        for (int e = 1; e < 4; e++) {
+            #pragma unroll
+            for (int f = 0; f < e; f++)
+                if (key[e] >= 0 && key[e] == key[f]) { cnt[f] += cnt[e]; key[e] = -1; }
+        }
+    }
+    int* tab = vote + (size_t)b * t.LC * C;
+    // first key of every lane: one atomic per distinct (tile, key) of the warp
+    {
+        const long long wkey = key[0] >= 0 ? (long long)b * ((long long)t.LC * C) + key[0] : -1;
+        const unsigned peers = __match_any_sync(CPB_FULL, wkey);
+        const int sum = __reduce_add_sync(peers, cnt[0]);
+        if (key[0] >= 0 && (threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&tab[key[0]], sum);
+    }
+    #pragma unroll
+    for (int e = 1; e < 4; e++) if (key[e] >= 0) atomicAdd(&tab[key[e]], cnt[e]);
+}
+
+CPB_KERNEL k_vote_finish(LabelTables t, int C, const int* CPB_RESTRICT vote, int* CPB_RESTRICT cell_class) {
+    const int b = blockIdx.x;
+    const int* tab = vote + (size_t)b * t.LC * C;
+    int* cc = cell_class + (size_t)b * t.LC;
+    const int nl = min(t.nlab[b], t.LC - 1);
+    for (int l = threadIdx.x; l <= nl; l += blockDim.x) {
+        int arg = 0;
+        if (l > 0) {
+            int best = tab[l * C];
+            for (int c = 1; c < C; c++) {
+                const int x = tab[l * C + c];
+                if (x > best) { best = x; arg = c; }
+            }
+        }
+        cc[l] = arg;
+    }
+}
+
 // after k_final the image holds ids 1..nlab: shrink the label bound accordingly (vote, border)
 CPB_KERNEL k_finish_bounds(LabelTables t, int B) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;

@@ -104,8 +104,18 @@ CPB_DEVICE double cpb_div9_fast(double x) {
 // (wA + 1 + wB <= 32, a zero column between them) share one pass: same arithmetic per label, half the issue slots.
 struct DiffSub { int l; size_t k; int y0, x0, h, w, coff; };
 
+// Fused flow error: a label whose bbox grown by one pixel holds no pixel of another live label ("clean") never
+// sees foreign T in its gradient and nobody reads its T, so its error is taken straight from the shared-memory
+// tile (same per-pixel arithmetic as k_flow_err) and T is not written to global memory at all.  Labels in
+// contact with another live label write T as before and are left to k_flow_err (t.done stays 0).
+struct DiffQC { const float* dPy; const float* dPx; const int* alive; double threshold; int H; };
+
+CPB_DEVICE bool cpb_foreign_live(int v, int l, const int* CPB_RESTRICT alive) {
+    return v > 0 && v != l && (alive == nullptr || alive[v] != 0);
+}
+
 CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTables& t, double* CPB_RESTRICT Tb,
-                                double* S, const DiffSub& A, const DiffSub& B, bool has_b, int n_it) {
+                                double* S, const DiffSub& A, const DiffSub& B, bool has_b, int n_it, const DiffQC& qc) {
     const int lane = threadIdx.x & 31;
     const bool inA = lane < A.w;
     const bool inB = has_b && lane >= B.coff && lane < B.coff + B.w;
@@ -113,12 +123,36 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
     const bool mine = inA || inB;
     const int col = lane - my.coff;
     const int hj = has_b ? max(A.h, B.h) : A.h;
+    const bool fuse = qc.dPy != nullptr;
     __syncwarp();
     for (int i = lane; i < (hj + 3) * CPB_DC_PITCH; i += 32) S[i] = 0.0;
     unsigned member = 0;               // bit r: pixel (y0+r, x0+col) belongs to this lane's label
-    if (mine)
-        for (int r = 0; r < my.h; r++)
-            if (L[(my.y0 + r) * W + my.x0 + col] == my.l) member |= 1u << r;
+    bool foreign = false;              // a pixel of another live label inside the bbox grown by one
+    if (mine) {
+        const int x = my.x0 + col;
+        for (int r = 0; r < my.h; r++) {
+            const int v = L[(my.y0 + r) * W + x];
+            if (v == my.l) member |= 1u << r;
+            else if (fuse) foreign |= cpb_foreign_live(v, my.l, qc.alive);
+        }
+        if (fuse) {
+            if (my.y0 > 0) foreign |= cpb_foreign_live(L[(my.y0 - 1) * W + x], my.l, qc.alive);
+            if (my.y0 + my.h < qc.H) foreign |= cpb_foreign_live(L[(my.y0 + my.h) * W + x], my.l, qc.alive);
+        }
+    }
+    bool clean[2] = {false, false};
+    if (fuse) {
+        for (int q = 0; q < (has_b ? 2 : 1); q++) {
+            const DiffSub& sub = q ? B : A;
+            bool f = (q ? inB : inA) && foreign;
+            const int y = sub.y0 - 1 + lane;                     // halo columns: lane -> row of the grown bbox
+            if (lane < sub.h + 2 && y >= 0 && y < qc.H) {
+                if (sub.x0 > 0) f |= cpb_foreign_live(L[y * W + sub.x0 - 1], sub.l, qc.alive);
+                if (sub.x0 + sub.w < W) f |= cpb_foreign_live(L[y * W + sub.x0 + sub.w], sub.l, qc.alive);
+            }
+            clean[q] = !__any_sync(CPB_FULL, f);
+        }
+    }
     // centres: member pixel nearest to the mean of (bbox-relative coordinate + 1); first in raster order on ties
     int ci[2] = {0, 0};
     for (int q = 0; q < (has_b ? 2 : 1); q++) {
@@ -178,9 +212,45 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
         }
         __syncwarp();
     }
-    if (mine)
+    const bool my_clean = inB ? clean[1] : clean[0];
+    if (mine && !my_clean)
         for (int r = 0; r < my.h; r++)
             if (member >> r & 1) Tb[(my.y0 + r) * W + my.x0 + col] = own[r * CPB_DC_PITCH];
+    if (!fuse || !(clean[0] || clean[1])) return;
+    // flow error of the clean labels from the tile (non-member cells and the halo hold 0, as global T would)
+    double ey = 0.0, ex = 0.0;
+    if (mine && my_clean) {
+        for (int r = 0; r < my.h; r++) {
+            if (!(member >> r & 1)) continue;
+            const double* c = own + r * CPB_DC_PITCH;
+            const double dy = __dsub_rn(c[CPB_DC_PITCH], c[-CPB_DC_PITCH]);
+            const double dx = __dsub_rn(c[1], c[-1]);
+            const double nrm = __dadd_rn(1e-60, __dsqrt_rn(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx))));
+            const double muy = __ddiv_rn(dy, nrm), mux = __ddiv_rn(dx, nrm);
+            const int pix = (my.y0 + r) * W + my.x0 + col;
+            const double ry = __dsub_rn(muy, (double)__fdiv_rn(qc.dPy[pix], 5.0f));
+            const double rx = __dsub_rn(mux, (double)__fdiv_rn(qc.dPx[pix], 5.0f));
+            ey += __dmul_rn(ry, ry);
+            ex += __dmul_rn(rx, rx);
+        }
+    }
+    for (int q = 0; q < (has_b ? 2 : 1); q++) {
+        if (!clean[q]) continue;                                  // warp-uniform
+        const DiffSub& sub = q ? B : A;
+        const bool in = q ? inB : inA;
+        double sy = in ? ey : 0.0, sx = in ? ex : 0.0;
+        for (int sft = 16; sft; sft >>= 1) {
+            sy += __shfl_xor_sync(CPB_FULL, sy, sft);
+            sx += __shfl_xor_sync(CPB_FULL, sx, sft);
+        }
+        if (lane == 0) {
+            const double c = (double)t.cnt[sub.k];
+            const double e = sy / c + sx / c;
+            t.err[sub.k] = e;
+            t.flag[sub.k] = e > qc.threshold ? 1 : 0;
+            t.done[sub.k] = 1;
+        }
+    }
 }
 
 // a label belongs to the kernel instance whose row capacity is the smallest that holds it
@@ -198,7 +268,7 @@ CPB_DEVICE bool cpb_diffuse_load_sub(const LabelTables& t, int b, int l, int lb,
 template <int MAXH>
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
 k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
-               int niter_override) {
+               int niter_override, const float* CPB_RESTRICT dP, double threshold) {
     CPB_SHARED double s_T[CPB_DW_WARPS][(MAXH + 3) * CPB_DC_PITCH];
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.y, N = H * W;
@@ -207,6 +277,8 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
     double* Tb = T + (size_t)b * N;
     const int n_it = niter_override > 0 ? niter_override : t.niter[b];
     double* S = s_T[warp];
+    const DiffQC qc{dP ? dP + ((size_t)b * 2 + 0) * N : nullptr, dP ? dP + ((size_t)b * 2 + 1) * N : nullptr,
+                    t.alive ? t.alive + (size_t)b * t.LC : nullptr, threshold, H};
     // work item = pair of consecutive labels (2i+1, 2i+2); everything below is warp-uniform
     for (int wi = blockIdx.x * CPB_DW_WARPS + warp; 2 * wi + 1 <= lb; wi += gridDim.x * CPB_DW_WARPS) {
         DiffSub A, B;
@@ -214,10 +286,10 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
         const bool okB = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 2, lb, B);
         if (okA && okB && A.w + 1 + B.w <= CPB_DC_MAXW) {
             B.coff = A.w + 1;
-            cpb_diffuse_job(L, W, t, Tb, S, A, B, true, n_it);
+            cpb_diffuse_job(L, W, t, Tb, S, A, B, true, n_it, qc);
         } else {
-            if (okA) cpb_diffuse_job(L, W, t, Tb, S, A, A, false, n_it);
-            if (okB) cpb_diffuse_job(L, W, t, Tb, S, B, B, false, n_it);
+            if (okA) cpb_diffuse_job(L, W, t, Tb, S, A, A, false, n_it, qc);
+            if (okB) cpb_diffuse_job(L, W, t, Tb, S, B, B, false, n_it, qc);
         }
     }
 }
@@ -248,7 +320,8 @@ CPB_KERNEL k_diffuse_jobs(const int* CPB_RESTRICT lbound, int B, int* CPB_RESTRI
 template <int MAXH>
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
 k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t, double* CPB_RESTRICT T,
-                 int niter_override, const int* CPB_RESTRICT joboff, int* CPB_RESTRICT counter) {
+                 int niter_override, const int* CPB_RESTRICT joboff, int* CPB_RESTRICT counter,
+                 const float* CPB_RESTRICT dP, double threshold) {
     CPB_SHARED double s_T[CPB_DW_WARPS][(MAXH + 3) * CPB_DC_PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = H * W;
@@ -269,15 +342,17 @@ k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t
         const int* L = lab + (size_t)b * N;
         double* Tb = T + (size_t)b * N;
         const int n_it = niter_override > 0 ? niter_override : t.niter[b];
+        const DiffQC qc{dP ? dP + ((size_t)b * 2 + 0) * N : nullptr, dP ? dP + ((size_t)b * 2 + 1) * N : nullptr,
+                        t.alive ? t.alive + (size_t)b * t.LC : nullptr, threshold, H};
         DiffSub A, Bs;
         const bool okA = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 1, lb, A);
         const bool okB = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 2, lb, Bs);
         if (okA && okB && A.w + 1 + Bs.w <= CPB_DC_MAXW) {
             Bs.coff = A.w + 1;
-            cpb_diffuse_job(L, W, t, Tb, S, A, Bs, true, n_it);
+            cpb_diffuse_job(L, W, t, Tb, S, A, Bs, true, n_it, qc);
         } else {
-            if (okA) cpb_diffuse_job(L, W, t, Tb, S, A, A, false, n_it);
-            if (okB) cpb_diffuse_job(L, W, t, Tb, S, Bs, Bs, false, n_it);
+            if (okA) cpb_diffuse_job(L, W, t, Tb, S, A, A, false, n_it, qc);
+            if (okB) cpb_diffuse_job(L, W, t, Tb, S, Bs, Bs, false, n_it, qc);
         }
     }
 }
@@ -412,6 +487,7 @@ k_flow_err(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         if (skip_small && w <= 32) continue;       // handled by k_flow_err_warp
+        if (t.done[k]) continue;                    // error already taken from the diffusion tile (block-uniform)
         double ey = 0.0, ex = 0.0;
         for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
             const int y = y0 + i / w, x = x0 + i % w;

@@ -12,7 +12,7 @@ CPB_KERNEL k_init_tables(LabelTables t) {
     const size_t k = (size_t)b * t.LC + l;
     t.cnt[k] = 0; t.first[k] = CPB_IMAX;
     t.ymin[k] = CPB_IMAX; t.ymax[k] = -1; t.xmin[k] = CPB_IMAX; t.xmax[k] = -1;
-    t.sumy[k] = 0; t.sumx[k] = 0; t.flag[k] = 0;
+    t.sumy[k] = 0; t.sumx[k] = 0; t.flag[k] = 0; t.done[k] = 0;
 }
 
 CPB_KERNEL k_fill_i32(int* p, int n, int v) {

@@ -81,6 +81,9 @@ class _Base:
     def set_follow_merge(self, mode):
         self._calls().lib.cpb_debug_set_follow_merge(int(mode))
 
+    def set_switch(self, which, value):
+        self._calls().lib.cpb_debug_set_switch(int(which), int(value))
+
     def label_offsets(self, counts, base=0):
         a, b = self._calls().label_offsets(self._in(counts), base)
         return _np(a), _np(b)

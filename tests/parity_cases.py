@@ -198,6 +198,29 @@ def case_remove_bad_flow_masks_exact(be):
         np.testing.assert_array_equal(out[0], ref)
 
 
+def case_flow_qc_fused_equals_unfused(be):
+    """Flow error taken inside the diffusion warp (isolated labels) vs k_flow_err on global T (every label), and
+    the job queue vs the static label map: same removal set, errors equal to 1e-12 (summation order differs)."""
+    SW_QUEUE, SW_QC = 1, 2
+    for t in (std_tile(1), std_tile(3), adv_tile(), std_tile(5, H=128, W=128, n_grid=16, axes=(2.5, 3.5))):
+        lab = t["labels"].astype(np.int32)
+        dP = corrupt_flows(t)
+        lcap = int(lab.max()) + 2
+        res = {}
+        try:
+            for queue in (0, 1):
+                for fused in (0, 1):
+                    be.set_switch(SW_QUEUE, queue); be.set_switch(SW_QC, fused)
+                    res[(queue, fused)] = be.remove_bad_flow_masks(c32(lab[None]).copy(), f32(dP[None]), lcap, 0.4, want_err=True)
+        finally:
+            be.set_switch(SW_QUEUE, -1); be.set_switch(SW_QC, -1)
+        out0, err0 = res[(0, 0)]
+        n = int(lab.max())
+        for k, (out, err) in res.items():
+            np.testing.assert_array_equal(out, out0, err_msg=str(k))
+            assert np.abs(err[0, 1:n + 1] - err0[0, 1:n + 1]).max() < 1e-12, k
+
+
 # ------------------------------------------------------------------------------------ (5)
 def nested_rings(H=96, W=96):
     yy, xx = np.mgrid[0:H, 0:W]
@@ -315,6 +338,12 @@ def fused_compare(be, tiles, C, **kw):
     cp = f32(np.stack([t["cellprob"] for t in tiles]))
     lg = f32(np.stack([t["logits"] for t in tiles]))
     masks, counts, cell_class, class_masks = be.compute_masks(dP, cp, lg, want_class_masks=True, **kw)
+    # without the class image the vote rides on the final label pass (k_final_vote_v4): identical results
+    m2, c2, cc2, _ = be.compute_masks(dP, cp, lg, want_class_masks=False, **kw)
+    np.testing.assert_array_equal(m2, masks)
+    np.testing.assert_array_equal(c2, counts)
+    for b in range(B):
+        np.testing.assert_array_equal(cc2[b, :int(counts[b]) + 1], cell_class[b, :int(counts[b]) + 1])
     tp = fp = fn = nref = nnew = 0
     for b, t in enumerate(tiles):
         ref = t["masks_oracle"] if not kw else dynamics.resize_and_compute_masks(t["dP"], t["cellprob"], **kw)
@@ -584,7 +613,7 @@ def case_label_offsets(be):
 
 ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_flows_merge_is_exact, case_get_masks_exact,
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
-             case_remove_bad_flow_masks_exact, case_fill_holes_exact, case_class_vote_reference_vectors,
+             case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_fill_holes_exact, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
              case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
              case_cell_contours_match_cv2, case_prepare_tiles, case_dedup_overlapping_tiles, case_dedup_random_points_components,
