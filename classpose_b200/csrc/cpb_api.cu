@@ -176,10 +176,10 @@ int follow_merge_mode() {
 }
 
 // merge points of k_follow_pool for `niter` Euler steps.  A merge costs about as much as three Euler steps of the
-// whole chunk, so six points where the live count falls fastest beat eleven (measured on B200: 2.59 ms vs 2.89 ms per
-// 1024 conic tiles; 16 points: 3.19 ms); CPB_FOLLOW_SCHEDULE="a,b,c" (step numbers) overrides for experiments
+// whole chunk, so a few points where the live count falls fastest beat many (measured on B200, ms per 1024 conic tiles:
+// 16 points 3.19, 11 points 2.89, 6 points 2.43, 4 points 2.31, 3 points 2.32); CPB_FOLLOW_SCHEDULE="a,b,c" (step numbers) overrides for experiments
 FollowSchedule follow_schedule(int niter) {
-    static const int kPer200[] = {28, 40, 56, 72, 96, 128};
+    static const int kPer200[] = {32, 48, 72, 112};
     FollowSchedule s{};
     static const char* env = getenv("CPB_FOLLOW_SCHEDULE");
     int last = 0;
@@ -333,12 +333,22 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
         // persistent warps pulling label pairs from one queue per size class (see k_diffuse_jobs)
         CPB_LAUNCH_COUNTED(k_diffuse_jobs, dim3(1), dim3(1024), 0, st, w.t.lbound, B, w.jobs, w.jobs + B + 1);
         CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED(k_diffuse_warp_q<CPB_DC_MIDH>, dim3(sm_count() * 8), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                           w.t, w.T, 0, w.jobs, w.jobs + B + 1, qc_dP, thr);
-        CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED(k_diffuse_warp_q<CPB_DC_MAXH>, dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                           w.t, w.T, 0, w.jobs, w.jobs + B + 2, qc_dP, thr);
-        CPB_CHECK_LAUNCH();
+        static const int rows = [] { const char* e = getenv("CPB_DIFFUSE_ROWS"); return (e && e[0] == '2') ? 2 : 4; }();
+        if (rows == 4) {
+            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 4>), dim3(sm_count() * CPB_DQ4_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st,
+                               masks, B, H, W, w.t, w.T, 0, w.jobs, w.jobs + B + 1, qc_dP, thr);
+            CPB_CHECK_LAUNCH();
+            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 4>), dim3(sm_count() * CPB_DQ4_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st,
+                               masks, B, H, W, w.t, w.T, 0, w.jobs, w.jobs + B + 2, qc_dP, thr);
+            CPB_CHECK_LAUNCH();
+        } else {
+            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 2>), dim3(sm_count() * 8), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
+                               w.t, w.T, 0, w.jobs, w.jobs + B + 1, qc_dP, thr);
+            CPB_CHECK_LAUNCH();
+            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 2>), dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
+                               w.t, w.T, 0, w.jobs, w.jobs + B + 2, qc_dP, thr);
+            CPB_CHECK_LAUNCH();
+        }
     } else {
         CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MIDH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
                            H, W, w.t, w.T, 0, qc_dP, thr);

@@ -125,10 +125,53 @@ k_prep_flow_v4(const float4* CPB_RESTRICT dP, const float4* CPB_RESTRICT cellpro
 
 // One Euler step in normalised coordinates, arithmetic order as ATen's grid_sampler_2d.
 // f points at pixel (0,0) of the padded tile; Wp is its row pitch.
+// Packed FP32 (Blackwell FADD2 / FMUL2 / FFMA2 through PTX add/mul/fma.rn.f32x2): the x and y components of a
+// position take the same arithmetic, so one instruction carries both -- each half is an ordinary IEEE
+// round-to-nearest op, bit-identical to the scalar form.  A scalar weight packed as {w, w} is encoded by
+// ptxas as a broadcast operand (R.F32), it costs no move.  The kernel is issue-bound: 28 instead of 39
+// instructions per Euler step.  No packed mul feeds a packed add anywhere (ptxas would contract the pair).
+#ifndef CPB_SIM
+CPB_DEVICE u64 cpb_pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+CPB_DEVICE void cpb_upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+CPB_DEVICE u64 cpb_add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+CPB_DEVICE u64 cpb_sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+CPB_DEVICE u64 cpb_mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+CPB_DEVICE u64 cpb_fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#endif
+
 // WP > 0: row pitch known at compile time (both tap rows are addressed off one base register).
-template <int WP>
+template <int WP, bool PACKED>
 CPB_DEVICE void cpb_euler_step_t(const float2* CPB_RESTRICT f, int Wp_rt, float fH, float fW, float& px, float& py) {
     const int Wp = WP > 0 ? WP : Wp_rt;
+#ifndef CPB_SIM
+  if (PACKED) {
+    // same operations, same order, two lanes (x, y) per instruction
+    const u64 i2 = cpb_fma2(cpb_add2(cpb_pk(px, py), cpb_pk(1.f, 1.f)), cpb_pk(fW, fH), cpb_pk(-0.5f, -0.5f));
+    float ix, iy;
+    cpb_upk(i2, ix, iy);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const u64 f0 = cpb_pk(fx0, fy0);
+    const int idx = (int)fmaf(fy0, (float)Wp, fx0);
+    const u64 f1 = cpb_add2(f0, cpb_pk(1.f, 1.f));
+    const float2* r0 = f + idx;
+    const float2* r1 = r0 + Wp;
+    const float2 vnw = __ldg(r0), vne = __ldg(r0 + 1), vsw = __ldg(r1), vse = __ldg(r1 + 1);
+    float ax1, ay1, ax0, ay0;
+    cpb_upk(cpb_sub2(f1, i2), ax1, ay1);          // (fx1 - ix, fy1 - iy)
+    cpb_upk(cpb_sub2(i2, f0), ax0, ay0);          // (ix - fx0, iy - fy0)
+    const float wnw = __fmul_rn(ax1, ay1), wne = __fmul_rn(ax0, ay1);
+    const float wsw = __fmul_rn(ax1, ay0), wse = __fmul_rn(ax0, ay0);
+    u64 o = cpb_mul2(cpb_pk(vnw.x, vnw.y), cpb_pk(wnw, wnw));   // 0 + v*w
+    o = cpb_fma2(cpb_pk(vne.x, vne.y), cpb_pk(wne, wne), o);
+    o = cpb_fma2(cpb_pk(vsw.x, vsw.y), cpb_pk(wsw, wsw), o);
+    o = cpb_fma2(cpb_pk(vse.x, vse.y), cpb_pk(wse, wse), o);
+    float nx, ny;
+    cpb_upk(cpb_add2(cpb_pk(px, py), o), nx, ny);
+    px = fminf(fmaxf(nx, -1.f), 1.f);
+    py = fminf(fmaxf(ny, -1.f), 1.f);
+    return;
+  }
+#endif
     // ATen: ix = ((x + 1) * W - 1) / 2, which nvcc contracts to fma(x + 1, W, -1) * 0.5.  Scaling by 0.5 commutes
     // with rounding, so fma(x + 1, W/2, -0.5) is the same float with one instruction less (fH, fW arrive halved).
     const float ix = fmaf(px + 1.f, fW, -0.5f);
@@ -145,14 +188,14 @@ CPB_DEVICE void cpb_euler_step_t(const float2* CPB_RESTRICT f, int Wp_rt, float 
     const float wsw = (fx1 - ix) * (iy - fy0);
     const float wse = (ix - fx0) * (iy - fy0);
     float ox = vnw.x * wnw, oy = vnw.y * wnw;   // 0 + v*w
-    ox += vne.x * wne; oy += vne.y * wne;
-    ox += vsw.x * wsw; oy += vsw.y * wsw;
-    ox += vse.x * wse; oy += vse.y * wse;
+    ox = fmaf(vne.x, wne, ox); oy = fmaf(vne.y, wne, oy);
+    ox = fmaf(vsw.x, wsw, ox); oy = fmaf(vsw.y, wsw, oy);
+    ox = fmaf(vse.x, wse, ox); oy = fmaf(vse.y, wse, oy);
     px = fminf(fmaxf(px + ox, -1.f), 1.f);
     py = fminf(fmaxf(py + oy, -1.f), 1.f);
 }
 CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int Wp, float fH, float fW, float& px, float& py) {
-    cpb_euler_step_t<0>(f, Wp, fH, fW, px, py);
+    cpb_euler_step_t<0, false>(f, Wp, fH, fW, px, py);      // scalar form: k_follow / k_follow_merge are the A/B references
 }
 
 // k_follow: grid-stride over the compacted foreground list, one pixel per thread.
@@ -440,7 +483,7 @@ k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list
 #ifndef CPB_SIM
                 asm volatile("" : "+l"(f));
 #endif
-                for (int s = step; s < until; s++) cpb_euler_step_t<WP>(f, Wp, fH, fW, p.x, p.y);
+                for (int s = step; s < until; s++) cpb_euler_step_t<WP, true>(f, Wp, fH, fW, p.x, p.y);
                 s_pos[i] = p;
             }
             step = until;

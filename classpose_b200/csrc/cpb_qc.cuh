@@ -114,6 +114,7 @@ CPB_DEVICE bool cpb_foreign_live(int v, int l, const int* CPB_RESTRICT alive) {
     return v > 0 && v != l && (alive == nullptr || alive[v] != 0);
 }
 
+template <int R>      // rows per step of the sliding window (independent add chains in flight per lane)
 CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTables& t, double* CPB_RESTRICT Tb,
                                 double* S, const DiffSub& A, const DiffSub& B, bool has_b, int n_it, const DiffQC& qc) {
     const int lane = threadIdx.x & 31;
@@ -125,7 +126,7 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
     const int hj = has_b ? max(A.h, B.h) : A.h;
     const bool fuse = qc.dPy != nullptr;
     __syncwarp();
-    for (int i = lane; i < (hj + 3) * CPB_DC_PITCH; i += 32) S[i] = 0.0;
+    for (int i = lane; i < (hj + R + 1) * CPB_DC_PITCH; i += 32) S[i] = 0.0;
     unsigned member = 0;               // bit r: pixel (y0+r, x0+col) belongs to this lane's label
     bool foreign = false;              // a pixel of another live label inside the bbox grown by one
     if (mine) {
@@ -188,27 +189,38 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
     for (int it = 0; it < n_it; it++) {
         if (lane == 0) { S[ci[0]] += 1.0; if (has_b) S[ci[1]] += 1.0; }   // T[centre] += 1 before averaging
         __syncwarp();
-        double uL = p[0], uC = p[1], uR = p[2];
-        double cL = p[CPB_DC_PITCH], cC = p[CPB_DC_PITCH + 1], cR = p[CPB_DC_PITCH + 2];
-        for (int r = 0; r < hj; r += 2) {
+        // win[k] = row r-1+k of the tile (left, centre, right of this lane's column)
+        double win[R + 2][3];
+        #pragma unroll
+        for (int k = 0; k < 2; k++) {
+            win[k][0] = p[k * CPB_DC_PITCH]; win[k][1] = p[k * CPB_DC_PITCH + 1]; win[k][2] = p[k * CPB_DC_PITCH + 2];
+        }
+        for (int r = 0; r < hj; r += R) {
             const double* q = p + (r + 2) * CPB_DC_PITCH;
-            const double dL = q[0], dC = q[1], dR = q[2];                                   // row r+1
-            const double eL = q[CPB_DC_PITCH], eC = q[CPB_DC_PITCH + 1], eR = q[CPB_DC_PITCH + 2];   // row r+2
-            // self, up, down, left, right, up-left, up-right, down-left, down-right
-            double s0 = __dadd_rn(cC, uC), s1 = __dadd_rn(dC, cC);
-            s0 = __dadd_rn(s0, dC); s1 = __dadd_rn(s1, eC);
-            s0 = __dadd_rn(s0, cL); s1 = __dadd_rn(s1, dL);
-            s0 = __dadd_rn(s0, cR); s1 = __dadd_rn(s1, dR);
-            s0 = __dadd_rn(s0, uL); s1 = __dadd_rn(s1, cL);
-            s0 = __dadd_rn(s0, uR); s1 = __dadd_rn(s1, cR);
-            s0 = __dadd_rn(s0, dL); s1 = __dadd_rn(s1, eL);
-            s0 = __dadd_rn(s0, dR); s1 = __dadd_rn(s1, eR);
-            const double v0 = cpb_div9_fast(s0), v1 = cpb_div9_fast(s1);
-            __syncwarp();              // every lane holds rows r .. r+2 before rows r, r+1 are overwritten
-            if (member >> r & 1) own[r * CPB_DC_PITCH] = v0;
-            if (member >> (r + 1) & 1) own[(r + 1) * CPB_DC_PITCH] = v1;
-            uL = dL; uC = dC; uR = dR;
-            cL = eL; cC = eC; cR = eR;
+            #pragma unroll
+            for (int k = 0; k < R; k++) {                       // rows r+1 .. r+R
+                win[k + 2][0] = q[k * CPB_DC_PITCH]; win[k + 2][1] = q[k * CPB_DC_PITCH + 1]; win[k + 2][2] = q[k * CPB_DC_PITCH + 2];
+            }
+            double v[R];
+            #pragma unroll
+            for (int k = 0; k < R; k++) {
+                // self, up, down, left, right, up-left, up-right, down-left, down-right
+                double s0 = __dadd_rn(win[k + 1][1], win[k][1]);
+                s0 = __dadd_rn(s0, win[k + 2][1]);
+                s0 = __dadd_rn(s0, win[k + 1][0]);
+                s0 = __dadd_rn(s0, win[k + 1][2]);
+                s0 = __dadd_rn(s0, win[k][0]);
+                s0 = __dadd_rn(s0, win[k][2]);
+                s0 = __dadd_rn(s0, win[k + 2][0]);
+                s0 = __dadd_rn(s0, win[k + 2][2]);
+                v[k] = cpb_div9_fast(s0);
+            }
+            __syncwarp();              // every lane holds rows r-1 .. r+R before rows r .. r+R-1 are overwritten
+            #pragma unroll
+            for (int k = 0; k < R; k++)
+                if (member >> (r + k) & 1) own[(r + k) * CPB_DC_PITCH] = v[k];
+            #pragma unroll
+            for (int k = 0; k < 2; k++) { win[k][0] = win[R + k][0]; win[k][1] = win[R + k][1]; win[k][2] = win[R + k][2]; }
         }
         __syncwarp();
     }
@@ -270,6 +282,7 @@ CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
 k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                int niter_override, const float* CPB_RESTRICT dP, double threshold) {
     CPB_SHARED double s_T[CPB_DW_WARPS][(MAXH + 3) * CPB_DC_PITCH];
+    constexpr int R = 2;
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.y, N = H * W;
     const int lb = t.lbound[b];
@@ -286,10 +299,10 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
         const bool okB = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 2, lb, B);
         if (okA && okB && A.w + 1 + B.w <= CPB_DC_MAXW) {
             B.coff = A.w + 1;
-            cpb_diffuse_job(L, W, t, Tb, S, A, B, true, n_it, qc);
+            cpb_diffuse_job<R>(L, W, t, Tb, S, A, B, true, n_it, qc);
         } else {
-            if (okA) cpb_diffuse_job(L, W, t, Tb, S, A, A, false, n_it, qc);
-            if (okB) cpb_diffuse_job(L, W, t, Tb, S, B, B, false, n_it, qc);
+            if (okA) cpb_diffuse_job<R>(L, W, t, Tb, S, A, A, false, n_it, qc);
+            if (okB) cpb_diffuse_job<R>(L, W, t, Tb, S, B, B, false, n_it, qc);
         }
     }
 }
@@ -317,12 +330,15 @@ CPB_KERNEL k_diffuse_jobs(const int* CPB_RESTRICT lbound, int B, int* CPB_RESTRI
     if (threadIdx.x == 0) joboff[B] = s_base;
 }
 
-template <int MAXH>
-CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
+#ifndef CPB_DQ4_MINBLOCKS
+#define CPB_DQ4_MINBLOCKS 6
+#endif
+template <int MAXH, int R>
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (R == 4 ? CPB_DQ4_MINBLOCKS : (MAXH == CPB_DC_MIDH ? 8 : 6)))
 k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                  int niter_override, const int* CPB_RESTRICT joboff, int* CPB_RESTRICT counter,
                  const float* CPB_RESTRICT dP, double threshold) {
-    CPB_SHARED double s_T[CPB_DW_WARPS][(MAXH + 3) * CPB_DC_PITCH];
+    CPB_SHARED double s_T[CPB_DW_WARPS][((MAXH + R - 1) / R * R + R + 1) * CPB_DC_PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = H * W;
     const int total = joboff[B];
@@ -349,10 +365,10 @@ k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t
         const bool okB = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 2, lb, Bs);
         if (okA && okB && A.w + 1 + Bs.w <= CPB_DC_MAXW) {
             Bs.coff = A.w + 1;
-            cpb_diffuse_job(L, W, t, Tb, S, A, Bs, true, n_it, qc);
+            cpb_diffuse_job<R>(L, W, t, Tb, S, A, Bs, true, n_it, qc);
         } else {
-            if (okA) cpb_diffuse_job(L, W, t, Tb, S, A, A, false, n_it, qc);
-            if (okB) cpb_diffuse_job(L, W, t, Tb, S, Bs, Bs, false, n_it, qc);
+            if (okA) cpb_diffuse_job<R>(L, W, t, Tb, S, A, A, false, n_it, qc);
+            if (okB) cpb_diffuse_job<R>(L, W, t, Tb, S, Bs, Bs, false, n_it, qc);
         }
     }
 }
