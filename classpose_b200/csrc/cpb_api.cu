@@ -93,7 +93,7 @@ struct Workspace {
     int* sinv;           // [B*LC]
     int* alive;          // [B*LC]
     int* vote;           // [B*LC*C]
-    int* jobs;           // [B+1] diffusion job offsets, then 2 queue counters
+    int* jobs;           // [B+1] diffusion job offsets, then 4 queue counters
     LabelTables t;
     size_t bytes;
     Prof* prof;          // optional stage timing
@@ -120,7 +120,7 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     w.sinv = c.take<int>(BL);
     w.alive = c.take<int>(BL);
     w.vote = c.take<int>(C > 0 ? BL * C : 0);
-    w.jobs = c.take<int>((size_t)B + 1 + 2);
+    w.jobs = c.take<int>((size_t)B + 1 + 4);
     LabelTables& t = w.t;
     t.LC = LC;
     t.cnt = c.take<int>(BL); t.first = c.take<int>(BL);
@@ -179,7 +179,7 @@ int follow_merge_mode() {
 // whole chunk, so a few points where the live count falls fastest beat many (measured on B200, ms per 1024 conic tiles:
 // 16 points 3.19, 11 points 2.89, 6 points 2.43, 4 points 2.31, 3 points 2.32); CPB_FOLLOW_SCHEDULE="a,b,c" (step numbers) overrides for experiments
 FollowSchedule follow_schedule(int niter) {
-    static const int kPer200[] = {32, 48, 72, 112};
+    static const int kPer200[] = {36, 56, 88, 136};
     FollowSchedule s{};
     static const char* env = getenv("CPB_FOLLOW_SCHEDULE");
     int last = 0;
@@ -205,7 +205,8 @@ FollowSchedule follow_schedule(int niter) {
 //   CPB_DIFFUSE_QUEUE=0  static (block, warp) -> label map instead of the job queue
 //   CPB_QC_FUSED=0       every label's flow error from T in global memory (k_flow_err) instead of the diffusion tile
 //   CPB_VOTE_FUSED=0     class vote as its own pass over the finished label image
-std::atomic<int> g_switch[4] = {{-1}, {-1}, {-1}, {-1}};
+//   CPB_DIFFUSE_REG=0    diffusion on the shared-memory tile for every nucleus-sized label (no register-resident columns)
+std::atomic<int> g_switch[5] = {{-1}, {-1}, {-1}, {-1}, {-1}};
 bool switch_on(int which, const char* env_name) {
     int v = g_switch[which].load(std::memory_order_relaxed);
     if (v < 0) {
@@ -217,6 +218,7 @@ bool switch_on(int which, const char* env_name) {
 bool diffuse_queue_enabled() { return switch_on(CPB_SWITCH_DIFFUSE_QUEUE, "CPB_DIFFUSE_QUEUE"); }
 bool qc_fused_enabled() { return switch_on(CPB_SWITCH_QC_FUSED, "CPB_QC_FUSED"); }
 bool vote_fused_enabled() { return switch_on(CPB_SWITCH_VOTE_FUSED, "CPB_VOTE_FUSED"); }
+bool diffuse_reg_enabled() { return switch_on(CPB_SWITCH_DIFFUSE_REG, "CPB_DIFFUSE_REG"); }
 
 #define CPB_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
@@ -245,25 +247,28 @@ int run_map_stats(const Workspace& w, int32_t* lab, int B, int H, int W, int nch
     return 0;
 }
 
+// zero_out != NULL (fused path): the prep kernel zeroes that label image instead of marking background in p_final
 int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B, int H, int W, int niter,
-               float thr, int32_t* pfinal, float* pfloat, int* hist, cudaStream_t st) {
+               float thr, int32_t* pfinal, float* pfloat, int* hist, cudaStream_t st, int32_t* zero_out = nullptr) {
     const long long BN = (long long)B * H * W;
     prof_begin(w.prof, S_PREP);
     cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
     if (hist) cudaMemsetAsync(hist, 0, BN * sizeof(int), st);
     const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
+    int32_t* bg_out = zero_out ? zero_out : pfinal;
+    const int bg_value = zero_out ? 0 : -1;
     const bool vec4 = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(dP) % 16 == 0) &&
-                      (reinterpret_cast<uintptr_t>(cellprob) % 16 == 0) && (reinterpret_cast<uintptr_t>(pfinal) % 16 == 0);
+                      (reinterpret_cast<uintptr_t>(cellprob) % 16 == 0) && (reinterpret_cast<uintptr_t>(bg_out) % 16 == 0);
     if (vec4) {
         const int patch = (W % 64 == 0) ? 1 : 0;
         const long long nblk = patch ? (long long)B * ((H + 2 + 15) / 16) * (W / 64)
                                      : (long long)blocks_for((long long)B * (H + 2) * (W / 4), 256);
         CPB_LAUNCH_COUNTED(k_prep_flow_v4, dim3((unsigned)nblk), dim3(256), 0, st,
                            reinterpret_cast<const float4*>(dP), reinterpret_cast<const float4*>(cellprob), B, H, W, thr, sx,
-                           sy, reinterpret_cast<float4*>(w.flow), reinterpret_cast<int4*>(pfinal), w.list, w.list_n, patch);
+                           sy, reinterpret_cast<float4*>(w.flow), reinterpret_cast<int4*>(bg_out), w.list, w.list_n, patch, bg_value);
     } else {
         CPB_LAUNCH_COUNTED(k_prep_flow, dim3(blocks_for((long long)B * (H + 2) * (W + 2 * CPB_FLOW_PADX), 256)), dim3(256),
-                           0, st, dP, cellprob, B, H, W, thr, sx, sy, w.flow, pfinal, w.list, w.list_n);
+                           0, st, dP, cellprob, B, H, W, thr, sx, sy, w.flow, bg_out, w.list, w.list_n, bg_value);
     }
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_PREP);
@@ -301,13 +306,12 @@ int run_get_masks(const Workspace& w, const int32_t* pfinal, int B, int H, int W
                   int32_t* counts, cudaStream_t st) {
     const long long BN = (long long)B * H * W;
     prof_begin(w.prof, S_SEEDS);
-    cudaMemsetAsync(w.M, 0, BN * sizeof(int), st);
-    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(table_threads(H, W)), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.M, w.t.lbound);
+    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(table_threads(H, W)), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.t.lbound);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_SEEDS);
     prof_begin(w.prof, S_LOOKUP);
     int e = run_init_tables(w, B, st); if (e) return e;
-    CPB_LAUNCH_COUNTED(k_lookup, dim3(blocks_for(BN, 256)), dim3(256), 0, st, pfinal, w.M, B, H, W, masks, w.t);
+    CPB_LAUNCH_COUNTED(k_lookup, dim3(blocks_for(BN, 256)), dim3(256), 0, st, pfinal, (const int*)w.hist, B, H, W, masks, w.t);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_LOOKUP);
     ProfScope ps(w.prof, S_FINALIZE);
@@ -333,20 +337,28 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
         // persistent warps pulling label pairs from one queue per size class (see k_diffuse_jobs)
         CPB_LAUNCH_COUNTED(k_diffuse_jobs, dim3(1), dim3(1024), 0, st, w.t.lbound, B, w.jobs, w.jobs + B + 1);
         CPB_CHECK_LAUNCH();
-        static const int rows = [] { const char* e = getenv("CPB_DIFFUSE_ROWS"); return (e && e[0] == '2') ? 2 : 4; }();
-        if (rows == 4) {
-            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 4>), dim3(sm_count() * CPB_DQ4_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st,
-                               masks, B, H, W, w.t, w.T, 0, w.jobs, w.jobs + B + 1, qc_dP, thr);
+        int* ctr = w.jobs + B + 1;
+        if (diffuse_reg_enabled()) {
+            // register-resident columns for bboxes up to 24 x 30 (two row classes); the shared-memory kernel takes
+            // what is left of the 30 x 32 range
+            static const bool two_classes = [] { const char* e = getenv("CPB_DIFFUSE_REG_CLASSES"); return !(e && e[0] == '1'); }();
+            if (two_classes) {
+                CPB_LAUNCH_COUNTED(k_diffuse_reg<16>, dim3(sm_count() * CPB_DR16_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st, masks,
+                                   B, H, W, w.t, w.T, 0, w.jobs, ctr + 0, qc_dP, thr, 0);
+                CPB_CHECK_LAUNCH();
+            }
+            CPB_LAUNCH_COUNTED(k_diffuse_reg<24>, dim3(sm_count() * CPB_DR24_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st, masks, B,
+                               H, W, w.t, w.T, 0, w.jobs, ctr + 1, qc_dP, thr, two_classes ? 16 : 0);
             CPB_CHECK_LAUNCH();
-            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 4>), dim3(sm_count() * CPB_DQ4_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st,
-                               masks, B, H, W, w.t, w.T, 0, w.jobs, w.jobs + B + 2, qc_dP, thr);
+            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 2>), dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
+                               w.t, w.T, 0, w.jobs, ctr + 2, qc_dP, thr, 1);
             CPB_CHECK_LAUNCH();
         } else {
             CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 2>), dim3(sm_count() * 8), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                               w.t, w.T, 0, w.jobs, w.jobs + B + 1, qc_dP, thr);
+                               w.t, w.T, 0, w.jobs, ctr + 0, qc_dP, thr, 0);
             CPB_CHECK_LAUNCH();
             CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 2>), dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                               w.t, w.T, 0, w.jobs, w.jobs + B + 2, qc_dP, thr);
+                               w.t, w.T, 0, w.jobs, ctr + 1, qc_dP, thr, 0);
             CPB_CHECK_LAUNCH();
         }
     } else {
@@ -542,21 +554,19 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     int e;
     const long long BN = (long long)B * H * W;
     // (2) Euler integration + end-point histogram
-    e = run_follow(w, dP, cellprob, B, H, W, prm->niter, prm->cellprob_threshold, w.pfinal, nullptr, w.hist, st);
+    e = run_follow(w, dP, cellprob, B, H, W, prm->niter, prm->cellprob_threshold, w.pfinal, nullptr, w.hist, st, masks);
     if (e) return e;
     // (3) seeds -> raw labels (seed order + 1) and their statistics; ids after get_masks live in t.remap
     prof_begin(w.prof, S_SEEDS);
-    cudaMemsetAsync(w.M, 0, BN * sizeof(int), st);
-    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(table_threads(H, W)), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.M, w.t.lbound);
+    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(table_threads(H, W)), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.t.lbound);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_SEEDS);
     prof_begin(w.prof, S_LOOKUP);
     e = run_init_tables(w, B, st); if (e) return e;
-    cudaMemsetAsync(masks, 0, BN * sizeof(int), st);
-    cudaMemsetAsync(w.t.misc, 0, B * sizeof(int), st);
+    cudaMemsetAsync(w.t.misc, 0, B * sizeof(int), st);      // (the label image was zeroed by the prep kernel)
     {
         const unsigned grid = (unsigned)std::min<long long>(blocks_for(BN, 256), (long long)sm_count() * 8);
-        CPB_LAUNCH_COUNTED(k_lookup_list, dim3(grid), dim3(256), 0, st, w.list, w.list_n, w.pfinal, w.M, H, W, masks, w.t);
+        CPB_LAUNCH_COUNTED(k_lookup_list, dim3(grid), dim3(256), 0, st, w.list, w.list_n, w.pfinal, (const int*)w.hist, H, W, masks, w.t);
         CPB_CHECK_LAUNCH();
     }
     prof_end(w.prof, S_LOOKUP);
@@ -660,7 +670,7 @@ const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames
 void cpb_debug_set_follow_merge(int mode) { g_follow_merge.store(mode, std::memory_order_relaxed); }
 void cpb_debug_set_switch(int which, int value) {
     if (which == CPB_SWITCH_FOLLOW_MERGE) g_follow_merge.store(value, std::memory_order_relaxed);
-    else if (which > 0 && which < 4) g_switch[which].store(value, std::memory_order_relaxed);
+    else if (which > 0 && which < 5) g_switch[which].store(value, std::memory_order_relaxed);
 }
 long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

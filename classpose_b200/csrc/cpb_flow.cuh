@@ -20,12 +20,13 @@ CPB_DEVICE float2 cpb_scaled_flow(float dy, float dx, bool fg, float sx, float s
     return make_float2(__fmul_rn(__fdiv_rn(__fmul_rn(dx, m), 5.0f), sx), __fmul_rn(__fdiv_rn(__fmul_rn(dy, m), 5.0f), sy));
 }
 
-// k_prep_flow: one thread per padded pixel (any W).  Also writes p_final = -1 on background and appends
+// k_prep_flow: one thread per padded pixel (any W).  Also writes bg_value on background (-1: the p_final contract;
+// 0: the fused path points `pfinal` at the label image, which saves zeroing it separately) and appends
 // foreground pixels to `list` (global pixel index in the un-padded layout), block-contiguous.
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, int B, int H, int W,
             float thr, float sx, float sy, float2* CPB_RESTRICT flow, int* CPB_RESTRICT pfinal,
-            unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n) {
+            unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n, int bg_value) {
     CPB_SHARED int s_scan[33];
     CPB_SHARED unsigned s_base;
     const int N = H * W, Wp = W + 2 * CPB_FLOW_PADX, Np = (H + 2) * Wp;
@@ -43,7 +44,7 @@ k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, in
             gi = (unsigned)b * (unsigned)N + (unsigned)r;
             fg = cellprob[gi] > thr;
             out = cpb_scaled_flow(dP[((size_t)b * 2 + 0) * N + r], dP[((size_t)b * 2 + 1) * N + r], fg, sx, sy);
-            if (!fg) pfinal[gi] = -1;
+            if (!fg || bg_value == 0) pfinal[gi] = bg_value;
         }
         flow[gp] = out;
     }
@@ -59,7 +60,7 @@ k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, in
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_prep_flow_v4(const float4* CPB_RESTRICT dP, const float4* CPB_RESTRICT cellprob, int B, int H, int W,
                float thr, float sx, float sy, float4* CPB_RESTRICT flow, int4* CPB_RESTRICT pfinal,
-               unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n, int patch) {
+               unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n, int patch, int bg_value) {
     CPB_SHARED int s_scan[33];
     CPB_SHARED unsigned s_base;
     const int W4 = W >> 2, N4 = (H * W) >> 2;
@@ -103,7 +104,7 @@ k_prep_flow_v4(const float4* CPB_RESTRICT dP, const float4* CPB_RESTRICT cellpro
             o0 = make_float4(a0.x, a0.y, a1.x, a1.y);
             o1 = make_float4(a2.x, a2.y, a3.x, a3.y);
             gi0 = (unsigned)b * (unsigned)(H * W) + (unsigned)(q << 2);
-            pfinal[(size_t)b * N4 + q] = make_int4(f0 ? 0 : -1, f1 ? 0 : -1, f2 ? 0 : -1, f3 ? 0 : -1);
+            pfinal[(size_t)b * N4 + q] = make_int4(f0 ? 0 : bg_value, f1 ? 0 : bg_value, f2 ? 0 : bg_value, f3 ? 0 : bg_value);
             nfg = (int)f0 + (int)f1 + (int)f2 + (int)f3;
         }
         row[1 + 2 * xg] = o0;                                   // pixels 4xg, 4xg+1  (padded x = 4xg + 2)
@@ -140,8 +141,15 @@ CPB_DEVICE u64 cpb_fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, 
 #endif
 
 // WP > 0: row pitch known at compile time (both tap rows are addressed off one base register).
+// The four taps of the previous step: a trajectory that has reached its sink keeps sampling the same 2 x 2 cell
+// (sub-pixel steps), so the gathers -- the L1 data pipe is the busiest unit of the packed kernel, ~3 wavefronts per
+// scattered 8-byte load -- are skipped while the tap index does not change.  Same values, same arithmetic.
+struct EulerTaps { int key; float2 nw, ne, sw, se; };
+#define CPB_TAPS_NONE 0x7fffffff
+
 template <int WP, bool PACKED>
-CPB_DEVICE void cpb_euler_step_t(const float2* CPB_RESTRICT f, int Wp_rt, float fH, float fW, float& px, float& py) {
+CPB_DEVICE void cpb_euler_step_t(const float2* CPB_RESTRICT f, int Wp_rt, float fH, float fW, float& px, float& py,
+                                 EulerTaps& tp) {
     const int Wp = WP > 0 ? WP : Wp_rt;
 #ifndef CPB_SIM
   if (PACKED) {
@@ -151,20 +159,25 @@ CPB_DEVICE void cpb_euler_step_t(const float2* CPB_RESTRICT f, int Wp_rt, float 
     cpb_upk(i2, ix, iy);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const u64 f0 = cpb_pk(fx0, fy0);
-    const int idx = (int)fmaf(fy0, (float)Wp, fx0);
+    // tap index: fy0 * Wp + fx0 is an exact small integer; adding 1.5 * 2^23 leaves it in the low mantissa bits, so
+    // the float -> int conversion (XU pipe) becomes an FADD.  `f` arrives biased by -0x4B400000 elements.
+    const int key = __float_as_int(fmaf(fy0, (float)Wp, fx0 + 12582912.f));
     const u64 f1 = cpb_add2(f0, cpb_pk(1.f, 1.f));
-    const float2* r0 = f + idx;
-    const float2* r1 = r0 + Wp;
-    const float2 vnw = __ldg(r0), vne = __ldg(r0 + 1), vsw = __ldg(r1), vse = __ldg(r1 + 1);
+    if (key != tp.key) {
+        const float2* r0 = f + key;
+        const float2* r1 = r0 + Wp;
+        tp.nw = __ldg(r0); tp.ne = __ldg(r0 + 1); tp.sw = __ldg(r1); tp.se = __ldg(r1 + 1);
+        tp.key = key;
+    }
     float ax1, ay1, ax0, ay0;
     cpb_upk(cpb_sub2(f1, i2), ax1, ay1);          // (fx1 - ix, fy1 - iy)
     cpb_upk(cpb_sub2(i2, f0), ax0, ay0);          // (ix - fx0, iy - fy0)
     const float wnw = __fmul_rn(ax1, ay1), wne = __fmul_rn(ax0, ay1);
     const float wsw = __fmul_rn(ax1, ay0), wse = __fmul_rn(ax0, ay0);
-    u64 o = cpb_mul2(cpb_pk(vnw.x, vnw.y), cpb_pk(wnw, wnw));   // 0 + v*w
-    o = cpb_fma2(cpb_pk(vne.x, vne.y), cpb_pk(wne, wne), o);
-    o = cpb_fma2(cpb_pk(vsw.x, vsw.y), cpb_pk(wsw, wsw), o);
-    o = cpb_fma2(cpb_pk(vse.x, vse.y), cpb_pk(wse, wse), o);
+    u64 o = cpb_mul2(cpb_pk(tp.nw.x, tp.nw.y), cpb_pk(wnw, wnw));   // 0 + v*w
+    o = cpb_fma2(cpb_pk(tp.ne.x, tp.ne.y), cpb_pk(wne, wne), o);
+    o = cpb_fma2(cpb_pk(tp.sw.x, tp.sw.y), cpb_pk(wsw, wsw), o);
+    o = cpb_fma2(cpb_pk(tp.se.x, tp.se.y), cpb_pk(wse, wse), o);
     float nx, ny;
     cpb_upk(cpb_add2(cpb_pk(px, py), o), nx, ny);
     px = fminf(fmaxf(nx, -1.f), 1.f);
@@ -172,6 +185,7 @@ CPB_DEVICE void cpb_euler_step_t(const float2* CPB_RESTRICT f, int Wp_rt, float 
     return;
   }
 #endif
+    (void)tp;
     // ATen: ix = ((x + 1) * W - 1) / 2, which nvcc contracts to fma(x + 1, W, -1) * 0.5.  Scaling by 0.5 commutes
     // with rounding, so fma(x + 1, W/2, -0.5) is the same float with one instruction less (fH, fW arrive halved).
     const float ix = fmaf(px + 1.f, fW, -0.5f);
@@ -195,7 +209,8 @@ CPB_DEVICE void cpb_euler_step_t(const float2* CPB_RESTRICT f, int Wp_rt, float 
     py = fminf(fmaxf(py + oy, -1.f), 1.f);
 }
 CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int Wp, float fH, float fW, float& px, float& py) {
-    cpb_euler_step_t<0, false>(f, Wp, fH, fW, px, py);      // scalar form: k_follow / k_follow_merge are the A/B references
+    EulerTaps unused;
+    cpb_euler_step_t<0, false>(f, Wp, fH, fW, px, py, unused);   // scalar form: k_follow / k_follow_merge are the A/B references
 }
 
 // k_follow: grid-stride over the compacted foreground list, one pixel per thread.
@@ -481,9 +496,12 @@ k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list
                 float2 p = s_pos[i];
                 const float2* f = flow + (size_t)s_tile[i] * Np + Wp + CPB_FLOW_PADX;
 #ifndef CPB_SIM
+                f -= 0x4B400000;       // bias of the FADD-based tap index (see cpb_euler_step_t)
                 asm volatile("" : "+l"(f));
 #endif
-                for (int s = step; s < until; s++) cpb_euler_step_t<WP, true>(f, Wp, fH, fW, p.x, p.y);
+                EulerTaps tp;
+                tp.key = CPB_TAPS_NONE;
+                for (int s = step; s < until; s++) cpb_euler_step_t<WP, true>(f, Wp, fH, fW, p.x, p.y, tp);
                 s_pos[i] = p;
             }
             step = until;

@@ -23,7 +23,7 @@ k_lookup_list(const unsigned* CPB_RESTRICT list, const unsigned* CPB_RESTRICT li
             b = (int)(gi / (unsigned)N);
             r = (int)(gi - (unsigned)b * (unsigned)N);
             const int pf = pfinal[gi];
-            l = M[(size_t)b * N + (pf >> 16) * W + (pf & 0xffff)];
+            l = max(-M[(size_t)b * N + (pf >> 16) * W + (pf & 0xffff)], 0);      // painted histogram, see k_seeds
             lab[gi] = l;
             y = r / W; x = r - y * W;
         }
@@ -247,7 +247,7 @@ k_final_vote_v4(int4* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, const f
     }
     int* tab = vote + (size_t)b * t.LC * C;
     // first key of every lane: one atomic per distinct (tile, key) of the warp
-    {
+    if (__any_sync(CPB_FULL, key[0] >= 0)) {
         const long long wkey = key[0] >= 0 ? (long long)b * ((long long)t.LC * C) + key[0] : -1;
         const unsigned peers = __match_any_sync(CPB_FULL, wkey);
         const int sum = __reduce_add_sync(peers, cnt[0]);

@@ -38,10 +38,19 @@ CPB_DEVICE int cpb_hist_at(const int* CPB_RESTRICT h, int H, int W, int y, int x
 //  1. seeds = pixels with h > 10 that equal the maximum of their 5x5 neighbourhood
 //  2. order: ascending count, ties by raster position (stable sort of a raster-ordered list)
 //  3. each seed grows inside its 11x11 window: 5 x { 3x3 dilation ; &= h > 2 }
-//  4. paint label = order+1; later (larger) labels overwrite -> atomicMax
+//  4. paint label = order+1; later (larger) labels overwrite.  The labels are painted INTO the histogram as
+//     negative numbers (atomicMin of -label): only pixels with h > 2 are ever painted and the only reads that
+//     follow are "h > 2" tests, which a painted pixel passes by construction -- so no separate label plane has to
+//     be zeroed, written and read.  Afterwards hist[p] < 0 means label -hist[p], anything else label 0.
+CPB_DEVICE bool cpb_hist_grow_ok(const int* h, int H, int W, int y, int x) {
+    if (!(y >= 0 && y < H && x >= 0 && x < W)) return false;
+    const int v = h[y * W + x];
+    return v > CPB_GROW_MIN || v < 0;
+}
+
 CPB_KERNEL CPB_LAUNCH_BOUNDS(1024, 1)
-k_seeds(const int* CPB_RESTRICT hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
-        int* CPB_RESTRICT seed_lab, int* CPB_RESTRICT M, int* CPB_RESTRICT nseeds) {
+k_seeds(int* hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
+        int* CPB_RESTRICT seed_lab, int* CPB_RESTRICT nseeds) {
     CPB_SHARED int s_n;
     CPB_SHARED u64 s_keys[CPB_RANK_CHUNK];
     const int b = blockIdx.x;
@@ -49,7 +58,7 @@ k_seeds(const int* CPB_RESTRICT hist, int H, int W, int LC, u64* CPB_RESTRICT se
     const int* h = hist + (size_t)b * N;
     u64* keys = seed_key + (size_t)b * LC;
     int* labs = seed_lab + (size_t)b * LC;
-    int* Mb = M + (size_t)b * N;
+    int* Mb = hist + (size_t)b * N;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     // the histogram is almost everywhere 0: scan it with 128-bit loads when the tile allows
@@ -95,7 +104,7 @@ k_seeds(const int* CPB_RESTRICT hist, int H, int W, int LC, u64* CPB_RESTRICT se
         unsigned allowed = 0;
         if (lane < 11)
             for (int c = 0; c < 11; c++)
-                if (cpb_hist_at(h, H, W, y, sx - 5 + c) > CPB_GROW_MIN) allowed |= 1u << c;
+                if (cpb_hist_grow_ok(Mb, H, W, y, sx - 5 + c)) allowed |= 1u << c;
         unsigned m = (lane == 5) ? (1u << 5) : 0u;
         for (int it = 0; it < 5; it++) {
             const unsigned d = m | (m << 1) | (m >> 1);
@@ -108,7 +117,7 @@ k_seeds(const int* CPB_RESTRICT hist, int H, int W, int LC, u64* CPB_RESTRICT se
         while (m) {
             const int c = __ffs((int)m) - 1;
             m &= m - 1;
-            atomicMax(&Mb[y * W + sx - 5 + c], label);
+            atomicMin(&Mb[y * W + sx - 5 + c], -label);
         }
     }
 }
@@ -128,7 +137,7 @@ k_lookup(const int* CPB_RESTRICT pfinal, const int* CPB_RESTRICT M, int B, int H
         b = (int)(gi / N);
         r = (int)(gi - (long long)b * N);
         const int pf = pfinal[gi];
-        if (pf >= 0) l = M[(size_t)b * N + (pf >> 16) * W + (pf & 0xffff)];
+        if (pf >= 0) l = max(-M[(size_t)b * N + (pf >> 16) * W + (pf & 0xffff)], 0);    // painted histogram, see k_seeds
         lab[gi] = l;
         y = r / W; x = r - y * W;
     }
