@@ -93,7 +93,7 @@ struct Workspace {
     int* sinv;           // [B*LC]
     int* alive;          // [B*LC]
     int* vote;           // [B*LC*C]
-    int* jobs;           // [B+1] diffusion job offsets, then 4 queue counters
+    int* jobs;           // [B+1] diffusion job offsets, then 2 queue counters
     LabelTables t;
     size_t bytes;
     Prof* prof;          // optional stage timing
@@ -120,7 +120,7 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     w.sinv = c.take<int>(BL);
     w.alive = c.take<int>(BL);
     w.vote = c.take<int>(C > 0 ? BL * C : 0);
-    w.jobs = c.take<int>((size_t)B + 1 + 4);
+    w.jobs = c.take<int>((size_t)B + 1 + 2);
     LabelTables& t = w.t;
     t.LC = LC;
     t.cnt = c.take<int>(BL); t.first = c.take<int>(BL);
@@ -205,8 +205,7 @@ FollowSchedule follow_schedule(int niter) {
 //   CPB_DIFFUSE_QUEUE=0  static (block, warp) -> label map instead of the job queue
 //   CPB_QC_FUSED=0       every label's flow error from T in global memory (k_flow_err) instead of the diffusion tile
 //   CPB_VOTE_FUSED=0     class vote as its own pass over the finished label image
-//   CPB_DIFFUSE_REG=0    diffusion on the shared-memory tile for every nucleus-sized label (no register-resident columns)
-std::atomic<int> g_switch[5] = {{-1}, {-1}, {-1}, {-1}, {-1}};
+std::atomic<int> g_switch[4] = {{-1}, {-1}, {-1}, {-1}};
 bool switch_on(int which, const char* env_name) {
     int v = g_switch[which].load(std::memory_order_relaxed);
     if (v < 0) {
@@ -218,7 +217,6 @@ bool switch_on(int which, const char* env_name) {
 bool diffuse_queue_enabled() { return switch_on(CPB_SWITCH_DIFFUSE_QUEUE, "CPB_DIFFUSE_QUEUE"); }
 bool qc_fused_enabled() { return switch_on(CPB_SWITCH_QC_FUSED, "CPB_QC_FUSED"); }
 bool vote_fused_enabled() { return switch_on(CPB_SWITCH_VOTE_FUSED, "CPB_VOTE_FUSED"); }
-bool diffuse_reg_enabled() { return switch_on(CPB_SWITCH_DIFFUSE_REG, "CPB_DIFFUSE_REG"); }
 
 #define CPB_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
@@ -338,29 +336,12 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
         CPB_LAUNCH_COUNTED(k_diffuse_jobs, dim3(1), dim3(1024), 0, st, w.t.lbound, B, w.jobs, w.jobs + B + 1);
         CPB_CHECK_LAUNCH();
         int* ctr = w.jobs + B + 1;
-        if (diffuse_reg_enabled()) {
-            // register-resident columns for bboxes up to 24 x 30 (two row classes); the shared-memory kernel takes
-            // what is left of the 30 x 32 range
-            static const bool two_classes = [] { const char* e = getenv("CPB_DIFFUSE_REG_CLASSES"); return !(e && e[0] == '1'); }();
-            if (two_classes) {
-                CPB_LAUNCH_COUNTED(k_diffuse_reg<16>, dim3(sm_count() * CPB_DR16_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                                   B, H, W, w.t, w.T, 0, w.jobs, ctr + 0, qc_dP, thr, 0);
-                CPB_CHECK_LAUNCH();
-            }
-            CPB_LAUNCH_COUNTED(k_diffuse_reg<24>, dim3(sm_count() * CPB_DR24_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st, masks, B,
-                               H, W, w.t, w.T, 0, w.jobs, ctr + 1, qc_dP, thr, two_classes ? 16 : 0);
-            CPB_CHECK_LAUNCH();
-            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 2>), dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                               w.t, w.T, 0, w.jobs, ctr + 2, qc_dP, thr, 1);
-            CPB_CHECK_LAUNCH();
-        } else {
-            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 2>), dim3(sm_count() * 8), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                               w.t, w.T, 0, w.jobs, ctr + 0, qc_dP, thr, 0);
-            CPB_CHECK_LAUNCH();
-            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 2>), dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                               w.t, w.T, 0, w.jobs, ctr + 1, qc_dP, thr, 0);
-            CPB_CHECK_LAUNCH();
-        }
+        CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 2>), dim3(sm_count() * 8), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
+                           w.t, w.T, 0, w.jobs, ctr + 0, qc_dP, thr);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 2>), dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
+                           w.t, w.T, 0, w.jobs, ctr + 1, qc_dP, thr);
+        CPB_CHECK_LAUNCH();
     } else {
         CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MIDH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
                            H, W, w.t, w.T, 0, qc_dP, thr);
@@ -670,7 +651,7 @@ const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames
 void cpb_debug_set_follow_merge(int mode) { g_follow_merge.store(mode, std::memory_order_relaxed); }
 void cpb_debug_set_switch(int which, int value) {
     if (which == CPB_SWITCH_FOLLOW_MERGE) g_follow_merge.store(value, std::memory_order_relaxed);
-    else if (which > 0 && which < 5) g_switch[which].store(value, std::memory_order_relaxed);
+    else if (which > 0 && which < 4) g_switch[which].store(value, std::memory_order_relaxed);
 }
 long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

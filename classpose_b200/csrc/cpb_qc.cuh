@@ -290,163 +290,15 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
         if (clean[q]) cpb_diffuse_publish_err(t, q ? B : A, q ? inB : inA, ey, ex, qc.threshold);   // warp-uniform
 }
 
-// ---- register-resident variant ---------------------------------------------------------------------------
-// The shared-memory tile costs 8 wavefronts per row (three 8-byte loads and one store per lane) against 5.5
-// cycles of float64 pipe, and the profile shows the kernel waiting on exactly that (short-scoreboard stalls,
-// shared-memory wavefronts 61 % of peak, fp64 pipe 46 %).  Here lane j keeps its whole column in registers
-// (rows are unrolled at compile time) and gets the left / right columns by warp shuffles: 4 shuffle wavefronts
-// per row, no stores.  Lanes 0 and 31 never belong to a label, so the shuffles need no edge handling: labels
-// sit at lanes >= 1 with one empty lane between and after them, empty lanes hold 0 for ever.
-template <int ROWS>
-CPB_DEVICE void cpb_diffuse_job_reg(const int* CPB_RESTRICT L, int W, const LabelTables& t, double* CPB_RESTRICT Tb,
-                                    const DiffSub& A, const DiffSub& B, bool has_b, int n_it, const DiffQC& qc) {
-    const int lane = threadIdx.x & 31;
-    const bool inA = lane >= A.coff && lane < A.coff + A.w;
-    const bool inB = has_b && lane >= B.coff && lane < B.coff + B.w;
-    const DiffSub& my = inB ? B : A;
-    const bool mine = inA || inB;
-    const int col = lane - my.coff;
-    const int hj = has_b ? max(A.h, B.h) : A.h;
-    const bool fuse = qc.dPy != nullptr;
-    DiffPro pro;
-    cpb_diffuse_prologue(L, W, t, A, B, has_b, qc, pro);
-    const unsigned member = pro.member;
-    unsigned cbits = 0;                // bit r: (row r, this lane) is a diffusion centre
-    if (lane == pro.cl[0]) cbits |= 1u << pro.cr[0];
-    if (has_b && lane == pro.cl[1]) cbits |= 1u << pro.cr[1];
-    double Tc[ROWS];
-    #pragma unroll
-    for (int r = 0; r < ROWS; r++) Tc[r] = 0.0;
-    for (int it = 0; it < n_it; it++) {
-        // (uC, uL, uR) = row r-1, (cC, cL, cR) = row r: OLD values, the centre already carrying its +1
-        double uC = 0.0, uL = 0.0, uR = 0.0;
-        double cC = Tc[0];
-        if (cbits & 1u) cC = __dadd_rn(cC, 1.0);
-        double cL = __shfl_up_sync(CPB_FULL, cC, 1), cR = __shfl_down_sync(CPB_FULL, cC, 1);
-        #pragma unroll
-        for (int r = 0; r < ROWS; r += 2) {
-            if (r < hj) {                                       // warp-uniform
-                double dC = Tc[r + 1];                          // row r+1
-                if (cbits >> (r + 1) & 1u) dC = __dadd_rn(dC, 1.0);
-                const double dL = __shfl_up_sync(CPB_FULL, dC, 1), dR = __shfl_down_sync(CPB_FULL, dC, 1);
-                double eC = 0.0, eL = 0.0, eR = 0.0;            // row r+2
-                if (r + 2 < ROWS) {
-                    eC = Tc[r + 2 < ROWS ? r + 2 : 0];
-                    if (cbits >> (r + 2) & 1u) eC = __dadd_rn(eC, 1.0);
-                    eL = __shfl_up_sync(CPB_FULL, eC, 1); eR = __shfl_down_sync(CPB_FULL, eC, 1);
-                }
-                // self, up, down, left, right, up-left, up-right, down-left, down-right
-                double s0 = __dadd_rn(cC, uC), s1 = __dadd_rn(dC, cC);
-                s0 = __dadd_rn(s0, dC); s1 = __dadd_rn(s1, eC);
-                s0 = __dadd_rn(s0, cL); s1 = __dadd_rn(s1, dL);
-                s0 = __dadd_rn(s0, cR); s1 = __dadd_rn(s1, dR);
-                s0 = __dadd_rn(s0, uL); s1 = __dadd_rn(s1, cL);
-                s0 = __dadd_rn(s0, uR); s1 = __dadd_rn(s1, cR);
-                s0 = __dadd_rn(s0, dL); s1 = __dadd_rn(s1, eL);
-                s0 = __dadd_rn(s0, dR); s1 = __dadd_rn(s1, eR);
-                const double v0 = cpb_div9_fast(s0), v1 = cpb_div9_fast(s1);
-                if (member >> r & 1u) Tc[r] = v0;
-                if (member >> (r + 1) & 1u) Tc[r + 1] = v1;
-                uC = dC; uL = dL; uR = dR;
-                cC = eC; cL = eL; cR = eR;
-            }
-        }
-    }
-    const bool my_clean = inB ? pro.clean[1] : pro.clean[0];
-    const bool any_clean = fuse && (pro.clean[0] || pro.clean[1]);
-    double ey = 0.0, ex = 0.0;
-    #pragma unroll
-    for (int r = 0; r < ROWS; r++) {
-        if (r < hj) {                                           // warp-uniform
-            const double c = Tc[r];
-            if (mine && !my_clean && (member >> r & 1u)) Tb[(my.y0 + r) * W + my.x0 + col] = c;
-            if (any_clean) {                                    // warp-uniform
-                const double l = __shfl_up_sync(CPB_FULL, c, 1), rr = __shfl_down_sync(CPB_FULL, c, 1);
-                if (mine && my_clean && (member >> r & 1u)) {
-                    const double up = r > 0 ? Tc[r > 0 ? r - 1 : 0] : 0.0, dn = r + 1 < ROWS ? Tc[r + 1 < ROWS ? r + 1 : 0] : 0.0;
-                    const int pix = (my.y0 + r) * W + my.x0 + col;
-                    cpb_flow_err_pixel(__dsub_rn(dn, up), __dsub_rn(rr, l), qc.dPy[pix], qc.dPx[pix], ey, ex);
-                }
-            }
-        }
-    }
-    if (!any_clean) return;
-    for (int q = 0; q < (has_b ? 2 : 1); q++)
-        if (pro.clean[q]) cpb_diffuse_publish_err(t, q ? B : A, q ? inB : inA, ey, ex, qc.threshold);   // warp-uniform
-}
-
-#define CPB_DR_MAXH 24         // register path: bbox up to 24 rows x 30 columns (lanes 1..30)
-#define CPB_DR_MAXW 30
-CPB_DEVICE bool cpb_diffuse_is_reg(int h, int w) { return h <= CPB_DR_MAXH && w <= CPB_DR_MAXW; }
-
-CPB_DEVICE bool cpb_diffuse_load_reg(const LabelTables& t, int b, int l, int lb, DiffSub& s) {
-    if (l > lb) return false;
-    s.l = l; s.k = (size_t)b * t.LC + l; s.coff = 1;
-    if (!cpb_label_live(t, s.k)) return false;
-    s.y0 = t.ymin[s.k]; s.x0 = t.xmin[s.k];
-    s.h = t.ymax[s.k] - s.y0 + 1; s.w = t.xmax[s.k] - s.x0 + 1;
-    return cpb_diffuse_is_reg(s.h, s.w);
-}
-
-// ROWS = 16 or 24: an instance takes the jobs (label pairs, or single labels) of rows_above < rows <= ROWS
-#ifndef CPB_DR16_MINBLOCKS
-#define CPB_DR16_MINBLOCKS 5
-#endif
-#ifndef CPB_DR24_MINBLOCKS
-#define CPB_DR24_MINBLOCKS 4
-#endif
-template <int ROWS>
-CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (ROWS <= 16 ? CPB_DR16_MINBLOCKS : CPB_DR24_MINBLOCKS))
-k_diffuse_reg(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t, double* CPB_RESTRICT T,
-              int niter_override, const int* CPB_RESTRICT joboff, int* CPB_RESTRICT counter,
-              const float* CPB_RESTRICT dP, double threshold, int rows_above) {
-    const int lane = threadIdx.x & 31;
-    const int N = H * W;
-    const int total = joboff[B];
-    for (;;) {
-        int j = 0;
-        if (lane == 0) j = atomicAdd(counter, 1);
-        j = __shfl_sync(CPB_FULL, j, 0);
-        if (j >= total) break;
-        int lo = 0, hi = B;                       // joboff[lo] <= j < joboff[hi]
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (joboff[mid] <= j) lo = mid; else hi = mid;
-        }
-        const int b = lo, wi = j - joboff[lo];
-        const int lb = t.lbound[b];
-        const int* L = lab + (size_t)b * N;
-        double* Tb = T + (size_t)b * N;
-        const int n_it = niter_override > 0 ? niter_override : t.niter[b];
-        const DiffQC qc{dP ? dP + ((size_t)b * 2 + 0) * N : nullptr, dP ? dP + ((size_t)b * 2 + 1) * N : nullptr,
-                        t.alive ? t.alive + (size_t)b * t.LC : nullptr, threshold, H};
-        DiffSub A, Bs;
-        const bool okA = cpb_diffuse_load_reg(t, b, 2 * wi + 1, lb, A);
-        const bool okB = cpb_diffuse_load_reg(t, b, 2 * wi + 2, lb, Bs);
-        #define CPB_DR_MINE(h) ((h) <= ROWS && (h) > rows_above)
-        if (okA && okB && A.w + Bs.w <= CPB_DR_MAXW - 1) {       // lanes: 0 | A | gap | B | >= 1 empty
-            if (CPB_DR_MINE(max(A.h, Bs.h))) {
-                Bs.coff = A.w + 2;
-                cpb_diffuse_job_reg<ROWS>(L, W, t, Tb, A, Bs, true, n_it, qc);
-            }
-        } else {
-            if (okA && CPB_DR_MINE(A.h)) cpb_diffuse_job_reg<ROWS>(L, W, t, Tb, A, A, false, n_it, qc);
-            if (okB && CPB_DR_MINE(Bs.h)) cpb_diffuse_job_reg<ROWS>(L, W, t, Tb, Bs, Bs, false, n_it, qc);
-        }
-        #undef CPB_DR_MINE
-    }
-}
-
 // a label belongs to the kernel instance whose row capacity is the smallest that holds it
 template <int MAXH>
-CPB_DEVICE bool cpb_diffuse_load_sub(const LabelTables& t, int b, int l, int lb, DiffSub& s, bool skip_reg = false) {
+CPB_DEVICE bool cpb_diffuse_load_sub(const LabelTables& t, int b, int l, int lb, DiffSub& s) {
     if (l > lb) return false;
     s.l = l; s.k = (size_t)b * t.LC + l; s.coff = 0;
     if (!cpb_label_live(t, s.k)) return false;
     s.y0 = t.ymin[s.k]; s.x0 = t.xmin[s.k];
     s.h = t.ymax[s.k] - s.y0 + 1; s.w = t.xmax[s.k] - s.x0 + 1;
     if (!cpb_diffuse_is_small(s.h, s.w)) return false;
-    if (skip_reg) return !cpb_diffuse_is_reg(s.h, s.w);          // the only shared-memory instance takes what is left
     return MAXH == CPB_DC_MIDH ? s.h <= CPB_DC_MIDH : s.h > CPB_DC_MIDH;
 }
 
@@ -488,7 +340,7 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
 CPB_KERNEL k_diffuse_jobs(const int* CPB_RESTRICT lbound, int B, int* CPB_RESTRICT joboff, int* CPB_RESTRICT counters) {
     CPB_SHARED int s_scan[33];
     CPB_SHARED int s_base;
-    if (threadIdx.x == 0) { s_base = 0; counters[0] = 0; counters[1] = 0; counters[2] = 0; counters[3] = 0; }
+    if (threadIdx.x == 0) { s_base = 0; counters[0] = 0; counters[1] = 0; }
     __syncthreads();
     for (int b0 = 0; b0 < B; b0 += blockDim.x) {
         const int b = b0 + threadIdx.x;
@@ -503,14 +355,11 @@ CPB_KERNEL k_diffuse_jobs(const int* CPB_RESTRICT lbound, int B, int* CPB_RESTRI
     if (threadIdx.x == 0) joboff[B] = s_base;
 }
 
-#ifndef CPB_DQ4_MINBLOCKS
-#define CPB_DQ4_MINBLOCKS 6
-#endif
 template <int MAXH, int R>
-CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (R == 4 ? CPB_DQ4_MINBLOCKS : (MAXH == CPB_DC_MIDH ? 8 : 6)))
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
 k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                  int niter_override, const int* CPB_RESTRICT joboff, int* CPB_RESTRICT counter,
-                 const float* CPB_RESTRICT dP, double threshold, int skip_reg) {
+                 const float* CPB_RESTRICT dP, double threshold) {
     CPB_SHARED double s_T[CPB_DW_WARPS][((MAXH + R - 1) / R * R + R + 1) * CPB_DC_PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = H * W;
@@ -534,8 +383,8 @@ k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t
         const DiffQC qc{dP ? dP + ((size_t)b * 2 + 0) * N : nullptr, dP ? dP + ((size_t)b * 2 + 1) * N : nullptr,
                         t.alive ? t.alive + (size_t)b * t.LC : nullptr, threshold, H};
         DiffSub A, Bs;
-        const bool okA = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 1, lb, A, skip_reg != 0);
-        const bool okB = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 2, lb, Bs, skip_reg != 0);
+        const bool okA = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 1, lb, A);
+        const bool okB = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 2, lb, Bs);
         if (okA && okB && A.w + 1 + Bs.w <= CPB_DC_MAXW) {
             Bs.coff = A.w + 1;
             cpb_diffuse_job<R>(L, W, t, Tb, S, A, Bs, true, n_it, qc);

@@ -93,7 +93,6 @@ void cpb_debug_set_follow_merge(int mode);
 #define CPB_SWITCH_DIFFUSE_QUEUE 1  /* CPB_DIFFUSE_QUEUE: diffusion warps pull label pairs from a queue */
 #define CPB_SWITCH_QC_FUSED 2       /* CPB_QC_FUSED: flow error of isolated labels inside the diffusion warp */
 #define CPB_SWITCH_VOTE_FUSED 3     /* CPB_VOTE_FUSED: class vote folded into the final label pass */
-#define CPB_SWITCH_DIFFUSE_REG 4    /* CPB_DIFFUSE_REG: register-resident diffusion columns (needs the queue) */
 void cpb_debug_set_switch(int which, int value);
 /* number of kernels this library has launched in this process (statistics for the benchmark) */
 long long cpb_debug_launch_count(void);

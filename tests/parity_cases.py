@@ -201,21 +201,21 @@ def case_remove_bad_flow_masks_exact(be):
 def case_flow_qc_fused_equals_unfused(be):
     """Flow error taken inside the diffusion warp (isolated labels) vs k_flow_err on global T (every label), and
     the job queue vs the static label map: same removal set, errors equal to 1e-12 (summation order differs)."""
-    SW_QUEUE, SW_QC, SW_REG = 1, 2, 4
+    SW_QUEUE, SW_QC = 1, 2
     for t in (std_tile(1), std_tile(3), adv_tile(), std_tile(5, H=128, W=128, n_grid=16, axes=(2.5, 3.5))):
         lab = t["labels"].astype(np.int32)
         dP = corrupt_flows(t)
         lcap = int(lab.max()) + 2
         res = {}
         try:
-            for queue, reg in ((0, 0), (1, 0), (1, 1)):      # static map / queue on the shared-memory tile / register columns
+            for queue, reg in ((0, 0), (1, 0)):              # static label map / job queue
                 for fused in (0, 1):
-                    be.set_switch(SW_QUEUE, queue); be.set_switch(SW_REG, reg); be.set_switch(SW_QC, fused)
+                    be.set_switch(SW_QUEUE, queue); be.set_switch(SW_QC, fused)
                     res[(queue, reg, fused)] = be.remove_bad_flow_masks(c32(lab[None]).copy(), f32(dP[None]), lcap, 0.4, want_err=True)
                     if fused == 0:
                         res[(queue, reg, "mu")] = be.masks_to_flows(c32(lab[None]), lcap)
         finally:
-            be.set_switch(SW_QUEUE, -1); be.set_switch(SW_QC, -1); be.set_switch(SW_REG, -1)
+            be.set_switch(SW_QUEUE, -1); be.set_switch(SW_QC, -1)
         out0, err0 = res[(0, 0, 0)]
         n = int(lab.max())
         for k, v in res.items():
