@@ -304,11 +304,13 @@ def run_ours(args):
     stage_runs = [eng.profile_stages(dP, cellprob, logits, **PARAMS) for _ in range(3)]
     stages = {k: statistics.median(r[k] for r in stage_runs) for k in stage_runs[0]}
     fg_frac = float((cellprob > PARAMS["cellprob_threshold"]).float().mean().item())
+    fg4_frac = float((out[0].reshape(-1, 4) > 0).any(dim=1).float().mean().item()) if (H * W) % 4 == 0 else 1.0
     stage_bytes = {   # algorithmic bytes per tile (SURVEY.md 8d / DESIGN.md)
         "follow_flows": 12 * N + 4 * fg_frac * N,
         "diffuse": 4 * N + 8 * fg_frac * N,
         "vote": 4 * C * N + 4 * N,
-        "final_map": 4 * C * N + 8 * N,          # final ids + class vote in one pass: labels in/out, logits in
+        # final ids + class vote in one pass: labels in / out, logits of the 4-pixel groups that hold a cell pixel
+        "final_map": 8 * N + 4 * C * N * fg4_frac,
         "prep_flow": 12 * N + 8 * N + 4 * N + 4 * fg_frac * N,   # dP, cellprob in; scaled flow, zeroed labels, fg list out
     }
     dom = max(stages, key=stages.get)

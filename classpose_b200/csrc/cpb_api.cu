@@ -603,9 +603,13 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         prof_begin(w.prof, S_MAP4);
         CPB_LAUNCH_COUNTED(k_vote_zero, dim3(B), dim3(256), 0, st, w.t, C, w.vote);
         CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED(k_final_vote_v4, dim3(blocks_for(BN / 4, 256)), dim3(256), 0, st, reinterpret_cast<int4*>(masks),
-                           prm->fill_holes ? (const u64*)w.holekey : (const u64*)nullptr,
-                           reinterpret_cast<const float4*>(logits), B, H, W, C, w.t, counts, w.vote);
+#define CPB_FV_LAUNCH(CT) CPB_LAUNCH_COUNTED(k_final_vote_v4<CT>, dim3(blocks_for(BN / 4, 256)), dim3(256), 0, st,        \
+                           reinterpret_cast<int4*>(masks), prm->fill_holes ? (const u64*)w.holekey : (const u64*)nullptr, \
+                           reinterpret_cast<const float4*>(logits), B, H, W, C, w.t, counts, w.vote)
+        // class counts of the reference's model configurations (conic / consep / nucls 7, puma 10, monusac / glysac 5)
+        if (C == 7) { CPB_FV_LAUNCH(7); } else if (C == 10) { CPB_FV_LAUNCH(10); } else if (C == 5) { CPB_FV_LAUNCH(5); }
+        else { CPB_FV_LAUNCH(0); }
+#undef CPB_FV_LAUNCH
         CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED(k_finish_bounds, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t, B);
         CPB_CHECK_LAUNCH();

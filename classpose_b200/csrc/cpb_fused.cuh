@@ -196,9 +196,11 @@ CPB_KERNEL k_vote_zero(LabelTables t, int C, int* CPB_RESTRICT vote) {
     for (int i = threadIdx.x; i < need; i += blockDim.x) tab[i] = 0;
 }
 
+template <int CT>      // CT > 0: number of classes known at compile time (all logit loads of a thread in flight at once)
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_final_vote_v4(int4* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, const float4* CPB_RESTRICT logits, int B, int H,
-                int W, int C, LabelTables t, int* CPB_RESTRICT counts_out, int* CPB_RESTRICT vote) {
+                int W, int C_rt, LabelTables t, int* CPB_RESTRICT counts_out, int* CPB_RESTRICT vote) {
+    const int C = CT > 0 ? CT : C_rt;
     const int N4 = (H * W) >> 2;
     const long long total = (long long)B * N4;
     const long long g0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,13 +228,26 @@ k_final_vote_v4(int4* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, const f
         const float4* G = logits + (size_t)b * C * N4 + q;
         float4 best = G[0];
         int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        #pragma unroll 4
-        for (int c = 1; c < C; c++) {
-            const float4 x = G[(size_t)c * N4];
-            if (x.x > best.x) { best.x = x.x; a0 = c; }
-            if (x.y > best.y) { best.y = x.y; a1 = c; }
-            if (x.z > best.z) { best.z = x.z; a2 = c; }
-            if (x.w > best.w) { best.w = x.w; a3 = c; }
+        if (CT > 0) {
+            float4 x[CT > 1 ? CT - 1 : 1];
+            #pragma unroll
+            for (int c = 1; c < CT; c++) x[c - 1] = G[(size_t)c * N4];
+            #pragma unroll
+            for (int c = 1; c < CT; c++) {
+                if (x[c - 1].x > best.x) { best.x = x[c - 1].x; a0 = c; }
+                if (x[c - 1].y > best.y) { best.y = x[c - 1].y; a1 = c; }
+                if (x[c - 1].z > best.z) { best.z = x[c - 1].z; a2 = c; }
+                if (x[c - 1].w > best.w) { best.w = x[c - 1].w; a3 = c; }
+            }
+        } else {
+            #pragma unroll 4
+            for (int c = 1; c < C; c++) {
+                const float4 x = G[(size_t)c * N4];
+                if (x.x > best.x) { best.x = x.x; a0 = c; }
+                if (x.y > best.y) { best.y = x.y; a1 = c; }
+                if (x.z > best.z) { best.z = x.z; a2 = c; }
+                if (x.w > best.w) { best.w = x.w; a3 = c; }
+            }
         }
         const int arg[4] = {a0, a1, a2, a3};
         #pragma unroll

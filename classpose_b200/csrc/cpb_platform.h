@@ -17,7 +17,6 @@
     cusim::launch(#kernel, (grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
 #define CPB_RESTRICT
 #define CPB_LAUNCH_BOUNDS(t, b)
-#define CPB_ALIGN16 __attribute__((aligned(16)))
 #else
 #include <cuda_runtime.h>
 #define CPB_KERNEL __global__ void
@@ -29,5 +28,4 @@
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define CPB_RESTRICT __restrict__
 #define CPB_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
-#define CPB_ALIGN16 __align__(16)
 #endif

@@ -231,17 +231,6 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
     const bool clean[2] = {pro.clean[0], pro.clean[1]};
     const int ci[2] = {(pro.cr[0] + 1) * CPB_DC_PITCH + pro.cl[0] + 1, (pro.cr[1] + 1) * CPB_DC_PITCH + pro.cl[1] + 1};
     const double* p = S + lane;        // p[0], p[1], p[2] = columns j-1, j, j+1 of the halo row
-    // Shared-memory wavefronts bound this kernel, so a row is fetched as ONE aligned 16-byte pair that holds the
-    // lane's own column (even and odd lanes of a pair read the same 16 bytes: a broadcast, 2 wavefronts per warp)
-    // plus ONE 8-byte load of the remaining neighbour (2 wavefronts): 4 wavefronts per row instead of 6 for three
-    // 8-byte loads.  Tile column of lane j is j + 1: when that is even the pair is (centre, right), else (left, centre).
-    const bool pair_cr = (lane & 1) != 0;
-    const int pair_off = pair_cr ? 1 : 0, one_off = pair_cr ? 0 : 2;
-#define CPB_DC_LOAD_ROW(rowp, dst) do {                                                          \
-        const double2 pr_ = *reinterpret_cast<const double2*>((rowp) + pair_off);                \
-        const double one_ = (rowp)[one_off];                                                      \
-        (dst)[0] = pair_cr ? one_ : pr_.x; (dst)[1] = pair_cr ? pr_.x : pr_.y; (dst)[2] = pair_cr ? pr_.y : one_; \
-    } while (0)
     double* own = S + CPB_DC_PITCH + lane + 1;
     __syncwarp();
     for (int it = 0; it < n_it; it++) {
@@ -250,11 +239,15 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
         // win[k] = row r-1+k of the tile (left, centre, right of this lane's column)
         double win[R + 2][3];
         #pragma unroll
-        for (int k = 0; k < 2; k++) CPB_DC_LOAD_ROW(p + k * CPB_DC_PITCH, win[k]);
+        for (int k = 0; k < 2; k++) {
+            win[k][0] = p[k * CPB_DC_PITCH]; win[k][1] = p[k * CPB_DC_PITCH + 1]; win[k][2] = p[k * CPB_DC_PITCH + 2];
+        }
         for (int r = 0; r < hj; r += R) {
             const double* q = p + (r + 2) * CPB_DC_PITCH;
             #pragma unroll
-            for (int k = 0; k < R; k++) CPB_DC_LOAD_ROW(q + k * CPB_DC_PITCH, win[k + 2]);      // rows r+1 .. r+R
+            for (int k = 0; k < R; k++) {                       // rows r+1 .. r+R
+                win[k + 2][0] = q[k * CPB_DC_PITCH]; win[k + 2][1] = q[k * CPB_DC_PITCH + 1]; win[k + 2][2] = q[k * CPB_DC_PITCH + 2];
+            }
             double v[R];
             #pragma unroll
             for (int k = 0; k < R; k++) {
@@ -278,7 +271,6 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
         }
         __syncwarp();
     }
-#undef CPB_DC_LOAD_ROW
     const bool my_clean = inB ? clean[1] : clean[0];
     if (mine && !my_clean)
         for (int r = 0; r < my.h; r++)
@@ -314,7 +306,7 @@ template <int MAXH>
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
 k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                int niter_override, const float* CPB_RESTRICT dP, double threshold) {
-    CPB_SHARED CPB_ALIGN16 double s_T[CPB_DW_WARPS][(MAXH + 3) * CPB_DC_PITCH];
+    CPB_SHARED double s_T[CPB_DW_WARPS][(MAXH + 3) * CPB_DC_PITCH];
     constexpr int R = 2;
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.y, N = H * W;
@@ -368,7 +360,7 @@ CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
 k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                  int niter_override, const int* CPB_RESTRICT joboff, int* CPB_RESTRICT counter,
                  const float* CPB_RESTRICT dP, double threshold) {
-    CPB_SHARED CPB_ALIGN16 double s_T[CPB_DW_WARPS][((MAXH + R - 1) / R * R + R + 1) * CPB_DC_PITCH];
+    CPB_SHARED double s_T[CPB_DW_WARPS][((MAXH + R - 1) / R * R + R + 1) * CPB_DC_PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = H * W;
     const int total = joboff[B];
