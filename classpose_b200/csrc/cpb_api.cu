@@ -93,7 +93,8 @@ struct Workspace {
     int* sinv;           // [B*LC]
     int* alive;          // [B*LC]
     int* vote;           // [B*LC*C]
-    int* jobs;           // [B+1] diffusion job offsets, then 2 queue counters
+    int* jobs;           // [B+1] diffusion job offsets, 2 queue counters, 2 counts of `todo` (front / back)
+    int2* todo;          // [B*LC] (tile, label) work list of the block-per-label kernels
     LabelTables t;
     size_t bytes;
     Prof* prof;          // optional stage timing
@@ -120,7 +121,8 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     w.sinv = c.take<int>(BL);
     w.alive = c.take<int>(BL);
     w.vote = c.take<int>(C > 0 ? BL * C : 0);
-    w.jobs = c.take<int>((size_t)B + 1 + 2);
+    w.jobs = c.take<int>((size_t)B + 1 + 4);
+    w.todo = c.take<int2>(BL);
     LabelTables& t = w.t;
     t.LC = LC;
     t.cnt = c.take<int>(BL); t.first = c.take<int>(BL);
@@ -318,43 +320,59 @@ int run_get_masks(const Workspace& w, const int32_t* pfinal, int B, int H, int W
     return 0;   // caller applies w.t.remap
 }
 
+// n_iter per tile and the work list of the block-per-label kernels (labels beyond the warp kernels' bbox range)
+int run_label_scan(const Workspace& w, int B, cudaStream_t st) {
+    cudaMemsetAsync(w.t.niter, 0, B * sizeof(int), st);
+    cudaMemsetAsync(w.jobs + B + 3, 0, 2 * sizeof(int), st);
+    CPB_LAUNCH_COUNTED(k_qc_scan, dim3(B), dim3(256), 0, st, w.t, w.todo, w.jobs + B + 3);
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
+inline LabelWork todo_work(const Workspace& w, int B, bool back) {
+    return LabelWork{w.todo, w.jobs + B + 3, (int)std::min<size_t>((size_t)B * w.t.LC, 0x7fffffff), back ? 1 : 0};
+}
+
 // labels with statistics in the tables -> T (and mu / err / bad flags)
 int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B, int H, int W, double thr,
                 double* mu_out, cudaStream_t st) {
-    cudaMemsetAsync(w.t.niter, 0, B * sizeof(int), st);
-    const dim3 grid(kLabelBlocksPerTile, B);
     prof_begin(w.prof, S_CENTRES);
-    CPB_LAUNCH_COUNTED(k_centres, grid, dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t, 1);
+    { int e = run_label_scan(w, B, st); if (e) return e; }
+    const LabelWork big = todo_work(w, B, false);
+    CPB_LAUNCH_COUNTED(k_centres, dim3(sm_count() * 8), dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t, 1, big);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_CENTRES);
     const size_t smem = (size_t)CPB_DIFF_SMEM_CELLS * 17;
     prof_begin(w.prof, S_DIFFUSE);
-    // labels that touch no other live label get their flow error inside the diffusion warp (no T round trip)
+    // labels that touch no other live label get their flow error inside the diffusion warp (no T round trip); the
+    // others are appended to the end of the work list for k_flow_err
     const float* qc_dP = (dP && !mu_out && qc_fused_enabled()) ? dP : nullptr;
+    int* todo_n = w.jobs + B + 3;
     if (diffuse_queue_enabled()) {
         // persistent warps pulling label pairs from one queue per size class (see k_diffuse_jobs)
         CPB_LAUNCH_COUNTED(k_diffuse_jobs, dim3(1), dim3(1024), 0, st, w.t.lbound, B, w.jobs, w.jobs + B + 1);
         CPB_CHECK_LAUNCH();
         int* ctr = w.jobs + B + 1;
         CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 2>), dim3(sm_count() * 8), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                           w.t, w.T, 0, w.jobs, ctr + 0, qc_dP, thr);
+                           w.t, w.T, 0, w.jobs, ctr + 0, qc_dP, thr, w.todo, todo_n, big.cap);
         CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 2>), dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                           w.t, w.T, 0, w.jobs, ctr + 1, qc_dP, thr);
+                           w.t, w.T, 0, w.jobs, ctr + 1, qc_dP, thr, w.todo, todo_n, big.cap);
         CPB_CHECK_LAUNCH();
     } else {
         CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MIDH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                           H, W, w.t, w.T, 0, qc_dP, thr);
+                           H, W, w.t, w.T, 0, qc_dP, thr, w.todo, todo_n, big.cap);
         CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MAXH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                           H, W, w.t, w.T, 0, qc_dP, thr);
+                           H, W, w.t, w.T, 0, qc_dP, thr, w.todo, todo_n, big.cap);
         CPB_CHECK_LAUNCH();
     }
-    CPB_LAUNCH_COUNTED(k_diffuse, grid, dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0, 1);
+    CPB_LAUNCH_COUNTED(k_diffuse, dim3(sm_count() * 4), dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0, 1, big);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_DIFFUSE);
     ProfScope ps(w.prof, S_FLOWERR);
-    CPB_LAUNCH_COUNTED(k_flow_err, grid, dim3(CPB_QC_THREADS), 0, st, masks, dP, H, W, w.t, w.T, thr, mu_out, 0);
+    CPB_LAUNCH_COUNTED(k_flow_err, dim3(sm_count() * 8), dim3(CPB_QC_THREADS), 0, st, masks, dP, H, W, w.t, w.T, thr, mu_out, 0,
+                       todo_work(w, B, true));
     CPB_CHECK_LAUNCH();
     return 0;
 }
@@ -376,7 +394,7 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
     CPB_LAUNCH_COUNTED(k_fill_holes_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(128), 0, st, masks, H, W, w.t, w.holekey);
     CPB_CHECK_LAUNCH();
     CPB_LAUNCH_COUNTED(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
-               masks, H, W, w.t, w.holekey, w.status, 1);
+               masks, H, W, w.t, w.holekey, w.status, 1, (LabelWork{nullptr, nullptr, 0, 0}));
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_FILL);
     e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, w.holekey, true, st, S_MAP3); if (e) return e;
@@ -560,6 +578,8 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     // (4) flow-error check on the raw labels; bad labels are only flagged
     if (prm->flow_threshold > 0.0) {
         e = run_flow_qc(w, masks, dP, B, H, W, prm->flow_threshold, nullptr, st); if (e) return e;
+    } else if (prm->fill_holes) {
+        e = run_label_scan(w, B, st); if (e) return e;       // the hole fill below wants the list of large labels
     }
     // (5) size filter / hole fill / size filter as table operations, one final pixel pass
     if (prm->fill_holes) {
@@ -573,12 +593,14 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         CPB_LAUNCH_COUNTED(k_fill_holes_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(128), 0, st, masks, H, W, w.t,
                            w.holekey);
         CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
-                           masks, H, W, w.t, w.holekey, w.status, 1);
+        CPB_LAUNCH_COUNTED(k_fill_holes, dim3(sm_count() * 3), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
+                           masks, H, W, w.t, w.holekey, w.status, 1, todo_work(w, B, false));
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_FILL);
         prof_begin(w.prof, S_MAP3);
-        CPB_LAUNCH_COUNTED(k_recount, dim3(B), dim3(1024), 0, st, masks, w.holekey, H, W, w.t);
+        CPB_LAUNCH_COUNTED(k_recount_reset, dim3(B), dim3(256), 0, st, w.t);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_recount, dim3(8, B), dim3(256), 0, st, masks, w.holekey, H, W, w.t);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_MAP3);
         prof_begin(w.prof, S_SIZE2);

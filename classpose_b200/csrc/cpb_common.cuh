@@ -28,6 +28,30 @@ struct LabelTables {
 
 CPB_DEVICE int cpb_lane() { return threadIdx.x & 31; }
 
+// Work items of the one-block-per-label kernels (centres, block diffusion, flow error, block hole fill).
+//   list == NULL: tile = blockIdx.y, labels 1 + blockIdx.x, 1 + blockIdx.x + gridDim.x, ... (stage calls: every label)
+//   list != NULL: explicit (tile, label) pairs, grid-stride over entries [0, count[0]) at the front of the list and,
+//                 when `back`, [cap - count[1], cap) at its end.  The fused path lists only the labels that need a
+//                 block (bbox beyond the warp kernels' 30 x 32, or in contact with another label): nuclei-scale
+//                 batches have almost none, and a (24, B) grid whose blocks only discover that costs 50-190 us per
+//                 kernel in block launches alone.
+struct LabelWork { const int2* list; const int* count; int cap; int back; };
+
+CPB_DEVICE bool cpb_next_label(const LabelWork& wk, const int* CPB_RESTRICT lbound, int& it, int& b, int& l) {
+    if (wk.list) {
+        const int nf = wk.count[0], nb = wk.back ? wk.count[1] : 0;
+        const int i = blockIdx.x + it * gridDim.x;
+        if (i >= nf + nb) return false;
+        const int2 e = i < nf ? wk.list[i] : wk.list[wk.cap - 1 - (i - nf)];
+        b = e.x; l = e.y;
+    } else {
+        b = blockIdx.y; l = 1 + blockIdx.x + it * gridDim.x;
+        if (l > lbound[b]) return false;
+    }
+    it++;
+    return true;
+}
+
 CPB_DEVICE bool cpb_label_live(const LabelTables& t, size_t k) {
     return t.cnt[k] > 0 && (t.alive == nullptr || t.alive[k] != 0);
 }

@@ -58,7 +58,7 @@ k_prep_flow(const float* CPB_RESTRICT dP, const float* CPB_RESTRICT cellprob, in
 // k_prep_flow_v4: W % 4 == 0.  One thread per group of 4 pixels of a padded row (rows -1 and H are the zero
 // rows): three 128-bit loads, two 128-bit flow stores, one 128-bit p_final store.
 #ifndef CPB_PREP_MINBLOCKS
-#define CPB_PREP_MINBLOCKS 4
+#define CPB_PREP_MINBLOCKS 8
 #endif
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, CPB_PREP_MINBLOCKS)
 k_prep_flow_v4(const float4* CPB_RESTRICT dP, const float4* CPB_RESTRICT cellprob, int B, int H, int W,

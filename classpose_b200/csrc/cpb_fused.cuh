@@ -110,21 +110,29 @@ k_fuse_size(LabelTables t, int H, int W, int min_size, int mode, const int* CPB_
     if (threadIdx.x == 0) t.nlab[b] = n2;
 }
 
-// k_recount: one block per tile, only tiles in which a hole was filled (t.misc[b] != 0) do any work: reset count /
-// first appearance of the tile's labels and recompute them on the image with the hole proposals applied.
-CPB_KERNEL CPB_LAUNCH_BOUNDS(1024, 1)
-k_recount(const int* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, int H, int W, LabelTables t) {
+// k_recount_reset + k_recount: only tiles in which a hole was filled (t.misc[b] != 0) do any work: reset count /
+// first appearance of the tile's labels, then recompute them on the image with the hole proposals applied (grid
+// (slices, B): a tile is shared by several blocks, so the reset is its own launch).
+CPB_KERNEL k_recount_reset(LabelTables t) {
     const int b = blockIdx.x;
     if (t.misc[b] == 0) return;
-    const int N = H * W, LC = t.LC, lb = t.lbound[b];
+    const int LC = t.LC, lb = t.lbound[b];
     for (int l = threadIdx.x; l <= lb; l += blockDim.x) { t.cnt[(size_t)b * LC + l] = 0; t.first[(size_t)b * LC + l] = CPB_IMAX; }
-    __syncthreads();
+}
+
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_recount(const int* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, int H, int W, LabelTables t) {
+    const int b = blockIdx.y;
+    if (t.misc[b] == 0) return;
+    const int N = H * W, LC = t.LC;
     const int* L = lab + (size_t)b * N;
     const u64* HK = holekey + (size_t)b * N;
-    for (int r0 = 0; r0 < N; r0 += blockDim.x) {
+    const int per = ((N + gridDim.x - 1) / gridDim.x + 31) & ~31;          // pixels per slice, whole warps
+    const int r_end = min(N, (int)(blockIdx.x + 1) * per);
+    for (int r0 = blockIdx.x * per; r0 < r_end; r0 += blockDim.x) {
         const int r = r0 + threadIdx.x;
         int l = 0, y = 0, x = 0;
-        if (r < N) {
+        if (r < r_end) {
             const u64 hk = HK[r];
             l = hk ? (int)(hk & 0xffffffffu) : L[r];
             if (l > 0 && t.alive[(size_t)b * LC + l] == 0) l = 0;

@@ -64,28 +64,36 @@ k_seeds(int* hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
     // the histogram is almost everywhere 0: scan it with 128-bit loads when the tile allows
     const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
     const int nq = vec ? N / 4 : N;
-    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-        int vals[4];
-        int nv = 1;
-        if (vec) {
-            const int4 v4 = *reinterpret_cast<const int4*>(h + 4 * q);
-            vals[0] = v4.x; vals[1] = v4.y; vals[2] = v4.z; vals[3] = v4.w; nv = 4;
-            if (max(max(v4.x, v4.y), max(v4.z, v4.w)) <= CPB_SEED_MIN) continue;
-        } else {
-            vals[0] = h[q];
+    // four independent loads per thread and trip: the scan is a chain of DRAM latencies otherwise
+    for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * blockDim.x) {
+        int4 v4[4];
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int q = q0 + j * blockDim.x;
+            v4[j] = make_int4(0, 0, 0, 0);
+            if (q < nq) {
+                if (vec) v4[j] = *reinterpret_cast<const int4*>(h + 4 * q);
+                else v4[j].x = h[q];
+            }
         }
-        for (int e = 0; e < nv; e++) {
-            const int v = vals[e];
-            if (v <= CPB_SEED_MIN) continue;
-            const int p = vec ? 4 * q + e : q;
-            const int y = p / W, x = p - y * W;
-            bool ismax = true;
-            for (int dy = -2; dy <= 2 && ismax; dy++)
-                for (int dx = -2; dx <= 2; dx++)
-                    if (cpb_hist_at(h, H, W, y + dy, x + dx) > v) { ismax = false; break; }
-            if (ismax) {
-                const int k = atomicAdd(&s_n, 1);
-                if (k < LC) keys[k] = ((u64)(unsigned)v << 32) | (unsigned)p;
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int q = q0 + j * blockDim.x;
+            if (max(max(v4[j].x, v4[j].y), max(v4[j].z, v4[j].w)) <= CPB_SEED_MIN) continue;     // also q >= nq
+            const int vals[4] = {v4[j].x, v4[j].y, v4[j].z, v4[j].w};
+            for (int e = 0; e < (vec ? 4 : 1); e++) {
+                const int v = vals[e];
+                if (v <= CPB_SEED_MIN) continue;
+                const int p = vec ? 4 * q + e : q;
+                const int y = p / W, x = p - y * W;
+                bool ismax = true;
+                for (int dy = -2; dy <= 2 && ismax; dy++)
+                    for (int dx = -2; dx <= 2; dx++)
+                        if (cpb_hist_at(h, H, W, y + dy, x + dx) > v) { ismax = false; break; }
+                if (ismax) {
+                    const int k = atomicAdd(&s_n, 1);
+                    if (k < LC) keys[k] = ((u64)(unsigned)v << 32) | (unsigned)p;
+                }
             }
         }
     }

@@ -13,16 +13,16 @@
 // outermost instance -- the one the reference's sequential loop ends with -- wins.
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FILL_THREADS, 3)
 k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_RESTRICT holekey,
-             int* CPB_RESTRICT status, int skip_small) {
+             int* CPB_RESTRICT status, int skip_small, LabelWork wk) {
     CPB_DYN_SMEM(unsigned, s_bits);     // free[CPB_FILL_WORDS] | reach[CPB_FILL_WORDS]
     CPB_SHARED int s_changed;
-    const int b = blockIdx.y, LC = t.LC, N = H * W;
-    const int lb = t.lbound[b];
-    const int* L = lab + (size_t)b * N;
-    u64* HK = holekey + (size_t)b * N;
+    const int LC = t.LC, N = H * W;
     unsigned* fr = s_bits;
     unsigned* rc = s_bits + CPB_FILL_WORDS;
-    for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
+    int it_ = 0, b, l;
+    while (cpb_next_label(wk, t.lbound, it_, b, l)) {
+        const int* L = lab + (size_t)b * N;
+        u64* HK = holekey + (size_t)b * N;
         const size_t k = (size_t)b * LC + l;
         if (!cpb_label_live(t, k)) continue;
         const int y0 = t.ymin[k], x0 = t.xmin[k];
@@ -105,6 +105,7 @@ k_fill_holes_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64*
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
         if (h < 3 || w < 3 || h > 32 || w > 32) continue;
         unsigned fr = 0;                       // row `lane`: bit c = pixel (lane, c) is not l
+        #pragma unroll 4
         for (int r = 0; r < h; r++) {
             const bool notl = lane < w && L[(y0 + r) * W + x0 + lane] != l;
             const unsigned m = __ballot_sync(CPB_FULL, notl);

@@ -24,14 +24,31 @@ CPB_DEVICE bool cpb_minkey_less(double d0, int i0, double d1, int i1) {
     return d0 < d1 || (d0 == d1 && i0 < i1);
 }
 
+// k_qc_scan: one block per tile over the label tables.  n_iter of the tile (2 * max ext over live labels) and the
+// list of labels whose bbox is beyond the warp kernels (they need the block kernels); count[0] / count[1] must be 0.
+CPB_KERNEL k_qc_scan(LabelTables t, int2* CPB_RESTRICT list, int* CPB_RESTRICT count) {
+    const int b = blockIdx.x, LC = t.LC;
+    const int lb = t.lbound[b];
+    int ext = 0;
+    for (int l = 1 + threadIdx.x; l <= lb; l += blockDim.x) {
+        const size_t k = (size_t)b * LC + l;
+        if (!cpb_label_live(t, k)) continue;
+        const int h = t.ymax[k] - t.ymin[k] + 1, w = t.xmax[k] - t.xmin[k] + 1;
+        ext = max(ext, 2 * (h + w + 2));
+        if (!cpb_diffuse_is_small(h, w)) list[atomicAdd(count, 1)] = make_int2(b, l);
+    }
+    for (int s = 16; s; s >>= 1) ext = max(ext, __shfl_xor_sync(CPB_FULL, ext, s));
+    if ((threadIdx.x & 31) == 0 && ext > 0) atomicMax(&t.niter[b], ext);
+}
+
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
-k_centres(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, int skip_small) {
+k_centres(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, int skip_small, LabelWork wk) {
     CPB_SHARED double s_d[CPB_QC_THREADS / 32];
     CPB_SHARED int s_i[CPB_QC_THREADS / 32];
-    const int b = blockIdx.y, LC = t.LC, N = H * W;
-    const int lb = t.lbound[b];
-    const int* L = lab + (size_t)b * N;
-    for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
+    const int LC = t.LC, N = H * W;
+    int it = 0, b, l;
+    while (cpb_next_label(wk, t.lbound, it, b, l)) {
+        const int* L = lab + (size_t)b * N;
         const size_t k = (size_t)b * LC + l;
         const int c = t.cnt[k];
         if (!cpb_label_live(t, k)) continue;   // block-uniform
@@ -108,7 +125,8 @@ struct DiffSub { int l; size_t k; int y0, x0, h, w, coff; };
 // sees foreign T in its gradient and nobody reads its T, so its error is taken straight from the shared-memory
 // tile (same per-pixel arithmetic as k_flow_err) and T is not written to global memory at all.  Labels in
 // contact with another live label write T as before and are left to k_flow_err (t.done stays 0).
-struct DiffQC { const float* dPy; const float* dPx; const int* alive; double threshold; int H; };
+struct DiffQC { const float* dPy; const float* dPx; const int* alive; double threshold; int H;
+                int2* list; int* count; int cap; int b; };    // labels left to k_flow_err go to the END of `list`
 
 CPB_DEVICE bool cpb_foreign_live(int v, int l, const int* CPB_RESTRICT alive) {
     return v > 0 && v != l && (alive == nullptr || alive[v] != 0);
@@ -229,6 +247,10 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
     cpb_diffuse_prologue(L, W, t, A, B, has_b, qc, pro);
     const unsigned member = pro.member;
     const bool clean[2] = {pro.clean[0], pro.clean[1]};
+    if (qc.list && lane == 0) {            // whatever this warp does not finish itself is queued for k_flow_err
+        if (!clean[0]) qc.list[qc.cap - 1 - atomicAdd(qc.count + 1, 1)] = make_int2(qc.b, A.l);
+        if (has_b && !clean[1]) qc.list[qc.cap - 1 - atomicAdd(qc.count + 1, 1)] = make_int2(qc.b, B.l);
+    }
     const int ci[2] = {(pro.cr[0] + 1) * CPB_DC_PITCH + pro.cl[0] + 1, (pro.cr[1] + 1) * CPB_DC_PITCH + pro.cl[1] + 1};
     const double* p = S + lane;        // p[0], p[1], p[2] = columns j-1, j, j+1 of the halo row
     double* own = S + CPB_DC_PITCH + lane + 1;
@@ -305,7 +327,7 @@ CPB_DEVICE bool cpb_diffuse_load_sub(const LabelTables& t, int b, int l, int lb,
 template <int MAXH>
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
 k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
-               int niter_override, const float* CPB_RESTRICT dP, double threshold) {
+               int niter_override, const float* CPB_RESTRICT dP, double threshold, int2* todo, int* todo_count, int todo_cap) {
     CPB_SHARED double s_T[CPB_DW_WARPS][(MAXH + 3) * CPB_DC_PITCH];
     constexpr int R = 2;
     const int warp = threadIdx.x >> 5;
@@ -316,7 +338,7 @@ k_diffuse_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double*
     const int n_it = niter_override > 0 ? niter_override : t.niter[b];
     double* S = s_T[warp];
     const DiffQC qc{dP ? dP + ((size_t)b * 2 + 0) * N : nullptr, dP ? dP + ((size_t)b * 2 + 1) * N : nullptr,
-                    t.alive ? t.alive + (size_t)b * t.LC : nullptr, threshold, H};
+                    t.alive ? t.alive + (size_t)b * t.LC : nullptr, threshold, H, todo, todo_count, todo_cap, b};
     // work item = pair of consecutive labels (2i+1, 2i+2); everything below is warp-uniform
     for (int wi = blockIdx.x * CPB_DW_WARPS + warp; 2 * wi + 1 <= lb; wi += gridDim.x * CPB_DW_WARPS) {
         DiffSub A, B;
@@ -359,7 +381,7 @@ template <int MAXH, int R>
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
 k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                  int niter_override, const int* CPB_RESTRICT joboff, int* CPB_RESTRICT counter,
-                 const float* CPB_RESTRICT dP, double threshold) {
+                 const float* CPB_RESTRICT dP, double threshold, int2* todo, int* todo_count, int todo_cap) {
     CPB_SHARED double s_T[CPB_DW_WARPS][((MAXH + R - 1) / R * R + R + 1) * CPB_DC_PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = H * W;
@@ -381,7 +403,7 @@ k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t
         double* Tb = T + (size_t)b * N;
         const int n_it = niter_override > 0 ? niter_override : t.niter[b];
         const DiffQC qc{dP ? dP + ((size_t)b * 2 + 0) * N : nullptr, dP ? dP + ((size_t)b * 2 + 1) * N : nullptr,
-                        t.alive ? t.alive + (size_t)b * t.LC : nullptr, threshold, H};
+                        t.alive ? t.alive + (size_t)b * t.LC : nullptr, threshold, H, todo, todo_count, todo_cap, b};
         DiffSub A, Bs;
         const bool okA = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 1, lb, A);
         const bool okB = cpb_diffuse_load_sub<MAXH>(t, b, 2 * wi + 2, lb, Bs);
@@ -398,15 +420,15 @@ k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t
 // Neighbour order of the reference: self, (-1,0), (1,0), (0,-1), (0,1), (-1,-1), (-1,1), (1,-1), (1,1)
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
 k_diffuse(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T,
-          double* CPB_RESTRICT T2, int niter_override, int skip_small) {
+          double* CPB_RESTRICT T2, int niter_override, int skip_small, LabelWork wk) {
     CPB_DYN_SMEM(double, s_buf);   // 2 * CPB_DIFF_SMEM_CELLS doubles + CPB_DIFF_SMEM_CELLS bytes
-    const int b = blockIdx.y, LC = t.LC, N = H * W;
-    const int lb = t.lbound[b];
-    const int* L = lab + (size_t)b * N;
-    double* Tb = T + (size_t)b * N;
-    double* T2b = T2 + (size_t)b * N;
-    const int n_it = niter_override > 0 ? niter_override : t.niter[b];
-    for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
+    const int LC = t.LC, N = H * W;
+    int it_ = 0, b, l;
+    while (cpb_next_label(wk, t.lbound, it_, b, l)) {
+        const int* L = lab + (size_t)b * N;
+        double* Tb = T + (size_t)b * N;
+        double* T2b = T2 + (size_t)b * N;
+        const int n_it = niter_override > 0 ? niter_override : t.niter[b];
         const size_t k = (size_t)b * LC + l;
         if (!cpb_label_live(t, k)) continue;
         const int y0 = t.ymin[k], x0 = t.xmin[k];
@@ -509,16 +531,16 @@ CPB_DEVICE double cpb_T_at(const double* CPB_RESTRICT Tb, const int* CPB_RESTRIC
 
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_QC_THREADS, 8)
 k_flow_err(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, LabelTables t,
-           const double* CPB_RESTRICT T, double threshold, double* CPB_RESTRICT mu_out, int skip_small) {
+           const double* CPB_RESTRICT T, double threshold, double* CPB_RESTRICT mu_out, int skip_small, LabelWork wk) {
     CPB_SHARED double s_ey[CPB_QC_THREADS / 32], s_ex[CPB_QC_THREADS / 32];
-    const int b = blockIdx.y, LC = t.LC, N = H * W;
-    const int lb = t.lbound[b];
-    const int* L = lab + (size_t)b * N;
-    const double* Tb = T + (size_t)b * N;
-    const int* alive = t.alive ? t.alive + (size_t)b * LC : nullptr;
-    const float* dPy = dP ? dP + ((size_t)b * 2 + 0) * N : nullptr;
-    const float* dPx = dP ? dP + ((size_t)b * 2 + 1) * N : nullptr;
-    for (int l = 1 + blockIdx.x; l <= lb; l += gridDim.x) {
+    const int LC = t.LC, N = H * W;
+    int it_ = 0, b, l;
+    while (cpb_next_label(wk, t.lbound, it_, b, l)) {
+        const int* L = lab + (size_t)b * N;
+        const double* Tb = T + (size_t)b * N;
+        const int* alive = t.alive ? t.alive + (size_t)b * LC : nullptr;
+        const float* dPy = dP ? dP + ((size_t)b * 2 + 0) * N : nullptr;
+        const float* dPx = dP ? dP + ((size_t)b * 2 + 1) * N : nullptr;
         const size_t k = (size_t)b * LC + l;
         const int c = t.cnt[k];
         if (!cpb_label_live(t, k)) continue;
@@ -558,62 +580,6 @@ k_flow_err(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int
             double sy = 0.0, sx = 0.0;
             for (int q = 0; q < CPB_QC_THREADS / 32; q++) { sy += s_ey[q]; sx += s_ex[q]; }
             const double e = sy / (double)c + sx / (double)c;
-            t.err[k] = e;
-            t.flag[k] = e > threshold ? 1 : 0;
-        }
-    }
-}
-
-// k_flow_err_warp: the same per-label flow error, one WARP per label for bboxes up to 32 px wide
-// (lane = column, loop over rows, coalesced row reads).
-CPB_KERNEL CPB_LAUNCH_BOUNDS(128, 8)
-k_flow_err_warp(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, LabelTables t,
-                const double* CPB_RESTRICT T, double threshold, double* CPB_RESTRICT mu_out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int b = blockIdx.y, LC = t.LC, N = H * W;
-    const int lb = t.lbound[b];
-    const int* L = lab + (size_t)b * N;
-    const double* Tb = T + (size_t)b * N;
-    const int* alive = t.alive ? t.alive + (size_t)b * LC : nullptr;
-    const float* dPy = dP ? dP + ((size_t)b * 2 + 0) * N : nullptr;
-    const float* dPx = dP ? dP + ((size_t)b * 2 + 1) * N : nullptr;
-    for (int l = 1 + blockIdx.x * nw + warp; l <= lb; l += gridDim.x * nw) {
-        const size_t k = (size_t)b * LC + l;
-        const int c = t.cnt[k];
-        if (!cpb_label_live(t, k)) continue;
-        const int y0 = t.ymin[k], x0 = t.xmin[k];
-        const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
-        if (w > 32) continue;
-        double ey = 0.0, ex = 0.0;
-        const int x = x0 + lane;
-        if (lane < w) {
-            for (int r = 0; r < h; r++) {
-                const int y = y0 + r;
-                const int p = y * W + x;
-                if (L[p] != l) continue;
-                const double dy = __dsub_rn(cpb_T_at(Tb, L, alive, H, W, y + 1, x), cpb_T_at(Tb, L, alive, H, W, y - 1, x));
-                const double dx = __dsub_rn(cpb_T_at(Tb, L, alive, H, W, y, x + 1), cpb_T_at(Tb, L, alive, H, W, y, x - 1));
-                const double nrm = __dadd_rn(1e-60, __dsqrt_rn(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx))));
-                const double my = __ddiv_rn(dy, nrm), mx = __ddiv_rn(dx, nrm);
-                if (mu_out) {
-                    mu_out[((size_t)b * 2 + 0) * N + p] = my;
-                    mu_out[((size_t)b * 2 + 1) * N + p] = mx;
-                }
-                if (dP) {
-                    const double ry = __dsub_rn(my, (double)__fdiv_rn(dPy[p], 5.0f));
-                    const double rx = __dsub_rn(mx, (double)__fdiv_rn(dPx[p], 5.0f));
-                    ey += __dmul_rn(ry, ry);
-                    ex += __dmul_rn(rx, rx);
-                }
-            }
-        }
-        if (!dP) continue;
-        for (int sft = 16; sft; sft >>= 1) {
-            ey += __shfl_xor_sync(CPB_FULL, ey, sft);
-            ex += __shfl_xor_sync(CPB_FULL, ex, sft);
-        }
-        if (lane == 0) {
-            const double e = ey / (double)c + ex / (double)c;
             t.err[k] = e;
             t.flag[k] = e > threshold ? 1 : 0;
         }
