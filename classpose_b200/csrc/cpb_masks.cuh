@@ -64,36 +64,28 @@ k_seeds(int* hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
     // the histogram is almost everywhere 0: scan it with 128-bit loads when the tile allows
     const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
     const int nq = vec ? N / 4 : N;
-    // four independent loads per thread and trip: the scan is a chain of DRAM latencies otherwise
-    for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * blockDim.x) {
-        int4 v4[4];
-        #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int q = q0 + j * blockDim.x;
-            v4[j] = make_int4(0, 0, 0, 0);
-            if (q < nq) {
-                if (vec) v4[j] = *reinterpret_cast<const int4*>(h + 4 * q);
-                else v4[j].x = h[q];
-            }
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        int vals[4];
+        int nv = 1;
+        if (vec) {
+            const int4 v4 = *reinterpret_cast<const int4*>(h + 4 * q);
+            vals[0] = v4.x; vals[1] = v4.y; vals[2] = v4.z; vals[3] = v4.w; nv = 4;
+            if (max(max(v4.x, v4.y), max(v4.z, v4.w)) <= CPB_SEED_MIN) continue;
+        } else {
+            vals[0] = h[q];
         }
-        #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int q = q0 + j * blockDim.x;
-            if (max(max(v4[j].x, v4[j].y), max(v4[j].z, v4[j].w)) <= CPB_SEED_MIN) continue;     // also q >= nq
-            const int vals[4] = {v4[j].x, v4[j].y, v4[j].z, v4[j].w};
-            for (int e = 0; e < (vec ? 4 : 1); e++) {
-                const int v = vals[e];
-                if (v <= CPB_SEED_MIN) continue;
-                const int p = vec ? 4 * q + e : q;
-                const int y = p / W, x = p - y * W;
-                bool ismax = true;
-                for (int dy = -2; dy <= 2 && ismax; dy++)
-                    for (int dx = -2; dx <= 2; dx++)
-                        if (cpb_hist_at(h, H, W, y + dy, x + dx) > v) { ismax = false; break; }
-                if (ismax) {
-                    const int k = atomicAdd(&s_n, 1);
-                    if (k < LC) keys[k] = ((u64)(unsigned)v << 32) | (unsigned)p;
-                }
+        for (int e = 0; e < nv; e++) {
+            const int v = vals[e];
+            if (v <= CPB_SEED_MIN) continue;
+            const int p = vec ? 4 * q + e : q;
+            const int y = p / W, x = p - y * W;
+            bool ismax = true;
+            for (int dy = -2; dy <= 2 && ismax; dy++)
+                for (int dx = -2; dx <= 2; dx++)
+                    if (cpb_hist_at(h, H, W, y + dy, x + dx) > v) { ismax = false; break; }
+            if (ismax) {
+                const int k = atomicAdd(&s_n, 1);
+                if (k < LC) keys[k] = ((u64)(unsigned)v << 32) | (unsigned)p;
             }
         }
     }
@@ -110,9 +102,17 @@ k_seeds(int* hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
         const int sy = p / W, sx = p - sy * W;
         const int y = sy - 5 + lane;
         unsigned allowed = 0;
-        if (lane < 11)
+        if (lane < 11 && y >= 0 && y < H) {
+            int v[11];                                 // the row's 11 loads in flight together
+            #pragma unroll
+            for (int c = 0; c < 11; c++) {
+                const int x = sx - 5 + c;
+                v[c] = (x >= 0 && x < W) ? Mb[y * W + x] : 0;
+            }
+            #pragma unroll
             for (int c = 0; c < 11; c++)
-                if (cpb_hist_grow_ok(Mb, H, W, y, sx - 5 + c)) allowed |= 1u << c;
+                if (v[c] > CPB_GROW_MIN || v[c] < 0) allowed |= 1u << c;
+        }
         unsigned m = (lane == 5) ? (1u << 5) : 0u;
         for (int it = 0; it < 5; it++) {
             const unsigned d = m | (m << 1) | (m >> 1);

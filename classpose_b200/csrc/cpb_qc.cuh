@@ -255,16 +255,21 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
     const double* p = S + lane;        // p[0], p[1], p[2] = columns j-1, j, j+1 of the halo row
     double* own = S + CPB_DC_PITCH + lane + 1;
     __syncwarp();
+    const int c_lo = has_b ? min(pro.cr[0], pro.cr[1]) : pro.cr[0], c_hi = has_b ? max(pro.cr[0], pro.cr[1]) : pro.cr[0];
     for (int it = 0; it < n_it; it++) {
         if (lane == 0) { S[ci[0]] += 1.0; if (has_b) S[ci[1]] += 1.0; }   // T[centre] += 1 before averaging
         __syncwarp();
+        // the heat front moves one row per iteration: rows further than it + 1 from a centre still have an all-zero
+        // 3 x 3 neighbourhood and stay exactly 0, so the first iterations only walk the rows the front has reached
+        const int r_lo = max(0, c_lo - it - 1) & ~(R - 1), r_hi = min(hj, c_hi + it + 2);
         // win[k] = row r-1+k of the tile (left, centre, right of this lane's column)
         double win[R + 2][3];
         #pragma unroll
         for (int k = 0; k < 2; k++) {
-            win[k][0] = p[k * CPB_DC_PITCH]; win[k][1] = p[k * CPB_DC_PITCH + 1]; win[k][2] = p[k * CPB_DC_PITCH + 2];
+            const double* q0 = p + (r_lo + k) * CPB_DC_PITCH;
+            win[k][0] = q0[0]; win[k][1] = q0[1]; win[k][2] = q0[2];
         }
-        for (int r = 0; r < hj; r += R) {
+        for (int r = r_lo; r < r_hi; r += R) {
             const double* q = p + (r + 2) * CPB_DC_PITCH;
             #pragma unroll
             for (int k = 0; k < R; k++) {                       // rows r+1 .. r+R
