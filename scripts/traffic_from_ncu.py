@@ -11,7 +11,7 @@ lines = [l for l in open(src) if not l.startswith("==")]
 acc = defaultdict(lambda: defaultdict(list))
 per_id = defaultdict(dict)
 for r in csv.DictReader(lines):
-    name = r["Kernel Name"].split("(")[0].split("<")[0]
+    name = r["Kernel Name"].split("(")[0].split("<")[0].replace("void ", "").strip()
     v = float(r["Metric Value"].replace(",", ""))
     unit = r.get("Metric Unit", "")
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(unit, 1)
