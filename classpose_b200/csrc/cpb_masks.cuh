@@ -42,12 +42,6 @@ CPB_DEVICE int cpb_hist_at(const int* CPB_RESTRICT h, int H, int W, int y, int x
 //     negative numbers (atomicMin of -label): only pixels with h > 2 are ever painted and the only reads that
 //     follow are "h > 2" tests, which a painted pixel passes by construction -- so no separate label plane has to
 //     be zeroed, written and read.  Afterwards hist[p] < 0 means label -hist[p], anything else label 0.
-CPB_DEVICE bool cpb_hist_grow_ok(const int* h, int H, int W, int y, int x) {
-    if (!(y >= 0 && y < H && x >= 0 && x < W)) return false;
-    const int v = h[y * W + x];
-    return v > CPB_GROW_MIN || v < 0;
-}
-
 CPB_KERNEL CPB_LAUNCH_BOUNDS(1024, 1)
 k_seeds(int* hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
         int* CPB_RESTRICT seed_lab, int* CPB_RESTRICT nseeds) {

@@ -32,6 +32,6 @@ for _ in range(5):
 print("oracle port on one core-ish (torch threads=%d): %.1f ms per tile" % (torch.get_num_threads(), (time.perf_counter() - t0) / 5 * 1e3))
 PY
 echo "== memcheck (smoke + selected parity cases)"
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -k "fused_path or contours or dedup or fill_holes or merge or average" > gpurun_out/memcheck2.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/memcheck2.log
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -k "fused or contours or dedup or fill_holes or merge or average or flows or get_masks or qc" > gpurun_out/memcheck2.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/memcheck2.log
 echo "== racecheck (smoke)"
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/racecheck.log
