@@ -301,13 +301,26 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     return 0;
 }
 
+// end-point histogram in w.hist -> seed labels painted into it, seed count per tile in t.lbound
+int run_seeds(const Workspace& w, int B, int H, int W, cudaStream_t st) {
+    const long long BN = (long long)B * H * W;
+    const int vec = ((long long)H * W % 4 == 0) && (reinterpret_cast<uintptr_t>(w.hist) % 16 == 0) ? 1 : 0;
+    cudaMemsetAsync(w.t.misc, 0, B * sizeof(int), st);                 // candidate counters
+    CPB_LAUNCH_COUNTED(k_seed_scan, dim3(blocks_for(vec ? BN / 4 : BN, 256)), dim3(256), 0, st, (const int*)w.hist, B, H, W,
+                       w.t.LC, vec, w.skey, w.t.misc);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(table_threads(H, W)), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.t.lbound,
+                       (const int*)w.t.misc);
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
 // end points (+ histogram already in w.hist) -> contiguous labels in `masks`
 int run_get_masks(const Workspace& w, const int32_t* pfinal, int B, int H, int W, double msf, int32_t* masks,
                   int32_t* counts, cudaStream_t st) {
     const long long BN = (long long)B * H * W;
     prof_begin(w.prof, S_SEEDS);
-    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(table_threads(H, W)), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.t.lbound);
-    CPB_CHECK_LAUNCH();
+    { int e_ = run_seeds(w, B, H, W, st); if (e_) return e_; }
     prof_end(w.prof, S_SEEDS);
     prof_begin(w.prof, S_LOOKUP);
     int e = run_init_tables(w, B, st); if (e) return e;
@@ -353,7 +366,7 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
         CPB_LAUNCH_COUNTED(k_diffuse_jobs, dim3(1), dim3(1024), 0, st, w.t.lbound, B, w.jobs, w.jobs + B + 1);
         CPB_CHECK_LAUNCH();
         int* ctr = w.jobs + B + 1;
-        CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 2>), dim3(sm_count() * 8), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
+        CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 2>), dim3(sm_count() * CPB_DQ_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
                            w.t, w.T, 0, w.jobs, ctr + 0, qc_dP, thr, w.todo, todo_n, big.cap);
         CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 2>), dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
@@ -391,10 +404,11 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
     e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, true, st, S_MAP2); if (e) return e;
     prof_begin(w.prof, S_FILL);
     cudaMemsetAsync(w.holekey, 0, BN * sizeof(u64), st);
-    CPB_LAUNCH_COUNTED(k_fill_holes_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(128), 0, st, masks, H, W, w.t, w.holekey);
+    CPB_LAUNCH_COUNTED(k_fill_holes_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(128), 0, st, masks, H, W, w.t, w.holekey,
+                       CPB_FILL_BOTH);
     CPB_CHECK_LAUNCH();
     CPB_LAUNCH_COUNTED(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
-               masks, H, W, w.t, w.holekey, w.status, 1, (LabelWork{nullptr, nullptr, 0, 0}));
+               masks, H, W, w.t, w.holekey, w.status, 1, (LabelWork{nullptr, nullptr, 0, 0}), CPB_FILL_BOTH);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_FILL);
     e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, w.holekey, true, st, S_MAP3); if (e) return e;
@@ -557,8 +571,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     if (e) return e;
     // (3) seeds -> raw labels (seed order + 1) and their statistics; ids after get_masks live in t.remap
     prof_begin(w.prof, S_SEEDS);
-    CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(table_threads(H, W)), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.t.lbound);
-    CPB_CHECK_LAUNCH();
+    { int e_ = run_seeds(w, B, H, W, st); if (e_) return e_; }
     prof_end(w.prof, S_SEEDS);
     prof_begin(w.prof, S_LOOKUP);
     e = run_init_tables(w, B, st); if (e) return e;
@@ -589,13 +602,19 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_SIZE1);
         prof_begin(w.prof, S_FILL);
-        cudaMemsetAsync(w.holekey, 0, BN * sizeof(u64), st);
-        CPB_LAUNCH_COUNTED(k_fill_holes_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(128), 0, st, masks, H, W, w.t,
-                           w.holekey);
-        CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED(k_fill_holes, dim3(sm_count() * 3), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
-                           masks, H, W, w.t, w.holekey, w.status, 1, todo_work(w, B, false));
-        CPB_CHECK_LAUNCH();
+        // detect -> zero the hole plane of the tiles that have a hole -> write the proposals of those tiles
+        for (int pass = CPB_FILL_DETECT; pass <= CPB_FILL_WRITE; pass++) {
+            CPB_LAUNCH_COUNTED(k_fill_holes_warp, dim3(kWarpDiffuseBlocksPerTile, B), dim3(128), 0, st, masks, H, W, w.t,
+                               w.holekey, pass);
+            CPB_CHECK_LAUNCH();
+            CPB_LAUNCH_COUNTED(k_fill_holes, dim3(sm_count() * 3), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
+                               masks, H, W, w.t, w.holekey, w.status, 1, todo_work(w, B, false), pass);
+            CPB_CHECK_LAUNCH();
+            if (pass == CPB_FILL_DETECT) {
+                CPB_LAUNCH_COUNTED(k_zero_hole_tiles, dim3(8, B), dim3(256), 0, st, w.holekey, H, W, w.t);
+                CPB_CHECK_LAUNCH();
+            }
+        }
         prof_end(w.prof, S_FILL);
         prof_begin(w.prof, S_MAP3);
         CPB_LAUNCH_COUNTED(k_recount_reset, dim3(B), dim3(256), 0, st, w.t);

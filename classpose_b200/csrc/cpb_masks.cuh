@@ -34,57 +34,62 @@ CPB_DEVICE int cpb_hist_at(const int* CPB_RESTRICT h, int H, int W, int y, int x
     return (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(&h[y * W + x]) : 0;
 }
 
-// k_seeds: one block per tile.
-//  1. seeds = pixels with h > 10 that equal the maximum of their 5x5 neighbourhood
+// k_seed_scan + k_seeds (one block per tile).
+//  1. seeds = pixels with h > 10 that equal the maximum of their 5x5 neighbourhood (k_seed_scan, below)
 //  2. order: ascending count, ties by raster position (stable sort of a raster-ordered list)
 //  3. each seed grows inside its 11x11 window: 5 x { 3x3 dilation ; &= h > 2 }
 //  4. paint label = order+1; later (larger) labels overwrite.  The labels are painted INTO the histogram as
 //     negative numbers (atomicMin of -label): only pixels with h > 2 are ever painted and the only reads that
 //     follow are "h > 2" tests, which a painted pixel passes by construction -- so no separate label plane has to
 //     be zeroed, written and read.  Afterwards hist[p] < 0 means label -hist[p], anything else label 0.
+// k_seed_scan: the whole batch as one stream (one thread per 4 pixels, 128-bit loads when vec != 0): pixels with
+// h > 10 that equal the maximum of their 5x5 neighbourhood are appended to their tile's candidate list
+// (cand_count must be zeroed).  The histogram is almost everywhere 0, so nearly every thread stops after its load.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_seed_scan(const int* CPB_RESTRICT hist, int B, int H, int W, int LC, int vec, u64* CPB_RESTRICT seed_key,
+            int* CPB_RESTRICT cand_count) {
+    const int N = H * W;
+    const long long nq = vec ? (long long)B * N / 4 : (long long)B * N;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int vals[4] = {0, 0, 0, 0};
+    if (vec) {
+        const int4 v4 = *reinterpret_cast<const int4*>(hist + 4 * q);
+        if (max(max(v4.x, v4.y), max(v4.z, v4.w)) <= CPB_SEED_MIN) return;
+        vals[0] = v4.x; vals[1] = v4.y; vals[2] = v4.z; vals[3] = v4.w;
+    } else {
+        vals[0] = hist[q];
+    }
+    const long long g0 = vec ? 4 * q : q;
+    const int b = (int)(g0 / N);
+    const int p0 = (int)(g0 - (long long)b * N);
+    const int* h = hist + (size_t)b * N;
+    for (int e = 0; e < (vec ? 4 : 1); e++) {
+        const int v = vals[e];
+        if (v <= CPB_SEED_MIN) continue;
+        const int p = p0 + e;
+        const int y = p / W, x = p - y * W;
+        bool ismax = true;
+        for (int dy = -2; dy <= 2 && ismax; dy++)
+            for (int dx = -2; dx <= 2; dx++)
+                if (cpb_hist_at(h, H, W, y + dy, x + dx) > v) { ismax = false; break; }
+        if (ismax) {
+            const int k = atomicAdd(&cand_count[b], 1);
+            if (k < LC) seed_key[(size_t)b * LC + k] = ((u64)(unsigned)v << 32) | (unsigned)p;
+        }
+    }
+}
+
 CPB_KERNEL CPB_LAUNCH_BOUNDS(1024, 1)
 k_seeds(int* hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
-        int* CPB_RESTRICT seed_lab, int* CPB_RESTRICT nseeds) {
-    CPB_SHARED int s_n;
+        int* CPB_RESTRICT seed_lab, int* CPB_RESTRICT nseeds, const int* CPB_RESTRICT cand_count) {
     CPB_SHARED u64 s_keys[CPB_RANK_CHUNK];
     const int b = blockIdx.x;
     const int N = H * W;
-    const int* h = hist + (size_t)b * N;
     u64* keys = seed_key + (size_t)b * LC;
     int* labs = seed_lab + (size_t)b * LC;
     int* Mb = hist + (size_t)b * N;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    // the histogram is almost everywhere 0: scan it with 128-bit loads when the tile allows
-    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
-    const int nq = vec ? N / 4 : N;
-    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-        int vals[4];
-        int nv = 1;
-        if (vec) {
-            const int4 v4 = *reinterpret_cast<const int4*>(h + 4 * q);
-            vals[0] = v4.x; vals[1] = v4.y; vals[2] = v4.z; vals[3] = v4.w; nv = 4;
-            if (max(max(v4.x, v4.y), max(v4.z, v4.w)) <= CPB_SEED_MIN) continue;
-        } else {
-            vals[0] = h[q];
-        }
-        for (int e = 0; e < nv; e++) {
-            const int v = vals[e];
-            if (v <= CPB_SEED_MIN) continue;
-            const int p = vec ? 4 * q + e : q;
-            const int y = p / W, x = p - y * W;
-            bool ismax = true;
-            for (int dy = -2; dy <= 2 && ismax; dy++)
-                for (int dx = -2; dx <= 2; dx++)
-                    if (cpb_hist_at(h, H, W, y + dy, x + dx) > v) { ismax = false; break; }
-            if (ismax) {
-                const int k = atomicAdd(&s_n, 1);
-                if (k < LC) keys[k] = ((u64)(unsigned)v << 32) | (unsigned)p;
-            }
-        }
-    }
-    __syncthreads();
-    const int n = min(s_n, LC - 1);
+    const int n = min(cand_count[b], LC - 1);
     if (threadIdx.x == 0) nseeds[b] = n;
     cpb_block_rank(keys, n, labs, s_keys);
 

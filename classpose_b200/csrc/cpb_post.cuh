@@ -5,6 +5,21 @@
 
 #define CPB_FILL_THREADS 128
 #define CPB_FILL_WORDS 8192          // 32-bit words per bitmap in shared memory (2 bitmaps = 64 KB)
+// Passes of the hole-fill kernels.  BOTH (stage calls): flag the tile and write the proposals into a zeroed
+// `holekey` plane.  The fused path avoids zeroing 8 bytes per pixel of every tile when few tiles have holes:
+// DETECT only flags tiles (t.misc), k_zero_hole_tiles clears the plane of the flagged tiles, WRITE redoes the
+// flagged tiles and writes the proposals.
+#define CPB_FILL_BOTH 0
+#define CPB_FILL_DETECT 1
+#define CPB_FILL_WRITE 2
+
+CPB_KERNEL k_zero_hole_tiles(u64* CPB_RESTRICT holekey, int H, int W, LabelTables t) {
+    const int b = blockIdx.y;
+    if (t.misc[b] == 0) return;
+    const int N = H * W;
+    u64* HK = holekey + (size_t)b * N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) HK[i] = 0;
+}
 
 // k_fill_holes: one block per label (labels strided over gridDim.x, tile = blockIdx.y).
 // Holes of label l = pixels of its bbox crop that are not l and are not 4-connected, through
@@ -13,7 +28,7 @@
 // outermost instance -- the one the reference's sequential loop ends with -- wins.
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FILL_THREADS, 3)
 k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_RESTRICT holekey,
-             int* CPB_RESTRICT status, int skip_small, LabelWork wk) {
+             int* CPB_RESTRICT status, int skip_small, LabelWork wk, int pass) {
     CPB_DYN_SMEM(unsigned, s_bits);     // free[CPB_FILL_WORDS] | reach[CPB_FILL_WORDS]
     CPB_SHARED int s_changed;
     const int LC = t.LC, N = H * W;
@@ -24,6 +39,7 @@ k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_
         const int* L = lab + (size_t)b * N;
         u64* HK = holekey + (size_t)b * N;
         const size_t k = (size_t)b * LC + l;
+        if (pass == CPB_FILL_WRITE && t.misc[b] == 0) continue;   // no hole anywhere in this tile (block-uniform)
         if (!cpb_label_live(t, k)) continue;
         const int y0 = t.ymin[k], x0 = t.xmin[k];
         const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
@@ -79,8 +95,8 @@ k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_
         for (int i = threadIdx.x; i < h * wpr; i += blockDim.x) {
             unsigned hole = fr[i] & ~rc[i];
             const int r = i / wpr, j = i - r * wpr;
-            if (hole) t.misc[b] = 1;     // tile has at least one filled hole
-            while (hole) {
+            if (hole && pass != CPB_FILL_WRITE) t.misc[b] = 1;     // tile has at least one filled hole
+            while (hole && pass != CPB_FILL_DETECT) {
                 const int c = __ffs((int)hole) - 1;
                 hole &= hole - 1;
                 atomicMax(&HK[(y0 + r) * W + x0 + j * 32 + c], prio | (unsigned)l);
@@ -92,9 +108,10 @@ k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_
 // k_fill_holes_warp: the same hole detection for bboxes up to 32 x 32, one WARP per label and no shared
 // memory: lane r holds row r of the crop as a 32-bit mask; the border flood runs on warp shuffles.
 CPB_KERNEL CPB_LAUNCH_BOUNDS(128, 8)
-k_fill_holes_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_RESTRICT holekey) {
+k_fill_holes_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_RESTRICT holekey, int pass) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int b = blockIdx.y, LC = t.LC, N = H * W;
+    if (pass == CPB_FILL_WRITE && t.misc[b] == 0) return;      // no hole anywhere in this tile
     const int lb = t.lbound[b];
     const int* L = lab + (size_t)b * N;
     u64* HK = holekey + (size_t)b * N;
@@ -128,9 +145,9 @@ k_fill_holes_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64*
             if (!__any_sync(CPB_FULL, ch)) break;
         }
         unsigned hole = fr & ~rc;
-        if (hole) t.misc[b] = 1;
+        if (hole && pass != CPB_FILL_WRITE) t.misc[b] = 1;
         const u64 prio = (u64)((unsigned)(h * w)) << 32;
-        while (hole) {
+        while (hole && pass != CPB_FILL_DETECT) {
             const int c = __ffs((int)hole) - 1;
             hole &= hole - 1;
             atomicMax(&HK[(y0 + lane) * W + x0 + c], prio | (unsigned)l);

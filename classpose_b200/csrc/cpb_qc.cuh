@@ -391,8 +391,11 @@ CPB_KERNEL k_diffuse_jobs(const int* CPB_RESTRICT lbound, int B, int* CPB_RESTRI
     if (threadIdx.x == 0) joboff[B] = s_base;
 }
 
+#ifndef CPB_DQ_MINBLOCKS
+#define CPB_DQ_MINBLOCKS 8
+#endif
 template <int MAXH, int R>
-CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? 8 : 6))
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, (MAXH == CPB_DC_MIDH ? CPB_DQ_MINBLOCKS : 6))
 k_diffuse_warp_q(const int* CPB_RESTRICT lab, int B, int H, int W, LabelTables t, double* CPB_RESTRICT T,
                  int niter_override, const int* CPB_RESTRICT joboff, int* CPB_RESTRICT counter,
                  const float* CPB_RESTRICT dP, double threshold, int2* todo, int* todo_count, int todo_cap) {

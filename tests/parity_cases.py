@@ -380,6 +380,14 @@ def case_fused_path_other_shapes(be):
     assert f1 >= 0.99 and abs(nnew - nref) <= 1
 
 
+def case_fused_generic_class_count(be):
+    """A class count that has no specialised final+vote instance (C = 4; the reference's configs use 5, 7, 10) on a
+    tile whose pixel count is a multiple of 4, so the vote still rides on the final pass (generic kernel)."""
+    tiles = [std_tile(11, H=64, W=64, n_grid=3, C=4), std_tile(12, H=64, W=64, n_grid=3, C=4)]
+    f1, nref, nnew = fused_compare(be, tiles, 4)
+    assert f1 >= 0.99 and nnew == nref
+
+
 def case_fused_odd_width(be):
     """W not a multiple of 4 (scalar prep kernel, unaligned rows) and a non-multiple-of-32 tile."""
     tiles = [std_tile(9, H=70, W=57, n_grid=3, C=3), std_tile(10, H=70, W=57, n_grid=3, C=3)]
@@ -621,6 +629,6 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_f
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
              case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_fill_holes_exact, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
-             case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
+             case_fused_generic_class_count, case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
              case_cell_contours_match_cv2, case_prepare_tiles, case_dedup_overlapping_tiles, case_dedup_random_points_components,
              case_label_offsets]
