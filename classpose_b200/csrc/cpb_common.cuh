@@ -107,68 +107,3 @@ CPB_DEVICE void cpb_stats_accum(const LabelTables& t, int b, int lab, int ridx, 
     }
 }
 
-// Block-aggregated variant for kernels whose consecutive threads walk one neighbourhood of a tile (the lookup over
-// the patch-ordered foreground list: a 256-entry chunk holds a handful of labels, each seen by most of the
-// block's warps).  Warps aggregate as above, the warp leaders merge into a small shared-memory table (CAS on the
-// key, shared-memory atomics), and one thread per occupied slot issues the global atomics: about four times fewer
-// L2 atomics per label.  A full table falls back to direct global atomics.  All threads of the block must call
-// (contains __syncthreads()).
-#define CPB_SA_SLOTS 64
-struct StatsTable {
-    int key[CPB_SA_SLOTS], cnt[CPB_SA_SLOTS], first[CPB_SA_SLOTS];
-    int y0[CPB_SA_SLOTS], y1[CPB_SA_SLOTS], x0[CPB_SA_SLOTS], x1[CPB_SA_SLOTS];
-    u64 sy[CPB_SA_SLOTS], sx[CPB_SA_SLOTS];
-};
-
-CPB_DEVICE void cpb_stats_accum_block(const LabelTables& t, int b, int lab, int ridx, int y, int x, StatsTable& s) {
-    const int lane = threadIdx.x & 31, tid = threadIdx.x;
-    if (tid < CPB_SA_SLOTS) {
-        s.key[tid] = -1; s.cnt[tid] = 0; s.first[tid] = CPB_IMAX;
-        s.y0[tid] = CPB_IMAX; s.y1[tid] = -1; s.x0[tid] = CPB_IMAX; s.x1[tid] = -1; s.sy[tid] = 0; s.sx[tid] = 0;
-    }
-    __syncthreads();
-    const bool act = lab > 0;
-    const unsigned amask = __ballot_sync(CPB_FULL, act);
-    if (act) {
-        const int key = b * t.LC + lab;
-        const unsigned peers = __match_any_sync(amask, key);
-        const int leader = __ffs((int)peers) - 1;
-        const int n = __popc(peers);
-        const int fmin = __reduce_min_sync(peers, ridx);
-        const int y0 = __reduce_min_sync(peers, y), y1 = __reduce_max_sync(peers, y);
-        const int x0 = __reduce_min_sync(peers, x), x1 = __reduce_max_sync(peers, x);
-        const int sy = __reduce_add_sync(peers, y), sx = __reduce_add_sync(peers, x);
-        if (lane == leader) {
-            unsigned h = ((unsigned)key * 2654435761u) >> 26;             // 6 bits
-            int slot = -1;
-            for (int probe = 0; probe < CPB_SA_SLOTS; probe++) {
-                const int old = atomicCAS(&s.key[h], -1, key);
-                if (old == -1 || old == key) { slot = (int)h; break; }
-                h = (h + 1) & (CPB_SA_SLOTS - 1);
-            }
-            if (slot >= 0) {
-                atomicAdd(&s.cnt[slot], n);
-                atomicMin(&s.first[slot], fmin);
-                atomicMin(&s.y0[slot], y0); atomicMax(&s.y1[slot], y1);
-                atomicMin(&s.x0[slot], x0); atomicMax(&s.x1[slot], x1);
-                atomicAdd(&s.sy[slot], (u64)sy); atomicAdd(&s.sx[slot], (u64)sx);
-            } else {
-                atomicAdd(&t.cnt[key], n);
-                atomicMin(&t.first[key], fmin);
-                atomicMin(&t.ymin[key], y0); atomicMax(&t.ymax[key], y1);
-                atomicMin(&t.xmin[key], x0); atomicMax(&t.xmax[key], x1);
-                atomicAdd(&t.sumy[key], (u64)sy); atomicAdd(&t.sumx[key], (u64)sx);
-            }
-        }
-    }
-    __syncthreads();
-    if (tid < CPB_SA_SLOTS && s.key[tid] >= 0) {
-        const int key = s.key[tid];
-        atomicAdd(&t.cnt[key], s.cnt[tid]);
-        atomicMin(&t.first[key], s.first[tid]);
-        atomicMin(&t.ymin[key], s.y0[tid]); atomicMax(&t.ymax[key], s.y1[tid]);
-        atomicMin(&t.xmin[key], s.x0[tid]); atomicMax(&t.xmax[key], s.x1[tid]);
-        atomicAdd(&t.sumy[key], s.sy[tid]); atomicAdd(&t.sumx[key], s.sx[tid]);
-    }
-    __syncthreads();
-}

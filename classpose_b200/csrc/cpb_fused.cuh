@@ -13,12 +13,6 @@ CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_lookup_list(const unsigned* CPB_RESTRICT list, const unsigned* CPB_RESTRICT list_n,
               const int* CPB_RESTRICT pfinal, const int* CPB_RESTRICT M, int H, int W,
               int* CPB_RESTRICT lab, LabelTables t) {
-#ifndef CPB_LOOKUP_BLOCK_STATS
-#define CPB_LOOKUP_BLOCK_STATS 1
-#endif
-#if CPB_LOOKUP_BLOCK_STATS
-    CPB_SHARED StatsTable s_stats;
-#endif
     const unsigned total = *list_n;
     const int N = H * W;
     for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {
@@ -33,11 +27,8 @@ k_lookup_list(const unsigned* CPB_RESTRICT list, const unsigned* CPB_RESTRICT li
             lab[gi] = l;
             y = r / W; x = r - y * W;
         }
-#if CPB_LOOKUP_BLOCK_STATS
-        cpb_stats_accum_block(t, b, l, r, y, x, s_stats);
-#else
-        cpb_stats_accum(t, b, l, r, y, x);
-#endif
+        cpb_stats_accum(t, b, l, r, y, x);      // (a block-level shared-memory merge before the L2 atomics was slower:
+                                                //  0.355 ms vs 0.261 ms, three block barriers per 256 pixels)
     }
 }
 
