@@ -83,17 +83,6 @@ CPB_DEVICE int cpb_block_scan_incl(int v, int* warp_tot, int* block_total) {
     return base + x;
 }
 
-#ifndef CPB_STATS_PEEK
-#define CPB_STATS_PEEK 1
-#endif
-CPB_DEVICE int cpb_peek(const int* p) {
-#ifdef CPB_SIM
-    return *reinterpret_cast<const volatile int*>(p);
-#else
-    return __ldcg(p);          // L2 (never a stale L1 line of another SM's update; stale would still be safe)
-#endif
-}
-
 // Warp-aggregated update of the label tables for one pixel per lane.
 // All 32 lanes must call; `lab` <= 0 lanes contribute nothing.  key = tile*LC + lab.
 CPB_DEVICE void cpb_stats_accum(const LabelTables& t, int b, int lab, int ridx, int y, int x) {
@@ -112,19 +101,11 @@ CPB_DEVICE void cpb_stats_accum(const LabelTables& t, int b, int lab, int ridx, 
     if (lane == leader) {
         atomicAdd(&t.cnt[key], n);
         atomicAdd(&t.sumy[key], (u64)sy); atomicAdd(&t.sumx[key], (u64)sx);
-#if CPB_STATS_PEEK
-        // min / max entries are monotone: a (possibly stale) read that already satisfies the bound makes the atomic a
-        // no-op, and most pixels of a label do not extend its box -- five L2 atomics become five L2 reads
-        if (fmin < cpb_peek(&t.first[key])) atomicMin(&t.first[key], fmin);
-        if (y0 < cpb_peek(&t.ymin[key])) atomicMin(&t.ymin[key], y0);
-        if (y1 > cpb_peek(&t.ymax[key])) atomicMax(&t.ymax[key], y1);
-        if (x0 < cpb_peek(&t.xmin[key])) atomicMin(&t.xmin[key], x0);
-        if (x1 > cpb_peek(&t.xmax[key])) atomicMax(&t.xmax[key], x1);
-#else
+        // (reading the monotone min / max entries first to skip no-op atomics was slower, 0.40 ms vs 0.26 ms in the
+        //  lookup: the fire-and-forget reductions do not stall the warp, the reads do)
         atomicMin(&t.first[key], fmin);
         atomicMin(&t.ymin[key], y0); atomicMax(&t.ymax[key], y1);
         atomicMin(&t.xmin[key], x0); atomicMax(&t.xmax[key], x1);
-#endif
     }
 }
 
