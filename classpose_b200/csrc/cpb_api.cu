@@ -255,6 +255,8 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
     if (hist) cudaMemsetAsync(hist, 0, BN * sizeof(int), st);
     const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
+    // tap indices are formed in float32 (exact below 2^24): one tile of more than ~4090 x 4090 pixels is out of range
+    if ((long long)(H + 2) * (W + 2 * CPB_FLOW_PADX) >= (1LL << 24)) return CPB_E_RANGE;
     int32_t* bg_out = zero_out ? zero_out : pfinal;
     const int bg_value = zero_out ? 0 : -1;
     const bool vec4 = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(dP) % 16 == 0) &&
@@ -275,7 +277,10 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     ProfScope ps(w.prof, S_FOLLOW);
     const unsigned grid = (unsigned)std::min<long long>(blocks_for(BN, 256), (long long)sm_count() * 16);
     const int mode = follow_merge_mode();
-    if (mode == 2 && niter >= 32) {
+    // the pool kernel forms the tap index with an FADD (1.5 * 2^23 + index): the padded tile must stay below 2^22
+    // pixels (about 2040 x 2040); larger tiles take the two-point merge kernel, whose index is a float -> int conversion
+    const bool pool_ok = (long long)(H + 2) * (W + 2 * CPB_FLOW_PADX) < (1LL << 22);
+    if (mode == 2 && niter >= 32 && pool_ok) {
         // one block per chunk of the list (blocks past the end of the list exit at once)
 #ifdef CPB_SIM
         const unsigned pgrid = (unsigned)std::min<long long>(blocks_for(BN, CPB_FP_POOL), 8);

@@ -37,7 +37,8 @@ extern "C" {
 
 #define CPB_E_ARG       (-1) /* bad shape / null pointer */
 #define CPB_E_WORKSPACE (-2) /* workspace too small */
-#define CPB_E_RANGE     (-3) /* B*H*W does not fit the 31-bit pixel index; split the batch */
+#define CPB_E_RANGE     (-3) /* B*H*W does not fit the 31-bit pixel index (split the batch), or one tile exceeds
+                                 2^24 padded pixels (about 4090 x 4090) in follow_flows */
 
 /* Parameters of dynamics.resize_and_compute_masks as called at
  * /root/reference/src/classpose/models.py:149-159; defaults from models.py:490-498,751-752. */

@@ -111,6 +111,33 @@ def case_follow_flows_merge_is_exact(be):
         be.set_follow_merge(-1)
 
 
+def case_follow_flows_large_tiles(be):
+    """Tiles around the 2^22-pixel limit of the trajectory-pool kernel's FADD-formed tap index: 2000 x 2000 still takes
+    the pool, 2100 x 2100 falls back to the two-point merge kernel; both must equal the plain scalar kernel bit for
+    bit (sparse foreground keeps the case fast).  A tile beyond 2^24 padded pixels is refused with CPB_E_RANGE."""
+    if be.name == "sim":
+        return      # millions of simulated fibres: GPU only
+    rng = np.random.default_rng(11)
+    for L in (2000, 2100):
+        dP = f32(rng.normal(0, 2.5, size=(1, 2, L, L)))
+        cp = np.full((1, L, L), -1.0, np.float32)
+        for _ in range(60):                                   # 60 foreground blobs of 24 x 24 pixels, some on the border
+            y, x = rng.integers(0, L - 24, size=2)
+            cp[0, y:y + 24, x:x + 24] = 1.0
+        cp[0, :24, :24] = 1.0; cp[0, L - 24:, L - 24:] = 1.0
+        try:
+            be.set_follow_merge(0)
+            p0, f0 = be.follow_flows(dP, cp, 200, 0.0, want_float=True)
+            be.set_follow_merge(-1)
+            p1, f1 = be.follow_flows(dP, cp, 200, 0.0, want_float=True)
+        finally:
+            be.set_follow_merge(-1)
+        fg = cp > 0
+        np.testing.assert_array_equal(p0, p1)
+        np.testing.assert_array_equal(f0[:, 0][fg], f1[:, 0][fg])
+        np.testing.assert_array_equal(f0[:, 1][fg], f1[:, 1][fg])
+
+
 # ------------------------------------------------------------------------------------ (3)
 def case_get_masks_exact(be):
     for t in (std_tile(0, H=128, W=128, n_grid=5), std_tile(1), adv_tile(), std_tile(2, H=96, W=160, n_grid=6),
@@ -625,7 +652,8 @@ def case_label_offsets(be):
     assert total[0] == counts.sum()
 
 
-ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_flows_merge_is_exact, case_get_masks_exact,
+ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_flows_merge_is_exact,
+             case_follow_flows_large_tiles, case_get_masks_exact,
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
              case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_fill_holes_exact, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
