@@ -290,6 +290,87 @@ def case_fill_holes_exact(be):
                 assert cnt[0] == ref.max()
 
 
+def random_label_image(rng, H, W, n, gaps=True):
+    """Random discs, rings (holes, some with a cell inside), slabs and specks painted over each other, with
+    non-contiguous ids when `gaps`: the shapes the table-driven relabelling has to get right."""
+    yy, xx = np.mgrid[0:H, 0:W]
+    lab = np.zeros((H, W), np.int32)
+    ids = rng.permutation(np.arange(1, (2 * n if gaps else n) + 1))[:n]
+    for l in ids:
+        cy, cx = rng.integers(0, H), rng.integers(0, W)
+        kind = rng.integers(0, 5)
+        r2 = (yy - cy) ** 2 + (xx - cx) ** 2
+        if kind == 0:
+            lab[r2 <= rng.integers(2, 9) ** 2] = l
+        elif kind == 1:                                    # ring, sometimes with a core of another id painted later
+            ro = rng.integers(5, 14); ri = rng.integers(2, ro - 1)
+            lab[(r2 <= ro * ro) & (r2 > ri * ri)] = l
+        elif kind == 2:                                    # slab touching whatever is there
+            h, w = rng.integers(2, 12, size=2)
+            lab[cy:cy + h, cx:cx + w] = l
+        elif kind == 3:                                    # speck below min_size
+            lab[cy:cy + rng.integers(1, 4), cx:cx + rng.integers(1, 4)] = l
+        else:                                              # disc with pin holes
+            m = r2 <= rng.integers(4, 10) ** 2
+            lab[m] = l
+            hy, hx = cy + rng.integers(-2, 3), cx + rng.integers(-2, 3)
+            if 0 <= hy < H and 0 <= hx < W:
+                lab[hy, hx] = 0
+    return lab
+
+
+def case_random_label_images(be):
+    """fill_holes_and_remove_small_masks, class vote and border removal on random label images against the oracle /
+    the reference's own functions: bit-exact, including nested holes, overwritten cells and the positional size filter."""
+    rng = np.random.default_rng(2024)
+    for trial in range(24):
+        H, W = (int(v) for v in rng.choice([48, 64, 80, 96], size=2))
+        lab = random_label_image(rng, H, W, int(rng.integers(3, 40)), gaps=bool(trial % 2))
+        lcap = int(lab.max()) + 2
+        for min_size in (15, 0):
+            ref = outils.fill_holes_and_remove_small_masks(lab.copy(), min_size=min_size)
+            out, _ = be.fill_holes_and_remove_small_masks(c32(lab[None]).copy(), lcap, min_size)
+            np.testing.assert_array_equal(out[0], ref, err_msg=f"trial {trial} min_size={min_size}")
+        C = int(rng.integers(2, 9))
+        logits = f32(rng.integers(-2, 3, size=(C, 1, H, W)))          # small integers: plenty of ties
+        ref_cm, _ = classpose_ref.compute_class_masks(lab, logits)
+        cc, cm = be.class_vote(c32(lab[None]), f32(logits[:, 0][None]), lcap, want_class_masks=True)
+        np.testing.assert_array_equal(cm[0].astype(np.int64), ref_cm, err_msg=f"trial {trial} vote")
+        ref_b = classpose_ref.remove_border_instances(lab.copy())
+        out_b = be.remove_border_instances(c32(lab[None]).copy(), lcap)
+        np.testing.assert_array_equal(out_b[0], ref_b, err_msg=f"trial {trial} border")
+
+
+def case_random_flow_qc(be):
+    """remove_bad_flow_masks on random label images full of touching / nested labels (the labels the diffusion warp
+    hands over to k_flow_err) with random flows: flow errors to 1e-9, identical removal set; masks_to_flows to 1e-12."""
+    rng = np.random.default_rng(77)
+    for trial in range(8):
+        H, W = (int(v) for v in rng.choice([48, 64, 80], size=2))
+        lab = random_label_image(rng, H, W, int(rng.integers(4, 30)), gaps=False)
+        # contiguous ids, as get_masks delivers them
+        u, inv = np.unique(lab, return_inverse=True)
+        lab = inv.reshape(lab.shape).astype(np.int32)
+        if lab.max() == 0:
+            continue
+        mu = dynamics.masks_to_flows(lab)
+        dP = (5.0 * mu + rng.normal(0, 1.5, size=mu.shape)).astype(np.float32)
+        err_ref, _ = dynamics.flow_error(lab, dP)
+        ref = dynamics.remove_bad_flow_masks(lab.copy(), dP, 0.4)
+        lcap = int(lab.max()) + 2
+        out, err = be.remove_bad_flow_masks(c32(lab[None]).copy(), f32(dP[None]), lcap, 0.4, want_err=True)
+        assert np.abs(err[0, 1:len(err_ref) + 1] - err_ref).max() < 1e-9, trial
+        decided = np.abs(err_ref - 0.4) > 1e-9          # a label sitting on the threshold may go either way
+        bad_ref = err_ref > 0.4
+        bad_out = ~np.isin(np.arange(1, len(err_ref) + 1), np.unique(out[0]))
+        present = np.isin(np.arange(1, len(err_ref) + 1), np.unique(lab))
+        assert ((bad_ref == bad_out) | ~decided | ~present).all(), trial
+        if decided.all():
+            np.testing.assert_array_equal(out[0], ref, err_msg=f"trial {trial}")
+        got = be.masks_to_flows(c32(lab[None]), lcap)
+        assert np.abs(got[0] - mu).max() <= 1e-12, trial
+
+
 # ------------------------------------------------------------------------------------ (6)
 def case_class_vote_reference_vectors(be):
     g = np.load(os.path.join(GOLDEN, "ref_class_vote.npz"))
@@ -655,7 +736,7 @@ def case_label_offsets(be):
 ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_flows_merge_is_exact,
              case_follow_flows_large_tiles, case_get_masks_exact,
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
-             case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_fill_holes_exact, case_class_vote_reference_vectors,
+             case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_fill_holes_exact, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
              case_fused_generic_class_count, case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
              case_cell_contours_match_cv2, case_prepare_tiles, case_dedup_overlapping_tiles, case_dedup_random_points_components,
