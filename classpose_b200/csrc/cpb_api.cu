@@ -145,6 +145,10 @@ int check_geom(int B, int H, int W) {
 
 inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
 
+// blocks per tile of the pixel passes that only run on flagged tiles (hole plane reset, recount): 8 for a 256 x 256
+// tile, more for larger tiles (a dense 512 x 512 batch has a hole in every tile)
+inline unsigned tile_slices(int H, int W) { return (unsigned)std::min<long long>(std::max<long long>((long long)H * W / 8192, 8), 256); }
+
 // per-tile table kernels (seed ranking, renumbering): one block per tile; big tiles can hold thousands of labels
 inline unsigned table_threads(int H, int W) { return (long long)H * W > 256 * 256 ? 1024u : 256u; }
 
@@ -616,7 +620,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
                                masks, H, W, w.t, w.holekey, w.status, 1, todo_work(w, B, false), pass);
             CPB_CHECK_LAUNCH();
             if (pass == CPB_FILL_DETECT) {
-                CPB_LAUNCH_COUNTED(k_zero_hole_tiles, dim3(8, B), dim3(256), 0, st, w.holekey, H, W, w.t);
+                CPB_LAUNCH_COUNTED(k_zero_hole_tiles, dim3(tile_slices(H, W), B), dim3(256), 0, st, w.holekey, H, W, w.t);
                 CPB_CHECK_LAUNCH();
             }
         }
@@ -624,7 +628,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         prof_begin(w.prof, S_MAP3);
         CPB_LAUNCH_COUNTED(k_recount_reset, dim3(B), dim3(256), 0, st, w.t);
         CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED(k_recount, dim3(8, B), dim3(256), 0, st, masks, w.holekey, H, W, w.t);
+        CPB_LAUNCH_COUNTED(k_recount, dim3(tile_slices(H, W), B), dim3(256), 0, st, masks, w.holekey, H, W, w.t);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_MAP3);
         prof_begin(w.prof, S_SIZE2);
