@@ -132,17 +132,6 @@ CPB_DEVICE bool cpb_foreign_live(int v, int l, const int* CPB_RESTRICT alive) {
     return v > 0 && v != l && (alive == nullptr || alive[v] != 0);
 }
 
-#ifndef CPB_DIFFUSE_PREFETCH
-#define CPB_DIFFUSE_PREFETCH 1
-#endif
-CPB_DEVICE void cpb_prefetch_l2(const void* p) {
-#if !defined(CPB_SIM) && CPB_DIFFUSE_PREFETCH
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-#else
-    (void)p;
-#endif
-}
-
 // Common head of a warp job: membership bit masks (lane = column, bit = row), contact with other live labels
 // (bbox grown by one pixel), diffusion centres.  Sub-label q occupies lanes [coff, coff + w).
 struct DiffPro { unsigned member; bool clean[2]; int cr[2], cl[2]; };   // centre row (bbox-relative) and lane
@@ -160,27 +149,11 @@ CPB_DEVICE void cpb_diffuse_prologue(const int* CPB_RESTRICT L, int W, const Lab
     bool foreign = false;              // a pixel of another live label inside the bbox grown by one
     if (mine) {
         const int x = my.x0 + col;
-#if CPB_DIFFUSE_PREFETCH
-        // The labels of a 1024-tile batch do not fit the L2: a column's rows are fetched eight at a time, otherwise
-        // every row is one exposed DRAM latency (the kernel runs 30 % faster with a warm L2, profiles/r01/README.md)
-        const int* Lp = L + my.y0 * W + x;
-        for (int r0 = 0; r0 < my.h; r0 += 8) {
-            int v[8];
-            #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = (r0 + k < my.h) ? Lp[(r0 + k) * W] : 0;
-            #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (v[k] == my.l) member |= 1u << (r0 + k);
-                else if (fuse) foreign |= cpb_foreign_live(v[k], my.l, qc.alive);
-            }
-        }
-#else
         for (int r = 0; r < my.h; r++) {
             const int v = L[(my.y0 + r) * W + x];
             if (v == my.l) member |= 1u << r;
             else if (fuse) foreign |= cpb_foreign_live(v, my.l, qc.alive);
         }
-#endif
         if (fuse) {
             if (my.y0 > 0) foreign |= cpb_foreign_live(L[(my.y0 - 1) * W + x], my.l, qc.alive);
             if (my.y0 + my.h < qc.H) foreign |= cpb_foreign_live(L[(my.y0 + my.h) * W + x], my.l, qc.alive);
@@ -277,14 +250,6 @@ CPB_DEVICE void cpb_diffuse_job(const int* CPB_RESTRICT L, int W, const LabelTab
     if (qc.list && lane == 0) {            // whatever this warp does not finish itself is queued for k_flow_err
         if (!clean[0]) qc.list[qc.cap - 1 - atomicAdd(qc.count + 1, 1)] = make_int2(qc.b, A.l);
         if (has_b && !clean[1]) qc.list[qc.cap - 1 - atomicAdd(qc.count + 1, 1)] = make_int2(qc.b, B.l);
-    }
-    if (fuse && mine && (inB ? clean[1] : clean[0])) {     // the error pass reads these after the iterations: start them now
-        const int pix0 = my.y0 * W + my.x0 + col;
-        for (int r = 0; r < my.h; r++) {
-            if (!(member >> r & 1)) continue;
-            cpb_prefetch_l2(qc.dPy + pix0 + r * W);
-            cpb_prefetch_l2(qc.dPx + pix0 + r * W);
-        }
     }
     const int ci[2] = {(pro.cr[0] + 1) * CPB_DC_PITCH + pro.cl[0] + 1, (pro.cr[1] + 1) * CPB_DC_PITCH + pro.cl[1] + 1};
     const double* p = S + lane;        // p[0], p[1], p[2] = columns j-1, j, j+1 of the halo row
