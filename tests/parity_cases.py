@@ -496,6 +496,36 @@ def case_fused_generic_class_count(be):
     assert f1 >= 0.99 and nnew == nref
 
 
+def case_fused_switch_matrix(be):
+    """Every combination of the A/B switches of the fused path (job queue, fused flow error, fused vote, follow_flows
+    variant) must give the same label images, counts and cell classes -- they only change how the work is scheduled."""
+    tiles = [std_tile(0, H=128, W=128, n_grid=5), adv_tile()]
+    outs = {}
+    try:
+        for t_i, t in enumerate(tiles):
+            dP, cp, lg = f32(t["dP"][None]), f32(t["cellprob"][None]), f32(t["logits"][None])
+            for follow in (0, 2):
+                for queue in (0, 1):
+                    for qc in (0, 1):
+                        for vote in (0, 1):
+                            be.set_follow_merge(follow)
+                            be.set_switch(1, queue); be.set_switch(2, qc); be.set_switch(3, vote)
+                            m, c, cc, _ = be.compute_masks(dP, cp, lg, want_class_masks=False)
+                            outs[(t_i, follow, queue, qc, vote)] = (m.copy(), c.copy(), cc[0, :int(c[0]) + 1].copy())
+    finally:
+        be.set_follow_merge(-1)
+        for sw in (1, 2, 3):
+            be.set_switch(sw, -1)
+    for t_i in range(len(tiles)):
+        m0, c0, cc0 = outs[(t_i, 0, 0, 0, 0)]
+        for k, (m, c, cc) in outs.items():
+            if k[0] != t_i:
+                continue
+            np.testing.assert_array_equal(m, m0, err_msg=str(k))
+            np.testing.assert_array_equal(c, c0, err_msg=str(k))
+            np.testing.assert_array_equal(cc, cc0, err_msg=str(k))
+
+
 def case_fused_odd_width(be):
     """W not a multiple of 4 (scalar prep kernel, unaligned rows) and a non-multiple-of-32 tile."""
     tiles = [std_tile(9, H=70, W=57, n_grid=3, C=3), std_tile(10, H=70, W=57, n_grid=3, C=3)]
@@ -738,6 +768,6 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_f
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
              case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_fill_holes_exact, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
-             case_fused_generic_class_count, case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
+             case_fused_generic_class_count, case_fused_switch_matrix, case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
              case_cell_contours_match_cv2, case_prepare_tiles, case_dedup_overlapping_tiles, case_dedup_random_points_components,
              case_label_offsets]
