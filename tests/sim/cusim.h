@@ -377,6 +377,7 @@ inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; i++
 // round-to-nearest single ops that must not be contracted (build with -ffp-contract=off)
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
