@@ -1,5 +1,5 @@
-// Exhaustive check (all 2^32 float32 bit patterns) that the three-operation division by 5 used in the prep
-// kernel -- q = RN(x * r), rem = fma(-5, q, x), result = fma(rem, r, q) with r = RN(1/5), inside a guarded
+// Exhaustive check (all 2^32 float32 bit patterns) that a three-operation division by 5 (tried in the prep kernel,
+// not adopted: no faster than nvcc's division by a constant) -- q = RN(x * r), rem = fma(-5, q, x), result = fma(rem, r, q) with r = RN(1/5), inside a guarded
 // exponent range, IEEE division outside -- equals __fdiv_rn(x, 5.0f) bit for bit.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -o div5_exhaustive tests/studies/div5_exhaustive.cu && ./div5_exhaustive
 #include <cstdio>
