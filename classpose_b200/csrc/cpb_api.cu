@@ -59,8 +59,8 @@ struct ProfScope {
     ~ProfScope() { prof_end(p, s); }
 };
 
-constexpr int kLabelBlocksPerTile = 24;
-constexpr int kWarpDiffuseBlocksPerTile = 16;// x CPB_DW_WARPS warps: labels of a tile in flight   // per-label kernels: grid (kLabelBlocksPerTile, B)
+constexpr int kLabelBlocksPerTile = 24;        // block-per-label kernels of the stage calls: grid (kLabelBlocksPerTile, B)
+constexpr int kWarpDiffuseBlocksPerTile = 16;  // warp-per-label kernels: grid (16, B) x 4 warps = 64 warp slots per tile
 constexpr int kVoteSmemInts = 6 * 1024;   // 24 KB (instance, class) table per tile: 4 blocks of 512 threads per SM;
                                           // tiles with more than 6144/C labels use the global table
 constexpr int kVoteSmemIntsMax = 24 * 1024; // 96 KB
