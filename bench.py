@@ -301,7 +301,9 @@ def run_ours(args):
 
     # ---- per-stage device times (CUDA events around every stage, separate pass) and the roofline of the
     #      dominant kernel
-    stage_runs = [eng.profile_stages(dP, cellprob, logits, **PARAMS) for _ in range(3)]
+    stage_runs = [eng.profile_stages(dP, cellprob, logits, with_qc=True, **PARAMS) for _ in range(3)]
+    qc_stats = stage_runs[-1][1]
+    stage_runs = [r[0] for r in stage_runs]
     stages = {k: statistics.median(r[k] for r in stage_runs) for k in stage_runs[0]}
     fg_frac = float((cellprob > PARAMS["cellprob_threshold"]).float().mean().item())
     fg4_frac = float((out[0].reshape(-1, 4) > 0).any(dim=1).float().mean().item()) if (H * W) % 4 == 0 else 1.0
@@ -317,7 +319,7 @@ def run_ours(args):
     peak, peak_src = load_peaks()
     # DRAM traffic of the dominant kernel: from the committed ncu capture of this same workload (per launch)
     traffic, traffic_src = None, None
-    kern = {"follow_flows": "k_follow_pool", "diffuse": "k_diffuse_warp_q", "vote": "k_vote", "prep_flow": "k_prep_flow_v4",
+    kern = {"follow_flows": "k_follow_pool", "diffuse": "k_diffuse32", "vote": "k_vote", "prep_flow": "k_prep_flow_v4",
             "final_map": "k_final_vote_v4"}.get(dom)
     try:
         import glob
@@ -372,6 +374,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "stages_ms": stages,
+        "flow_check": qc_stats,
     }
     emit(line)
     if world > 1:

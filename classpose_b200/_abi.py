@@ -41,6 +41,7 @@ SIGNATURES = {
     "cpb_stage_name": (C.c_char_p, [_I]),
     "cpb_compute_masks_profiled_device": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, _P, _Z, _P, _P]),
     "cpb_debug_launch_count": (C.c_longlong, []),
+    "cpb_debug_qc_stats": (None, [_P]),
     "cpb_debug_set_follow_merge": (None, [_I]),
     "cpb_debug_set_switch": (None, [_I, _I]),
     "cpb_compute_masks_host": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, _I, _I]),

@@ -47,6 +47,30 @@ class Calls:
         self.mem.keep_alive(ws, dP, cellprob, logits)
         return masks, counts, cell_class, class_masks
 
+    def compute_masks_profiled(self, dP, cellprob, logits=None, params: Params | None = None):
+        """The fused path once with CUDA events around every stage (synchronises the stream).
+        Returns (masks, counts, cell_class, {stage: ms}, flow-check counters)."""
+        B, two, H, W = dP.shape
+        Cc = 0 if logits is None else int(logits.shape[1])
+        prm = params or make_params()
+        LC = self.label_capacity(H, W)
+        masks = self.mem.empty((B, H, W), "int32")
+        counts = self.mem.empty((B,), "int32")
+        cell_class = self.mem.zeros((B, LC), "int32") if logits is not None else None
+        ws, n = self._ws(B, H, W, Cc, 0)
+        ns = int(self.lib.cpb_num_stages())
+        ms = (C.c_float * ns)()
+        rc = self.lib.cpb_compute_masks_profiled_device(self._p(dP), self._p(cellprob), self._p(logits), B, H, W, Cc,
+                                                        C.byref(prm), self._p(masks), self._p(counts),
+                                                        self._p(cell_class), None, self._p(ws), n, self.stream(), ms)
+        check(rc, "cpb_compute_masks_profiled_device")
+        qc = (C.c_int32 * 8)()
+        self.lib.cpb_debug_qc_stats(qc)
+        stats = {"screen_jobs": int(qc[0]), "float64_labels": int(qc[2]), "screen_decided": int(qc[4]),
+                 "screen_undecided": int(qc[5])}
+        stages = {self.lib.cpb_stage_name(i).decode(): float(ms[i]) for i in range(ns)}
+        return masks, counts, cell_class, stages, stats
+
     # ---- stages ----------------------------------------------------------------------------
     def follow_flows(self, dP, cellprob, niter=200, cellprob_threshold=0.0, want_float=False):
         B, _, H, W = dP.shape

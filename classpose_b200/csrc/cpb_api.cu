@@ -3,12 +3,14 @@
 // mutable state; every call runs on the caller's stream with the caller's workspace.
 #include "classpose_b200.h"
 
+#define CPB_QCTR_INTS 8
 #include "cpb_platform.h"
 #include "cpb_common.cuh"
 #include "cpb_flow.cuh"
 #include "cpb_masks.cuh"
 #include "cpb_tables.cuh"
 #include "cpb_qc.cuh"
+#include "cpb_qc32.cuh"
 #include "cpb_post.cuh"
 #include "cpb_fused.cuh"
 #include "cpb_contour.cuh"
@@ -26,6 +28,7 @@ static_assert(sizeof(cpb_params) == 40, "cpb_params layout is part of the ABI (p
 namespace {
 
 std::atomic<long long> g_launches{0};   // statistics only: kernels launched by this library
+std::atomic<int> g_last_qc[CPB_QCTR_INTS];   // statistics only: flow-check counters of the last profiled call
 #define CPB_LAUNCH_COUNTED(...) do { g_launches.fetch_add(1, std::memory_order_relaxed); CPB_LAUNCH(__VA_ARGS__); } while (0)
 
 // Optional per-stage timing of the fused path (cpb_compute_masks_profiled_device).
@@ -95,6 +98,7 @@ struct Workspace {
     int* vote;           // [B*LC*C]
     int* jobs;           // [B+1] diffusion job offsets, 2 queue counters, 2 counts of `todo` (front / back)
     int2* todo;          // [B*LC] (tile, label) work list of the block-per-label kernels
+    Q32 q;               // float32 flow-check screen: label info, class lists, job queue, float64 list, counters
     LabelTables t;
     size_t bytes;
     Prof* prof;          // optional stage timing
@@ -123,6 +127,8 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     w.vote = c.take<int>(C > 0 ? BL * C : 0);
     w.jobs = c.take<int>((size_t)B + 1 + 4);
     w.todo = c.take<int2>(BL);
+    w.q.info = c.take<int>(BL); w.q.ent = c.take<int>(BL); w.q.jobs = c.take<int4>(BL); w.q.l64 = c.take<int2>(BL);
+    w.q.ctr = c.take<int>(CPB_QCTR_INTS);
     LabelTables& t = w.t;
     t.LC = LC;
     t.cnt = c.take<int>(BL); t.first = c.take<int>(BL);
@@ -211,7 +217,8 @@ FollowSchedule follow_schedule(int niter) {
 //   CPB_DIFFUSE_QUEUE=0  static (block, warp) -> label map instead of the job queue
 //   CPB_QC_FUSED=0       every label's flow error from T in global memory (k_flow_err) instead of the diffusion tile
 //   CPB_VOTE_FUSED=0     class vote as its own pass over the finished label image
-std::atomic<int> g_switch[4] = {{-1}, {-1}, {-1}, {-1}};
+//   CPB_QC_SCREEN=0      every label through the float64 diffusion (no float32 screen in front of it)
+std::atomic<int> g_switch[5] = {{-1}, {-1}, {-1}, {-1}, {-1}};
 bool switch_on(int which, const char* env_name) {
     int v = g_switch[which].load(std::memory_order_relaxed);
     if (v < 0) {
@@ -223,6 +230,10 @@ bool switch_on(int which, const char* env_name) {
 bool diffuse_queue_enabled() { return switch_on(CPB_SWITCH_DIFFUSE_QUEUE, "CPB_DIFFUSE_QUEUE"); }
 bool qc_fused_enabled() { return switch_on(CPB_SWITCH_QC_FUSED, "CPB_QC_FUSED"); }
 bool vote_fused_enabled() { return switch_on(CPB_SWITCH_VOTE_FUSED, "CPB_VOTE_FUSED"); }
+bool qc_screen_enabled() { return switch_on(CPB_SWITCH_QC_SCREEN, "CPB_QC_SCREEN"); }
+// value 2 (tests only): the screen also runs when the caller asks for the per-label errors, and reports
+// (float32 error, bound) bit-packed into the float64 error of the labels it decided
+bool qc_screen_debug() { return g_switch[CPB_SWITCH_QC_SCREEN].load(std::memory_order_relaxed) == 2; }
 
 #define CPB_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
@@ -356,38 +367,60 @@ inline LabelWork todo_work(const Workspace& w, int B, bool back) {
 }
 
 // labels with statistics in the tables -> T (and mu / err / bad flags)
+// exact_err: the caller wants the float64 error of every label (no float32 screen)
 int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B, int H, int W, double thr,
-                double* mu_out, cudaStream_t st) {
-    prof_begin(w.prof, S_CENTRES);
-    { int e = run_label_scan(w, B, st); if (e) return e; }
-    const LabelWork big = todo_work(w, B, false);
-    CPB_LAUNCH_COUNTED(k_centres, dim3(sm_count() * 8), dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t, 1, big);
-    CPB_CHECK_LAUNCH();
-    prof_end(w.prof, S_CENTRES);
+                double* mu_out, cudaStream_t st, bool exact_err = false) {
     const size_t smem = (size_t)CPB_DIFF_SMEM_CELLS * 17;
-    prof_begin(w.prof, S_DIFFUSE);
     // labels that touch no other live label get their flow error inside the diffusion warp (no T round trip); the
     // others are appended to the end of the work list for k_flow_err
     const float* qc_dP = (dP && !mu_out && qc_fused_enabled()) ? dP : nullptr;
     int* todo_n = w.jobs + B + 3;
-    if (diffuse_queue_enabled()) {
-        // persistent warps pulling label pairs from one queue per size class (see k_diffuse_jobs)
-        CPB_LAUNCH_COUNTED(k_diffuse_jobs, dim3(1), dim3(1024), 0, st, w.t.lbound, B, w.jobs, w.jobs + B + 1);
+    const LabelWork big = todo_work(w, B, false);
+    if (qc_dP && diffuse_queue_enabled()) {
+        // decision-exact path: k_qc_pack (centres, contact, classes, jobs) -> float32 screen in registers ->
+        // float64 warp kernel for whatever the screen does not decide (see cpb_qc32.cuh)
+        prof_begin(w.prof, S_CENTRES);
+        cudaMemsetAsync(w.jobs + B + 3, 0, 2 * sizeof(int), st);
+        cudaMemsetAsync(w.q.ctr, 0, CPB_QCTR_INTS * sizeof(int), st);
+        CPB_LAUNCH_COUNTED(k_qc_pack, dim3(B), dim3(256), 0, st, masks, H, W, w.t, w.q, w.todo, todo_n,
+                           ((!exact_err || qc_screen_debug()) && qc_screen_enabled()) ? 1 : 0);
         CPB_CHECK_LAUNCH();
-        int* ctr = w.jobs + B + 1;
-        CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 2>), dim3(sm_count() * CPB_DQ_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                           w.t, w.T, 0, w.jobs, ctr + 0, qc_dP, thr, w.todo, todo_n, big.cap);
+        CPB_LAUNCH_COUNTED(k_centres, dim3(sm_count() * 8), dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t, 1, big);
         CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 2>), dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
-                           w.t, w.T, 0, w.jobs, ctr + 1, qc_dP, thr, w.todo, todo_n, big.cap);
+        prof_end(w.prof, S_CENTRES);
+        prof_begin(w.prof, S_DIFFUSE);
+        CPB_LAUNCH_COUNTED(k_diffuse32, dim3(sm_count() * CPB_Q32_MINBLOCKS), dim3(128), 0, st, masks, qc_dP, H, W, w.t, w.q, thr,
+                           (exact_err && qc_screen_debug()) ? 1 : 0);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_diffuse64_list, dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, H, W, w.t, w.T, w.q,
+                           qc_dP, thr, w.todo, todo_n, big.cap);
         CPB_CHECK_LAUNCH();
     } else {
-        CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MIDH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                           H, W, w.t, w.T, 0, qc_dP, thr, w.todo, todo_n, big.cap);
+        prof_begin(w.prof, S_CENTRES);
+        { int e = run_label_scan(w, B, st); if (e) return e; }
+        CPB_LAUNCH_COUNTED(k_centres, dim3(sm_count() * 8), dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t, 1, big);
         CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MAXH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
-                           H, W, w.t, w.T, 0, qc_dP, thr, w.todo, todo_n, big.cap);
-        CPB_CHECK_LAUNCH();
+        prof_end(w.prof, S_CENTRES);
+        prof_begin(w.prof, S_DIFFUSE);
+        if (diffuse_queue_enabled()) {
+            // persistent warps pulling label pairs from one queue per size class (see k_diffuse_jobs)
+            CPB_LAUNCH_COUNTED(k_diffuse_jobs, dim3(1), dim3(1024), 0, st, w.t.lbound, B, w.jobs, w.jobs + B + 1);
+            CPB_CHECK_LAUNCH();
+            int* ctr = w.jobs + B + 1;
+            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MIDH, 2>), dim3(sm_count() * CPB_DQ_MINBLOCKS), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
+                               w.t, w.T, 0, w.jobs, ctr + 0, qc_dP, thr, w.todo, todo_n, big.cap);
+            CPB_CHECK_LAUNCH();
+            CPB_LAUNCH_COUNTED((k_diffuse_warp_q<CPB_DC_MAXH, 2>), dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, B, H, W,
+                               w.t, w.T, 0, w.jobs, ctr + 1, qc_dP, thr, w.todo, todo_n, big.cap);
+            CPB_CHECK_LAUNCH();
+        } else {
+            CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MIDH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
+                               H, W, w.t, w.T, 0, qc_dP, thr, w.todo, todo_n, big.cap);
+            CPB_CHECK_LAUNCH();
+            CPB_LAUNCH_COUNTED(k_diffuse_warp<CPB_DC_MAXH>, dim3(kWarpDiffuseBlocksPerTile, B), dim3(CPB_DW_WARPS * 32), 0, st, masks,
+                               H, W, w.t, w.T, 0, qc_dP, thr, w.todo, todo_n, big.cap);
+            CPB_CHECK_LAUNCH();
+        }
     }
     CPB_LAUNCH_COUNTED(k_diffuse, dim3(sm_count() * 4), dim3(CPB_QC_THREADS), smem, st, masks, H, W, w.t, w.T, w.T2, 0, 1, big);
     CPB_CHECK_LAUNCH();
@@ -529,7 +562,7 @@ int cpb_remove_bad_flow_masks_device(int32_t* masks, const float* dP, int B, int
     int e = run_set_lbound(w, B, lcap - 1, st); if (e) return e;
     e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, nullptr, true, st); if (e) return e;
     if (flow_err) cudaMemsetAsync(w.t.err, 0, (size_t)B * w.t.LC * sizeof(double), st);
-    e = run_flow_qc(w, masks, dP, B, H, W, threshold, nullptr, st); if (e) return e;
+    e = run_flow_qc(w, masks, dP, B, H, W, threshold, nullptr, st, flow_err != nullptr); if (e) return e;
     if (flow_err) cudaMemcpyAsync(flow_err, w.t.err, (size_t)B * w.t.LC * sizeof(double), cudaMemcpyDeviceToDevice, st);
     return run_map_stats(w, masks, B, H, W, 1, nullptr, w.t.flag, nullptr, false, st);
 }
@@ -705,9 +738,12 @@ const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames
 void cpb_debug_set_follow_merge(int mode) { g_follow_merge.store(mode, std::memory_order_relaxed); }
 void cpb_debug_set_switch(int which, int value) {
     if (which == CPB_SWITCH_FOLLOW_MERGE) g_follow_merge.store(value, std::memory_order_relaxed);
-    else if (which > 0 && which < 4) g_switch[which].store(value, std::memory_order_relaxed);
+    else if (which > 0 && which < 5) g_switch[which].store(value, std::memory_order_relaxed);
 }
 long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void cpb_debug_qc_stats(int32_t* out) {
+    for (int i = 0; i < CPB_QCTR_INTS; i++) out[i] = g_last_qc[i].load(std::memory_order_relaxed);
+}
 
 int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, const float* logits, int B, int H,
                                       int W, int C, const cpb_params* prm, int32_t* masks, int32_t* counts,
@@ -715,8 +751,14 @@ int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, co
                                       size_t workspace_bytes, void* stream, float* stage_ms) {
 #ifdef CPB_SIM
     (void)stage_ms;
-    return compute_masks_impl(dP, cellprob, logits, B, H, W, C, prm, masks, counts, cell_class, class_masks, workspace,
-                              workspace_bytes, stream, nullptr);
+    const int rc_ = compute_masks_impl(dP, cellprob, logits, B, H, W, C, prm, masks, counts, cell_class, class_masks, workspace,
+                                       workspace_bytes, stream, nullptr);
+    if (rc_ == 0) {
+        const uintptr_t wsa = (reinterpret_cast<uintptr_t>(workspace) + kAlign - 1) / kAlign * kAlign;
+        const Workspace w = carve(reinterpret_cast<void*>(wsa), B, H, W, logits ? C : 0, 0);
+        for (int i = 0; i < CPB_QCTR_INTS; i++) g_last_qc[i].store(w.q.ctr[i], std::memory_order_relaxed);
+    }
+    return rc_;
 #else
     if (!stage_ms) return CPB_E_ARG;
     Prof prof{};
@@ -724,6 +766,13 @@ int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, co
     int rc = compute_masks_impl(dP, cellprob, logits, B, H, W, C, prm, masks, counts, cell_class, class_masks,
                                 workspace, workspace_bytes, stream, &prof);
     cudaError_t ce = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+    if (rc == 0 && ce == cudaSuccess) {      // flow-check statistics of this call (cpb_debug_qc_stats)
+        const uintptr_t wsa = (reinterpret_cast<uintptr_t>(workspace) + kAlign - 1) / kAlign * kAlign;
+        const Workspace w = carve(reinterpret_cast<void*>(wsa), B, H, W, logits ? C : 0, 0);
+        int host[CPB_QCTR_INTS] = {0};
+        if (cudaMemcpy(host, w.q.ctr, sizeof(host), cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int i = 0; i < CPB_QCTR_INTS; i++) g_last_qc[i].store(host[i], std::memory_order_relaxed);
+    }
     for (int i = 0; i < S_COUNT; i++) {
         stage_ms[i] = 0.f;
         if (rc == 0 && ce == cudaSuccess && prof.used[i]) cudaEventElapsedTime(&stage_ms[i], prof.begin[i], prof.end[i]);

@@ -1,0 +1,399 @@
+// Row (4), decision-exact: a float32 screen in front of the float64 diffusion of cpb_qc.cuh.
+//
+// remove_bad_flow_masks only needs the DECISION err > flow_threshold per label (north_star: instance F1, class
+// labels and cell counts -- not the bits of T).  The screen runs the same Jacobi iteration in float32 with the
+// label's T held in REGISTERS, takes the flow error from it and carries a rigorous bound on
+// |err32 - err64| (derivation below).  A label is decided by the screen only when err32 +- bound clears the
+// threshold; every other label (and every label the screen cannot hold or whose gradient sees a foreign label)
+// is handed to the float64 warp kernel, so the removal set is identical to the float64 path by construction.
+//
+// Layout of a job (one warp): a strip of 64 columns, lane j owns columns 2j (.x) and 2j+1 (.y) as one packed
+// f32x2 register per row; up to CPB_Q32_MAXSUB labels of one tile sit side by side, separated by one empty
+// column (the last column of the strip is always empty, so the wrap-around shuffles read zeros).  Every label is
+// shifted vertically so that its diffusion centre lies on register row RC = NR/2: the source injection is ONE
+// packed add per iteration instead of a dynamically indexed row.  Per row and iteration: vertical 3-sums in
+// registers (2 FADD2), the two values a lane lacks by shuffle (2 SHFL), 3 FADD, and one FMUL2 by M = member ? 1/9 : 0
+// (non-members stay exactly 0).  No shared memory in the loop.
+//
+// Error bound.  All T are >= 0 and the iteration only adds non-negative numbers and multiplies by a positive
+// constant, so rounding errors stay RELATIVE: with u = 2^-24 and at most 11 roundings between a value and its
+// successor (1 source add, 4 adds on the longest path of the separable 9-sum, the constant fl(1/9) and the
+// multiply -- 11 is the budget of the plain 9-term order and covers both),
+//     T32 = T_exact (1 + e),  |e| <= (1 + u)^(11 k) - 1 =: eta  after k iterations,
+// and likewise for the float64 reference with u = 2^-53 (absorbed by the 2 % head-room on eta).  Results in the
+// float32 subnormal range carry an absolute error instead, bounded by alpha = 1e-40 in total.  Hence per pixel
+//     |dy32 - dy64| <= eta (T_dn + T_up) + u |dy32| + 2 alpha   (same for dx),   e_g := e_y + e_x >= |g32 - g64|,
+//     |mu32 - mu64| <= e_g / (|g32| - e_g)        (Dunkl-Williams; used when |g32| > 4 e_g),
+//     otherwise mu32 := 0 and |mu32 - mu64| <= 1  (mu64 is a unit vector or 0),
+//     | |mu32 - a|^2 - |mu64 - a|^2 | <= 2 |mu32 - a| d + d^2   with d the bound above, a = dP / 5,
+// plus generous slack for the float32 evaluation of these expressions and of the sums.
+#pragma once
+#include "cpb_common.cuh"
+#include "cpb_flow.cuh"
+#include "cpb_qc.cuh"
+
+#define CPB_Q32_MAXSUB 8
+#define CPB_Q32_COLS 64            // columns of a job strip (two per lane); column 63 stays empty
+#define CPB_Q32_NCLS 4             // register-row classes NR = 9, 13, 17, 21 (centre row RC = NR / 2 = 4, 6, 8, 10)
+#define CPB_Q32_CLS64 4            // info class of labels left to the float64 warp kernel
+#define CPB_Q32_CLSBIG 5           // info class of labels left to the block kernels
+
+#define CPB_QI_CLEAN 8             // info bit: no pixel of another live label in the bbox grown by one
+
+// counters: [0] jobs appended, [1] jobs pulled, [2] float64 list appended, [3] float64 list pulled,
+//           [4] labels decided by the screen, [5] labels the screen left undecided (statistics)
+#ifndef CPB_QCTR_INTS
+#define CPB_QCTR_INTS 8
+#endif
+
+struct Q32 {
+    int* info;        // [B*LC]  class (bits 0..2) | CPB_QI_CLEAN | bbox width << 8
+    int* ent;         // [B*LC]  per tile: the screen's labels, grouped by class
+    int4* jobs;       // [B*LC]  (tile, first entry, nsub, class)
+    int2* l64;        // [B*LC]  (tile, label) for the float64 warp kernel
+    int* ctr;         // [CPB_QCTR_INTS]
+};
+
+CPB_DEVICE int cpb_q32_class(int cr, int h) {
+    const int rho = max(cr, h - 1 - cr);
+    return rho <= 4 ? 0 : rho <= 6 ? 1 : rho <= 8 ? 2 : rho <= 10 ? 3 : CPB_Q32_CLS64;
+}
+
+// ---- k_qc_pack: one block per tile ---------------------------------------------------------------------
+//  pass A (warp per label): diffusion centre, contact with other live labels, class; labels beyond the warp kernels go
+//         to `big_list`, small labels the screen cannot take go to q.l64; n_iter of the tile
+//  pass B: the screen's labels grouped by class into q.ent
+//  pack  : warp c packs class c greedily into jobs of up to 8 labels / 63 columns
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_qc_pack(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int2* CPB_RESTRICT big_list,
+          int* CPB_RESTRICT big_count, int screen) {
+    CPB_SHARED int s_cnt[CPB_Q32_NCLS], s_base[CPB_Q32_NCLS], s_pos[CPB_Q32_NCLS];
+    CPB_SHARED int s_ext;
+    const int b = blockIdx.x, LC = t.LC, N = H * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lb = t.lbound[b];
+    const int* L = lab + (size_t)b * N;
+    const int* alive = t.alive ? t.alive + (size_t)b * LC : nullptr;
+    if (threadIdx.x < CPB_Q32_NCLS) { s_cnt[threadIdx.x] = 0; s_pos[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) s_ext = 0;
+    __syncthreads();
+    int ext = 0;
+    for (int l = 1 + warp; l <= lb; l += nw) {
+        const size_t k = (size_t)b * LC + l;
+        int info = 0;
+        if (cpb_label_live(t, k)) {                              // warp-uniform
+            const int y0 = t.ymin[k], x0 = t.xmin[k];
+            const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+            ext = max(ext, 2 * (h + w + 2));
+            if (!cpb_diffuse_is_small(h, w)) {
+                if (lane == 0) big_list[atomicAdd(big_count, 1)] = make_int2(b, l);
+                info = CPB_Q32_CLSBIG;
+            } else {
+                // means of (bbox-relative coordinate + 1), as the reference computes them (same ops as k_centres)
+                const int c = t.cnt[k];
+                const double ymed = __ddiv_rn(__ll2double_rn((long long)t.sumy[k] - (long long)c * y0 + c), __int2double_rn(c));
+                const double xmed = __ddiv_rn(__ll2double_rn((long long)t.sumx[k] - (long long)c * x0 + c), __int2double_rn(c));
+                double bd = 1e300; int bi = CPB_IMAX;
+                bool foreign = false;
+                // grown bbox: columns x0-1 .. x0+w (two passes when w + 2 > 32), rows y0-1 .. y0+h
+                for (int c0 = 0; c0 < w + 2; c0 += 32) {
+                    const int gc = c0 + lane;                    // grown column index; bbox column gc - 1
+                    const int x = x0 - 1 + gc;
+                    if (gc < w + 2 && x >= 0 && x < W) {
+                        const double dx = __dsub_rn(__int2double_rn(gc), xmed);
+                        const double dx2 = __dmul_rn(dx, dx);
+                        for (int ry = -1; ry <= h; ry++) {
+                            const int y = y0 + ry;
+                            if (y < 0 || y >= H) continue;
+                            const int v = L[y * W + x];
+                            if (v == l) {
+                                const double dy = __dsub_rn(__int2double_rn(ry + 1), ymed);
+                                const double d = __dadd_rn(dx2, __dmul_rn(dy, dy));
+                                const int idx = ry * w + gc - 1;
+                                if (cpb_minkey_less(d, idx, bd, bi)) { bd = d; bi = idx; }
+                            } else {
+                                foreign |= cpb_foreign_live(v, l, alive);
+                            }
+                        }
+                    }
+                }
+                for (int sft = 16; sft; sft >>= 1) {
+                    const double od = __shfl_xor_sync(CPB_FULL, bd, sft);
+                    const int oi = __shfl_xor_sync(CPB_FULL, bi, sft);
+                    if (cpb_minkey_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+                }
+                const bool clean = !__any_sync(CPB_FULL, foreign);
+                const int cr = bi / w, cc = bi - cr * w;
+                int cls = cpb_q32_class(cr, h);
+                if (!screen || !clean) cls = CPB_Q32_CLS64;
+                if (lane == 0) {
+                    t.cy[k] = y0 + cr; t.cx[k] = x0 + cc;
+                    if (cls == CPB_Q32_CLS64) q.l64[atomicAdd(&q.ctr[2], 1)] = make_int2(b, l);
+                    else atomicAdd(&s_cnt[cls], 1);
+                }
+                info = cls | (clean ? CPB_QI_CLEAN : 0) | (w << 8);
+            }
+        }
+        if (lane == 0) q.info[k] = info;
+    }
+    for (int s = 16; s; s >>= 1) ext = max(ext, __shfl_xor_sync(CPB_FULL, ext, s));
+    if (lane == 0 && ext > 0) atomicMax(&s_ext, ext);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        t.niter[b] = s_ext;
+        int acc = 0;
+        for (int c = 0; c < CPB_Q32_NCLS; c++) { s_base[c] = acc; acc += s_cnt[c]; }
+    }
+    __syncthreads();
+    int* ent = q.ent + (size_t)b * LC;
+    for (int l = 1 + threadIdx.x; l <= lb; l += blockDim.x) {
+        const int cls = q.info[(size_t)b * LC + l] & 7;
+        if (cls < CPB_Q32_NCLS && (q.info[(size_t)b * LC + l] >> 8) != 0) ent[s_base[cls] + atomicAdd(&s_pos[cls], 1)] = l;
+    }
+    __syncthreads();
+    if (warp < CPB_Q32_NCLS) {
+        const int cls = warp, n = s_cnt[cls];
+        const int* e = ent + s_base[cls];
+        int coff = 0, nsub = 0, first = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const int wi = i < n ? (q.info[(size_t)b * LC + e[i]] >> 8) & 0xff : 0;
+            const int m = min(32, n - i0);
+            for (int j = 0; j < m; j++) {
+                const int wj = __shfl_sync(CPB_FULL, wi, j);
+                if (nsub == CPB_Q32_MAXSUB || coff + wj > CPB_Q32_COLS - 1) {
+                    if (lane == 0) q.jobs[atomicAdd(&q.ctr[0], 1)] = make_int4(b, (int)(e - q.ent) + first, nsub, cls);
+                    first = i0 + j; nsub = 0; coff = 0;
+                }
+                nsub++; coff += wj + 1;
+            }
+        }
+        if (nsub > 0 && lane == 0) q.jobs[atomicAdd(&q.ctr[0], 1)] = make_int4(b, (int)(e - q.ent) + first, nsub, cls);
+    }
+}
+
+// ---- packed float32 pairs ------------------------------------------------------------------------------
+#ifdef CPB_SIM
+struct pf2 { float x, y; };
+CPB_DEVICE pf2 pf2_make(float x, float y) { pf2 r; r.x = x; r.y = y; return r; }
+CPB_DEVICE void pf2_get(pf2 a, float& x, float& y) { x = a.x; y = a.y; }
+CPB_DEVICE pf2 pf2_add(pf2 a, pf2 b) { return pf2_make(a.x + b.x, a.y + b.y); }
+CPB_DEVICE pf2 pf2_mul(pf2 a, pf2 b) { return pf2_make(a.x * b.x, a.y * b.y); }
+#else
+typedef u64 pf2;
+CPB_DEVICE pf2 pf2_make(float x, float y) { return cpb_pk(x, y); }
+CPB_DEVICE void pf2_get(pf2 a, float& x, float& y) { cpb_upk(a, x, y); }
+CPB_DEVICE pf2 pf2_add(pf2 a, pf2 b) { return cpb_add2(a, b); }
+CPB_DEVICE pf2 pf2_mul(pf2 a, pf2 b) { return cpb_mul2(a, b); }
+#endif
+
+// one pixel of the float32 flow error and of its bound (see the header comment)
+CPB_DEVICE void cpb_q32_pixel(float up, float dn, float lf, float rt, float dpy, float dpx, float eta, float& sc, float& sb) {
+    const float U = 5.9604645e-8f, ALPHA2 = 2e-40f;
+    const float dy = __fsub_rn(dn, up), dx = __fsub_rn(rt, lf);
+    const float eg = __fadd_rn(__fadd_rn(__fmul_rn(eta, __fadd_rn(__fadd_rn(dn, up), __fadd_rn(rt, lf))),
+                                         __fmul_rn(U, __fadd_rn(fabsf(dy), fabsf(dx)))), 2.f * ALPHA2);
+    const float gn = sqrtf(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+    float muy = 0.f, mux = 0.f, d = 1.000001f;
+    if (gn > 4.f * eg && gn > 1e-18f) {
+        const float inv = 1.f / gn;
+        muy = __fmul_rn(dy, inv); mux = __fmul_rn(dx, inv);
+        d = __fadd_rn(__fmul_rn(1.01f, eg / __fsub_rn(gn, eg)), 1e-6f);
+    }
+    const float ry = __fsub_rn(muy, __fdiv_rn(dpy, 5.0f)), rx = __fsub_rn(mux, __fdiv_rn(dpx, 5.0f));
+    const float c = __fadd_rn(__fmul_rn(ry, ry), __fmul_rn(rx, rx));
+    const float rn = sqrtf(c);
+    sc = __fadd_rn(sc, c);
+    sb = __fadd_rn(sb, __fadd_rn(__fadd_rn(__fmul_rn(2.000001f * rn, d), __fmul_rn(d, d)), __fmul_rn(1e-6f, __fadd_rn(1.f, c))));
+}
+
+// Per-lane description of the two strip columns (2 * lane, 2 * lane + 1) of a job.
+struct Q32Cols { int l[2], x[2], yb[2]; float inj[2]; };
+
+// The iteration proper: M (member ? 1/9 : 0) comes from the warp's shared-memory tile, T lives in registers for all
+// n_it iterations and goes back to the tile at the end as (member ? T : -0.0f) -- the sign bit carries membership.
+// Only this part is instantiated per row class; the set-up and the error pass are rolled loops shared by all classes
+// (fully unrolled they are ~5000 instructions per class, which the instruction cache does not forgive).
+template <int NR>
+CPB_DEVICE void cpb_q32_iterate(float2* S, float inj0, float inj1, int n_it) {
+    constexpr int RC = NR / 2;
+    const int lane = threadIdx.x & 31;
+    pf2 T[NR], M[NR];
+    #pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const float2 m = S[(r + 1) * 32 + lane];
+        M[r] = pf2_make(m.x, m.y);
+        T[r] = pf2_make(0.f, 0.f);
+    }
+    const pf2 J = pf2_make(inj0, inj1);
+    const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
+    for (int it = 0; it < n_it; it++) {
+        T[RC] = pf2_add(T[RC], J);                                  // T[centre] += 1 before averaging
+        pf2 vcur = pf2_add(T[0], T[1]);
+        #pragma unroll
+        for (int r = 0; r < NR; r++) {
+            pf2 vnext = vcur;
+            if (r + 2 < NR) vnext = pf2_add(pf2_add(T[r], T[r + 1]), T[r + 2]);      // old rows r .. r+2
+            else if (r + 1 < NR) vnext = pf2_add(T[r], T[r + 1]);
+            float vx, vy;
+            pf2_get(vcur, vx, vy);
+            const float ly = __shfl_sync(CPB_FULL, vy, lm);          // column 2j-1
+            const float rx = __shfl_sync(CPB_FULL, vx, lp);          // column 2j+2
+            const float s = __fadd_rn(vx, vy);
+            T[r] = pf2_mul(pf2_make(__fadd_rn(s, ly), __fadd_rn(s, rx)), M[r]);
+            vcur = vnext;
+        }
+    }
+    #pragma unroll
+    for (int r = 0; r < NR; r++) {
+        float tx, ty, mx, my;
+        pf2_get(T[r], tx, ty);
+        pf2_get(M[r], mx, my);
+        S[(r + 1) * 32 + lane] = make_float2(mx != 0.f ? tx : -0.0f, my != 0.f ? ty : -0.0f);
+    }
+}
+
+CPB_DEVICE bool cpb_q32_member(float v) { return (__float_as_uint(v) >> 31) == 0u; }
+
+// One job: set-up (rolled), iteration (per class), error pass (rolled).  S: the warp's tile of (21 + 2) x 32 float2.
+CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, const LabelTables& t,
+                            const Q32& q, int b, int first, int nsub, int cls, double threshold, float2* S, int pack_err) {
+    const int NR = 9 + 4 * cls, RC = NR / 2;
+    const int lane = threadIdx.x & 31;
+    const int N = H * W, LC = t.LC;
+    const int* L = lab + (size_t)b * N;
+    const float* dPy = dP + ((size_t)b * 2 + 0) * N;
+    const float* dPx = dP + ((size_t)b * 2 + 1) * N;
+    const int n_it = t.niter[b];
+    // sub i lives on lane i: label, width, first column of the strip
+    int e_l = 0, e_w = 0;
+    if (lane < nsub) { e_l = q.ent[first + lane]; e_w = (q.info[(size_t)b * LC + e_l] >> 8) & 0xff; }
+    int e_off = lane < nsub ? e_w + 1 : 0;
+    for (int d = 1; d < CPB_Q32_MAXSUB; d <<= 1) {
+        const int v = __shfl_up_sync(CPB_FULL, e_off, d);
+        if (lane >= d) e_off += v;
+    }
+    e_off -= lane < nsub ? e_w + 1 : 0;
+    // this lane's two columns
+    Q32Cols c;
+    int rlo[2] = {0, 0}, rhi[2] = {-1, -1};
+    c.l[0] = c.l[1] = 0; c.x[0] = c.x[1] = 0; c.yb[0] = c.yb[1] = 0; c.inj[0] = c.inj[1] = 0.f;
+    for (int s = 0; s < nsub; s++) {
+        const int sl = __shfl_sync(CPB_FULL, e_l, s), sw = __shfl_sync(CPB_FULL, e_w, s), so = __shfl_sync(CPB_FULL, e_off, s);
+        const size_t k = (size_t)b * LC + sl;
+        const int y0 = t.ymin[k], x0 = t.xmin[k], h = t.ymax[k] - y0 + 1, cy = t.cy[k], cx = t.cx[k];
+        #pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+            const int col = 2 * lane + hf;
+            if (col >= so && col < so + sw) {
+                c.l[hf] = sl; c.x[hf] = x0 + col - so; c.yb[hf] = cy - RC;
+                rlo[hf] = y0 - (cy - RC); rhi[hf] = y0 + h - 1 - (cy - RC);
+                c.inj[hf] = (x0 + col - so == cx) ? 1.f : 0.f;
+            }
+        }
+    }
+    const float ninth = 1.f / 9.f;
+    __syncwarp();
+    for (int r = 0; r < NR; r++) {
+        float m[2] = {0.f, 0.f};
+        #pragma unroll
+        for (int hf = 0; hf < 2; hf++)
+            if (c.l[hf] != 0 && r >= rlo[hf] && r <= rhi[hf] && L[(c.yb[hf] + r) * W + c.x[hf]] == c.l[hf]) m[hf] = ninth;
+        S[(r + 1) * 32 + lane] = make_float2(m[0], m[1]);
+    }
+    S[lane] = make_float2(-0.0f, -0.0f);
+    S[(NR + 1) * 32 + lane] = make_float2(-0.0f, -0.0f);
+    switch (cls) {              // each lane reads back only what it wrote: no warp barrier needed here
+        case 0: cpb_q32_iterate<9>(S, c.inj[0], c.inj[1], n_it); break;
+        case 1: cpb_q32_iterate<13>(S, c.inj[0], c.inj[1], n_it); break;
+        case 2: cpb_q32_iterate<17>(S, c.inj[0], c.inj[1], n_it); break;
+        default: cpb_q32_iterate<21>(S, c.inj[0], c.inj[1], n_it); break;
+    }
+    __syncwarp();
+    // flow error and its bound from the tile
+    // eta >= (1 + u)^(11 k) - 1:  e^x - 1 <= x + x^2 for 0 <= x <= 1, x = 11 k u  (k < 1.5e6 iterations)
+    const double xk = 11.0 * (double)n_it * 5.9604644775390625e-08;
+    const float eta = (float)(1.02 * (xk + xk * xk) + 1e-9);
+    float sc[2] = {0.f, 0.f}, sb[2] = {0.f, 0.f};
+    const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
+    for (int r = 0; r < NR; r++) {
+        const float2 v = S[(r + 1) * 32 + lane];
+        if (!cpb_q32_member(v.x) && !cpb_q32_member(v.y)) continue;
+        const float2 up = S[r * 32 + lane], dn = S[(r + 2) * 32 + lane];
+        const float lf = fabsf(S[(r + 1) * 32 + lm].y), rt = fabsf(S[(r + 1) * 32 + lp].x);
+        if (cpb_q32_member(v.x)) {
+            const int pix = (c.yb[0] + r) * W + c.x[0];
+            cpb_q32_pixel(fabsf(up.x), fabsf(dn.x), lf, fabsf(v.y), dPy[pix], dPx[pix], eta, sc[0], sb[0]);
+        }
+        if (cpb_q32_member(v.y)) {
+            const int pix = (c.yb[1] + r) * W + c.x[1];
+            cpb_q32_pixel(fabsf(up.y), fabsf(dn.y), fabsf(v.x), rt, dPy[pix], dPx[pix], eta, sc[1], sb[1]);
+        }
+    }
+    __syncwarp();
+    float* red = reinterpret_cast<float*>(S);
+    red[4 * lane + 0] = sc[0]; red[4 * lane + 1] = sb[0];
+    red[4 * lane + 2] = sc[1]; red[4 * lane + 3] = sb[1];
+    __syncwarp();
+    if (lane < nsub) {
+        float cs = 0.f, bd = 0.f;
+        for (int i = e_off; i < e_off + e_w; i++) { cs += red[2 * i]; bd += red[2 * i + 1]; }
+        const size_t k = (size_t)b * LC + e_l;
+        const double cnt = (double)t.cnt[k];
+        const double err = (double)cs / cnt;
+        const double bound = 1.01 * (double)bd / cnt + 1e-5 * err + 1e-7;
+        // pack_err (tests): sign bit set, float32 error in the high word, its bound (rounded) in the low word of t.err
+        t.err[k] = pack_err ? __longlong_as_double((long long)((1ull << 63) | ((u64)__float_as_uint((float)err) << 32) | (u64)__float_as_uint((float)bound))) : err;
+        if (err - bound > threshold) { t.flag[k] = 1; t.done[k] = 1; atomicAdd(&q.ctr[4], 1); }
+        else if (err + bound < threshold) { t.flag[k] = 0; t.done[k] = 1; atomicAdd(&q.ctr[4], 1); }
+        else { q.l64[atomicAdd(&q.ctr[2], 1)] = make_int2(b, e_l); atomicAdd(&q.ctr[5], 1); }
+    }
+    __syncwarp();
+}
+
+// k_diffuse32: persistent warps pull jobs (tile, first entry, nsub, class) from the queue k_qc_pack filled.
+#ifndef CPB_Q32_MINBLOCKS
+#define CPB_Q32_MINBLOCKS 4
+#endif
+CPB_KERNEL CPB_LAUNCH_BOUNDS(128, CPB_Q32_MINBLOCKS)
+k_diffuse32(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, LabelTables t, Q32 q, double threshold,
+            int pack_err) {
+    CPB_SHARED float2 s_tile[4][(21 + 2) * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int njobs = q.ctr[0];
+    for (;;) {
+        int j = 0;
+        if (lane == 0) j = atomicAdd(&q.ctr[1], 1);
+        j = __shfl_sync(CPB_FULL, j, 0);
+        if (j >= njobs) break;
+        const int4 jb = q.jobs[j];
+        cpb_q32_run(lab, dP, H, W, t, q, jb.x, jb.y, jb.z, jb.w, threshold, s_tile[warp], pack_err);
+    }
+}
+
+// k_diffuse64_list: the float64 warp kernel of cpb_qc.cuh driven by the explicit list q.l64 (one label per warp):
+// labels in contact with another live label (they write T; their error comes from k_flow_err), labels the screen
+// cannot hold, and labels the screen left undecided (error taken from the float64 tile, as before).
+CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_DW_WARPS * 32, 6)
+k_diffuse64_list(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, double* CPB_RESTRICT T, Q32 q,
+                 const float* CPB_RESTRICT dP, double threshold, int2* todo, int* todo_count, int todo_cap) {
+    CPB_SHARED double s_T[CPB_DW_WARPS][(CPB_DC_MAXH + 3) * CPB_DC_PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = H * W;
+    const int total = q.ctr[2];
+    for (;;) {
+        int j = 0;
+        if (lane == 0) j = atomicAdd(&q.ctr[3], 1);
+        j = __shfl_sync(CPB_FULL, j, 0);
+        if (j >= total) break;
+        const int2 e = q.l64[j];
+        const int b = e.x;
+        DiffSub A;
+        A.l = e.y; A.k = (size_t)b * t.LC + e.y; A.coff = 0;
+        A.y0 = t.ymin[A.k]; A.x0 = t.xmin[A.k];
+        A.h = t.ymax[A.k] - A.y0 + 1; A.w = t.xmax[A.k] - A.x0 + 1;
+        const DiffQC qc{dP + ((size_t)b * 2 + 0) * N, dP + ((size_t)b * 2 + 1) * N,
+                        t.alive ? t.alive + (size_t)b * t.LC : nullptr, threshold, H, todo, todo_count, todo_cap, b};
+        cpb_diffuse_job<2>(lab + (size_t)b * N, W, t, T + (size_t)b * N, s_T[warp], A, A, false, t.niter[b], qc);
+    }
+}

@@ -205,27 +205,12 @@ def get_engine(device=None) -> Engine:
     return _engines[key]
 
 
-def _profile_stages(self, dP, cellprob, logits=None, **kw):
-    """Fused path once with CUDA events around every stage -> {stage name: device ms}.  Synchronises."""
-    import ctypes
+def _profile_stages(self, dP, cellprob, logits=None, with_qc=False, **kw):
+    """Fused path once with CUDA events around every stage -> {stage name: device ms}.  Synchronises.
+    with_qc: also return the flow-check counters (float32 screen decided / undecided, float64 labels)."""
     with torch.cuda.device(self.device):
-        B, _, H, W = dP.shape
-        Cc = 0 if logits is None else int(logits.shape[1])
-        LC = self.label_capacity(H, W)
-        prm = make_params(**kw)
-        masks = torch.empty((B, H, W), dtype=torch.int32, device=self.device)
-        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
-        cc = torch.zeros((B, LC), dtype=torch.int32, device=self.device) if logits is not None else None
-        n = int(self.lib.cpb_workspace_bytes(B, H, W, Cc, 0))
-        ws = torch.empty((n,), dtype=torch.uint8, device=self.device)
-        ns = int(self.lib.cpb_num_stages())
-        ms = (ctypes.c_float * ns)()
-        p = lambda t: None if t is None else t.data_ptr()
-        rc = self.lib.cpb_compute_masks_profiled_device(p(dP), p(cellprob), p(logits), B, H, W, Cc, ctypes.byref(prm),
-                                                        p(masks), p(counts), p(cc), None, p(ws), n,
-                                                        torch.cuda.current_stream(self.device).cuda_stream, ms)
-        check(rc, "cpb_compute_masks_profiled_device")
-        return {self.lib.cpb_stage_name(i).decode(): float(ms[i]) for i in range(ns)}
+        _, _, _, stages, qc = self.calls.compute_masks_profiled(dP, cellprob, logits, make_params(**kw))
+        return (stages, qc) if with_qc else stages
 
 
 Engine.profile_stages = _profile_stages

@@ -94,9 +94,15 @@ void cpb_debug_set_follow_merge(int mode);
 #define CPB_SWITCH_DIFFUSE_QUEUE 1  /* CPB_DIFFUSE_QUEUE: diffusion warps pull label pairs from a queue */
 #define CPB_SWITCH_QC_FUSED 2       /* CPB_QC_FUSED: flow error of isolated labels inside the diffusion warp */
 #define CPB_SWITCH_VOTE_FUSED 3     /* CPB_VOTE_FUSED: class vote folded into the final label pass */
+#define CPB_SWITCH_QC_SCREEN 4      /* CPB_QC_SCREEN: float32 screen with a proven error bound in front of the float64
+                                       flow check; labels it cannot decide take the float64 path (same removal set) */
 void cpb_debug_set_switch(int which, int value);
 /* number of kernels this library has launched in this process (statistics for the benchmark) */
 long long cpb_debug_launch_count(void);
+/* flow-check counters of the last cpb_compute_masks_profiled_device call in this process, 8 ints: [0] float32 screen
+ * jobs, [2] labels that took the float64 warp kernel (contact, too large for the screen, or undecided), [4] labels the
+ * screen decided, [5] labels the screen left undecided (statistics for the benchmark and the tests) */
+void cpb_debug_qc_stats(int32_t* out);
 
 /* Same, HOST buffers in / out (pageable or pinned).  tiles_per_chunk <= 0 picks a default.
  * device = CUDA device ordinal.  This is the call the e2e benchmark times. */

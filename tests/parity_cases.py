@@ -254,6 +254,83 @@ def case_flow_qc_fused_equals_unfused(be):
             assert np.abs(err[0, 1:n + 1] - err0[0, 1:n + 1]).max() < 1e-12, k
 
 
+def near_threshold_flows(lab, rng, thr=0.4):
+    """Flows whose per-label error sits at thr + delta for a ladder of deltas: dP / 5 is the label's own unit flow
+    rotated by phi with 2 - 2 cos(phi) = thr + delta (every unit-vector pixel then contributes exactly that much)."""
+    mu = dynamics.masks_to_flows(lab)
+    deltas = [0.0, 1e-7, -1e-7, 1e-6, -1e-6, 1e-5, -1e-5, 1e-4, -1e-4, 1e-3, -1e-3, 1e-2, -1e-2, 0.2, -0.2]
+    dP = np.zeros_like(mu)
+    for l in range(1, int(lab.max()) + 1):
+        m = lab == l
+        if not m.any():
+            continue
+        e = thr + deltas[int(rng.integers(len(deltas)))]
+        phi = np.arccos(1.0 - e / 2.0) * (1 if rng.random() < 0.5 else -1)
+        c, s_ = np.cos(phi), np.sin(phi)
+        dP[0][m] = 5.0 * (c * mu[0][m] - s_ * mu[1][m])
+        dP[1][m] = 5.0 * (s_ * mu[0][m] + c * mu[1][m])
+    return dP.astype(np.float32)
+
+
+def unpack_screen_err(err):
+    """CPB_QC_SCREEN=2: labels decided by the float32 screen report -(err32 << 32 | bound) bit-packed."""
+    bits = err.view(np.int64)
+    packed = bits < 0
+    b = bits & 0x7FFFFFFFFFFFFFFF
+    e32 = (b >> 32).astype(np.uint32).view(np.float32).astype(np.float64)
+    bnd = (b & 0xFFFFFFFF).astype(np.uint32).view(np.float32).astype(np.float64)
+    return packed, e32, bnd
+
+
+def case_flow_qc_screen_is_decision_exact(be):
+    """The float32 screen in front of the float64 flow check: (a) its proven bound holds, |err32 - err64| <= bound for
+    every label it decides; (b) the removal set equals the float64 path's on planted cells, corrupted flows, random
+    touching labels and a ladder of errors within 1e-7 .. 1e-2 of the threshold; (c) labels it cannot separate from
+    the threshold are left to the float64 kernel (some must be, on the ladder)."""
+    SW = 4
+    rng = np.random.default_rng(123)
+    jobs = []
+    for seed in (1, 3, 6, 7):
+        t = std_tile(seed)
+        lab = t["labels"].astype(np.int32)
+        jobs.append((lab, corrupt_flows(t, seed=seed)))
+        jobs.append((lab, near_threshold_flows(lab, rng)))
+    t = std_tile(5, H=128, W=128, n_grid=16, axes=(2.5, 3.5))
+    jobs.append((t["labels"].astype(np.int32), near_threshold_flows(t["labels"].astype(np.int32), rng)))
+    t = adv_tile()
+    jobs.append((t["labels"].astype(np.int32), corrupt_flows(t)))
+    for trial in range(4):
+        lab = random_label_image(rng, 64, 80, int(rng.integers(8, 30)), gaps=False)
+        u, inv = np.unique(lab, return_inverse=True)
+        lab = inv.reshape(lab.shape).astype(np.int32)
+        if lab.max() > 0:
+            jobs.append((lab, (5.0 * dynamics.masks_to_flows(lab) + rng.normal(0, 1.2, size=(2,) + lab.shape)).astype(np.float32)))
+    n_screened = n_left = n_total = 0
+    try:
+        for lab, dP in jobs:
+            lcap = int(lab.max()) + 2
+            be.set_switch(SW, 0)
+            out0, err0 = be.remove_bad_flow_masks(c32(lab[None]).copy(), f32(dP[None]), lcap, 0.4, want_err=True)
+            be.set_switch(SW, 1)
+            out1, _ = be.remove_bad_flow_masks(c32(lab[None]).copy(), f32(dP[None]), lcap, 0.4, want_err=False)
+            be.set_switch(SW, 2)
+            out2, err2 = be.remove_bad_flow_masks(c32(lab[None]).copy(), f32(dP[None]), lcap, 0.4, want_err=True)
+            np.testing.assert_array_equal(out1, out0)
+            np.testing.assert_array_equal(out2, out0)
+            present = np.isin(np.arange(lcap), np.unique(lab)) & (np.arange(lcap) > 0)
+            packed, e32, bnd = unpack_screen_err(err2[0])
+            packed &= present
+            assert (np.abs(e32 - err0[0])[packed] <= bnd[packed]).all(), "screen bound violated"
+            # whatever the screen did not decide carries the float64 error itself
+            rest = present & ~packed
+            assert np.abs(err2[0][rest] - err0[0][rest]).max(initial=0.0) < 1e-12
+            n_screened += int(packed.sum()); n_left += int(rest.sum()); n_total += int(present.sum())
+    finally:
+        be.set_switch(SW, -1)
+    assert n_screened > 0.5 * n_total, (n_screened, n_total)
+    assert n_left > 0
+
+
 # ------------------------------------------------------------------------------------ (5)
 def nested_rings(H=96, W=96):
     yy, xx = np.mgrid[0:H, 0:W]
@@ -766,7 +843,8 @@ def case_label_offsets(be):
 ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_flows_merge_is_exact,
              case_follow_flows_large_tiles, case_get_masks_exact,
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
-             case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_fill_holes_exact, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
+             case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_flow_qc_screen_is_decision_exact,
+             case_fill_holes_exact, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
              case_fused_generic_class_count, case_fused_switch_matrix, case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
              case_cell_contours_match_cv2, case_prepare_tiles, case_dedup_overlapping_tiles, case_dedup_random_points_components,
