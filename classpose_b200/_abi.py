@@ -3,11 +3,12 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
-E_ARG, E_WORKSPACE, E_RANGE = -1, -2, -3
+E_ARG, E_WORKSPACE, E_RANGE, E_CAPACITY = -1, -2, -3, -4
 _ERR = {E_ARG: "bad argument (shape / null pointer)", E_WORKSPACE: "workspace too small",
-        E_RANGE: "B*H*W exceeds the 31-bit pixel index; split the batch"}
+        E_RANGE: "B*H*W exceeds the 31-bit pixel index; split the batch",
+        E_CAPACITY: "a tile exhausted an internal pool (counts[b] = -1): its masks are incomplete"}
 
 
 class Params(C.Structure):

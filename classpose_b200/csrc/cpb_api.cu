@@ -89,8 +89,7 @@ struct Workspace {
     double* T2;          // [B*N]   (aliases holekey)
     u64* holekey;        // [B*N]
     unsigned* list;      // [B*N]
-    unsigned* list_n;    // [1] (+ status word)
-    int* status;
+    unsigned* list_n;    // [64]: [0] foreground count, [2..3] bump cursor of the hole-fill bitmap pool (u64)
     u64* skey;           // [B*LC]
     int* sidx;           // [B*LC]
     int* sinv;           // [B*LC]
@@ -119,7 +118,6 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     w.holekey = reinterpret_cast<u64*>(w.T2);
     w.list = c.take<unsigned>(BN);
     w.list_n = c.take<unsigned>(64);
-    w.status = reinterpret_cast<int*>(w.list_n) + 1;
     w.skey = c.take<u64>(BL);
     w.sidx = c.take<int>(BL);
     w.sinv = c.take<int>(BL);
@@ -139,6 +137,7 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     t.err = c.take<double>(BL);
     t.done = c.take<int>(BL);
     t.lbound = c.take<int>(B); t.nlab = c.take<int>(B); t.niter = c.take<int>(B); t.misc = c.take<int>(B);
+    t.fail = c.take<int>(B);
     w.bytes = c.off;
     return w;
 }
@@ -147,6 +146,12 @@ int check_geom(int B, int H, int W) {
     if (B <= 0 || H < 2 || W < 2 || H > 32767 || W > 32767) return CPB_E_ARG;
     if ((long long)B * H * W >= (1LL << 31)) return CPB_E_RANGE;
     return 0;
+}
+
+// bitmap pool of the block hole-fill kernel for crops beyond its shared memory: the float64 T plane, free once
+// the flow check is over (2 words per pixel of the batch); cursor in the zeroed scratch words after list_n
+inline FillPool fill_pool(const Workspace& w, int B, int H, int W) {
+    return FillPool{reinterpret_cast<unsigned*>(w.T), reinterpret_cast<u64*>(w.list_n + 2), 2ull * (u64)B * H * W};
 }
 
 inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
@@ -159,16 +164,29 @@ inline unsigned tile_slices(int H, int W) { return (unsigned)std::min<long long>
 inline unsigned table_threads(int H, int W) { return (long long)H * W > 256 * 256 ? 1024u : 256u; }
 
 #ifndef CPB_SIM
+// Function attributes and the SM count belong to a DEVICE (context), and one process may drive several devices
+// (cpb_compute_masks_host takes a device ordinal; the python engine caches one Engine per device): both are
+// tracked per device ordinal.
+constexpr int kMaxDevices = 64;
+std::atomic<int> g_attr_done[kMaxDevices];
+std::atomic<int> g_sm_count[kMaxDevices];
+int current_device() { int dev = 0; cudaGetDevice(&dev); return (dev >= 0 && dev < kMaxDevices) ? dev : 0; }
 void ensure_attributes() {
-    static std::once_flag once;
-    std::call_once(once, [] {
-        cudaFuncSetAttribute(k_fill_holes, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CPB_FILL_WORDS * 4);
-        cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, kVoteSmemIntsMax * 4);
-    });
+    const int dev = current_device();
+    if (g_attr_done[dev].load(std::memory_order_acquire)) return;
+    cudaFuncSetAttribute(k_fill_holes, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CPB_FILL_WORDS * 4);
+    cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, kVoteSmemIntsMax * 4);
+    g_attr_done[dev].store(1, std::memory_order_release);      // (setting them twice from two threads is harmless)
 }
 int sm_count() {
-    static int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev);
-                        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v > 0 ? v : 148; }();
+    const int dev = current_device();
+    int n = g_sm_count[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        int v = 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n = v > 0 ? v : 148;
+        g_sm_count[dev].store(n, std::memory_order_relaxed);
+    }
     return n;
 }
 #else
@@ -268,6 +286,7 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     const long long BN = (long long)B * H * W;
     prof_begin(w.prof, S_PREP);
     cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
+    cudaMemsetAsync(w.t.fail, 0, B * sizeof(int), st);
     if (hist) cudaMemsetAsync(hist, 0, BN * sizeof(int), st);
     const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
     // tap indices are formed in float32 (exact below 2^24): one tile of more than ~4090 x 4090 pixels is out of range
@@ -437,6 +456,8 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
                    bool have_stats, cudaStream_t st) {
     const long long BN = (long long)B * H * W;
     int e;
+    cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);          // bump cursor of the bitmap pool
+    cudaMemsetAsync(w.t.fail, 0, B * sizeof(int), st);
     if (!have_stats) { e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, nullptr, true, st); if (e) return e; }
     const int mode = min_size > 0 ? 1 : 0;
     prof_begin(w.prof, S_SIZE1);
@@ -450,7 +471,7 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
                        CPB_FILL_BOTH);
     CPB_CHECK_LAUNCH();
     CPB_LAUNCH_COUNTED(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
-               masks, H, W, w.t, w.holekey, w.status, 1, (LabelWork{nullptr, nullptr, 0, 0}), CPB_FILL_BOTH);
+               masks, H, W, w.t, w.holekey, fill_pool(w, B, H, W), 1, (LabelWork{nullptr, nullptr, 0, 0}), CPB_FILL_BOTH);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_FILL);
     e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, w.holekey, true, st, S_MAP3); if (e) return e;
@@ -462,6 +483,10 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
         e = run_map_stats(w, masks, B, H, W, 1, w.t.remap, nullptr, nullptr, false, st, S_MAP4); if (e) return e;
     } else if (counts) {
         cudaMemcpyAsync(counts, w.t.lbound, B * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    }
+    if (counts) {
+        CPB_LAUNCH_COUNTED(k_apply_fail, dim3(blocks_for(B, 256)), dim3(256), 0, st, (const int*)w.t.fail, B, counts);
+        CPB_CHECK_LAUNCH();
     }
     return 0;
 }
@@ -639,8 +664,9 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     // (5) size filter / hole fill / size filter as table operations, one final pixel pass
     if (prm->fill_holes) {
         prof_begin(w.prof, S_SIZE1);
-        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, prm->min_size, 1, (const int*)nullptr,
-                           w.skey, w.sidx, w.sinv);
+        // min_size <= 0: upstream skips both size filters and with them every first-appearance renumbering
+        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, prm->min_size,
+                           prm->min_size > 0 ? 1 : 3, (const int*)nullptr, w.skey, w.sidx, w.sinv);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_SIZE1);
         prof_begin(w.prof, S_FILL);
@@ -650,7 +676,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
                                w.holekey, pass);
             CPB_CHECK_LAUNCH();
             CPB_LAUNCH_COUNTED(k_fill_holes, dim3(sm_count() * 3), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
-                               masks, H, W, w.t, w.holekey, w.status, 1, todo_work(w, B, false), pass);
+                               masks, H, W, w.t, w.holekey, fill_pool(w, B, H, W), 1, todo_work(w, B, false), pass);
             CPB_CHECK_LAUNCH();
             if (pass == CPB_FILL_DETECT) {
                 CPB_LAUNCH_COUNTED(k_zero_hole_tiles, dim3(tile_slices(H, W), B), dim3(256), 0, st, w.holekey, H, W, w.t);
@@ -667,8 +693,8 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         prof_begin(w.prof, S_SIZE2);
         // second filter on every tile: besides holes, labels that survived the positional first filter are
         // caught here (labels are contiguous again, so position == value)
-        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, prm->min_size, 1, (const int*)nullptr,
-                           w.skey, w.sidx, w.sinv);
+        CPB_LAUNCH_COUNTED(k_fuse_size, dim3(B), dim3(table_threads(H, W)), 0, st, w.t, H, W, prm->min_size,
+                           prm->min_size > 0 ? 1 : 4, (const int*)nullptr, w.skey, w.sidx, w.sinv);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_SIZE2);
     } else {
@@ -694,7 +720,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
         else { CPB_FV_LAUNCH(0); }
 #undef CPB_FV_LAUNCH
         CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED(k_finish_bounds, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t, B);
+        CPB_LAUNCH_COUNTED(k_finish_bounds, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t, B, counts);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_MAP4);
         w.t.alive = nullptr;
@@ -712,7 +738,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
                            prm->fill_holes ? (const u64*)w.holekey : (const u64*)nullptr, B, H, W, w.t, counts);
     }
     CPB_CHECK_LAUNCH();
-    CPB_LAUNCH_COUNTED(k_finish_bounds, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t, B);
+    CPB_LAUNCH_COUNTED(k_finish_bounds, dim3(blocks_for(B, 256)), dim3(256), 0, st, w.t, B, counts);
     CPB_CHECK_LAUNCH();
     prof_end(w.prof, S_MAP4);
     w.t.alive = nullptr;

@@ -24,6 +24,7 @@ struct LabelTables {
     int* nlab;       // [B] number of instances after the last renumbering
     int* niter;      // [B] diffusion iterations (2 * max ext)
     int* misc;       // [B] stage scratch (seed count, hole flag, ...)
+    int* fail;       // [B] != 0: a stage could not process this tile (reported as counts[b] = -1)
 };
 
 CPB_DEVICE int cpb_lane() { return threadIdx.x & 31; }

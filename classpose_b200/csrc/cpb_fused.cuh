@@ -35,6 +35,9 @@ k_lookup_list(const unsigned* CPB_RESTRICT list, const unsigned* CPB_RESTRICT li
 // k_fuse_size: one block per tile.  Table form of "drop flagged labels, size filter, renumber":
 //   present(l) = alive[l] && !flag[l] && cnt[l] > 0        (flag = bad flow, set by k_flow_err)
 //   mode 2: no hole fill / size filter requested: remap = present ? current id : 0, nothing renumbered
+//   mode 3 / 4 (hole fill with min_size <= 0, where upstream never renumbers by first appearance): 3 = before the
+//           fill, ids compacted in increasing id order (the fill loop's `j` counter); 4 = after it, labels that were
+//           overwritten inside a hole vanish and leave their gap, nlab = highest surviving id
 //   otherwise: position of a present label = rank of its CURRENT id (remap) among present labels; when
 //   min_size > 0 every present label with cnt < min_size removes the label whose current id equals that
 //   position (upstream indexes by position, see k_size_renumber); survivors get new ids 1..n in order of
@@ -57,10 +60,20 @@ k_fuse_size(LabelTables t, int H, int W, int min_size, int mode, const int* CPB_
     int* rank = scratch_idx + (size_t)b * LC;
     int* inv = scratch_inv + (size_t)b * LC;     // current id -> raw label
     const int n_cur = t.nlab[b];
-    if (mode == 2) {
+    if (mode == 2 || mode == 4) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        int top = 0;
         for (int l = threadIdx.x; l <= lb; l += blockDim.x) {
             const bool pres = l >= 1 && alive[l] && !flag[l] && cnt[l] > 0;
             if (!pres) { remap[l] = 0; alive[l] = 0; }
+            else top = max(top, remap[l]);
+        }
+        if (mode == 4) {
+            for (int d = 16; d; d >>= 1) top = max(top, __shfl_xor_sync(CPB_FULL, top, d));
+            if ((threadIdx.x & 31) == 0) atomicMax(&s_n, top);
+            __syncthreads();
+            if (threadIdx.x == 0) t.nlab[b] = s_n;
         }
         return;
     }
@@ -99,7 +112,7 @@ k_fuse_size(LabelTables t, int H, int W, int min_size, int mode, const int* CPB_
         const bool pres = l >= 1 && alive[l] && !flag[l] && cnt[l] > 0;
         if (pres) {
             const int k = atomicAdd(&s_n, 1);
-            keys[k] = ((u64)(unsigned)first[l] << 32) | (unsigned)l;
+            keys[k] = ((u64)(unsigned)(mode == 3 ? remap[l] : first[l]) << 32) | (unsigned)l;
         } else {
             remap[l] = 0; alive[l] = 0;
         }
@@ -299,8 +312,16 @@ CPB_KERNEL k_vote_finish(LabelTables t, int C, const int* CPB_RESTRICT vote, int
     }
 }
 
-// after k_final the image holds ids 1..nlab: shrink the label bound accordingly (vote, border)
-CPB_KERNEL k_finish_bounds(LabelTables t, int B) {
+// after k_final the image holds ids 1..nlab: shrink the label bound accordingly (vote, border); a tile some
+// stage could not process (t.fail, e.g. the hole-fill bitmap pool ran out) reports counts[b] = -1
+CPB_KERNEL k_finish_bounds(LabelTables t, int B, int* CPB_RESTRICT counts_out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B) t.lbound[b] = t.nlab[b];
+    if (b >= B) return;
+    t.lbound[b] = t.nlab[b];
+    if (counts_out && t.fail[b]) counts_out[b] = -1;
+}
+
+CPB_KERNEL k_apply_fail(const int* CPB_RESTRICT fail, int B, int* CPB_RESTRICT counts_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && fail[b]) counts_out[b] = -1;
 }

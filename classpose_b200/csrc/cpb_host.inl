@@ -108,5 +108,7 @@ extern "C" int cpb_compute_masks_host(const float* dP, const float* cellprob, co
         ce = cudaStreamSynchronize(s.stream);
         if (ce != cudaSuccess && rc == 0) rc = (int)ce;
     }
+    if (rc == 0)
+        for (int b = 0; b < B; b++) if (counts[b] < 0) { rc = CPB_E_CAPACITY; break; }
     return rc;
 }

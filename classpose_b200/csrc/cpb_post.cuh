@@ -26,14 +26,19 @@ CPB_KERNEL k_zero_hole_tiles(u64* CPB_RESTRICT holekey, int H, int W, LabelTable
 // non-l pixels, to the border of the crop (fill_voids.fill on `crop == l`).
 // Every hole pixel proposes (bbox area, l) into holekey with atomicMax: when holes nest, the
 // outermost instance -- the one the reference's sequential loop ends with -- wins.
+// The two bitmaps of the crop live in shared memory up to CPB_FILL_WORDS words each; a larger crop (a label
+// spanning more than ~512 x 512 pixels) takes them from `pool`, a bump allocator over a free global plane
+// (pool.cursor must be zeroed per call).  If even that is exhausted the tile is marked failed (t.fail[b]),
+// which the final pass reports as counts[b] = -1: never a silently unfilled mask.
+struct FillPool { unsigned* words; u64* cursor; u64 cap; };
+
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FILL_THREADS, 3)
 k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_RESTRICT holekey,
-             int* CPB_RESTRICT status, int skip_small, LabelWork wk, int pass) {
+             FillPool pool, int skip_small, LabelWork wk, int pass) {
     CPB_DYN_SMEM(unsigned, s_bits);     // free[CPB_FILL_WORDS] | reach[CPB_FILL_WORDS]
     CPB_SHARED int s_changed;
+    CPB_SHARED long long s_off;
     const int LC = t.LC, N = H * W;
-    unsigned* fr = s_bits;
-    unsigned* rc = s_bits + CPB_FILL_WORDS;
     int it_ = 0, b, l;
     while (cpb_next_label(wk, t.lbound, it_, b, l)) {
         const int* L = lab + (size_t)b * N;
@@ -46,10 +51,23 @@ k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_
         if (h < 3 || w < 3) continue;
         if (skip_small && h <= 32 && w <= 32) continue;     // handled by k_fill_holes_warp
         const int wpr = (w + 31) >> 5;
-        if (h * wpr > CPB_FILL_WORDS) { if (threadIdx.x == 0) atomicOr(status, 1); continue; }
+        const int words = h * wpr;
+        volatile unsigned* fr = s_bits;
+        volatile unsigned* rc = s_bits + CPB_FILL_WORDS;
         __syncthreads();
+        if (words > CPB_FILL_WORDS) {                        // block-uniform
+            if (threadIdx.x == 0) {
+                const u64 off = atomicAdd(pool.cursor, (u64)(2 * words));
+                s_off = (pool.words && off + 2ull * words <= pool.cap) ? (long long)off : -1;
+                if (s_off < 0) t.fail[b] = 1;
+            }
+            __syncthreads();
+            if (s_off < 0) continue;
+            fr = pool.words + s_off;
+            rc = fr + words;
+        }
         // bitmaps: fr = pixel is not l ; rc = fr on the crop border
-        for (int i = threadIdx.x; i < h * wpr; i += blockDim.x) {
+        for (int i = threadIdx.x; i < words; i += blockDim.x) {
             const int r = i / wpr, j = i - r * wpr;
             unsigned f = 0, e = 0;
             const int cmax = min(32, w - j * 32);
@@ -68,7 +86,7 @@ k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_
             if (threadIdx.x == 0) s_changed = 0;
             __syncthreads();
             bool ch = false;
-            for (int i = threadIdx.x; i < h * wpr; i += blockDim.x) {
+            for (int i = threadIdx.x; i < words; i += blockDim.x) {
                 const int r = i / wpr, j = i - r * wpr;
                 const unsigned f = fr[i];
                 unsigned cur = rc[i];
@@ -92,7 +110,7 @@ k_fill_holes(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64* CPB_
             if (!any) break;
         }
         const u64 prio = (u64)((unsigned)(h * w)) << 32;
-        for (int i = threadIdx.x; i < h * wpr; i += blockDim.x) {
+        for (int i = threadIdx.x; i < words; i += blockDim.x) {
             unsigned hole = fr[i] & ~rc[i];
             const int r = i / wpr, j = i - r * wpr;
             if (hole && pass != CPB_FILL_WRITE) t.misc[b] = 1;     // tile has at least one filled hole

@@ -102,10 +102,19 @@ k_qc_pack(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int2*
                     if (gc < w + 2 && x >= 0 && x < W) {
                         const double dx = __dsub_rn(__int2double_rn(gc), xmed);
                         const double dx2 = __dmul_rn(dx, dx);
-                        for (int ry = -1; ry <= h; ry++) {
-                            const int y = y0 + ry;
-                            if (y < 0 || y >= H) continue;
-                            const int v = L[y * W + x];
+                        // the column's h + 2 <= 32 pixels: loads first (eight in flight), then the arithmetic
+                        for (int rb = -1; rb <= h; rb += 8) {
+                          int vv[8];
+                          #pragma unroll
+                          for (int q8 = 0; q8 < 8; q8++) {
+                              const int y = y0 + rb + q8;
+                              vv[q8] = (rb + q8 <= h && y >= 0 && y < H) ? L[y * W + x] : 0;
+                          }
+                          #pragma unroll
+                          for (int q8 = 0; q8 < 8; q8++) {
+                            const int ry = rb + q8;
+                            const int v = vv[q8];
+                            if (ry > h) break;
                             if (v == l) {
                                 const double dy = __dsub_rn(__int2double_rn(ry + 1), ymed);
                                 const double d = __dadd_rn(dx2, __dmul_rn(dy, dy));
@@ -114,6 +123,7 @@ k_qc_pack(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int2*
                             } else {
                                 foreign |= cpb_foreign_live(v, l, alive);
                             }
+                          }
                         }
                     }
                 }
@@ -187,24 +197,38 @@ CPB_DEVICE pf2 pf2_add(pf2 a, pf2 b) { return cpb_add2(a, b); }
 CPB_DEVICE pf2 pf2_mul(pf2 a, pf2 b) { return cpb_mul2(a, b); }
 #endif
 
-// one pixel of the float32 flow error and of its bound (see the header comment)
+// approximate reciprocal / square roots (MUFU, <= 2 ulp): their error is part of the bound's slack below
+#ifdef CPB_SIM
+CPB_DEVICE float cpb_rsqrt_approx(float x) { return 1.0f / std::sqrt(x); }
+CPB_DEVICE float cpb_sqrt_approx(float x) { return std::sqrt(x); }
+CPB_DEVICE float cpb_div_approx(float a, float b) { return a / b; }
+#else
+CPB_DEVICE float cpb_rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+CPB_DEVICE float cpb_sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+CPB_DEVICE float cpb_div_approx(float a, float b) { return __fdividef(a, b); }
+#endif
+
+// one pixel of the float32 flow error and of its bound (see the header comment).  Slack: mu32 carries <= 1e-6 of
+// absolute error from the approximate rsqrt and the multiplies (added to d), the squared distance c and the
+// rounded dP / 5 <= 3e-6 (1 + c) relative-ish (last term), the quotient eg / (gn - eg) 2 ulp (inside the 1.01).
 CPB_DEVICE void cpb_q32_pixel(float up, float dn, float lf, float rt, float dpy, float dpx, float eta, float& sc, float& sb) {
-    const float U = 5.9604645e-8f, ALPHA2 = 2e-40f;
+    const float U = 5.9604645e-8f, ALPHA4 = 4e-40f;
     const float dy = __fsub_rn(dn, up), dx = __fsub_rn(rt, lf);
     const float eg = __fadd_rn(__fadd_rn(__fmul_rn(eta, __fadd_rn(__fadd_rn(dn, up), __fadd_rn(rt, lf))),
-                                         __fmul_rn(U, __fadd_rn(fabsf(dy), fabsf(dx)))), 2.f * ALPHA2);
-    const float gn = sqrtf(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+                                         __fmul_rn(U, __fadd_rn(fabsf(dy), fabsf(dx)))), ALPHA4);
+    const float g2 = __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+    const float inv = cpb_rsqrt_approx(fmaxf(g2, 1e-37f));
+    const float gn = __fmul_rn(g2, inv);
     float muy = 0.f, mux = 0.f, d = 1.000001f;
     if (gn > 4.f * eg && gn > 1e-18f) {
-        const float inv = 1.f / gn;
         muy = __fmul_rn(dy, inv); mux = __fmul_rn(dx, inv);
-        d = __fadd_rn(__fmul_rn(1.01f, eg / __fsub_rn(gn, eg)), 1e-6f);
+        d = __fadd_rn(__fmul_rn(1.01f, cpb_div_approx(eg, __fsub_rn(gn, eg))), 2e-6f);
     }
     const float ry = __fsub_rn(muy, __fdiv_rn(dpy, 5.0f)), rx = __fsub_rn(mux, __fdiv_rn(dpx, 5.0f));
     const float c = __fadd_rn(__fmul_rn(ry, ry), __fmul_rn(rx, rx));
-    const float rn = sqrtf(c);
+    const float rn = __fmul_rn(1.00001f, cpb_sqrt_approx(c));
     sc = __fadd_rn(sc, c);
-    sb = __fadd_rn(sb, __fadd_rn(__fadd_rn(__fmul_rn(2.000001f * rn, d), __fmul_rn(d, d)), __fmul_rn(1e-6f, __fadd_rn(1.f, c))));
+    sb = __fadd_rn(sb, __fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(rn, rn), d), __fmul_rn(d, d)), __fmul_rn(3e-6f, __fadd_rn(1.f, c))));
 }
 
 // Per-lane description of the two strip columns (2 * lane, 2 * lane + 1) of a job.
@@ -240,7 +264,7 @@ CPB_DEVICE void cpb_q32_iterate(float2* S, float inj0, float inj1, int n_it) {
             const float ly = __shfl_sync(CPB_FULL, vy, lm);          // column 2j-1
             const float rx = __shfl_sync(CPB_FULL, vx, lp);          // column 2j+2
             const float s = __fadd_rn(vx, vy);
-            T[r] = pf2_mul(pf2_make(__fadd_rn(s, ly), __fadd_rn(s, rx)), M[r]);
+            T[r] = pf2_mul(pf2_add(pf2_make(s, s), pf2_make(ly, rx)), M[r]);    // ({s, s} is a broadcast operand)
             vcur = vnext;
         }
     }
@@ -294,11 +318,24 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
     }
     const float ninth = 1.f / 9.f;
     __syncwarp();
+    // membership: unconditional loads at clamped addresses so that all of a lane's loads are in flight together;
+    // the flows the error pass will read (long evicted from L2 by the batch) are prefetched on the way
+    #pragma unroll 7
     for (int r = 0; r < NR; r++) {
-        float m[2] = {0.f, 0.f};
+        float m[2];
         #pragma unroll
-        for (int hf = 0; hf < 2; hf++)
-            if (c.l[hf] != 0 && r >= rlo[hf] && r <= rhi[hf] && L[(c.yb[hf] + r) * W + c.x[hf]] == c.l[hf]) m[hf] = ninth;
+        for (int hf = 0; hf < 2; hf++) {
+            const bool in = c.l[hf] != 0 && r >= rlo[hf] && r <= rhi[hf];
+            const int pix = in ? (c.yb[hf] + r) * W + c.x[hf] : 0;
+            const bool mem = L[pix] == c.l[hf] && in;
+            m[hf] = mem ? ninth : 0.f;
+#ifndef CPB_SIM
+            if (mem) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(dPy + pix));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(dPx + pix));
+            }
+#endif
+        }
         S[(r + 1) * 32 + lane] = make_float2(m[0], m[1]);
     }
     S[lane] = make_float2(-0.0f, -0.0f);
@@ -316,18 +353,27 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
     const float eta = (float)(1.02 * (xk + xk * xk) + 1e-9);
     float sc[2] = {0.f, 0.f}, sb[2] = {0.f, 0.f};
     const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
-    for (int r = 0; r < NR; r++) {
-        const float2 v = S[(r + 1) * 32 + lane];
-        if (!cpb_q32_member(v.x) && !cpb_q32_member(v.y)) continue;
-        const float2 up = S[r * 32 + lane], dn = S[(r + 2) * 32 + lane];
-        const float lf = fabsf(S[(r + 1) * 32 + lm].y), rt = fabsf(S[(r + 1) * 32 + lp].x);
-        if (cpb_q32_member(v.x)) {
-            const int pix = (c.yb[0] + r) * W + c.x[0];
-            cpb_q32_pixel(fabsf(up.x), fabsf(dn.x), lf, fabsf(v.y), dPy[pix], dPx[pix], eta, sc[0], sb[0]);
+    for (int r0 = 0; r0 < NR; r0 += 4) {
+        // the flows of four rows first (unconditional loads at clamped addresses), then the arithmetic
+        float a[4][4];
+        #pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) {
+            const int r = min(r0 + q4, NR - 1);
+            const float2 v = S[(r + 1) * 32 + lane];
+            const int p0 = cpb_q32_member(v.x) ? (c.yb[0] + r) * W + c.x[0] : 0;
+            const int p1 = cpb_q32_member(v.y) ? (c.yb[1] + r) * W + c.x[1] : 0;
+            a[q4][0] = dPy[p0]; a[q4][1] = dPx[p0]; a[q4][2] = dPy[p1]; a[q4][3] = dPx[p1];
         }
-        if (cpb_q32_member(v.y)) {
-            const int pix = (c.yb[1] + r) * W + c.x[1];
-            cpb_q32_pixel(fabsf(up.y), fabsf(dn.y), fabsf(v.x), rt, dPy[pix], dPx[pix], eta, sc[1], sb[1]);
+        #pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) {
+            const int r = r0 + q4;
+            if (r >= NR) break;
+            const float2 v = S[(r + 1) * 32 + lane];
+            if (!cpb_q32_member(v.x) && !cpb_q32_member(v.y)) continue;
+            const float2 up = S[r * 32 + lane], dn = S[(r + 2) * 32 + lane];
+            const float lf = fabsf(S[(r + 1) * 32 + lm].y), rt = fabsf(S[(r + 1) * 32 + lp].x);
+            if (cpb_q32_member(v.x)) cpb_q32_pixel(fabsf(up.x), fabsf(dn.x), lf, fabsf(v.y), a[q4][0], a[q4][1], eta, sc[0], sb[0]);
+            if (cpb_q32_member(v.y)) cpb_q32_pixel(fabsf(up.y), fabsf(dn.y), fabsf(v.x), rt, a[q4][2], a[q4][3], eta, sc[1], sb[1]);
         }
     }
     __syncwarp();

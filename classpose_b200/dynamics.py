@@ -46,7 +46,9 @@ def _run(dP, cellprob, niter, cellprob_threshold, flow_threshold, min_size, max_
                                                   max_size_fraction=max_size_fraction, fill_holes=fill_holes)
     single = (dP.dim() if isinstance(dP, torch.Tensor) else np.ndim(dP)) == 3
     if _is_dev(dP):
-        return masks[0] if single else masks
+        return masks[0] if single else masks      # asynchronous: a failed tile shows as counts[b] = -1 (engine API)
+    if bool((counts < 0).any().item()):
+        raise ClassposeB200Error("a tile exhausted the hole-fill bitmap pool (counts = -1): masks are incomplete")
     m = masks.cpu().numpy()
     m = m.astype(_label_dtype(m))
     return m[0] if single else m

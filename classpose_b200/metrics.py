@@ -15,9 +15,19 @@ def remove_border_instances(mask: np.ndarray, device=None) -> np.ndarray:
     inst = mask[..., 0] if mask.ndim == 3 else mask
     if inst.size == 0 or inst.max() <= 0:
         return mask
-    nch = mask.shape[2] if mask.ndim == 3 else 1
+    # Only the instance channel goes to the device, as int32 ids: directly when the dtype allows it, otherwise
+    # (float masks, ids >= 2^31) through the ranks of the distinct values.  The device returns which pixels
+    # belong to a border instance; those are zeroed here in the caller's array and dtype, so surviving pixels
+    # -- every channel of them -- keep their exact values, as in the reference.
+    if np.issubdtype(inst.dtype, np.integer) and int(inst.max()) < 2 ** 31 - 2 and int(inst.min()) >= 0:
+        ids = np.ascontiguousarray(inst, dtype=np.int32)
+    else:
+        uniq, inv = np.unique(inst, return_inverse=True)
+        rank = np.arange(1, len(uniq) + 1, dtype=np.int32)      # every distinct value is an instance ...
+        rank[uniq == 0] = 0                                     # ... except 0, the background (pq.py:88)
+        ids = np.ascontiguousarray(rank[inv].reshape(inst.shape), dtype=np.int32)
     eng = get_engine(device)
-    m = np.ascontiguousarray(mask.astype(np.int32)).reshape(1, mask.shape[0], mask.shape[1], nch)
-    out = eng.remove_border_instances(m, int(inst.max()) + 2, nch=nch)
-    mask[...] = out.cpu().numpy().reshape(mask.shape).astype(mask.dtype)
+    out = eng.remove_border_instances(ids[None], int(ids.max()) + 2, nch=1)
+    removed = (ids > 0) & (out[0].cpu().numpy() == 0)
+    mask[removed] = 0
     return mask

@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from ._abi import ClassposeB200Error
 from .engine import get_engine
 
 
@@ -14,6 +15,8 @@ def fill_holes_and_remove_small_masks(masks, min_size=15, device=None):
     if m.size == 0 or m.max() <= 0:
         return masks
     eng = get_engine(device)
-    out, _ = eng.fill_holes_and_remove_small_masks(np.ascontiguousarray(m.astype(np.int32))[None], int(m.max()) + 2,
-                                                   min_size)
+    out, counts = eng.fill_holes_and_remove_small_masks(np.ascontiguousarray(m.astype(np.int32))[None], int(m.max()) + 2,
+                                                        min_size)
+    if int(counts[0].item()) < 0:
+        raise ClassposeB200Error("hole fill exhausted its bitmap pool (counts = -1): masks would be incomplete")
     return out[0].cpu().numpy().astype(m.dtype)

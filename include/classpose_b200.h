@@ -33,12 +33,15 @@
 extern "C" {
 #endif
 
-#define CPB_ABI_VERSION 1
+#define CPB_ABI_VERSION 2
 
 #define CPB_E_ARG       (-1) /* bad shape / null pointer */
 #define CPB_E_WORKSPACE (-2) /* workspace too small */
 #define CPB_E_RANGE     (-3) /* B*H*W does not fit the 31-bit pixel index (split the batch), or one tile exceeds
                                  2^24 padded pixels (about 4090 x 4090) in follow_flows */
+#define CPB_E_CAPACITY  (-4) /* a tile exhausted an internal pool (hole fill of labels spanning more than ~512 x 512
+                                 pixels draws its bitmaps from a bounded pool).  *_device calls are asynchronous and
+                                 report this as counts[b] = -1 for the tile; *_host calls return this code. */
 
 /* Parameters of dynamics.resize_and_compute_masks as called at
  * /root/reference/src/classpose/models.py:149-159; defaults from models.py:490-498,751-752. */

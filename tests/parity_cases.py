@@ -367,6 +367,26 @@ def case_fill_holes_exact(be):
                 assert cnt[0] == ref.max()
 
 
+def case_fill_holes_oversized_label(be):
+    """A label whose crop exceeds the shared-memory bitmaps of the block kernel (bbox 600 x 600 > 8192 words): a ring
+    with a thick wall, another label and background inside its hole, an L-shaped label with a big bbox and no hole.
+    The bitmaps then come from the global pool; the result must equal the oracle (it used to be skipped silently)."""
+    H = W = 640
+    yy, xx = np.mgrid[0:H, 0:W]
+    r2 = (yy - 320) ** 2 + (xx - 320) ** 2
+    lab = np.zeros((H, W), np.int32)
+    lab[(r2 <= 300 ** 2) & (r2 >= 270 ** 2)] = 1            # ring: bbox 601 x 601
+    lab[(np.abs(yy - 320) < 20) & (np.abs(xx - 300) < 30)] = 2     # label inside the hole (gets overwritten)
+    lab[(yy < 12) & (xx < 610)] = 3                                  # L shape, bbox 610 x 610, nothing enclosed
+    lab[(xx < 12) & (yy < 610)] = 3
+    lab[600:630, 600:630] = 4
+    lab[610:620, 610:620] = 0                                        # small label with a hole (warp kernel)
+    ref = outils.fill_holes_and_remove_small_masks(lab.copy(), 15)
+    out, cnt = be.fill_holes_and_remove_small_masks(c32(lab[None]).copy(), int(lab.max()) + 2, 15)
+    np.testing.assert_array_equal(out[0], ref)
+    assert cnt[0] == ref.max()
+
+
 def random_label_image(rng, H, W, n, gaps=True):
     """Random discs, rings (holes, some with a cell inside), slabs and specks painted over each other, with
     non-contiguous ids when `gaps`: the shapes the table-driven relabelling has to get right."""
@@ -633,6 +653,26 @@ def case_fused_empty_and_params(be):
     assert r["fp"] == 0 and r["fn"] == 0
 
 
+def case_fused_min_size_zero_keeps_upstream_ids(be):
+    """resize_and_compute_masks(min_size=0): upstream fills holes but never renumbers by first appearance, so ids follow
+    the label order and a label swallowed by a hole leaves a gap.  The fused path must give the same ids (counts = highest id)
+    and the stage call must agree with it."""
+    t = adv_tile()
+    ref = dynamics.resize_and_compute_masks(t["dP"], t["cellprob"], min_size=0)
+    assert len(np.unique(ref)) - 1 < ref.max(), "scenario must contain a swallowed label"
+    masks, counts, _, _ = be.compute_masks(f32(t["dP"][None]), f32(t["cellprob"][None]), None, min_size=0)
+    np.testing.assert_array_equal(masks[0], ref.astype(np.int32))
+    assert counts[0] == ref.max()
+    for s in (1, 3):
+        t = std_tile(s)
+        ref = dynamics.resize_and_compute_masks(t["dP"], t["cellprob"], min_size=-1)
+        masks, counts, _, _ = be.compute_masks(f32(t["dP"][None]), f32(t["cellprob"][None]), None, min_size=-1)
+        r = metrics.match_instances(ref.astype(np.int32), masks[0])
+        assert r["f1"] >= 0.995
+        same = (masks[0] > 0) == (ref > 0)
+        assert same.mean() > 0.999
+
+
 def case_fused_qc_then_positional_size_filter(be):
     """Fused path where the flow check removes labels first, so the later size filter (which upstream
     indexes by POSITION in the sorted unique list) removes labels other than the small ones."""
@@ -844,8 +884,9 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_f
              case_follow_flows_large_tiles, case_get_masks_exact,
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
              case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_flow_qc_screen_is_decision_exact,
-             case_fill_holes_exact, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
+             case_fill_holes_exact, case_fill_holes_oversized_label, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
-             case_fused_generic_class_count, case_fused_switch_matrix, case_fused_odd_width, case_fused_empty_and_params, case_fused_qc_then_positional_size_filter,
+             case_fused_generic_class_count, case_fused_switch_matrix, case_fused_odd_width, case_fused_empty_and_params, case_fused_min_size_zero_keeps_upstream_ids,
+             case_fused_qc_then_positional_size_filter,
              case_cell_contours_match_cv2, case_prepare_tiles, case_dedup_overlapping_tiles, case_dedup_random_points_components,
              case_label_offsets]
