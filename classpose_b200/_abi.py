@@ -19,6 +19,14 @@ class Params(C.Structure):
                 ("fill_holes", C.c_int32)]
 
 
+class HostOptions(C.Structure):
+    """cpb_host_options (include/classpose_b200.h)."""
+    _fields_ = [("tiles_per_chunk", C.c_int32), ("device", C.c_int32), ("logits_mode", C.c_int32), ("masks_u16", C.c_int32)]
+
+
+LOGITS_AUTO, LOGITS_UPLOAD, LOGITS_MAPPED = 0, 1, 2
+
+
 class ClassposeB200Error(RuntimeError):
     pass
 
@@ -46,6 +54,7 @@ SIGNATURES = {
     "cpb_debug_set_follow_merge": (None, [_I]),
     "cpb_debug_set_switch": (None, [_I, _I]),
     "cpb_compute_masks_host": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, _I, _I]),
+    "cpb_compute_masks_host_ex": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, C.POINTER(HostOptions)]),
     "cpb_follow_flows_device": (C.c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "cpb_get_masks_device": (C.c_int, [_P, _I, _I, _I, _D, _P, _P, _P, _Z, _P]),
     "cpb_masks_to_flows_device": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _Z, _P]),
@@ -63,7 +72,7 @@ SIGNATURES = {
 }
 
 # entry points that exist only in the CUDA build (host-buffer path does real H2D/D2H copies)
-CUDA_ONLY = {"cpb_compute_masks_host"}
+CUDA_ONLY = {"cpb_compute_masks_host", "cpb_compute_masks_host_ex"}
 
 
 def declare(lib: C.CDLL, cuda: bool = True) -> C.CDLL:

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._abi import ClassposeB200Error, check, make_params
+from ._abi import LOGITS_AUTO, LOGITS_MAPPED, LOGITS_UPLOAD, ClassposeB200Error, HostOptions, check, make_params
 from ._calls import Calls
 
 _DT = {"int32": torch.int32, "int16": torch.int16, "uint8": torch.uint8, "float32": torch.float32, "float64": torch.float64,
@@ -92,10 +92,12 @@ class Engine:
 
     def compute_masks_host(self, dP, cellprob, logits=None, niter=200, cellprob_threshold=0.0, flow_threshold=0.4,
                            min_size=15, max_size_fraction=0.4, remove_border=False, fill_holes=True,
-                           want_class_masks=False, tiles_per_chunk=0, out=None):
+                           want_class_masks=False, tiles_per_chunk=0, out=None, logits_mode="auto", masks_u16=False):
         """Host buffers in / out (numpy arrays or CPU torch tensors, ideally pinned).  The library
-        performs chunked H2D -> kernels -> D2H itself.  Returns numpy views (masks, counts, cell_class,
-        class_masks).  `out` may hold pre-allocated (pinned) output tensors with the same keys."""
+        performs chunked H2D -> kernels -> D2H itself.  Returns (masks, counts, cell_class, class_masks) as CPU
+        tensors.  `out` may hold pre-allocated (pinned) output tensors with the same keys.
+        logits_mode: "auto" (pinned logits are read in place through the mapped pointer, only under cells),
+        "upload" (copy all of them) or "mapped" (insist); masks_u16: deliver uint16 label images."""
         def host(x, dtype):
             if x is None:
                 return None
@@ -109,7 +111,10 @@ class Engine:
         Cc = 0 if logits is None else int(logits.shape[1])
         LC = self.label_capacity(H, W)
         out = out or {}
-        masks = out.get("masks") if out.get("masks") is not None else torch.empty((B, H, W), dtype=torch.int32)
+        mdt = torch.uint16 if masks_u16 else torch.int32
+        masks = out.get("masks") if out.get("masks") is not None else torch.empty((B, H, W), dtype=mdt)
+        if masks.dtype != mdt:
+            raise ClassposeB200Error(f"out['masks'] must be {mdt}")
         counts = out.get("counts") if out.get("counts") is not None else torch.empty((B,), dtype=torch.int32)
         cell_class = None
         class_masks = None
@@ -120,10 +125,12 @@ class Engine:
         prm = make_params(niter, cellprob_threshold, flow_threshold, min_size, max_size_fraction, remove_border,
                           fill_holes)
         p = lambda t: None if t is None else t.data_ptr()
-        rc = self.lib.cpb_compute_masks_host(p(dP), p(cellprob), p(logits), B, H, W, Cc, C.byref(prm), p(masks),
-                                             p(counts), p(cell_class), p(class_masks), int(tiles_per_chunk),
-                                             int(self.device.index))
-        check(rc, "cpb_compute_masks_host")
+        opt = HostOptions(int(tiles_per_chunk), int(self.device.index),
+                          {"auto": LOGITS_AUTO, "upload": LOGITS_UPLOAD, "mapped": LOGITS_MAPPED}[logits_mode],
+                          1 if masks_u16 else 0)
+        rc = self.lib.cpb_compute_masks_host_ex(p(dP), p(cellprob), p(logits), B, H, W, Cc, C.byref(prm), p(masks),
+                                                p(counts), p(cell_class), p(class_masks), C.byref(opt))
+        check(rc, "cpb_compute_masks_host_ex")
         return masks, counts, cell_class, class_masks
 
     # -- stages (device tensors) -----------------------------------------------------------

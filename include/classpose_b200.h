@@ -108,11 +108,29 @@ long long cpb_debug_launch_count(void);
 void cpb_debug_qc_stats(int32_t* out);
 
 /* Same, HOST buffers in / out (pageable or pinned).  tiles_per_chunk <= 0 picks a default.
- * device = CUDA device ordinal.  This is the call the e2e benchmark times. */
+ * device = CUDA device ordinal.  Equivalent to cpb_compute_masks_host_ex with default options. */
 int cpb_compute_masks_host(const float* dP, const float* cellprob, const float* logits,
                            int B, int H, int W, int C, const cpb_params* prm,
                            int32_t* masks, int32_t* counts, int32_t* cell_class,
                            uint8_t* class_masks, int tiles_per_chunk, int device);
+
+/* The host path is bound by the bytes that cross PCIe; the options say how to spend them.  This is the call the
+ * e2e benchmark times. */
+#define CPB_HOST_LOGITS_AUTO   0  /* mapped when the logits buffer is pinned / registered host memory, else upload */
+#define CPB_HOST_LOGITS_UPLOAD 1  /* copy every logit to the device (4*C bytes per pixel) */
+#define CPB_HOST_LOGITS_MAPPED 2  /* the final label pass reads the logits through the mapped host pointer and only
+                                     touches the 4-pixel groups that hold a cell; CPB_E_ARG if the buffer is pageable */
+typedef struct cpb_host_options {
+    int32_t tiles_per_chunk;   /* <= 0: default (128) */
+    int32_t device;            /* CUDA device ordinal */
+    int32_t logits_mode;       /* CPB_HOST_LOGITS_* */
+    int32_t masks_u16;         /* 1: `masks` is uint16 [B,H,W] (Cellpose's dtype below 65536 labels; ids are
+                                  truncated to 16 bits), 0: int32 */
+} cpb_host_options;
+int cpb_compute_masks_host_ex(const float* dP, const float* cellprob, const float* logits,
+                              int B, int H, int W, int C, const cpb_params* prm,
+                              void* masks, int32_t* counts, int32_t* cell_class,
+                              uint8_t* class_masks, const cpb_host_options* opt);
 
 /* ---- stage entry points (each is one row of SURVEY.md section 8a) ------------------------ */
 

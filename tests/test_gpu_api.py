@@ -110,6 +110,51 @@ def test_host_buffer_path_matches_device_path():
         np.testing.assert_array_equal(cch[b, :n + 1].numpy(), ccd[b, :n + 1].cpu().numpy())
 
 
+def test_host_buffer_path_mapped_logits_and_u16_masks():
+    """Pinned logits are read in place by the final label pass (no upload); pageable ones are uploaded; uint16 masks;
+    the speculative cell_class row width is widened when a tile holds more cells than it (forced by a tiny width)."""
+    import torch
+    from classpose_b200 import ClassposeB200Error
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    tiles = [pc.std_tile(s) for s in (1, 3, 4, 6, 7)]
+    dP = torch.from_numpy(np.stack([t["dP"] for t in tiles])); cp = torch.from_numpy(np.stack([t["cellprob"] for t in tiles]))
+    lg = torch.from_numpy(np.stack([t["logits"] for t in tiles]))
+    md, cd, ccd, _ = eng.compute_masks_batch(dP, cp, lg)
+    md, cd, ccd = md.cpu().numpy(), cd.cpu().numpy(), ccd.cpu().numpy()
+    pin = [x.pin_memory() for x in (dP, cp, lg)]
+    for mode, args in (("mapped", pin), ("auto", pin), ("upload", pin), ("auto", (dP, cp, lg))):
+        for u16 in (False, True):
+            mh, ch, cch, _ = eng.compute_masks_host(*args, tiles_per_chunk=2, logits_mode=mode, masks_u16=u16)
+            assert mh.dtype == (torch.uint16 if u16 else torch.int32)
+            np.testing.assert_array_equal(mh.numpy().astype(np.int32), md, err_msg=f"{mode} u16={u16}")
+            np.testing.assert_array_equal(ch.numpy(), cd)
+            for b in range(len(tiles)):
+                n = int(ch[b])
+                np.testing.assert_array_equal(cch[b, :n + 1].numpy(), ccd[b, :n + 1])
+    with pytest.raises(ClassposeB200Error):
+        eng.compute_masks_host(dP, cp, lg, logits_mode="mapped")          # pageable logits cannot be mapped
+
+
+def test_two_devices_in_one_process():
+    """Function attributes (dynamic shared memory of the block hole-fill / vote kernels) and the SM count are per
+    device: a second engine on a second GPU of the same process must work, host path included."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from classpose_b200.engine import get_engine
+    t = pc.std_tile(1)
+    lab = pc.nested_rings().astype(np.int32)
+    for d in (0, 1):
+        eng = get_engine(f"cuda:{d}")
+        m, c, cc, cm = eng.compute_masks_batch(t["dP"][None], t["cellprob"][None], t["logits"][None], want_class_masks=True)
+        assert metrics.match_instances(t["masks_oracle"], m[0].cpu().numpy())["f1"] >= 0.995
+        out, _ = eng.fill_holes_and_remove_small_masks(lab[None], int(lab.max()) + 2, 15)
+        np.testing.assert_array_equal(out[0].cpu().numpy(), outils.fill_holes_and_remove_small_masks(lab.copy(), 15))
+        mh, ch, _, _ = eng.compute_masks_host(t["dP"][None], t["cellprob"][None], t["logits"][None])
+        np.testing.assert_array_equal(mh.numpy(), m.cpu().numpy())
+
+
 def test_concurrent_calls_from_two_threads():
     """The reference runs two inference threads per process; calls must be re-entrant."""
     import threading
