@@ -21,7 +21,8 @@ class Params(C.Structure):
 
 class HostOptions(C.Structure):
     """cpb_host_options (include/classpose_b200.h)."""
-    _fields_ = [("tiles_per_chunk", C.c_int32), ("device", C.c_int32), ("logits_mode", C.c_int32), ("masks_u16", C.c_int32)]
+    _fields_ = [("tiles_per_chunk", C.c_int32), ("device", C.c_int32), ("logits_mode", C.c_int32),
+                ("flows_mode", C.c_int32), ("masks_u16", C.c_int32)]
 
 
 LOGITS_AUTO, LOGITS_UPLOAD, LOGITS_MAPPED = 0, 1, 2

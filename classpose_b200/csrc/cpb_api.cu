@@ -3,7 +3,7 @@
 // mutable state; every call runs on the caller's stream with the caller's workspace.
 #include "classpose_b200.h"
 
-#define CPB_QCTR_INTS 8
+#define CPB_QCTR_INTS 16
 #include "cpb_platform.h"
 #include "cpb_common.cuh"
 #include "cpb_flow.cuh"
@@ -125,7 +125,7 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     w.vote = c.take<int>(C > 0 ? BL * C : 0);
     w.jobs = c.take<int>((size_t)B + 1 + 4);
     w.todo = c.take<int2>(BL);
-    w.q.info = c.take<int>(BL); w.q.ent = c.take<int>(BL); w.q.jobs = c.take<int4>(BL); w.q.l64 = c.take<int2>(BL);
+    w.q.info = c.take<int>(BL); w.q.ent = c.take<int>(BL); w.q.jobs = c.take<int4>(BL); w.q.sorted = c.take<int4>(BL); w.q.l64 = c.take<int2>(BL);
     w.q.ctr = c.take<int>(CPB_QCTR_INTS);
     LabelTables& t = w.t;
     t.LC = LC;
@@ -282,7 +282,8 @@ int run_map_stats(const Workspace& w, int32_t* lab, int B, int H, int W, int nch
 
 // zero_out != NULL (fused path): the prep kernel zeroes that label image instead of marking background in p_final
 int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B, int H, int W, int niter,
-               float thr, int32_t* pfinal, float* pfloat, int* hist, cudaStream_t st, int32_t* zero_out = nullptr) {
+               float thr, int32_t* pfinal, float* pfloat, int* hist, cudaStream_t st, int32_t* zero_out = nullptr,
+               float* dP_copy = nullptr) {
     const long long BN = (long long)B * H * W;
     prof_begin(w.prof, S_PREP);
     cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
@@ -295,13 +296,15 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     const int bg_value = zero_out ? 0 : -1;
     const bool vec4 = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(dP) % 16 == 0) &&
                       (reinterpret_cast<uintptr_t>(cellprob) % 16 == 0) && (reinterpret_cast<uintptr_t>(bg_out) % 16 == 0);
+    if (dP_copy && !(vec4 && reinterpret_cast<uintptr_t>(dP_copy) % 16 == 0)) return CPB_E_ARG;   // (only the host path asks)
     if (vec4) {
         const int patch = (W % 64 == 0) ? 1 : 0;
         const long long nblk = patch ? (long long)B * ((H + 2 + 15) / 16) * (W / 64)
                                      : (long long)blocks_for((long long)B * (H + 2) * (W / 4), 256);
         CPB_LAUNCH_COUNTED(k_prep_flow_v4, dim3((unsigned)nblk), dim3(256), 0, st,
                            reinterpret_cast<const float4*>(dP), reinterpret_cast<const float4*>(cellprob), B, H, W, thr, sx,
-                           sy, reinterpret_cast<float4*>(w.flow), reinterpret_cast<int4*>(bg_out), w.list, w.list_n, patch, bg_value);
+                           sy, reinterpret_cast<float4*>(w.flow), reinterpret_cast<int4*>(bg_out), w.list, w.list_n, patch, bg_value,
+                           reinterpret_cast<float4*>(dP_copy));
     } else {
         CPB_LAUNCH_COUNTED(k_prep_flow, dim3(blocks_for((long long)B * (H + 2) * (W + 2 * CPB_FLOW_PADX), 256)), dim3(256),
                            0, st, dP, cellprob, B, H, W, thr, sx, sy, w.flow, bg_out, w.list, w.list_n, bg_value);
@@ -407,6 +410,8 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
         CPB_LAUNCH_COUNTED(k_centres, dim3(sm_count() * 8), dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t, 1, big);
         CPB_CHECK_LAUNCH();
         prof_end(w.prof, S_CENTRES);
+        CPB_LAUNCH_COUNTED(k_q32_sort, dim3(sm_count()), dim3(256), 0, st, w.q);
+        CPB_CHECK_LAUNCH();
         prof_begin(w.prof, S_DIFFUSE);
         CPB_LAUNCH_COUNTED(k_diffuse32, dim3(sm_count() * CPB_Q32_MINBLOCKS), dim3(128), 0, st, masks, qc_dP, H, W, w.t, w.q, thr,
                            (exact_err && qc_screen_debug()) ? 1 : 0);
@@ -622,9 +627,12 @@ int cpb_remove_border_instances_device(int32_t* masks, int B, int H, int W, int 
 
 }  // extern "C"
 
+// dP_copy (host path only): dP is a mapped HOST pointer; the prep kernel reads the groups that hold foreground
+// through it and keeps them in dP_copy [B,2,H,W] on the device, which is what the flow check then reads
 static int compute_masks_impl(const float* dP, const float* cellprob, const float* logits, int B, int H, int W,
                              int C, const cpb_params* prm, int32_t* masks, int32_t* counts, int32_t* cell_class,
-                             uint8_t* class_masks, void* workspace, size_t workspace_bytes, void* stream, Prof* prof) {
+                             uint8_t* class_masks, void* workspace, size_t workspace_bytes, void* stream, Prof* prof,
+                             float* dP_copy = nullptr) {
     if (!dP || !cellprob || !prm || !masks || !counts) return CPB_E_ARG;
     if (logits && (!cell_class || C < 1 || C > 255)) return CPB_E_ARG;
     if (prm->niter < 0) return CPB_E_ARG;
@@ -634,8 +642,9 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     int e;
     const long long BN = (long long)B * H * W;
     // (2) Euler integration + end-point histogram
-    e = run_follow(w, dP, cellprob, B, H, W, prm->niter, prm->cellprob_threshold, w.pfinal, nullptr, w.hist, st, masks);
+    e = run_follow(w, dP, cellprob, B, H, W, prm->niter, prm->cellprob_threshold, w.pfinal, nullptr, w.hist, st, masks, dP_copy);
     if (e) return e;
+    if (dP_copy) dP = dP_copy;          // every later reader (flow check) sits on a foreground pixel
     // (3) seeds -> raw labels (seed order + 1) and their statistics; ids after get_masks live in t.remap
     prof_begin(w.prof, S_SEEDS);
     { int e_ = run_seeds(w, B, H, W, st); if (e_) return e_; }

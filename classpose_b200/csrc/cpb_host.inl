@@ -7,6 +7,9 @@
 //  * logits of a PINNED (or registered) host buffer are not uploaded at all: the final label pass reads them
 //    through the mapped host pointer, and it only touches the 4-pixel groups that hold a cell (about a quarter
 //    of them), so only those cross the bus (CPB_HOST_LOGITS_MAPPED, the default when the buffer allows it);
+//  * dP of a pinned buffer is likewise read in place by the prep kernel, only where a 4-pixel group holds
+//    foreground; those groups are kept in a device copy for the flow check.  cellprob is needed everywhere and is
+//    always uploaded.  (Kernel reads of host memory move 64-byte half lines: tests/studies/zerocopy_bw.cu.)
 //  * cell_class rows are copied back `cc_width` entries wide (the table is LC ~ N/11 entries per tile, a tile
 //    holds ~100 cells); a chunk whose largest count exceeds the width is copied again in full after the sync;
 //  * label masks can be delivered as uint16 (the dtype Cellpose returns below 65536 labels).
@@ -48,7 +51,7 @@ ChunkBufs carve_chunk(char* base, int Bc, int H, int W, int C, bool has_logits, 
     const int LC = cpb_label_capacity(H, W);
     Carver c{base, 0};
     ChunkBufs b{};
-    b.dP = c.take<float>(2 * N * Bc);
+    b.dP = c.take<float>(2 * N * Bc);                 // uploaded flows, or the device copy of the groups read in place
     b.cellprob = c.take<float>(N * Bc);
     b.logits = c.take<float>(upload_logits ? (size_t)C * N * Bc : 0);
     b.masks = c.take<int32_t>(N * Bc);
@@ -103,6 +106,11 @@ extern "C" int cpb_compute_masks_host_ex(const float* dP, const float* cellprob,
         lg_alias = mapped_alias(logits);
     if (has_logits && opt->logits_mode == CPB_HOST_LOGITS_MAPPED && !lg_alias) return CPB_E_ARG;
     const bool upload_logits = has_logits && !lg_alias;
+    // dP through the mapped pointer: the vectorised prep kernel reads only the groups with foreground
+    const float* dp_alias = nullptr;
+    if (opt->flows_mode != CPB_HOST_LOGITS_UPLOAD && W % 4 == 0 && reinterpret_cast<uintptr_t>(dP) % 16 == 0)
+        dp_alias = mapped_alias(dP);
+    if (opt->flows_mode == CPB_HOST_LOGITS_MAPPED && !dp_alias) return CPB_E_ARG;
     const size_t need = carve_chunk(nullptr, Bc, H, W, C, has_logits, upload_logits, has_cm, u16).total + kAlign;
 
     HostCtx& ctx = tl_ctx;
@@ -123,7 +131,8 @@ extern "C" int cpb_compute_masks_host_ex(const float* dP, const float* cellprob,
         HostSlot& s = ctx.slot[k % kHostSlots];
         ChunkBufs cb = carve_chunk(s.blob, Bc, H, W, C, has_logits, upload_logits, has_cm, u16);
         cudaStream_t st = s.stream;
-        cudaMemcpyAsync(cb.dP, dP + (size_t)b0 * 2 * N, (size_t)nb * 2 * N * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (!dp_alias)
+            cudaMemcpyAsync(cb.dP, dP + (size_t)b0 * 2 * N, (size_t)nb * 2 * N * sizeof(float), cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(cb.cellprob, cellprob + (size_t)b0 * N, (size_t)nb * N * sizeof(float), cudaMemcpyHostToDevice, st);
         const float* lg = nullptr;
         if (upload_logits) {
@@ -132,9 +141,9 @@ extern "C" int cpb_compute_masks_host_ex(const float* dP, const float* cellprob,
         } else if (has_logits) {
             lg = lg_alias + (size_t)b0 * C * N;
         }
-        rc = cpb_compute_masks_device(cb.dP, cb.cellprob, lg, nb, H, W, C, prm, cb.masks, cb.counts,
-                                      has_logits ? cb.cell_class : nullptr, has_cm ? cb.class_masks : nullptr, cb.ws,
-                                      cb.ws_bytes, st);
+        rc = compute_masks_impl(dp_alias ? dp_alias + (size_t)b0 * 2 * N : cb.dP, cb.cellprob, lg, nb, H, W, C, prm, cb.masks,
+                                cb.counts, has_logits ? cb.cell_class : nullptr, has_cm ? cb.class_masks : nullptr, cb.ws,
+                                cb.ws_bytes, st, nullptr, dp_alias ? cb.dP : nullptr);
         if (rc) break;
         if (u16) {
             const long long n4 = (long long)nb * (long long)(N / 4);
@@ -178,6 +187,7 @@ extern "C" int cpb_compute_masks_host(const float* dP, const float* cellprob, co
                                       int W, int C, const cpb_params* prm, int32_t* masks, int32_t* counts,
                                       int32_t* cell_class, uint8_t* class_masks, int tiles_per_chunk, int device) {
     cpb_host_options opt{};
-    opt.tiles_per_chunk = tiles_per_chunk; opt.device = device; opt.logits_mode = CPB_HOST_LOGITS_AUTO; opt.masks_u16 = 0;
+    opt.tiles_per_chunk = tiles_per_chunk; opt.device = device; opt.logits_mode = CPB_HOST_LOGITS_AUTO;
+    opt.flows_mode = CPB_HOST_LOGITS_AUTO; opt.masks_u16 = 0;
     return cpb_compute_masks_host_ex(dP, cellprob, logits, B, H, W, C, prm, masks, counts, cell_class, class_masks, &opt);
 }

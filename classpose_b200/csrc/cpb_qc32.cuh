@@ -41,15 +41,17 @@
 #define CPB_QI_CLEAN 8             // info bit: no pixel of another live label in the bbox grown by one
 
 // counters: [0] jobs appended, [1] jobs pulled, [2] float64 list appended, [3] float64 list pulled,
-//           [4] labels decided by the screen, [5] labels the screen left undecided (statistics)
+//           [4] labels decided by the screen, [5] labels the screen left undecided (statistics),
+//           [8..11] jobs per class, [12..15] scatter cursors of k_q32_sort
 #ifndef CPB_QCTR_INTS
-#define CPB_QCTR_INTS 8
+#define CPB_QCTR_INTS 16
 #endif
 
 struct Q32 {
     int* info;        // [B*LC]  class (bits 0..2) | CPB_QI_CLEAN | bbox width << 8
     int* ent;         // [B*LC]  per tile: the screen's labels, grouped by class
-    int4* jobs;       // [B*LC]  (tile, first entry, nsub, class)
+    int4* jobs;       // [B*LC]  (tile, first entry, nsub, class) in the order k_qc_pack emitted them
+    int4* sorted;     // [B*LC]  the same jobs, tallest class first (k_q32_sort)
     int2* l64;        // [B*LC]  (tile, label) for the float64 warp kernel
     int* ctr;         // [CPB_QCTR_INTS]
 };
@@ -69,6 +71,7 @@ k_qc_pack(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int2*
           int* CPB_RESTRICT big_count, int screen) {
     CPB_SHARED int s_cnt[CPB_Q32_NCLS], s_base[CPB_Q32_NCLS], s_pos[CPB_Q32_NCLS];
     CPB_SHARED int s_ext;
+    CPB_SHARED unsigned s_bits[8][36];            // per warp: member bits of the grown bbox columns
     const int b = blockIdx.x, LC = t.LC, N = H * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int lb = t.lbound[b];
@@ -93,40 +96,68 @@ k_qc_pack(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int2*
                 const int c = t.cnt[k];
                 const double ymed = __ddiv_rn(__ll2double_rn((long long)t.sumy[k] - (long long)c * y0 + c), __int2double_rn(c));
                 const double xmed = __ddiv_rn(__ll2double_rn((long long)t.sumx[k] - (long long)c * x0 + c), __int2double_rn(c));
-                double bd = 1e300; int bi = CPB_IMAX;
+                // scan of the bbox grown by one pixel (columns x0-1 .. x0+w: two passes when w + 2 > 32; rows y0-1 .. y0+h):
+                // integer work only -- member bits of this lane's column (bit r = row y0 + r) and contact with other labels
+                unsigned member = 0;               // bbox column `lane` (first pass: grown column lane + 1)
                 bool foreign = false;
-                // grown bbox: columns x0-1 .. x0+w (two passes when w + 2 > 32), rows y0-1 .. y0+h
                 for (int c0 = 0; c0 < w + 2; c0 += 32) {
                     const int gc = c0 + lane;                    // grown column index; bbox column gc - 1
                     const int x = x0 - 1 + gc;
                     if (gc < w + 2 && x >= 0 && x < W) {
-                        const double dx = __dsub_rn(__int2double_rn(gc), xmed);
-                        const double dx2 = __dmul_rn(dx, dx);
-                        // the column's h + 2 <= 32 pixels: loads first (eight in flight), then the arithmetic
-                        for (int rb = -1; rb <= h; rb += 8) {
-                          int vv[8];
-                          #pragma unroll
-                          for (int q8 = 0; q8 < 8; q8++) {
-                              const int y = y0 + rb + q8;
-                              vv[q8] = (rb + q8 <= h && y >= 0 && y < H) ? L[y * W + x] : 0;
-                          }
-                          #pragma unroll
-                          for (int q8 = 0; q8 < 8; q8++) {
-                            const int ry = rb + q8;
-                            const int v = vv[q8];
-                            if (ry > h) break;
-                            if (v == l) {
-                                const double dy = __dsub_rn(__int2double_rn(ry + 1), ymed);
-                                const double d = __dadd_rn(dx2, __dmul_rn(dy, dy));
-                                const int idx = ry * w + gc - 1;
-                                if (cpb_minkey_less(d, idx, bd, bi)) { bd = d; bi = idx; }
-                            } else {
-                                foreign |= cpb_foreign_live(v, l, alive);
+                        unsigned mb = 0;
+                        for (int rb = -1; rb <= h; rb += 8) {      // eight loads in flight, then the tests
+                            int vv[8];
+                            #pragma unroll
+                            for (int q8 = 0; q8 < 8; q8++) {
+                                const int y = y0 + rb + q8;
+                                vv[q8] = (rb + q8 <= h && y >= 0 && y < H) ? L[y * W + x] : 0;
                             }
-                          }
+                            #pragma unroll
+                            for (int q8 = 0; q8 < 8; q8++) {
+                                const int ry = rb + q8;
+                                if (vv[q8] == l) mb |= 1u << (ry & 31);          // members only occur for 0 <= ry < h <= 30
+                                else foreign |= cpb_foreign_live(vv[q8], l, alive);
+                            }
+                        }
+                        // hand the bits to the lane that owns bbox column gc - 1
+                        s_bits[warp][gc] = mb;
+                    }
+                }
+                __syncwarp();
+                member = (lane < w) ? s_bits[warp][lane + 1] : 0u;
+                __syncwarp();
+                // centre = member pixel nearest to the mean, first in raster order on ties.  Every pixel outside the
+                // 4 x 4 window around the mean is at least 2 away along one axis (squared distance >= 4, exactly, in
+                // float64 too), so a member of the window with squared distance < 4 decides -- one candidate per
+                // lane; otherwise (a label whose mean falls outside itself) every member is evaluated.
+                double bd = 1e300; int bi = CPB_IMAX;
+                {
+                    const int wy = (int)floor(ymed) - 2 + (lane >> 2), wx = (int)floor(xmed) - 2 + (lane & 3);   // bbox-relative
+                    if (lane < 16 && wy >= 0 && wy < h && wx >= 0 && wx < w) {
+                        const unsigned colbits = s_bits[warp][wx + 1];
+                        if (colbits >> wy & 1) {
+                            const double dx = __dsub_rn(__int2double_rn(wx + 1), xmed), dy = __dsub_rn(__int2double_rn(wy + 1), ymed);
+                            bd = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)); bi = wy * w + wx;
+                        }
+                    }
+                    double wbd = bd;
+                    for (int sft = 16; sft; sft >>= 1) wbd = fmin(wbd, __shfl_xor_sync(CPB_FULL, wbd, sft));
+                    if (!(wbd < 4.0)) {                          // warp-uniform: no member that close, look at all of them
+                        bd = 1e300; bi = CPB_IMAX;
+                        if (lane < w) {
+                            const double dx = __dsub_rn(__int2double_rn(lane + 1), xmed);
+                            const double dx2 = __dmul_rn(dx, dx);
+                            for (int r = 0; r < h; r++) {
+                                if (!(member >> r & 1)) continue;
+                                const double dy = __dsub_rn(__int2double_rn(r + 1), ymed);
+                                const double d = __dadd_rn(dx2, __dmul_rn(dy, dy));
+                                const int idx = r * w + lane;
+                                if (cpb_minkey_less(d, idx, bd, bi)) { bd = d; bi = idx; }
+                            }
                         }
                     }
                 }
+                __syncwarp();
                 for (int sft = 16; sft; sft >>= 1) {
                     const double od = __shfl_xor_sync(CPB_FULL, bd, sft);
                     const int oi = __shfl_xor_sync(CPB_FULL, bi, sft);
@@ -172,13 +203,25 @@ k_qc_pack(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int2*
             for (int j = 0; j < m; j++) {
                 const int wj = __shfl_sync(CPB_FULL, wi, j);
                 if (nsub == CPB_Q32_MAXSUB || coff + wj > CPB_Q32_COLS - 1) {
-                    if (lane == 0) q.jobs[atomicAdd(&q.ctr[0], 1)] = make_int4(b, (int)(e - q.ent) + first, nsub, cls);
+                    if (lane == 0) { q.jobs[atomicAdd(&q.ctr[0], 1)] = make_int4(b, (int)(e - q.ent) + first, nsub, cls); atomicAdd(&q.ctr[8 + cls], 1); }
                     first = i0 + j; nsub = 0; coff = 0;
                 }
                 nsub++; coff += wj + 1;
             }
         }
-        if (nsub > 0 && lane == 0) q.jobs[atomicAdd(&q.ctr[0], 1)] = make_int4(b, (int)(e - q.ent) + first, nsub, cls);
+        if (nsub > 0 && lane == 0) { q.jobs[atomicAdd(&q.ctr[0], 1)] = make_int4(b, (int)(e - q.ent) + first, nsub, cls); atomicAdd(&q.ctr[8 + cls], 1); }
+    }
+}
+
+// k_q32_sort: jobs grouped by class, tallest first.  Warps of k_diffuse32 then run the same unrolled loop most of the
+// time (with the classes interleaved the instruction cache was the top stall reason) and the longest jobs start first.
+CPB_KERNEL k_q32_sort(Q32 q) {
+    const int n = q.ctr[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 jb = q.jobs[i];
+        int base = 0;
+        for (int c = CPB_Q32_NCLS - 1; c > jb.w; c--) base += q.ctr[8 + c];
+        q.sorted[base + atomicAdd(&q.ctr[12 + jb.w], 1)] = jb;
     }
 }
 
@@ -412,7 +455,7 @@ k_diffuse32(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, in
         if (lane == 0) j = atomicAdd(&q.ctr[1], 1);
         j = __shfl_sync(CPB_FULL, j, 0);
         if (j >= njobs) break;
-        const int4 jb = q.jobs[j];
+        const int4 jb = q.sorted[j];
         cpb_q32_run(lab, dP, H, W, t, q, jb.x, jb.y, jb.z, jb.w, threshold, s_tile[warp], pack_err);
     }
 }

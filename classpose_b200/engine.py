@@ -92,12 +92,14 @@ class Engine:
 
     def compute_masks_host(self, dP, cellprob, logits=None, niter=200, cellprob_threshold=0.0, flow_threshold=0.4,
                            min_size=15, max_size_fraction=0.4, remove_border=False, fill_holes=True,
-                           want_class_masks=False, tiles_per_chunk=0, out=None, logits_mode="auto", masks_u16=False):
+                           want_class_masks=False, tiles_per_chunk=0, out=None, logits_mode="auto", flows_mode="auto",
+                           masks_u16=False):
         """Host buffers in / out (numpy arrays or CPU torch tensors, ideally pinned).  The library
         performs chunked H2D -> kernels -> D2H itself.  Returns (masks, counts, cell_class, class_masks) as CPU
         tensors.  `out` may hold pre-allocated (pinned) output tensors with the same keys.
-        logits_mode: "auto" (pinned logits are read in place through the mapped pointer, only under cells),
-        "upload" (copy all of them) or "mapped" (insist); masks_u16: deliver uint16 label images."""
+        logits_mode / flows_mode: "auto" (a pinned buffer is read in place through its mapped pointer -- logits
+        only under cells, dP only where there is foreground), "upload" (copy everything) or "mapped" (insist);
+        masks_u16: deliver uint16 label images."""
         def host(x, dtype):
             if x is None:
                 return None
@@ -125,8 +127,8 @@ class Engine:
         prm = make_params(niter, cellprob_threshold, flow_threshold, min_size, max_size_fraction, remove_border,
                           fill_holes)
         p = lambda t: None if t is None else t.data_ptr()
-        opt = HostOptions(int(tiles_per_chunk), int(self.device.index),
-                          {"auto": LOGITS_AUTO, "upload": LOGITS_UPLOAD, "mapped": LOGITS_MAPPED}[logits_mode],
+        modes = {"auto": LOGITS_AUTO, "upload": LOGITS_UPLOAD, "mapped": LOGITS_MAPPED}
+        opt = HostOptions(int(tiles_per_chunk), int(self.device.index), modes[logits_mode], modes[flows_mode],
                           1 if masks_u16 else 0)
         rc = self.lib.cpb_compute_masks_host_ex(p(dP), p(cellprob), p(logits), B, H, W, Cc, C.byref(prm), p(masks),
                                                 p(counts), p(cell_class), p(class_masks), C.byref(opt))

@@ -102,7 +102,7 @@ void cpb_debug_set_follow_merge(int mode);
 void cpb_debug_set_switch(int which, int value);
 /* number of kernels this library has launched in this process (statistics for the benchmark) */
 long long cpb_debug_launch_count(void);
-/* flow-check counters of the last cpb_compute_masks_profiled_device call in this process, 8 ints: [0] float32 screen
+/* flow-check counters of the last cpb_compute_masks_profiled_device call in this process, 16 ints: [0] float32 screen
  * jobs, [2] labels that took the float64 warp kernel (contact, too large for the screen, or undecided), [4] labels the
  * screen decided, [5] labels the screen left undecided (statistics for the benchmark and the tests) */
 void cpb_debug_qc_stats(int32_t* out);
@@ -124,6 +124,9 @@ typedef struct cpb_host_options {
     int32_t tiles_per_chunk;   /* <= 0: default (128) */
     int32_t device;            /* CUDA device ordinal */
     int32_t logits_mode;       /* CPB_HOST_LOGITS_* */
+    int32_t flows_mode;        /* same values, for dP: mapped = the prep kernel reads dP in place and only the 4-pixel
+                                  groups that hold foreground (cellprob > threshold) cross the bus; they are kept in a
+                                  device copy for the flow check.  cellprob is always uploaded (every pixel is needed) */
     int32_t masks_u16;         /* 1: `masks` is uint16 [B,H,W] (Cellpose's dtype below 65536 labels; ids are
                                   truncated to 16 bits), 0: int32 */
 } cpb_host_options;

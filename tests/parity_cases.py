@@ -585,6 +585,16 @@ def case_fused_path_other_shapes(be):
     assert f1 >= 0.99 and abs(nnew - nref) <= 1
 
 
+def case_fused_baseline_config_shapes(be):
+    """The exact tile shape / class count pairs of BASELINE.json's model configs on 256 x 256 tiles:
+    puma (C = 10, configs[2]) and monusac (C = 5, configs[3]); conic (C = 7) is case_fused_path."""
+    for C, seeds in ((10, (21, 22)), (5, (23, 24))):
+        tiles = [std_tile(s, C=C) for s in seeds]
+        f1, nref, nnew = fused_compare(be, tiles, C)
+        assert f1 >= 0.995, (C, f1)
+        assert abs(nnew - nref) <= max(1, 0.001 * nref), (C, nref, nnew)
+
+
 def case_fused_generic_class_count(be):
     """A class count that has no specialised final+vote instance (C = 4; the reference's configs use 5, 7, 10) on a
     tile whose pixel count is a multiple of 4, so the vote still rides on the final pass (generic kernel)."""
@@ -885,7 +895,7 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_f
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
              case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_flow_qc_screen_is_decision_exact,
              case_fill_holes_exact, case_fill_holes_oversized_label, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
-             case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes,
+             case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes, case_fused_baseline_config_shapes,
              case_fused_generic_class_count, case_fused_switch_matrix, case_fused_odd_width, case_fused_empty_and_params, case_fused_min_size_zero_keeps_upstream_ids,
              case_fused_qc_then_positional_size_filter,
              case_cell_contours_match_cv2, case_prepare_tiles, case_dedup_overlapping_tiles, case_dedup_random_points_components,

@@ -125,7 +125,7 @@ def test_host_buffer_path_mapped_logits_and_u16_masks():
     pin = [x.pin_memory() for x in (dP, cp, lg)]
     for mode, args in (("mapped", pin), ("auto", pin), ("upload", pin), ("auto", (dP, cp, lg))):
         for u16 in (False, True):
-            mh, ch, cch, _ = eng.compute_masks_host(*args, tiles_per_chunk=2, logits_mode=mode, masks_u16=u16)
+            mh, ch, cch, _ = eng.compute_masks_host(*args, tiles_per_chunk=2, logits_mode=mode, flows_mode=mode, masks_u16=u16)
             assert mh.dtype == (torch.uint16 if u16 else torch.int32)
             np.testing.assert_array_equal(mh.numpy().astype(np.int32), md, err_msg=f"{mode} u16={u16}")
             np.testing.assert_array_equal(ch.numpy(), cd)
@@ -134,6 +134,8 @@ def test_host_buffer_path_mapped_logits_and_u16_masks():
                 np.testing.assert_array_equal(cch[b, :n + 1].numpy(), ccd[b, :n + 1])
     with pytest.raises(ClassposeB200Error):
         eng.compute_masks_host(dP, cp, lg, logits_mode="mapped")          # pageable logits cannot be mapped
+    with pytest.raises(ClassposeB200Error):
+        eng.compute_masks_host(dP, cp, lg, flows_mode="mapped")
 
 
 def test_two_devices_in_one_process():
@@ -278,9 +280,9 @@ def test_device_resident_eval_tail_matches_host_path():
     against the reference's host sequence (unaugment, average_tiles, crop, dynamics, class vote) on the oracle."""
     import torch
     from classpose_b200 import core
-    t = pc.std_tile(4)
-    C = t["logits"].shape[0]
-    for augment in (False, True):
+    # conic (C = 7) and the monusac class count (C = 5) of BASELINE configs[3], each with and without --tta
+    for t, augment in ((pc.std_tile(4), False), (pc.std_tile(4), True), (pc.std_tile(23, C=5), True), (pc.std_tile(23, C=5), False)):
+        C = t["logits"].shape[0]
         pads, geo = core.tile_layout(256, 256, 256, augment=augment)
         Ly, Lx = geo["Ly"], geo["Lx"]
         full = np.zeros((C + 3, Ly, Lx), np.float32)
@@ -311,6 +313,47 @@ def test_device_resident_eval_tail_matches_host_path():
         np.testing.assert_allclose(dP[0].cpu().numpy(), yf[:2], rtol=0, atol=1e-6)
         r = metrics.class_agreement(ref, ref_cm, masks[0].cpu().numpy(), cm[0].cpu().numpy().astype(np.int64))
         assert r["f1"] >= 0.995 and not r["class_mismatch"] and r["n_pred"] == r["n_true"]
+
+
+def test_follow_flows_against_torch_cuda_grid_sample():
+    """Independent cross-check on the B200: cellpose's steps_interp op sequence run with torch's CUDA grid_sample (an ATen
+    kernel this repo does not own) against k_follow_pool.  float32 rounding differs between implementations and is
+    amplified by pixels orbiting a sink, so the bar is the one used against torch-CPU: >= 99.9 % identical truncated end
+    points; with few steps nothing can amplify and the match must be (almost) total."""
+    import torch
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    dev = eng.device
+    tiles = [pc.std_tile(s) for s in (1, 3, 4)] + [pc.adv_tile()]
+    for niter, bar in ((200, 0.999), (3, 0.9999)):
+        tot = same = 0
+        for t in tiles:
+            H, W = t["cellprob"].shape
+            fg = t["cellprob"] > 0
+            ys, xs = np.nonzero(fg)
+            d = (t["dP"] * fg / 5.0).astype(np.float32)
+            pt = torch.zeros((1, 1, len(ys), 2), dtype=torch.float32, device=dev)
+            im = torch.zeros((1, 2, H, W), dtype=torch.float32, device=dev)
+            pt[0, 0, :, 0] = torch.from_numpy(xs).to(dev).float(); pt[0, 0, :, 1] = torch.from_numpy(ys).to(dev).float()
+            im[0, 0] = torch.from_numpy(d[1]).to(dev); im[0, 1] = torch.from_numpy(d[0]).to(dev)
+            shape = np.array([W, H]).astype("float") - 1
+            for k in range(2):
+                im[:, k] *= 2.0 / shape[k]
+                pt[..., k] /= shape[k]
+            pt *= 2; pt -= 1
+            for _ in range(niter):
+                dPt = torch.nn.functional.grid_sample(im, pt, align_corners=False)
+                for k in range(2):
+                    pt[..., k] = torch.clamp(pt[..., k] + dPt[:, k], -1.0, 1.0)
+            pt += 1; pt *= 0.5
+            for k in range(2):
+                pt[..., k] *= shape[k]
+            ref = pt[0, 0].int().cpu().numpy()                         # (x, y) truncated
+            pf, _ = eng.follow_flows(t["dP"][None], t["cellprob"][None], niter, 0.0)
+            pf = pf[0].cpu().numpy()
+            eq = ((pf[ys, xs] >> 16) == ref[:, 1]) & ((pf[ys, xs] & 0xFFFF) == ref[:, 0])
+            tot += len(ys); same += int(eq.sum())
+        assert same / tot >= bar, (niter, same, tot)
 
 
 def test_dedup_feature_list_signature():
