@@ -103,14 +103,17 @@ k_prep_flow_v4(const float4* CPB_RESTRICT dP, const float4* CPB_RESTRICT cellpro
             const int q = y * W4 + xg;                          // float4 index inside the tile plane
             const float4 cp = cellprob[(size_t)b * N4 + q];
             f0 = cp.x > thr; f1 = cp.y > thr; f2 = cp.z > thr; f3 = cp.w > thr;
-            // the flow is only read where it is used: a group without foreground is all zeros whatever dP holds
-            // (dP may be a mapped HOST pointer: then only these groups cross PCIe, and dP_copy keeps them on
-            // the device for the flow check)
+            // host path (dP_copy != NULL): dP is a mapped HOST pointer and is only read where it is used -- a group
+            // without foreground is all zeros whatever dP holds -- so only these groups cross PCIe; dP_copy keeps
+            // them on the device for the flow check
             float4 dy = make_float4(0.f, 0.f, 0.f, 0.f), dx = dy;
-            if (f0 || f1 || f2 || f3) {
+            if (dP_copy == nullptr) {          // device-resident flows: unconditional loads, in flight with cellprob's
                 dy = dP[((size_t)b * 2 + 0) * N4 + q];
                 dx = dP[((size_t)b * 2 + 1) * N4 + q];
-                if (dP_copy) { dP_copy[((size_t)b * 2 + 0) * N4 + q] = dy; dP_copy[((size_t)b * 2 + 1) * N4 + q] = dx; }
+            } else if (f0 || f1 || f2 || f3) {
+                dy = dP[((size_t)b * 2 + 0) * N4 + q];
+                dx = dP[((size_t)b * 2 + 1) * N4 + q];
+                dP_copy[((size_t)b * 2 + 0) * N4 + q] = dy; dP_copy[((size_t)b * 2 + 1) * N4 + q] = dx;
             }
             const float2 a0 = cpb_scaled_flow(dy.x, dx.x, f0, sx, sy), a1 = cpb_scaled_flow(dy.y, dx.y, f1, sx, sy);
             const float2 a2 = cpb_scaled_flow(dy.z, dx.z, f2, sx, sy), a3 = cpb_scaled_flow(dy.w, dx.w, f3, sx, sy);

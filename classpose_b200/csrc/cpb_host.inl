@@ -125,9 +125,27 @@ extern "C" int cpb_compute_masks_host_ex(const float* dP, const float* cellprob,
         }
     }
     const int ccw = std::min(LC, std::max(ctx.cc_width, 16));
+    // chunk schedule: small chunks at both ends (the first upload and the last download are not overlapped by
+    // anything), full chunks in between
+    std::vector<int> sizes;
+    {
+        const int small = std::max(1, Bc / 8);
+        int left = B, up = small;
+        std::vector<int> tail;
+        while (left > 0) {
+            const int n = std::min(left, up);
+            sizes.push_back(n); left -= n;
+            if (left > 0 && up < Bc) {          // mirror the ramp at the end
+                const int m = std::min(left, up);
+                tail.push_back(m); left -= m;
+            }
+            up = std::min(Bc, up * 2);
+        }
+        sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
+    }
     int rc = 0;
-    for (int b0 = 0, k = 0; b0 < B; b0 += Bc, k++) {
-        const int nb = std::min(Bc, B - b0);
+    for (int b0 = 0, k = 0; b0 < B; b0 += sizes[k], k++) {
+        const int nb = sizes[k];
         HostSlot& s = ctx.slot[k % kHostSlots];
         ChunkBufs cb = carve_chunk(s.blob, Bc, H, W, C, has_logits, upload_logits, has_cm, u16);
         cudaStream_t st = s.stream;

@@ -26,6 +26,7 @@ SEED_MIN = 10      # seeds need h > 10
 GROW_MIN = 2       # region growing allowed where h > 2
 GROW_ITERS = 5
 FLOW_SCALE = 5.0   # network flows are 5x unit vectors
+DIFFUSE_LOG = False  # cellpose < 3 took log(1 + T) before the gradient; 3.x / 4.x do not
 
 
 # --------------------------------------------------------------------------
@@ -192,6 +193,8 @@ def extend_centers(neighbors, centers, isneighbor, shape, n_iter: int) -> np.nda
         Tneigh = T[ny, nx]
         Tneigh *= isneighbor
         T[ny[0], nx[0]] = Tneigh.mean(axis=0)
+    if DIFFUSE_LOG:
+        T = np.log(1.0 + T)
     dy = T[ny[2], nx[2]] - T[ny[1], nx[1]]
     dx = T[ny[4], nx[4]] - T[ny[3], nx[3]]
     return np.stack((dy, dx), axis=0)
