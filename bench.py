@@ -48,7 +48,25 @@ EXTRA = {
                 name="monusac C=5 with TTA: 9 sub-tile maps per padded 272^2 tile blended, then dynamics (BASELINE configs[3])"),
     "dense": dict(H=512, W=512, C=7, tiles=256, n_grid=45, axes=(3.5, 5.0),
                   name="dense nuclei stress: 512x512 tiles, ~2k cells per tile, flow check on (BASELINE configs[4])"),
+    "touching": dict(H=256, W=256, C=7, tiles=512, n_grid=10, axes=(5.0, 9.0), style="touching",
+                     name="hostile conic variant: Voronoi-clipped touching cells, 15 % of the cells with noise for flows, "
+                          "every 8th tile a 43-px cell (block kernels), every 16th a ring (hole fill)"),
 }
+
+
+def cpu_sample_size(B):
+    """Tiles the CPU arms time per step (about 10-30 s of host work on the box's cores)."""
+    cores = os.cpu_count() or 1
+    return min(B, 256, max(64, 4 * cores))
+
+
+def shared_config(B):
+    """The workload description BOTH arms print, so that their lines describe the same configuration."""
+    S = cpu_sample_size(B)
+    return {"workload": WORKLOAD, "tiles_per_gpu": B, "tile": [H, W], "classes": C, **PARAMS,
+            "inputs": f"tiles 0..{S - 1} of every batch come from oracle.synth.make_tile(seed = tile index) on the host and are "
+                      f"the tiles the CPU arms time; the remaining tiles come from the device generator of the same "
+                      f"specification (SURVEY 8d)"}
 
 
 _REAL_STDOUT = None
@@ -121,14 +139,25 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
+def _real():
+    """The real cellpose, if this box has it (scripts/probe_reference.py); None -> the oracle port is timed."""
+    from oracle import real
+    return real.find()
+
+
 def _oracle_tile(args):
-    """One tile through the oracle port (worker process)."""
+    """One tile through the reference path on the host (worker process): the real cellpose when importable,
+    otherwise the oracle port of it; the class vote is the reference's own arithmetic either way."""
     import numpy as np
     import torch
     torch.set_num_threads(1)
-    from oracle import classpose_ref, dynamics
+    from oracle import classpose_ref, dynamics, real
     dP, cellprob, logits = args
-    m = dynamics.resize_and_compute_masks(dP, cellprob, **PARAMS)
+    r = real.find()
+    if r is not None:
+        m = real.resize_and_compute_masks(r, dP, cellprob, **PARAMS)
+    else:
+        m = dynamics.resize_and_compute_masks(dP, cellprob, **PARAMS)
     cm, _ = classpose_ref.compute_class_masks(m, logits[:, None])
     return int(m.max())
 
@@ -163,9 +192,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    REAL = _real()
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    sample = min(256, max(32, 2 * cores))
+    sample = cpu_sample_size(args.tiles)
     ctx = mp.get_context("spawn")
     with ctx.Pool(min(cores, sample)) as pool:
         tiles = pool.map(_oracle_make, range(sample))
@@ -188,11 +218,12 @@ def run_reference(args):
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "cells_per_sec": cells * steps / total,
-        "config": {"workload": WORKLOAD, "tile": [H, W], "classes": C, **PARAMS,
-                   "note": "reference arithmetic lives in cellpose==4.0.8 (absent, not installable offline); "
-                           "this arm times the oracle port of it on host cores"},
-        "cpu_baseline": {"value": value, "unit": "tiles/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} tiles of the workload per step, one process per core"},
+        "config": shared_config(args.tiles),
+        "note": ("times the real cellpose " + REAL["version"] if REAL else
+                 "reference arithmetic lives in cellpose==4.0.8 (absent, not installable offline: scripts/probe_reference.py); "
+                 "this arm times the oracle port of it") + " on the host cores, one process per core",
+        "cpu_baseline": {"value": value, "unit": "tiles/s", "cores": cores, "kind": "reference" if REAL else "port",
+                         "sample": f"tiles 0..{sample - 1} of the workload per step, one process per core"},
         "e2e": {"value": value, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -222,6 +253,13 @@ def run_ours(args):
     data = synth.make_batch(B, H, W, C, seed=1234 + 7919 * rank, device=dev)
     dP, cellprob, logits = data["dP"], data["cellprob"], data["logits"]
     del data
+    # the first S tiles are the host-generated ones the CPU arms time (same generator, same seeds in both arms)
+    S = cpu_sample_size(B)
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(min(os.cpu_count() or 1, S)) as pool:
+        host_tiles = pool.map(_oracle_make, range(S))
+    for i, (a_, b_, c_) in enumerate(host_tiles):
+        dP[i].copy_(torch.from_numpy(a_)); cellprob[i].copy_(torch.from_numpy(b_)); logits[i].copy_(torch.from_numpy(c_))
     torch.cuda.synchronize()
 
     def step():
@@ -389,13 +427,14 @@ def run_ours(args):
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample of the same workload
     cores = os.cpu_count() or 1
-    sample = min(B, max(64, 8 * cores), 256)      # ~10-30 s of CPU work
+    sample = S
     cpu = None
     if not args.no_cpu_baseline:
-        tiles = [(dP[i].cpu().numpy(), cellprob[i].cpu().numpy(), logits[i].cpu().numpy()) for i in range(sample)]
-        tps, cps, dt = cpu_reference_throughput(tiles, min(cores, sample))
-        cpu = {"value": tps, "unit": "tiles/s", "cores": min(cores, sample), "kind": "port",
-               "sample": f"first {sample} tiles of the batch, oracle port, one process per core, {dt:.1f} s",
+        REAL = _real()
+        tps, cps, dt = cpu_reference_throughput(host_tiles, min(cores, sample))
+        cpu = {"value": tps, "unit": "tiles/s", "cores": min(cores, sample), "kind": "reference" if REAL else "port",
+               "sample": f"tiles 0..{sample - 1} of the batch (host-generated), " +
+                         (f"real cellpose {REAL['version']}" if REAL else "oracle port") + f", one process per core, {dt:.1f} s",
                "cells_per_sec": cps}
 
     line = {
@@ -403,9 +442,9 @@ def run_ours(args):
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "cells_per_sec": cells_per_s, "cells_per_step": n_cells_all,
-        "config": {"workload": WORKLOAD, "tiles_per_gpu": B, "tile": [H, W], "classes": C, **PARAMS,
-                   "foreground_fraction": fg_frac, "parallelism": f"tiles sharded over {world} GPU(s), no data-path collective",
-                   "cache": "inputs 2.5 GiB per step >> 126 MB L2 (no flush needed)"},
+        "config": shared_config(B),
+        "run": {"foreground_fraction": fg_frac, "parallelism": f"tiles sharded over {world} GPU(s), no data-path collective",
+                "cache": "inputs 2.5 GiB per step >> 126 MB L2 (no flush needed)"},
         "e2e": {"value": world * B / e2e_s, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "matches_device_path": same,
                 "inputs": "cellprob copied; dP and logits read in place from the pinned host buffers (dP where a 4-pixel group holds "
@@ -424,39 +463,27 @@ def run_ours(args):
         "stages_ms": stages,
         "flow_check": qc_stats,
     }
+    if world == 1 and not args.no_extras:
+        del dP, cellprob, logits, hdP, hcp, hlg, outbuf, out
+        torch.cuda.empty_cache()
+        line["extra_configs"] = brief_extras(eng, dev, peak)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def run_extra(args):
-    """BASELINE configs[2..4]; same timing rules as the main arm (CUDA events, max over ranks)."""
+def build_extra(eng, dev, workload, B, seed):
+    """Inputs and the step function of one of the additional BASELINE configs (device-resident)."""
     import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    from classpose_b200 import distributed as cdist, synth, transforms as btf
-    from classpose_b200.engine import get_engine
-    eng = get_engine(dev)
-    cfg = EXTRA[args.workload]
-    Hh, Ww, Cc, B = cfg["H"], cfg["W"], cfg["C"], (args.tiles if args.tiles != 1024 or args.workload == "wsi" else cfg["tiles"])
-    data = synth.make_batch(B, Hh, Ww, Cc, n_grid=cfg["n_grid"], axes=cfg["axes"], seed=99 + 7919 * rank, device=dev,
-                            chunk=min(64, B))
+    from classpose_b200 import synth, transforms as btf
+    cfg = EXTRA[workload]
+    Hh, Ww, Cc = cfg["H"], cfg["W"], cfg["C"]
+    data = synth.make_batch(B, Hh, Ww, Cc, n_grid=cfg["n_grid"], axes=cfg["axes"], seed=seed, device=dev,
+                            chunk=min(64, B), style=cfg.get("style", "isolated"))
     dP, cellprob, logits = data["dP"], data["cellprob"], data["logits"]
     extra = {}
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    if args.workload == "tta":
+    if workload == "tta":
         # what run_net holds after the network when augment=True: 9 flipped sub-tile maps of the padded tile
         pad = btf.get_pad_yx(Hh, Ww, min_size=(256, 256))
         Ly, Lx = Hh + pad[0] + pad[1], Ww + pad[2] + pad[3]
@@ -481,7 +508,6 @@ def run_extra(args):
         ty, tx = btf.taper_1d(256, 256)
         g = {k: torch.from_numpy(geo[k]).to(dev) for k in ("y0", "x0", "flip")}
         tyd, txd = torch.from_numpy(ty).to(dev), torch.from_numpy(tx).to(dev)
-
         x4, cover = btf.tile_cover(geo["y0"], geo["x0"], 256, 256, Ly, Lx)
 
         def step():
@@ -493,15 +519,87 @@ def run_extra(args):
         extra["blend_max_abs_err_vs_unblended"] = float((eng.calls.average_tiles(
             y_flow, g["y0"], g["x0"], g["flip"], True, tyd, txd, Ly, Lx, pad)[:, :2] - dP).abs().max().item())
         extra["cells_vs_unblended"] = [int(out[1].sum().item()), int(ref[1].sum().item())]
-        nbatches = 1
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(3):
+            eng.calls.average_tiles(y_flow, g["y0"], g["x0"], g["flip"], True, tyd, txd, Ly, Lx, pad, x4, cover)
+            eng.calls.average_tiles(y_cls, g["y0"], g["x0"], g["flip"], False, tyd, txd, Ly, Lx, pad, x4, cover)
+        ev[1].record(); torch.cuda.synchronize()
+        blend_ms = ev[0].elapsed_time(ev[1]) / 3
+        blend_bytes = B * (3 + Cc) * 4 * (nt * 256 * 256 + Hh * Ww)
+        extra["blend_ms"] = blend_ms
+        extra["blend_GBs"] = blend_bytes / (blend_ms * 1e-3) / 1e9
     else:
         def step():
             return eng.compute_masks_batch(dP, cellprob, logits, **PARAMS)
-        nbatches = 1
-        if args.workload == "wsi":
-            a, b_ = cdist.shard_range(cfg["total_tiles"], rank, world)
-            nbatches = -(-(b_ - a) // B)
-            extra["tiles_this_rank"] = b_ - a
+    return cfg, step, (dP, cellprob, logits), extra
+
+
+def brief_extras(eng, dev, peak):
+    """Short device-resident passes over the other BASELINE configs and the hostile workload (N = 1 only), so that the
+    driver's line carries them: tiles/s, cells/s, per-stage device times, flow-check statistics."""
+    import torch
+    out = {}
+    for name, B in (("wsi", 512), ("tta", 128), ("dense", 64), ("touching", 512)):
+        try:
+            cfg, step, (dP, cellprob, logits), extra = build_extra(eng, dev, name, B, seed=99)
+            for _ in range(3):
+                res = step()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 5
+            ev0.record()
+            for _ in range(n):
+                res = step()
+            ev1.record(); torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / n
+            cells = int(res[1].sum().item())
+            stages, qc = eng.profile_stages(dP, cellprob, logits, with_qc=True, **PARAMS)
+            N_ = cfg["H"] * cfg["W"]
+            line = {"workload": cfg["name"], "tiles": B, "tile": [cfg["H"], cfg["W"]], "classes": cfg["C"],
+                    "tiles_per_sec": B / (ms * 1e-3), "cells_per_sec": cells / (ms * 1e-3), "cells_per_tile": cells / B,
+                    "ms_per_step": ms, "whole_path_frac_of_hbm_peak": (16 + 4 * cfg["C"]) * N_ * B / (ms * 1e-3) / 1e9 / peak,
+                    "stages_ms": {k: round(v, 4) for k, v in stages.items() if v > 0}, "flow_check": qc, **extra}
+            if name == "wsi":
+                line["slide_seconds_1gpu_at_this_rate"] = cfg["total_tiles"] / line["tiles_per_sec"]
+            if name == "tta":
+                line["note"] = "stages_ms is the dynamics part on unblended inputs; ms_per_step includes the two 9-way blends"
+            out[name] = line
+            del dP, cellprob, logits, res, step
+            torch.cuda.empty_cache()
+        except Exception as e:          # an extra must never cost the main line
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
+def run_extra(args):
+    """BASELINE configs[2..4]; same timing rules as the main arm (CUDA events, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from classpose_b200 import distributed as cdist
+    from classpose_b200.engine import get_engine
+    eng = get_engine(dev)
+    cfg = EXTRA[args.workload]
+    Hh, Ww, Cc, B = cfg["H"], cfg["W"], cfg["C"], (args.tiles if args.tiles != 1024 or args.workload == "wsi" else cfg["tiles"])
+    cfg, step, (dP, cellprob, logits), extra = build_extra(eng, dev, args.workload, B, seed=99 + 7919 * rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nbatches = 1
+    if args.workload == "wsi":
+        a, b_ = cdist.shard_range(cfg["total_tiles"], rank, world)
+        nbatches = -(-(b_ - a) // B)
+        extra["tiles_this_rank"] = b_ - a
 
     for _ in range(max(3, args.warmup)):
         out = step()
@@ -516,7 +614,7 @@ def run_extra(args):
         out = step()
         total_cells += out[1].sum()
     if world > 1:      # the one exchange: per-rank instance totals -> global label offsets
-        base = cdist.rank_base_offset(total_cells.reshape(1))
+        base = cdist.rank_base_offset(total_cells.reshape(1))      # stays on the device
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -563,7 +661,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=128, help="tiles per chunk of the host-buffer call")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="conic1024", choices=["conic1024", "wsi", "tta", "dense"])
+    ap.add_argument("--workload", default="conic1024", choices=["conic1024", "wsi", "tta", "dense", "touching"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the short passes over the other configs")
     args = ap.parse_args()
     global _REAL_STDOUT
     _REAL_STDOUT = _protect_stdout()

@@ -20,21 +20,23 @@ def shard_range(n_tiles: int, rank: int, world_size: int):
     return start, start + base + (1 if rank < rem else 0)
 
 
-def rank_base_offset(local_total: torch.Tensor, group=None) -> int:
-    """Exclusive prefix sum over ranks of the per-rank instance totals (one all_gather of an int64)."""
+def rank_base_offset(local_total: torch.Tensor, group=None) -> torch.Tensor:
+    """Exclusive prefix sum over ranks of the per-rank instance totals: one all_gather_into_tensor of an int64 per
+    rank.  Returns a 0-d int64 tensor ON THE DEVICE of `local_total` -- nothing is read back to the host, so the
+    exchange stays asynchronous on the stream (callers that want a python int call .item() themselves)."""
+    mine = local_total.reshape(1).to(torch.int64)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return 0
+        return torch.zeros((), dtype=torch.int64, device=mine.device)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    mine = local_total.reshape(1).to(torch.int64)
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine, group=group)
-    return int(torch.stack(gathered).reshape(-1)[:rank].sum().item())
+    gathered = torch.empty((world,), dtype=torch.int64, device=mine.device)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    return gathered[:rank].sum()
 
 
 def global_label_offsets(counts: torch.Tensor, engine=None, group=None):
-    """counts int32 [B] (this rank's tiles, device tensor) -> (offsets int64 [B], local_total, base):
-    global id of label l of tile b = offsets[b] + l."""
+    """counts int32 [B] (this rank's tiles, device tensor) -> (offsets int64 [B], local_total, base), all tensors on
+    the device of `counts`: global id of label l of tile b = offsets[b] + l.  No host synchronisation."""
     if counts.is_cuda:
         if engine is None:
             from .engine import get_engine
@@ -45,4 +47,4 @@ def global_label_offsets(counts: torch.Tensor, engine=None, group=None):
         offs = torch.cumsum(c64, 0) - c64
         total = c64.sum().reshape(1)
     base = rank_base_offset(total, group)
-    return offs + base, int(total.item()), base
+    return offs + base, total.reshape(()), base
