@@ -464,6 +464,10 @@ def run_ours(args):
         "flow_check": qc_stats,
     }
     if world == 1 and not args.no_extras:
+        try:
+            line["hooks_e2e"] = hooks_e2e(host_tiles)
+        except Exception as e:
+            line["hooks_e2e"] = {"error": f"{type(e).__name__}: {e}"}
         del dP, cellprob, logits, hdP, hcp, hlg, outbuf, out
         torch.cuda.empty_cache()
         line["extra_configs"] = brief_extras(eng, dev, peak)
@@ -533,6 +537,44 @@ def build_extra(eng, dev, workload, B, seed):
         def step():
             return eng.compute_masks_batch(dP, cellprob, logits, **PARAMS)
     return cfg, step, (dP, cellprob, logits), extra
+
+
+def hooks_e2e(host_tiles, threads=2, n=200):
+    """Numpy in / numpy out through the callables install() puts in place of the reference's (hooks A and C), one tile per
+    call as predict_wsi.py:749-756 does: single-thread latency and the throughput of `threads` host threads."""
+    import numpy as np
+    from classpose_b200 import models
+    tiles = [(np.ascontiguousarray(a[:, None]), b[None], c[:, None]) for a, b, c in host_tiles[:16]]
+
+    def one(i):
+        dP, cp, lg = tiles[i % len(tiles)]
+        m = models.compute_masks(dP, cp, (1, H, W), False, PARAMS["niter"], PARAMS["cellprob_threshold"],
+                                 PARAMS["flow_threshold"], PARAMS["min_size"], PARAMS["max_size_fraction"], 0.0, None)
+        cm, _ = models.compute_class_masks(m, lg)
+        return m
+    for i in range(8):
+        one(i)
+    lat = []
+    for i in range(n):
+        t0 = time.perf_counter(); one(i); lat.append(time.perf_counter() - t0)
+    lat.sort()
+
+    def worker(k):
+        for i in range(4):
+            one(i)
+        bar.wait()
+        for i in range(n):
+            one(i + k)
+    bar = threading.Barrier(threads + 1)
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(threads)]
+    [t.start() for t in th]
+    bar.wait(); t0 = time.perf_counter()
+    [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    return {"single_tile_ms_median": 1e3 * lat[len(lat) // 2], "single_tile_ms_p90": 1e3 * lat[int(0.9 * len(lat))],
+            "threads": threads, "tiles_per_sec": threads * n / dt,
+            "path": "models.compute_masks -> models.compute_class_masks (hooks A, C), host numpy in / out, one 256x256 "
+                    "tile per call: CUDA-graph plan + labels kept on the device between the two hooks"}
 
 
 def brief_extras(eng, dev, peak):

@@ -62,6 +62,7 @@ SIGNATURES = {
     "cpb_remove_bad_flow_masks_device": (C.c_int, [_P, _P, _I, _I, _I, _I, _D, _P, _P, _Z, _P]),
     "cpb_fill_holes_and_remove_small_masks_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "cpb_class_vote_device": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "cpb_class_vote_counts_device": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "cpb_remove_border_instances_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "cpb_average_tiles_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "cpb_average_tiles_ex_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),

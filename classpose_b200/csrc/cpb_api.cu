@@ -499,6 +499,28 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
 int run_vote(const Workspace& w, const int32_t* masks, const float* logits, int B, int H, int W, int C,
              int32_t* cell_class, uint8_t* class_masks, cudaStream_t st) {
     ProfScope ps(w.prof, S_VOTE);
+    const long long BN = (long long)B * H * W;
+    if ((H * W) % 4 == 0 && reinterpret_cast<uintptr_t>(masks) % 16 == 0 && reinterpret_cast<uintptr_t>(logits) % 16 == 0 &&
+        (!class_masks || reinterpret_cast<uintptr_t>(class_masks) % 4 == 0)) {
+        // streaming form: the whole grid reads labels and logits with 128-bit loads, histogram in the global table
+        CPB_LAUNCH_COUNTED(k_vote_zero_lb, dim3(B), dim3(256), 0, st, (const int*)w.t.lbound, w.t.LC, C, w.vote);
+        CPB_CHECK_LAUNCH();
+#define CPB_VP_LAUNCH(CT) CPB_LAUNCH_COUNTED(k_vote_px_v4<CT>, dim3(blocks_for(BN / 4, 256)), dim3(256), 0, st,                \
+                           reinterpret_cast<const int4*>(masks), reinterpret_cast<const float4*>(logits), B, H, W, C, w.t.LC, \
+                           (const int*)w.t.lbound, w.vote)
+        if (C == 7) { CPB_VP_LAUNCH(7); } else if (C == 10) { CPB_VP_LAUNCH(10); } else if (C == 5) { CPB_VP_LAUNCH(5); }
+        else { CPB_VP_LAUNCH(0); }
+#undef CPB_VP_LAUNCH
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_vote_finish_lb, dim3(B), dim3(256), 0, st, (const int*)w.t.lbound, w.t.LC, C, (const int*)w.vote, cell_class);
+        CPB_CHECK_LAUNCH();
+        if (class_masks) {
+            CPB_LAUNCH_COUNTED(k_class_image_v4, dim3(blocks_for(BN / 4, 256)), dim3(256), 0, st, reinterpret_cast<const int4*>(masks),
+                               B, H, W, w.t.LC, (const int*)w.t.lbound, (const int*)cell_class, reinterpret_cast<unsigned*>(class_masks));
+            CPB_CHECK_LAUNCH();
+        }
+        return 0;
+    }
     // (instance, class) table in shared memory: 24 KB for nuclei-scale tiles, up to 96 KB on big tiles
     const int smem_ints = (int)std::min<long long>(std::max<long long>((long long)H * W / 16, kVoteSmemInts), kVoteSmemIntsMax);
     CPB_LAUNCH_COUNTED(k_vote, dim3(B), dim3(512), smem_ints * 4, st, masks, logits, H, W, C, w.t.LC, w.t.lbound,
@@ -612,6 +634,21 @@ int cpb_class_vote_device(const int32_t* masks, const float* logits, int B, int 
     if (!masks || !logits || !cell_class || C < 1 || C > 255 || lcap < 2) return CPB_E_ARG;
     CPB_PROLOGUE(C, lcap)
     int e = run_set_lbound(w, B, lcap - 1, st); if (e) return e;
+    return run_vote(w, masks, logits, B, H, W, C, cell_class, class_masks, st);
+}
+
+CPB_KERNEL k_lbound_from_counts(const int* CPB_RESTRICT counts, int B, int cap, int* CPB_RESTRICT lbound) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) lbound[b] = min(max(counts[b], 0), cap);
+}
+
+int cpb_class_vote_counts_device(const int32_t* masks, const float* logits, const int32_t* counts, int B, int H, int W,
+                                 int C, int lcap, int32_t* cell_class, uint8_t* class_masks, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    if (!masks || !logits || !counts || !cell_class || C < 1 || C > 255 || lcap < 2) return CPB_E_ARG;
+    CPB_PROLOGUE(C, lcap)
+    CPB_LAUNCH_COUNTED(k_lbound_from_counts, dim3(blocks_for(B, 256)), dim3(256), 0, st, counts, B, lcap - 1, w.t.lbound);
+    CPB_CHECK_LAUNCH();
     return run_vote(w, masks, logits, B, H, W, C, cell_class, class_masks, st);
 }
 

@@ -312,6 +312,84 @@ CPB_KERNEL k_vote_finish(LabelTables t, int C, const int* CPB_RESTRICT vote, int
     }
 }
 
+// ---- stand-alone streaming vote (stage call on finished labels): the same per-pixel arg-max / histogram as the
+// fused pass, spread over the whole grid -- one block per tile (k_vote) leaves a single-tile call on one SM.
+CPB_KERNEL k_vote_zero_lb(const int* CPB_RESTRICT lbound, int LC, int C, int* CPB_RESTRICT vote) {
+    const int b = blockIdx.x;
+    int* tab = vote + (size_t)b * LC * C;
+    const int need = (min(lbound[b], LC - 1) + 1) * C;
+    for (int i = threadIdx.x; i < need; i += blockDim.x) tab[i] = 0;
+}
+
+template <int CT>
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_vote_px_v4(const int4* CPB_RESTRICT lab, const float4* CPB_RESTRICT logits, int B, int H, int W, int C_rt, int LC,
+             const int* CPB_RESTRICT lbound, int* CPB_RESTRICT vote) {
+    const int C = CT > 0 ? CT : C_rt;
+    const int N4 = (H * W) >> 2;
+    const long long total = (long long)B * N4;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const int b = (int)(g / N4);
+    const int q = (int)(g - (long long)b * N4);
+    const int lb = min(lbound[b], LC - 1);
+    const int4 v = lab[g];
+    int o[4] = {v.x, v.y, v.z, v.w};
+    #pragma unroll
+    for (int e = 0; e < 4; e++) if (o[e] < 0 || o[e] > lb) o[e] = 0;
+    if ((o[0] | o[1] | o[2] | o[3]) == 0) return;
+    const float4* G = logits + (size_t)b * C * N4 + q;
+    float4 best = G[0];
+    int arg[4] = {0, 0, 0, 0};
+    #pragma unroll 4
+    for (int c = 1; c < C; c++) {
+        const float4 x = G[(size_t)c * N4];
+        if (x.x > best.x) { best.x = x.x; arg[0] = c; }
+        if (x.y > best.y) { best.y = x.y; arg[1] = c; }
+        if (x.z > best.z) { best.z = x.z; arg[2] = c; }
+        if (x.w > best.w) { best.w = x.w; arg[3] = c; }
+    }
+    int* tab = vote + (size_t)b * LC * C;
+    #pragma unroll
+    for (int e = 0; e < 4; e++) if (o[e] > 0) atomicAdd(&tab[o[e] * C + arg[e]], 1);
+}
+
+CPB_KERNEL k_vote_finish_lb(const int* CPB_RESTRICT lbound, int LC, int C, const int* CPB_RESTRICT vote,
+                            int* CPB_RESTRICT cell_class) {
+    const int b = blockIdx.x;
+    const int* tab = vote + (size_t)b * LC * C;
+    int* cc = cell_class + (size_t)b * LC;
+    const int nl = min(lbound[b], LC - 1);
+    for (int l = threadIdx.x; l <= nl; l += blockDim.x) {
+        int arg = 0;
+        if (l > 0) {
+            int best = tab[l * C];
+            for (int c = 1; c < C; c++) {
+                const int x = tab[l * C + c];
+                if (x > best) { best = x; arg = c; }
+            }
+        }
+        cc[l] = arg;
+    }
+}
+
+CPB_KERNEL k_class_image_v4(const int4* CPB_RESTRICT lab, int B, int H, int W, int LC, const int* CPB_RESTRICT lbound,
+                            const int* CPB_RESTRICT cell_class, unsigned* CPB_RESTRICT class_masks) {
+    const int N4 = (H * W) >> 2;
+    const long long total = (long long)B * N4;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const int b = (int)(g / N4);
+    const int lb = min(lbound[b], LC - 1);
+    const int* cc = cell_class + (size_t)b * LC;
+    const int4 v = lab[g];
+    const int l[4] = {v.x, v.y, v.z, v.w};
+    unsigned out = 0;
+    #pragma unroll
+    for (int e = 0; e < 4; e++) if (l[e] > 0 && l[e] <= lb) out |= (unsigned)(cc[l[e]] & 0xff) << (8 * e);
+    class_masks[g] = out;
+}
+
 // after k_final the image holds ids 1..nlab: shrink the label bound accordingly (vote, border); a tile some
 // stage could not process (t.fail, e.g. the hole-fill bitmap pool ran out) reports counts[b] = -1
 CPB_KERNEL k_finish_bounds(LabelTables t, int B, int* CPB_RESTRICT counts_out) {

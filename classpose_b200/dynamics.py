@@ -41,6 +41,15 @@ def _as_batch(dP, cellprob):
 def _run(dP, cellprob, niter, cellprob_threshold, flow_threshold, min_size, max_size_fraction, fill_holes, device):
     eng = get_engine(device if _is_dev(dP) is False else dP.device)
     dP_b, cp_b = _as_batch(dP, cellprob)
+    if not isinstance(dP_b, torch.Tensor) and dP_b.shape[0] == 1 and (dP_b.shape[2] * dP_b.shape[3]) % 4 == 0:
+        # one tile of host data (the reference's WSI loop): static buffers + one CUDA-graph launch (fastpath.py)
+        from . import fastpath
+        plan = fastpath.tile_plan(eng, dP_b.shape[2], dP_b.shape[3], niter, cellprob_threshold, flow_threshold, min_size,
+                                  max_size_fraction, fill_holes)
+        m32, n = plan.run(dP_b[0], cp_b[0])
+        m = m32.astype(np.uint16 if n < 2 ** 16 else np.uint32)
+        plan.remember(m)                 # hook C finds the labels still on the device when it is handed this array
+        return m if np.ndim(dP) == 3 else m[None]
     masks, counts, _, _ = eng.compute_masks_batch(dP_b, cp_b, None, niter=niter, cellprob_threshold=cellprob_threshold,
                                                   flow_threshold=flow_threshold, min_size=min_size,
                                                   max_size_fraction=max_size_fraction, fill_holes=fill_holes)

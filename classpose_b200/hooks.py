@@ -4,6 +4,9 @@
   B  cellpose.dynamics.resize_and_compute_masks / compute_masks   (models.py:120, 149)
   C  classpose.models.compute_class_masks           (models.py:766 -> :191)
   D  cellpose.transforms.average_tiles              (core.py:215, 218)
+  D' cellpose.transforms.unaugment_tiles            (core.py:209, --tta) and classpose.core.unaugment_class_tiles
+     (core.py:8 binds the NAME at import time, so the attribute of classpose.core is what core.py:213 resolves;
+     the defining modules classpose.transforms[.transforms] are patched too for later importers)
 
 `install()` patches whichever of those modules can be imported in the running interpreter and
 returns the list of patched names; `uninstall()` restores the originals.
@@ -26,6 +29,10 @@ _HOOKS = [
     ("cellpose.dynamics", "compute_masks", _dyn.compute_masks),
     ("cellpose.utils", "fill_holes_and_remove_small_masks", _utils.fill_holes_and_remove_small_masks),
     ("cellpose.transforms", "average_tiles", _tf.average_tiles),
+    ("cellpose.transforms", "unaugment_tiles", _tf.unaugment_tiles),
+    ("classpose.core", "unaugment_class_tiles", _tf.unaugment_class_tiles),
+    ("classpose.transforms", "unaugment_class_tiles", _tf.unaugment_class_tiles),
+    ("classpose.transforms.transforms", "unaugment_class_tiles", _tf.unaugment_class_tiles),
 ]
 
 

@@ -26,11 +26,13 @@ def compute_masks(dP, cellprob, shape, do_3D, niter, cellprob_threshold, flow_th
     cellprob = np.asarray(cellprob, np.float32)
     if dP.ndim != 4 or cellprob.ndim != 3 or dP.shape[1] != cellprob.shape[0]:
         raise ValueError(f"expected dP [2,nimg,H,W] and cellprob [nimg,H,W], got {dP.shape} and {cellprob.shape}")
-    masks = dynamics.resize_and_compute_masks(np.ascontiguousarray(dP.transpose(1, 0, 2, 3)), cellprob, niter=niter,
-                                              cellprob_threshold=cellprob_threshold, flow_threshold=flow_threshold,
-                                              min_size=min_size, max_size_fraction=max_size_fraction, resize=None,
-                                              device=device)
-    return masks[0] if nimg == 1 else masks
+    kw = dict(niter=niter, cellprob_threshold=cellprob_threshold, flow_threshold=flow_threshold, min_size=min_size,
+              max_size_fraction=max_size_fraction, resize=None, device=device)
+    if nimg == 1:
+        # the WSI loop's case (predict_wsi.py:750-751): one tile; the array returned here is the very object
+        # compute_class_masks receives next (models.py:753-768), which lets the vote reuse the labels on the device
+        return dynamics.resize_and_compute_masks(np.ascontiguousarray(dP[:, 0]), np.ascontiguousarray(cellprob[0]), **kw)
+    return dynamics.resize_and_compute_masks(np.ascontiguousarray(dP.transpose(1, 0, 2, 3)), cellprob, **kw)
 
 
 def compute_class_masks(masks, y_class, device=None):
@@ -38,6 +40,21 @@ def compute_class_masks(masks, y_class, device=None):
     may win, label 0 -> class 0.  Returns (class_masks int64, np.unique(masks)).  As in the reference the
     vote table is indexed by label value over the whole array: planes of a stack that reuse an id vote
     together."""
+    if isinstance(masks, np.ndarray):
+        from . import fastpath
+        plan = fastpath.plan_holding(masks)
+        lg = np.asarray(y_class)
+        if plan is not None and lg.size % masks.size == 0 and lg.size // masks.size >= 1:
+            # `masks` is the array hook A / B returned last on this thread: its labels are still on the device, only
+            # the logits travel (models.py:753-768 hands the array straight through)
+            cm = plan.vote(lg.reshape(lg.size // masks.size, masks.shape[0], masks.shape[1])).astype(np.int64)
+            if plan.contiguous_ids:
+                n = plan.last_count
+                first = 0 if (n == 0 or masks.min() == 0) else 1
+                unique_instances = np.arange(first, n + 1, dtype=masks.dtype)
+            else:
+                unique_instances = np.unique(masks)
+            return cm, unique_instances
     masks = np.asarray(masks)
     logits = np.squeeze(np.asarray(y_class, np.float32))
     C = int(logits.shape[0])

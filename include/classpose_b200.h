@@ -175,6 +175,13 @@ int cpb_class_vote_device(const int32_t* masks, const float* logits, int B, int 
                           int lcap, int32_t* cell_class, uint8_t* class_masks, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Same vote with the per-tile label bound taken from a DEVICE array (counts [B], e.g. the one the fused path wrote)
+ * instead of lcap - 1: no host knowledge of the counts is needed, so the call can sit in a CUDA graph behind
+ * cpb_compute_masks_device, and the (instance, class) table stays in shared memory for nuclei-scale tiles. */
+int cpb_class_vote_counts_device(const int32_t* masks, const float* logits, const int32_t* counts, int B, int H,
+                                 int W, int C, int lcap, int32_t* cell_class, uint8_t* class_masks,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* (7) metrics.pq.remove_border_instances (pq.py:65-92).  masks [B,H,W,nch] int32, channel 0
  * holds the instance ids, every channel is zeroed for border instances (nch = 1 for a plain
  * label image).  In place, as the reference mutates its argument. */

@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out/r02e
 O=gpurun_out/r02e
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 $O/pytest_gpu.log
-/usr/bin/time -v timeout 900 python bench.py 2>$O/bench.err > $O/bench.json; echo "bench rc=$?"; grep -i "elapsed\|Maximum resident" $O/bench.err
+SECONDS=0; timeout 900 python bench.py 2>$O/bench.err > $O/bench.json; echo "bench rc=$? wall=${SECONDS}s"; tail -3 $O/bench.err
 python - <<'PY'
 import json
 d=json.load(open("gpurun_out/r02e/bench.json"))

@@ -102,6 +102,71 @@ def test_hooks_patch_and_restore_by_attribute():
     assert fake_models.compute_masks == "orig_a" and fake_tf.average_tiles == "orig_d"
 
 
+def test_install_on_a_package_tree_with_the_reference_import_style(tmp_path, monkeypatch):
+    """install() against real packages laid out and imported the way the reference does it: `from cellpose import
+    dynamics, transforms, utils` (attribute lookups at call time, models.py:13-22, 120, 149), module-global functions called
+    by bare name from inside the same module (models.py:464, 766) and a NAME import at module load
+    (core.py:8 `from classpose.transforms import unaugment_class_tiles`, used bare at core.py:213)."""
+    import sys
+    import textwrap
+    root = tmp_path / "site"
+    files = {
+        "cellpose/__init__.py": "",
+        "cellpose/dynamics.py": "def resize_and_compute_masks(*a, **k):\n    return 'stock-b'\ndef compute_masks(*a, **k):\n    return 'stock-b2'\n",
+        "cellpose/utils.py": "def fill_holes_and_remove_small_masks(*a, **k):\n    return 'stock-u'\n",
+        "cellpose/transforms.py": "def average_tiles(*a, **k):\n    return 'stock-d'\ndef unaugment_tiles(*a, **k):\n    return 'stock-ua'\n",
+        "classpose/__init__.py": "",
+        "classpose/transforms/__init__.py": "from .transforms import unaugment_class_tiles\n",
+        "classpose/transforms/transforms.py": "def unaugment_class_tiles(y):\n    return 'stock-uc'\n",
+        "classpose/core.py": textwrap.dedent("""
+            from cellpose import transforms
+            from classpose.transforms import unaugment_class_tiles
+            def run_net_tail():
+                return transforms.unaugment_tiles, unaugment_class_tiles, transforms.average_tiles
+            """),
+        "classpose/models.py": textwrap.dedent("""
+            from cellpose import dynamics, transforms, utils
+            def compute_masks(*a, **k):
+                return dynamics.resize_and_compute_masks(*a, **k)
+            def compute_class_masks(masks, y_class):
+                return 'stock-c'
+            class ClassposeModel:
+                def _compute_masks(self):
+                    return compute_masks            # bare module-global lookup, as models.py:464
+                def eval_tail(self):
+                    return self._compute_masks(), compute_class_masks, dynamics.resize_and_compute_masks, utils.fill_holes_and_remove_small_masks
+            """),
+    }
+    for rel, src in files.items():
+        f = root / rel
+        f.parent.mkdir(parents=True, exist_ok=True)
+        f.write_text(src)
+    monkeypatch.syspath_prepend(str(root))
+    for m in [k for k in sys.modules if k.split(".")[0] in ("cellpose", "classpose")]:
+        monkeypatch.delitem(sys.modules, m)
+    import classpose.core as rcore
+    import classpose.models as rmodels
+    from classpose_b200 import dynamics, models, transforms as btf, utils as butils
+    try:
+        patched = hooks.install()
+        assert {"classpose.models.compute_masks", "classpose.models.compute_class_masks", "classpose.core.unaugment_class_tiles",
+                "cellpose.dynamics.resize_and_compute_masks", "cellpose.transforms.average_tiles",
+                "cellpose.transforms.unaugment_tiles", "cellpose.utils.fill_holes_and_remove_small_masks"} <= set(patched)
+        a, c, b, u = rmodels.ClassposeModel().eval_tail()
+        assert a is models.compute_masks and c is models.compute_class_masks
+        assert b is dynamics.resize_and_compute_masks and u is butils.fill_holes_and_remove_small_masks
+        ua, uc, d = rcore.run_net_tail()
+        assert ua is btf.unaugment_tiles and uc is btf.unaugment_class_tiles and d is btf.average_tiles
+    finally:
+        hooks.uninstall()
+    a, c, b, u = rmodels.ClassposeModel().eval_tail()
+    assert a() == "stock-b" and c(None, None) == "stock-c" and b() == "stock-b" and u() == "stock-u"
+    ua, uc, d = rcore.run_net_tail()
+    assert ua() == "stock-ua" and uc(None) == "stock-uc" and d() == "stock-d"
+    for m in [k for k in sys.modules if k.split(".")[0] in ("cellpose", "classpose")]:
+        sys.modules.pop(m, None)
+
+
 def test_reference_signatures_are_honoured():
     import inspect
     from classpose_b200 import dynamics, models

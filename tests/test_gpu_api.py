@@ -157,6 +157,46 @@ def test_two_devices_in_one_process():
         np.testing.assert_array_equal(mh.numpy(), m.cpu().numpy())
 
 
+def test_single_tile_fast_path_graph_and_identity_cache():
+    """Hooks A / B and C as the WSI loop calls them (one tile, numpy in / out): the CUDA-graph plan must give the same
+    label image as the batched engine call, hook C must find the labels of the array hook A returned on the device
+    (identity cache) and give the same classes as a fresh vote on a copy of that array; a second tile through the
+    same plan must not leak state from the first."""
+    from classpose_b200 import dynamics, fastpath, models
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    for seeds, C in (((1, 3, 4), 7), ((21,), 10)):
+        for s_ in seeds:
+            t = pc.std_tile(s_, C=C) if C != 7 else pc.std_tile(s_)
+            ref_m, ref_c, _, _ = eng.compute_masks_batch(t["dP"][None], t["cellprob"][None])
+            ref_m = ref_m[0].cpu().numpy()
+            m = models.compute_masks(t["dP"][:, None], t["cellprob"][None], (1, 256, 256), False, 200, 0.0, 0.4, 15, 0.4, 0.0, None)
+            assert m.dtype == np.uint16 and m.shape == (256, 256)
+            np.testing.assert_array_equal(m.astype(np.int32), ref_m)
+            assert fastpath.plan_holding(m) is not None
+            cm, uniq = models.compute_class_masks(m, t["logits"][:, None])             # cached labels, logits only
+            assert fastpath.plan_holding(m.copy()) is None
+            cm2, uniq2 = models.compute_class_masks(m.copy(), t["logits"][:, None])    # a copy: the general path
+            np.testing.assert_array_equal(cm, cm2)
+            np.testing.assert_array_equal(uniq, uniq2)
+            assert cm.dtype == np.int64 and uniq.dtype == m.dtype
+            ref_cm, ref_u = classpose_ref.compute_class_masks(m, t["logits"][:, None])
+            np.testing.assert_array_equal(cm, ref_cm)
+            np.testing.assert_array_equal(uniq, ref_u)
+    # the array of an older call is not confused with the current device labels
+    t1, t2 = pc.std_tile(1), pc.std_tile(3)
+    m1 = dynamics.resize_and_compute_masks(t1["dP"], t1["cellprob"])
+    m2 = dynamics.resize_and_compute_masks(t2["dP"], t2["cellprob"])
+    assert fastpath.plan_holding(m1) is None and fastpath.plan_holding(m2) is not None
+    cm1, _ = models.compute_class_masks(m1, t1["logits"][:, None])
+    np.testing.assert_array_equal(cm1, classpose_ref.compute_class_masks(m1, t1["logits"][:, None])[0])
+    # empty tile
+    z = dynamics.resize_and_compute_masks(np.zeros((2, 256, 256), np.float32), -np.ones((256, 256), np.float32))
+    assert not z.any()
+    cmz, uz = models.compute_class_masks(z, t1["logits"][:, None])
+    assert not cmz.any() and uz.tolist() == [0]
+
+
 def test_concurrent_calls_from_two_threads():
     """The reference runs two inference threads per process; calls must be re-entrant."""
     import threading
