@@ -559,18 +559,31 @@ def hooks_e2e(host_tiles, threads=2, n=200):
         t0 = time.perf_counter(); one(i); lat.append(time.perf_counter() - t0)
     lat.sort()
 
+    errors = []
+
     def worker(k):
-        for i in range(4):
-            one(i)
-        bar.wait()
-        for i in range(n):
-            one(i + k)
+        try:
+            for i in range(4):
+                one(i)
+            bar.wait(timeout=120)
+            for i in range(n):
+                one(i + k)
+        except Exception as e:            # a failing thread must not leave the others waiting
+            errors.append(f"{type(e).__name__}: {e}")
+            bar.abort()
     bar = threading.Barrier(threads + 1)
-    th = [threading.Thread(target=worker, args=(k,)) for k in range(threads)]
+    th = [threading.Thread(target=worker, args=(k,), daemon=True) for k in range(threads)]
     [t.start() for t in th]
-    bar.wait(); t0 = time.perf_counter()
-    [t.join() for t in th]
+    try:
+        bar.wait(timeout=120)
+    except threading.BrokenBarrierError:
+        pass
+    t0 = time.perf_counter()
+    [t.join(timeout=300) for t in th]
     dt = time.perf_counter() - t0
+    if errors or any(t.is_alive() for t in th):
+        return {"single_tile_ms_median": 1e3 * lat[len(lat) // 2], "single_tile_ms_p90": 1e3 * lat[int(0.9 * len(lat))],
+                "threads": threads, "tiles_per_sec": None, "error": errors or ["a hook thread did not finish"]}
     return {"single_tile_ms_median": 1e3 * lat[len(lat) // 2], "single_tile_ms_p90": 1e3 * lat[int(0.9 * len(lat))],
             "threads": threads, "tiles_per_sec": threads * n / dt,
             "path": "models.compute_masks -> models.compute_class_masks (hooks A, C), host numpy in / out, one 256x256 "

@@ -56,6 +56,14 @@ SIGNATURES = {
     "cpb_debug_set_switch": (None, [_I, _I]),
     "cpb_compute_masks_host": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, _I, _I]),
     "cpb_compute_masks_host_ex": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, C.POINTER(HostOptions)]),
+    "cpb_tile_plan_create": (C.c_int, [_I, _I, C.POINTER(Params), _I, C.POINTER(C.c_void_p)]),
+    "cpb_tile_plan_destroy": (None, [_P]),
+    "cpb_tile_plan_dP": (_P, [_P]),
+    "cpb_tile_plan_cellprob": (_P, [_P]),
+    "cpb_tile_plan_masks": (_P, [_P]),
+    "cpb_tile_plan_run": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "cpb_tile_plan_logits": (_P, [_P, _I]),
+    "cpb_tile_plan_vote": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "cpb_follow_flows_device": (C.c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "cpb_get_masks_device": (C.c_int, [_P, _I, _I, _I, _D, _P, _P, _P, _Z, _P]),
     "cpb_masks_to_flows_device": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _Z, _P]),
@@ -74,7 +82,9 @@ SIGNATURES = {
 }
 
 # entry points that exist only in the CUDA build (host-buffer path does real H2D/D2H copies)
-CUDA_ONLY = {"cpb_compute_masks_host", "cpb_compute_masks_host_ex"}
+CUDA_ONLY = {"cpb_compute_masks_host", "cpb_compute_masks_host_ex", "cpb_tile_plan_create", "cpb_tile_plan_destroy",
+             "cpb_tile_plan_dP", "cpb_tile_plan_cellprob", "cpb_tile_plan_masks", "cpb_tile_plan_run", "cpb_tile_plan_logits",
+             "cpb_tile_plan_vote"}
 
 
 def declare(lib: C.CDLL, cuda: bool = True) -> C.CDLL:

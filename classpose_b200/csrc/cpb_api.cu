@@ -992,4 +992,5 @@ int cpb_label_offsets_device(const int32_t* counts, int B, int64_t base, int64_t
 
 #ifndef CPB_SIM
 #include "cpb_host.inl"
+#include "cpb_plan.inl"
 #endif

@@ -8,11 +8,45 @@
 
 #define CPB_SEED_MIN 10
 #define CPB_GROW_MIN 2
-#define CPB_RANK_CHUNK 1024
+#define CPB_RANK_CHUNK 2048
 
-// rank[k] = #{ j : key[j] < key[k] } for n distinct 64-bit keys (block-cooperative, O(n^2/blockDim)).
-// s_keys: CPB_RANK_CHUNK u64 of shared memory.  out[k] = rank + 1 for k < n.
+// rank[k] = #{ j : key[j] < key[k] } for n distinct 64-bit keys.  s_keys: CPB_RANK_CHUNK u64 of shared memory.
+// out[k] = rank + 1 for k < n.
+//   n <= CPB_RANK_CHUNK: bitonic sort of a copy in shared memory, then every key finds its position by binary search
+//                        (O(n log^2 n / blockDim): a dense 512 x 512 tile ranks ~1,800 labels several times per call);
+//   larger n           : block-cooperative O(n^2 / blockDim) counting, chunk by chunk.
 CPB_DEVICE void cpb_block_rank(const u64* CPB_RESTRICT keys, int n, int* CPB_RESTRICT out, u64* s_keys) {
+    if (n <= CPB_RANK_CHUNK) {
+        int m = 32;
+        while (m < n) m <<= 1;
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x) s_keys[i] = i < n ? keys[i] : ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                    const int p = i ^ j;
+                    if (p > i) {
+                        const u64 a = s_keys[i], b = s_keys[p];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { s_keys[i] = b; s_keys[p] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const u64 mine = keys[k];
+            int lo = 0, hi = n - 1;                   // keys are distinct: exactly one match
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_keys[mid] < mine) lo = mid + 1; else hi = mid;
+            }
+            out[k] = lo + 1;
+        }
+        __syncthreads();
+        return;
+    }
     for (int kb = 0; kb < n; kb += blockDim.x) {
         const int k = kb + threadIdx.x;
         const u64 mine = k < n ? keys[k] : 0;

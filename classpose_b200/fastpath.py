@@ -2,19 +2,15 @@
 
 The reference's WSI loop calls `model.eval([tile])` one tile at a time from two inference threads per process
 (/root/reference/src/classpose/entrypoints/predict_wsi.py:728-797), i.e. hook A/B (masks) and then hook C (class
-vote) with host numpy arrays, ~100 times per second and thread.  What such a call costs is not arithmetic but
-plumbing: allocations, ~30 kernel launches and four pageable copies.  A `TilePlan` removes the plumbing:
+vote) with host numpy arrays.  What such a call costs is not arithmetic but plumbing: allocations, ~30 kernel
+launches and four pageable copies.  The library's tile plans (`cpb_tile_plan_*`, csrc/cpb_plan.inl) remove it:
+pinned staging + static device buffers per (thread, tile shape, parameters) and the whole sequence -- upload, fused
+path, download -- captured once into a CUDA graph and replayed with one launch per call.
 
-* static device buffers, workspace and PINNED staging buffers per (thread, tile shape, parameters);
-* the whole sequence -- upload, fused path, download -- captured once into a CUDA graph and replayed with a single
-  launch per call (the kernels take every size from the arguments and read every count from device memory, so the
-  captured sequence is valid for any tile content);
-* an identity cache: hook A/B remembers which numpy array it returned; when hook C is handed that very array
-  (models.py:753-768 passes it straight through) the label image is still on the device, so only the logits are
-  uploaded and the vote runs on the cached labels (second graph).
-
-torch is plumbing here as everywhere in this package (pinned memory, streams, graph capture); the arithmetic is
-the library's.  Plans are per thread (thread-local) and never shared, so no locking is needed.
+This module is the thin python side of that: numpy views over the plan's pinned buffers, and an identity cache --
+hook A/B remembers which numpy array it returned; when hook C is handed that very array (models.py:753-768 passes it
+straight through) the label image is still on the device, so only the logits are uploaded and the vote (a second
+graph) runs on the cached labels.  Plans are per thread (thread-local) and never shared.
 """
 from __future__ import annotations
 
@@ -23,7 +19,6 @@ import threading
 import weakref
 
 import numpy as np
-import torch
 
 from ._abi import ClassposeB200Error, check, make_params
 
@@ -31,61 +26,40 @@ _tls = threading.local()
 MAX_PLANS = 8          # per thread: distinct (shape, parameter) combinations kept alive
 
 
+def _view(ptr, shape, dtype):
+    n = int(np.prod(shape))
+    ctype = {np.float32: C.c_float, np.int32: C.c_int32, np.uint8: C.c_uint8}[dtype]
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).reshape(shape)
+
+
 class TilePlan:
     def __init__(self, eng, H, W, prm_key):
         self.eng, self.H, self.W = eng, H, W
-        self.prm = make_params(*prm_key)
-        dev = eng.device
-        self.stream = torch.cuda.Stream(device=dev)
-        self.h_dP = torch.empty((1, 2, H, W), dtype=torch.float32, pin_memory=True)
-        self.h_cp = torch.empty((1, H, W), dtype=torch.float32, pin_memory=True)
-        self.h_masks = torch.empty((1, H, W), dtype=torch.int32, pin_memory=True)
-        self.h_counts = torch.empty((1,), dtype=torch.int32, pin_memory=True)
-        self.d_dP = torch.empty((1, 2, H, W), dtype=torch.float32, device=dev)
-        self.d_cp = torch.empty((1, H, W), dtype=torch.float32, device=dev)
-        self.d_masks = torch.empty((1, H, W), dtype=torch.int32, device=dev)
-        self.d_counts = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self.ws_bytes = int(eng.lib.cpb_workspace_bytes(1, H, W, 0, 0))
-        self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
-        self.graph = None
-        self.votes = {}                 # C -> VotePlan
-        self.returned = None            # weakref to the numpy array handed to the caller last
+        self.lib = eng.lib
+        prm = make_params(*prm_key)
+        handle = C.c_void_p()
+        check(self.lib.cpb_tile_plan_create(H, W, C.byref(prm), int(eng.device.index), C.byref(handle)), "cpb_tile_plan_create")
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, self.lib.cpb_tile_plan_destroy, handle)
+        self.h_dP = _view(self.lib.cpb_tile_plan_dP(handle), (2, H, W), np.float32)
+        self.h_cp = _view(self.lib.cpb_tile_plan_cellprob(handle), (H, W), np.float32)
+        self.h_masks = _view(self.lib.cpb_tile_plan_masks(handle), (H, W), np.int32)
+        self.h_lg = None                # numpy view of the logits staging buffer
+        self.lg_classes = 0
+        self.returned = None            # (weakref to the numpy array handed to the caller last, generation)
         self.generation = 0
         self.contiguous_ids = bool(prm_key[6]) and prm_key[3] > 0     # ids are exactly 1..count (no gaps)
         self.last_count = 0
 
-    def _enqueue(self):
-        s = torch.cuda.current_stream(self.eng.device)
-        self.d_dP.copy_(self.h_dP, non_blocking=True)
-        self.d_cp.copy_(self.h_cp, non_blocking=True)
-        rc = self.eng.lib.cpb_compute_masks_device(self.d_dP.data_ptr(), self.d_cp.data_ptr(), None, 1, self.H, self.W, 0,
-                                                   C.byref(self.prm), self.d_masks.data_ptr(), self.d_counts.data_ptr(),
-                                                   None, None, self.ws.data_ptr(), self.ws_bytes, s.cuda_stream)
-        check(rc, "cpb_compute_masks_device")
-        self.h_masks.copy_(self.d_masks, non_blocking=True)
-        self.h_counts.copy_(self.d_counts, non_blocking=True)
-
     def run(self, dP, cellprob):
-        """dP [2,H,W], cellprob [H,W] numpy float32 -> (label image int32 view of the pinned buffer, count)."""
-        self.h_dP[0].numpy()[...] = dP
-        self.h_cp[0].numpy()[...] = cellprob
-        with torch.cuda.device(self.eng.device):
-            if self.graph is None:
-                with torch.cuda.stream(self.stream):
-                    self._enqueue()                      # warm-up outside capture (function attributes, lazy loading)
-                self.stream.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
-                    self._enqueue()
-                self.graph = g
-            with torch.cuda.stream(self.stream):
-                self.graph.replay()
-            self.stream.synchronize()
+        """dP [2,H,W], cellprob [H,W] numpy -> (label image: int32 view of the pinned buffer, count)."""
+        self.h_dP[...] = dP
+        self.h_cp[...] = cellprob
+        n = C.c_int32(0)
+        check(self.lib.cpb_tile_plan_run(self.handle, C.byref(n)), "cpb_tile_plan_run")
         self.generation += 1
-        n = self.last_count = int(self.h_counts[0])
-        if n < 0:
-            raise ClassposeB200Error("the tile exhausted the hole-fill bitmap pool (counts = -1): masks are incomplete")
-        return self.h_masks[0].numpy(), n
+        self.last_count = int(n.value)
+        return self.h_masks, self.last_count
 
     def remember(self, arr):
         self.returned = (weakref.ref(arr), self.generation)
@@ -95,55 +69,18 @@ class TilePlan:
                 and arr.shape == (self.H, self.W))
 
     def vote(self, logits):
-        """logits [C,H,W] numpy float32 -> class image uint8 view of a pinned buffer; labels are the cached ones."""
+        """logits [C,H,W] numpy -> class image uint8 [H,W] (view of a pinned buffer); labels are the cached ones."""
         Cc = int(logits.shape[0])
-        vp = self.votes.get(Cc)
-        if vp is None:
-            vp = self.votes[Cc] = VotePlan(self, Cc)
-        return vp.run(logits)
-
-
-class VotePlan:
-    def __init__(self, tile: TilePlan, Cc):
-        self.t, self.C = tile, Cc
-        eng, H, W = tile.eng, tile.H, tile.W
-        dev = eng.device
-        self.LC = eng.label_capacity(H, W)
-        self.h_lg = torch.empty((1, Cc, H, W), dtype=torch.float32, pin_memory=True)
-        self.d_lg = torch.empty((1, Cc, H, W), dtype=torch.float32, device=dev)
-        self.d_cc = torch.zeros((1, self.LC), dtype=torch.int32, device=dev)
-        self.d_cm = torch.empty((1, H, W), dtype=torch.uint8, device=dev)
-        self.h_cm = torch.empty((1, H, W), dtype=torch.uint8, pin_memory=True)
-        self.ws_bytes = int(eng.lib.cpb_workspace_bytes(1, H, W, Cc, 0))
-        self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
-        self.graph = None
-
-    def _enqueue(self):
-        t = self.t
-        s = torch.cuda.current_stream(t.eng.device)
-        self.d_lg.copy_(self.h_lg, non_blocking=True)
-        rc = t.eng.lib.cpb_class_vote_counts_device(t.d_masks.data_ptr(), self.d_lg.data_ptr(), t.d_counts.data_ptr(), 1,
-                                                    t.H, t.W, self.C, self.LC, self.d_cc.data_ptr(), self.d_cm.data_ptr(),
-                                                    self.ws.data_ptr(), self.ws_bytes, s.cuda_stream)
-        check(rc, "cpb_class_vote_counts_device")
-        self.h_cm.copy_(self.d_cm, non_blocking=True)
-
-    def run(self, logits):
-        t = self.t
-        self.h_lg[0].numpy()[...] = logits
-        with torch.cuda.device(t.eng.device):
-            if self.graph is None:
-                with torch.cuda.stream(t.stream):
-                    self._enqueue()
-                t.stream.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=t.stream, capture_error_mode="thread_local"):
-                    self._enqueue()
-                self.graph = g
-            with torch.cuda.stream(t.stream):
-                self.graph.replay()
-            t.stream.synchronize()
-        return self.h_cm[0].numpy()
+        if self.lg_classes != Cc:
+            ptr = self.lib.cpb_tile_plan_logits(self.handle, Cc)
+            if not ptr:
+                raise ClassposeB200Error("cpb_tile_plan_logits failed (device memory?)")
+            self.h_lg = _view(ptr, (Cc, self.H, self.W), np.float32)
+            self.lg_classes = Cc
+        self.h_lg[...] = logits
+        cm, cc = C.c_void_p(), C.c_void_p()
+        check(self.lib.cpb_tile_plan_vote(self.handle, C.byref(cm), C.byref(cc)), "cpb_tile_plan_vote")
+        return _view(cm.value, (self.H, self.W), np.uint8)
 
 
 def _plans():

@@ -135,6 +135,28 @@ int cpb_compute_masks_host_ex(const float* dP, const float* cellprob, const floa
                               void* masks, int32_t* counts, int32_t* cell_class,
                               uint8_t* class_masks, const cpb_host_options* opt);
 
+/* ---- single-tile plans: the per-tile call of the reference's WSI loop -----------------------------------------
+ * The loop calls model.eval([tile]) one tile at a time from two inference threads per process
+ * (predict_wsi.py:728-797), which reaches compute_masks (models.py:464 -> :97) and then compute_class_masks
+ * (models.py:766 -> :191) with host arrays.  A plan owns pinned staging buffers, device buffers and CUDA graphs for
+ * "upload -> fused path -> download" and "upload logits -> vote on the labels still on the device -> download", so a
+ * call costs one copy into the staging buffer, one graph launch and one synchronise.  One plan per host thread and
+ * tile shape; the calls of one plan must not overlap.
+ *   cpb_tile_plan_dP / _cellprob   pinned float32 [2,H,W] / [H,W] the caller fills before cpb_tile_plan_run
+ *   cpb_tile_plan_masks            pinned int32 [H,W], valid after cpb_tile_plan_run until the next run
+ *   cpb_tile_plan_logits(p, C)     pinned float32 [C,H,W] to fill before cpb_tile_plan_vote (sets up the vote for C classes)
+ *   cpb_tile_plan_vote             class image uint8 [H,W] and per-instance classes (first min(lcap, 1024) entries),
+ *                                  both pinned, for the labels of the LAST cpb_tile_plan_run */
+typedef struct cpb_tile_plan cpb_tile_plan;
+int  cpb_tile_plan_create(int H, int W, const cpb_params* prm, int device, cpb_tile_plan** out);
+void cpb_tile_plan_destroy(cpb_tile_plan* plan);
+float* cpb_tile_plan_dP(cpb_tile_plan* plan);
+float* cpb_tile_plan_cellprob(cpb_tile_plan* plan);
+const int32_t* cpb_tile_plan_masks(cpb_tile_plan* plan);
+int  cpb_tile_plan_run(cpb_tile_plan* plan, int32_t* count);
+float* cpb_tile_plan_logits(cpb_tile_plan* plan, int C);
+int  cpb_tile_plan_vote(cpb_tile_plan* plan, const uint8_t** class_masks, const int32_t** cell_class);
+
 /* ---- stage entry points (each is one row of SURVEY.md section 8a) ------------------------ */
 
 /* (2) dynamics.follow_flows / steps_interp on dP*(cellprob>thr)/5 (SURVEY A.2-A.3;
