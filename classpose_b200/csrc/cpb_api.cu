@@ -125,7 +125,8 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     w.vote = c.take<int>(C > 0 ? BL * C : 0);
     w.jobs = c.take<int>((size_t)B + 1 + 4);
     w.todo = c.take<int2>(BL);
-    w.q.info = c.take<int>(BL); w.q.ent = c.take<int>(BL); w.q.jobs = c.take<int4>(BL); w.q.sorted = c.take<int4>(BL); w.q.l64 = c.take<int2>(BL);
+    w.q.info = c.take<int>(BL); w.q.ent = c.take<int>(BL); w.q.jobs = c.take<int4>(BL); w.q.sorted = c.take<int4>(BL); w.q.l64 = c.take<int2>(BL); w.q.lc = c.take<int2>(BL);
+    w.q.cls_cnt = c.take<int>((size_t)B * CPB_Q32_NCLS); w.q.T32 = reinterpret_cast<float*>(w.M);
     w.q.ctr = c.take<int>(CPB_QCTR_INTS);
     LabelTables& t = w.t;
     t.LC = LC;
@@ -399,22 +400,29 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
     int* todo_n = w.jobs + B + 3;
     const LabelWork big = todo_work(w, B, false);
     if (qc_dP && diffuse_queue_enabled()) {
-        // decision-exact path: k_qc_pack (centres, contact, classes, jobs) -> float32 screen in registers ->
-        // float64 warp kernel for whatever the screen does not decide (see cpb_qc32.cuh)
+        // decision-exact path (cpb_qc32.cuh): k_qc_scan32 (centres, contact, classes) + k_qc_pack (jobs) -> float32
+        // screen in registers (isolated labels decided in place, labels in contact via the float32 T plane and
+        // k_flow_err32) -> float64 warp kernel for whatever the screen cannot hold or decide
         prof_begin(w.prof, S_CENTRES);
+        const int screen = ((!exact_err || qc_screen_debug()) && qc_screen_enabled()) ? 1 : 0;
+        const int pack_err = (exact_err && qc_screen_debug()) ? 1 : 0;
         cudaMemsetAsync(w.jobs + B + 3, 0, 2 * sizeof(int), st);
         cudaMemsetAsync(w.q.ctr, 0, CPB_QCTR_INTS * sizeof(int), st);
-        CPB_LAUNCH_COUNTED(k_qc_pack, dim3(B), dim3(256), 0, st, masks, H, W, w.t, w.q, w.todo, todo_n,
-                           ((!exact_err || qc_screen_debug()) && qc_screen_enabled()) ? 1 : 0);
+        cudaMemsetAsync(w.q.cls_cnt, 0, (size_t)B * CPB_Q32_NCLS * sizeof(int), st);
+        cudaMemsetAsync(w.t.niter, 0, B * sizeof(int), st);
+        CPB_LAUNCH_COUNTED(k_qc_scan32, dim3(tile_slices(H, W), B), dim3(256), 0, st, masks, H, W, w.t, w.q, w.todo, todo_n, screen);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_qc_pack, dim3(B), dim3(128), 0, st, w.t, w.q);
         CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED(k_centres, dim3(sm_count() * 8), dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t, 1, big);
         CPB_CHECK_LAUNCH();
-        prof_end(w.prof, S_CENTRES);
         CPB_LAUNCH_COUNTED(k_q32_sort, dim3(sm_count()), dim3(256), 0, st, w.q);
         CPB_CHECK_LAUNCH();
+        prof_end(w.prof, S_CENTRES);
         prof_begin(w.prof, S_DIFFUSE);
-        CPB_LAUNCH_COUNTED(k_diffuse32, dim3(sm_count() * CPB_Q32_MINBLOCKS), dim3(128), 0, st, masks, qc_dP, H, W, w.t, w.q, thr,
-                           (exact_err && qc_screen_debug()) ? 1 : 0);
+        CPB_LAUNCH_COUNTED(k_diffuse32, dim3(sm_count() * CPB_Q32_MINBLOCKS), dim3(128), 0, st, masks, qc_dP, H, W, w.t, w.q, thr, pack_err);
+        CPB_CHECK_LAUNCH();
+        CPB_LAUNCH_COUNTED(k_flow_err32, dim3(sm_count() * 8), dim3(128), 0, st, masks, qc_dP, H, W, w.t, w.q, thr, pack_err);
         CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED(k_diffuse64_list, dim3(sm_count() * 6), dim3(CPB_DW_WARPS * 32), 0, st, masks, H, W, w.t, w.T, w.q,
                            qc_dP, thr, w.todo, todo_n, big.cap);

@@ -39,9 +39,12 @@
 #define CPB_Q32_CLSBIG 5           // info class of labels left to the block kernels
 
 #define CPB_QI_CLEAN 8             // info bit: no pixel of another live label in the bbox grown by one
+#define CPB_QI_T32 16              // info bit: the screen wrote this label's float32 T to the global plane
+#define CPB_QI_QUEUED64 32         // info bit: the label is already on the float64 list
 
 // counters: [0] jobs appended, [1] jobs pulled, [2] float64 list appended, [3] float64 list pulled,
 //           [4] labels decided by the screen, [5] labels the screen left undecided (statistics),
+//           [6] contact list appended, [7] contact list pulled,
 //           [8..11] jobs per class, [12..15] scatter cursors of k_q32_sort
 #ifndef CPB_QCTR_INTS
 #define CPB_QCTR_INTS 16
@@ -53,35 +56,37 @@ struct Q32 {
     int4* jobs;       // [B*LC]  (tile, first entry, nsub, class) in the order k_qc_pack emitted them
     int4* sorted;     // [B*LC]  the same jobs, tallest class first (k_q32_sort)
     int2* l64;        // [B*LC]  (tile, label) for the float64 warp kernel
+    int2* lc;         // [B*LC]  (tile, label): screened labels in contact with another label (k_flow_err32)
+    int* cls_cnt;     // [B*4]   screened labels per tile and class
+    float* T32;       // [B*N]   float32 T of the screened labels in contact (their neighbours read it)
     int* ctr;         // [CPB_QCTR_INTS]
 };
+
+// append (tile, label) to the float64 list once
+CPB_DEVICE void cpb_q32_queue64(const Q32& q, int b, int l, size_t k) {
+    if ((atomicOr(&q.info[k], CPB_QI_QUEUED64) & CPB_QI_QUEUED64) == 0) q.l64[atomicAdd(&q.ctr[2], 1)] = make_int2(b, l);
+}
 
 CPB_DEVICE int cpb_q32_class(int cr, int h) {
     const int rho = max(cr, h - 1 - cr);
     return rho <= 4 ? 0 : rho <= 6 ? 1 : rho <= 8 ? 2 : rho <= 10 ? 3 : CPB_Q32_CLS64;
 }
 
-// ---- k_qc_pack: one block per tile ---------------------------------------------------------------------
-//  pass A (warp per label): diffusion centre, contact with other live labels, class; labels beyond the warp kernels go
-//         to `big_list`, small labels the screen cannot take go to q.l64; n_iter of the tile
-//  pass B: the screen's labels grouped by class into q.ent
-//  pack  : warp c packs class c greedily into jobs of up to 8 labels / 63 columns
+// ---- k_qc_scan32: one warp per label, grid (slices, B) ------------------------------------------------------
+//  diffusion centre, contact with other live labels, class; labels beyond the warp kernels go to `big_list`, small
+//  labels the register classes cannot hold go to q.l64; per-tile n_iter (t.niter, zeroed) and class counts
+//  (q.cls_cnt, zeroed).
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
-k_qc_pack(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int2* CPB_RESTRICT big_list,
-          int* CPB_RESTRICT big_count, int screen) {
-    CPB_SHARED int s_cnt[CPB_Q32_NCLS], s_base[CPB_Q32_NCLS], s_pos[CPB_Q32_NCLS];
-    CPB_SHARED int s_ext;
+k_qc_scan32(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int2* CPB_RESTRICT big_list,
+            int* CPB_RESTRICT big_count, int screen) {
     CPB_SHARED unsigned s_bits[8][36];            // per warp: member bits of the grown bbox columns
-    const int b = blockIdx.x, LC = t.LC, N = H * W;
+    const int b = blockIdx.y, LC = t.LC, N = H * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int lb = t.lbound[b];
     const int* L = lab + (size_t)b * N;
     const int* alive = t.alive ? t.alive + (size_t)b * LC : nullptr;
-    if (threadIdx.x < CPB_Q32_NCLS) { s_cnt[threadIdx.x] = 0; s_pos[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) s_ext = 0;
-    __syncthreads();
     int ext = 0;
-    for (int l = 1 + warp; l <= lb; l += nw) {
+    for (int l = 1 + blockIdx.x * nw + warp; l <= lb; l += gridDim.x * nw) {
         const size_t k = (size_t)b * LC + l;
         int info = 0;
         if (cpb_label_live(t, k)) {                              // warp-uniform
@@ -125,7 +130,6 @@ k_qc_pack(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int2*
                 }
                 __syncwarp();
                 member = (lane < w) ? s_bits[warp][lane + 1] : 0u;
-                __syncwarp();
                 // centre = member pixel nearest to the mean, first in raster order on ties.  Every pixel outside the
                 // 4 x 4 window around the mean is at least 2 away along one axis (squared distance >= 4, exactly, in
                 // float64 too), so a member of the window with squared distance < 4 decides -- one candidate per
@@ -166,34 +170,44 @@ k_qc_pack(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int2*
                 const bool clean = !__any_sync(CPB_FULL, foreign);
                 const int cr = bi / w, cc = bi - cr * w;
                 int cls = cpb_q32_class(cr, h);
-                if (!screen || !clean) cls = CPB_Q32_CLS64;
+                if (!screen) cls = CPB_Q32_CLS64;
+                info = cls | (clean ? CPB_QI_CLEAN : 0) | (w << 8);
                 if (lane == 0) {
                     t.cy[k] = y0 + cr; t.cx[k] = x0 + cc;
-                    if (cls == CPB_Q32_CLS64) q.l64[atomicAdd(&q.ctr[2], 1)] = make_int2(b, l);
-                    else atomicAdd(&s_cnt[cls], 1);
+                    if (cls == CPB_Q32_CLS64) { info |= CPB_QI_QUEUED64; q.l64[atomicAdd(&q.ctr[2], 1)] = make_int2(b, l); }
+                    else atomicAdd(&q.cls_cnt[b * CPB_Q32_NCLS + cls], 1);
                 }
-                info = cls | (clean ? CPB_QI_CLEAN : 0) | (w << 8);
             }
         }
         if (lane == 0) q.info[k] = info;
     }
     for (int s = 16; s; s >>= 1) ext = max(ext, __shfl_xor_sync(CPB_FULL, ext, s));
-    if (lane == 0 && ext > 0) atomicMax(&s_ext, ext);
-    __syncthreads();
+    if (lane == 0 && ext > 0) atomicMax(&t.niter[b], ext);
+}
+
+// ---- k_qc_pack: one block of four warps per tile -------------------------------------------------------------
+//  the screen's labels grouped by class into q.ent; warp c packs class c greedily into jobs of up to 8 labels / 63 columns
+CPB_KERNEL CPB_LAUNCH_BOUNDS(128, 8)
+k_qc_pack(LabelTables t, Q32 q) {
+    CPB_SHARED int s_base[CPB_Q32_NCLS], s_pos[CPB_Q32_NCLS];
+    const int b = blockIdx.x, LC = t.LC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lb = t.lbound[b];
+    const int* cnt = q.cls_cnt + b * CPB_Q32_NCLS;
     if (threadIdx.x == 0) {
-        t.niter[b] = s_ext;
         int acc = 0;
-        for (int c = 0; c < CPB_Q32_NCLS; c++) { s_base[c] = acc; acc += s_cnt[c]; }
+        for (int c = 0; c < CPB_Q32_NCLS; c++) { s_base[c] = acc; s_pos[c] = 0; acc += cnt[c]; }
     }
     __syncthreads();
     int* ent = q.ent + (size_t)b * LC;
     for (int l = 1 + threadIdx.x; l <= lb; l += blockDim.x) {
-        const int cls = q.info[(size_t)b * LC + l] & 7;
-        if (cls < CPB_Q32_NCLS && (q.info[(size_t)b * LC + l] >> 8) != 0) ent[s_base[cls] + atomicAdd(&s_pos[cls], 1)] = l;
+        const int info = q.info[(size_t)b * LC + l];
+        const int cls = info & 7;
+        if (cls < CPB_Q32_NCLS && (info >> 8) != 0) ent[s_base[cls] + atomicAdd(&s_pos[cls], 1)] = l;
     }
     __syncthreads();
     if (warp < CPB_Q32_NCLS) {
-        const int cls = warp, n = s_cnt[cls];
+        const int cls = warp, n = cnt[cls];
         const int* e = ent + s_base[cls];
         int coff = 0, nsub = 0, first = 0;
         for (int i0 = 0; i0 < n; i0 += 32) {
@@ -274,6 +288,20 @@ CPB_DEVICE void cpb_q32_pixel(float up, float dn, float lf, float rt, float dpy,
     sb = __fadd_rn(sb, __fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(rn, rn), d), __fmul_rn(d, d)), __fmul_rn(3e-6f, __fadd_rn(1.f, c))));
 }
 
+// decision of one screened label from the float32 error sum and the bound sum (see the header comment)
+CPB_DEVICE bool cpb_q32_decide(const LabelTables& t, const Q32& q, int b, int l, size_t k, float cs, float bd, double threshold,
+                               int pack_err) {
+    const double cnt = (double)t.cnt[k];
+    const double err = (double)cs / cnt;
+    const double bound = 1.01 * (double)bd / cnt + 1e-5 * err + 1e-7;
+    // pack_err (tests): sign bit set, float32 error in the high word, its bound (rounded) in the low word of t.err
+    t.err[k] = pack_err ? __longlong_as_double((long long)((1ull << 63) | ((u64)__float_as_uint((float)err) << 32) | (u64)__float_as_uint((float)bound))) : err;
+    if (err - bound > threshold) { t.flag[k] = 1; t.done[k] = 1; atomicAdd(&q.ctr[4], 1); return true; }
+    if (err + bound < threshold) { t.flag[k] = 0; t.done[k] = 1; atomicAdd(&q.ctr[4], 1); return true; }
+    cpb_q32_queue64(q, b, l, k); atomicAdd(&q.ctr[5], 1);
+    return false;
+}
+
 // Per-lane description of the two strip columns (2 * lane, 2 * lane + 1) of a job.
 struct Q32Cols { int l[2], x[2], yb[2]; float inj[2]; };
 
@@ -333,8 +361,12 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
     const float* dPx = dP + ((size_t)b * 2 + 1) * N;
     const int n_it = t.niter[b];
     // sub i lives on lane i: label, width, first column of the strip
-    int e_l = 0, e_w = 0;
-    if (lane < nsub) { e_l = q.ent[first + lane]; e_w = (q.info[(size_t)b * LC + e_l] >> 8) & 0xff; }
+    int e_l = 0, e_w = 0, e_clean = 0;
+    if (lane < nsub) {
+        e_l = q.ent[first + lane];
+        const int info = q.info[(size_t)b * LC + e_l];
+        e_w = (info >> 8) & 0xff; e_clean = (info & CPB_QI_CLEAN) ? 1 : 0;
+    }
     int e_off = lane < nsub ? e_w + 1 : 0;
     for (int d = 1; d < CPB_Q32_MAXSUB; d <<= 1) {
         const int v = __shfl_up_sync(CPB_FULL, e_off, d);
@@ -344,9 +376,11 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
     // this lane's two columns
     Q32Cols c;
     int rlo[2] = {0, 0}, rhi[2] = {-1, -1};
+    bool col_clean[2] = {true, true};
     c.l[0] = c.l[1] = 0; c.x[0] = c.x[1] = 0; c.yb[0] = c.yb[1] = 0; c.inj[0] = c.inj[1] = 0.f;
     for (int s = 0; s < nsub; s++) {
         const int sl = __shfl_sync(CPB_FULL, e_l, s), sw = __shfl_sync(CPB_FULL, e_w, s), so = __shfl_sync(CPB_FULL, e_off, s);
+        const int sc_ = __shfl_sync(CPB_FULL, e_clean, s);
         const size_t k = (size_t)b * LC + sl;
         const int y0 = t.ymin[k], x0 = t.xmin[k], h = t.ymax[k] - y0 + 1, cy = t.cy[k], cx = t.cx[k];
         #pragma unroll
@@ -356,6 +390,7 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
                 c.l[hf] = sl; c.x[hf] = x0 + col - so; c.yb[hf] = cy - RC;
                 rlo[hf] = y0 - (cy - RC); rhi[hf] = y0 + h - 1 - (cy - RC);
                 c.inj[hf] = (x0 + col - so == cx) ? 1.f : 0.f;
+                col_clean[hf] = sc_ != 0;
             }
         }
     }
@@ -373,7 +408,7 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
             const bool mem = L[pix] == c.l[hf] && in;
             m[hf] = mem ? ninth : 0.f;
 #ifndef CPB_SIM
-            if (mem) {
+            if (mem && col_clean[hf]) {
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(dPy + pix));
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(dPx + pix));
             }
@@ -396,6 +431,9 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
     const float eta = (float)(1.02 * (xk + xk * xk) + 1e-9);
     float sc[2] = {0.f, 0.f}, sb[2] = {0.f, 0.f};
     const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
+    // labels in contact with another label: their gradient needs the neighbour's T, so T goes to the global float32
+    // plane and k_flow_err32 takes the error from there
+    float* T32b = q.T32 + (size_t)b * N;
     for (int r0 = 0; r0 < NR; r0 += 4) {
         // the flows of four rows first (unconditional loads at clamped addresses), then the arithmetic
         float a[4][4];
@@ -403,8 +441,8 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
         for (int q4 = 0; q4 < 4; q4++) {
             const int r = min(r0 + q4, NR - 1);
             const float2 v = S[(r + 1) * 32 + lane];
-            const int p0 = cpb_q32_member(v.x) ? (c.yb[0] + r) * W + c.x[0] : 0;
-            const int p1 = cpb_q32_member(v.y) ? (c.yb[1] + r) * W + c.x[1] : 0;
+            const int p0 = (cpb_q32_member(v.x) && col_clean[0]) ? (c.yb[0] + r) * W + c.x[0] : 0;
+            const int p1 = (cpb_q32_member(v.y) && col_clean[1]) ? (c.yb[1] + r) * W + c.x[1] : 0;
             a[q4][0] = dPy[p0]; a[q4][1] = dPx[p0]; a[q4][2] = dPy[p1]; a[q4][3] = dPx[p1];
         }
         #pragma unroll
@@ -415,8 +453,14 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
             if (!cpb_q32_member(v.x) && !cpb_q32_member(v.y)) continue;
             const float2 up = S[r * 32 + lane], dn = S[(r + 2) * 32 + lane];
             const float lf = fabsf(S[(r + 1) * 32 + lm].y), rt = fabsf(S[(r + 1) * 32 + lp].x);
-            if (cpb_q32_member(v.x)) cpb_q32_pixel(fabsf(up.x), fabsf(dn.x), lf, fabsf(v.y), a[q4][0], a[q4][1], eta, sc[0], sb[0]);
-            if (cpb_q32_member(v.y)) cpb_q32_pixel(fabsf(up.y), fabsf(dn.y), fabsf(v.x), rt, a[q4][2], a[q4][3], eta, sc[1], sb[1]);
+            if (cpb_q32_member(v.x)) {
+                if (col_clean[0]) cpb_q32_pixel(fabsf(up.x), fabsf(dn.x), lf, fabsf(v.y), a[q4][0], a[q4][1], eta, sc[0], sb[0]);
+                else T32b[(c.yb[0] + r) * W + c.x[0]] = v.x;
+            }
+            if (cpb_q32_member(v.y)) {
+                if (col_clean[1]) cpb_q32_pixel(fabsf(up.y), fabsf(dn.y), fabsf(v.x), rt, a[q4][2], a[q4][3], eta, sc[1], sb[1]);
+                else T32b[(c.yb[1] + r) * W + c.x[1]] = v.y;
+            }
         }
     }
     __syncwarp();
@@ -425,17 +469,15 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
     red[4 * lane + 2] = sc[1]; red[4 * lane + 3] = sb[1];
     __syncwarp();
     if (lane < nsub) {
-        float cs = 0.f, bd = 0.f;
-        for (int i = e_off; i < e_off + e_w; i++) { cs += red[2 * i]; bd += red[2 * i + 1]; }
         const size_t k = (size_t)b * LC + e_l;
-        const double cnt = (double)t.cnt[k];
-        const double err = (double)cs / cnt;
-        const double bound = 1.01 * (double)bd / cnt + 1e-5 * err + 1e-7;
-        // pack_err (tests): sign bit set, float32 error in the high word, its bound (rounded) in the low word of t.err
-        t.err[k] = pack_err ? __longlong_as_double((long long)((1ull << 63) | ((u64)__float_as_uint((float)err) << 32) | (u64)__float_as_uint((float)bound))) : err;
-        if (err - bound > threshold) { t.flag[k] = 1; t.done[k] = 1; atomicAdd(&q.ctr[4], 1); }
-        else if (err + bound < threshold) { t.flag[k] = 0; t.done[k] = 1; atomicAdd(&q.ctr[4], 1); }
-        else { q.l64[atomicAdd(&q.ctr[2], 1)] = make_int2(b, e_l); atomicAdd(&q.ctr[5], 1); }
+        if (!e_clean) {
+            atomicOr(&q.info[k], CPB_QI_T32);
+            q.lc[atomicAdd(&q.ctr[6], 1)] = make_int2(b, e_l);
+        } else {
+            float cs = 0.f, bd = 0.f;
+            for (int i = e_off; i < e_off + e_w; i++) { cs += red[2 * i]; bd += red[2 * i + 1]; }
+            cpb_q32_decide(t, q, b, e_l, k, cs, bd, threshold, pack_err);
+        }
     }
     __syncwarp();
 }
@@ -457,6 +499,89 @@ k_diffuse32(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, in
         if (j >= njobs) break;
         const int4 jb = q.sorted[j];
         cpb_q32_run(lab, dP, H, W, t, q, jb.x, jb.y, jb.z, jb.w, threshold, s_tile[warp], pack_err);
+    }
+}
+
+// k_flow_err32: screened labels in contact with another label, one warp per label (lane = bbox column).  Same per-pixel
+// arithmetic and bound as the register path, with T read from the global float32 plane: a neighbouring pixel of another
+// live label contributes that label's T (as the reference's padded array does) -- it carries the same relative bound,
+// having run the same number of iterations of the same arithmetic.  If a neighbour has no float32 T (it took the
+// float64 path) or the bound does not clear the threshold, the label goes to the float64 list together with every
+// label it touches (k_flow_err then finds the float64 T of all of them).
+CPB_DEVICE float cpb_q32_T_at(const float* CPB_RESTRICT Tb, const int* CPB_RESTRICT L, const int* CPB_RESTRICT alive,
+                              const int* CPB_RESTRICT info, int H, int W, int y, int x, int l, bool& missing) {
+    if (y < 0 || y >= H || x < 0 || x >= W) return 0.f;
+    const int p = y * W + x;
+    const int v = L[p];
+    if (v == l) return Tb[p];
+    if (!cpb_foreign_live(v, l, alive)) return 0.f;
+    if (!(info[v] & CPB_QI_T32)) { missing = true; return 0.f; }
+    return Tb[p];
+}
+
+CPB_KERNEL CPB_LAUNCH_BOUNDS(128, 8)
+k_flow_err32(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, LabelTables t, Q32 q, double threshold,
+             int pack_err) {
+    const int lane = threadIdx.x & 31;
+    const int N = H * W, LC = t.LC;
+    const int total = q.ctr[6];
+    for (;;) {
+        int j = 0;
+        if (lane == 0) j = atomicAdd(&q.ctr[7], 1);
+        j = __shfl_sync(CPB_FULL, j, 0);
+        if (j >= total) break;
+        const int2 e = q.lc[j];
+        const int b = e.x, l = e.y;
+        const size_t k = (size_t)b * LC + l;
+        const int* L = lab + (size_t)b * N;
+        const float* Tb = q.T32 + (size_t)b * N;
+        const int* alive = t.alive ? t.alive + (size_t)b * LC : nullptr;
+        const int* info = q.info + (size_t)b * LC;
+        const float* dPy = dP + ((size_t)b * 2 + 0) * N;
+        const float* dPx = dP + ((size_t)b * 2 + 1) * N;
+        const int y0 = t.ymin[k], x0 = t.xmin[k];
+        const int h = t.ymax[k] - y0 + 1, w = t.xmax[k] - x0 + 1;
+        const double xk = 11.0 * (double)t.niter[b] * 5.9604644775390625e-08;
+        const float eta = (float)(1.02 * (xk + xk * xk) + 1e-9);
+        float sc = 0.f, sb = 0.f;
+        bool missing = false;
+        if (lane < w) {
+            const int x = x0 + lane;
+            for (int r = 0; r < h; r++) {
+                const int y = y0 + r, p = y * W + x;
+                if (L[p] != l) continue;
+                const float up = cpb_q32_T_at(Tb, L, alive, info, H, W, y - 1, x, l, missing);
+                const float dn = cpb_q32_T_at(Tb, L, alive, info, H, W, y + 1, x, l, missing);
+                const float lf = cpb_q32_T_at(Tb, L, alive, info, H, W, y, x - 1, l, missing);
+                const float rt = cpb_q32_T_at(Tb, L, alive, info, H, W, y, x + 1, l, missing);
+                cpb_q32_pixel(up, dn, lf, rt, dPy[p], dPx[p], eta, sc, sb);
+            }
+        }
+        for (int sft = 16; sft; sft >>= 1) {
+            sc += __shfl_xor_sync(CPB_FULL, sc, sft);
+            sb += __shfl_xor_sync(CPB_FULL, sb, sft);
+        }
+        missing = __any_sync(CPB_FULL, missing);
+        int decided = 0;
+        if (lane == 0) {
+            if (missing) cpb_q32_queue64(q, b, l, k);
+            else decided = cpb_q32_decide(t, q, b, l, k, sc, sb, threshold, pack_err) ? 1 : 0;
+        }
+        decided = __shfl_sync(CPB_FULL, decided, 0);
+        if (!decided && lane < w) {
+            // the float64 flow error of this label reads the float64 T of every label it touches
+            const int x = x0 + lane;
+            for (int r = 0; r < h; r++) {
+                const int y = y0 + r;
+                if (L[y * W + x] != l) continue;
+                const int ny[4] = {y - 1, y + 1, y, y}, nx[4] = {x, x, x - 1, x + 1};
+                for (int q4 = 0; q4 < 4; q4++) {
+                    if (ny[q4] < 0 || ny[q4] >= H || nx[q4] < 0 || nx[q4] >= W) continue;
+                    const int v = L[ny[q4] * W + nx[q4]];
+                    if (cpb_foreign_live(v, l, alive)) cpb_q32_queue64(q, b, v, (size_t)b * LC + v);
+                }
+            }
+        }
     }
 }
 
