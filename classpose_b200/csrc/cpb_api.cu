@@ -237,7 +237,9 @@ FollowSchedule follow_schedule(int niter) {
 //   CPB_QC_FUSED=0       every label's flow error from T in global memory (k_flow_err) instead of the diffusion tile
 //   CPB_VOTE_FUSED=0     class vote as its own pass over the finished label image
 //   CPB_QC_SCREEN=0      every label through the float64 diffusion (no float32 screen in front of it)
-std::atomic<int> g_switch[5] = {{-1}, {-1}, {-1}, {-1}, {-1}};
+//   CPB_BLEND_EFT=0      blend with float64 arithmetic per element (numpy's literal op sequence) instead of the float32
+//                        error-free form (identical up to ~1e-6 of the elements by one ulp)
+std::atomic<int> g_switch[6] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
 bool switch_on(int which, const char* env_name) {
     int v = g_switch[which].load(std::memory_order_relaxed);
     if (v < 0) {
@@ -250,6 +252,7 @@ bool diffuse_queue_enabled() { return switch_on(CPB_SWITCH_DIFFUSE_QUEUE, "CPB_D
 bool qc_fused_enabled() { return switch_on(CPB_SWITCH_QC_FUSED, "CPB_QC_FUSED"); }
 bool vote_fused_enabled() { return switch_on(CPB_SWITCH_VOTE_FUSED, "CPB_VOTE_FUSED"); }
 bool qc_screen_enabled() { return switch_on(CPB_SWITCH_QC_SCREEN, "CPB_QC_SCREEN"); }
+bool blend_eft_enabled() { return switch_on(CPB_SWITCH_BLEND_EFT, "CPB_BLEND_EFT"); }
 // value 2 (tests only): the screen also runs when the caller asks for the per-label errors, and reports
 // (float32 error, bound) bit-packed into the float64 error of the labels it decided
 bool qc_screen_debug() { return g_switch[CPB_SWITCH_QC_SCREEN].load(std::memory_order_relaxed) == 2; }
@@ -818,7 +821,7 @@ const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames
 void cpb_debug_set_follow_merge(int mode) { g_follow_merge.store(mode, std::memory_order_relaxed); }
 void cpb_debug_set_switch(int which, int value) {
     if (which == CPB_SWITCH_FOLLOW_MERGE) g_follow_merge.store(value, std::memory_order_relaxed);
-    else if (which > 0 && which < 5) g_switch[which].store(value, std::memory_order_relaxed);
+    else if (which > 0 && which < 6) g_switch[which].store(value, std::memory_order_relaxed);
 }
 long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void cpb_debug_qc_stats(int32_t* out) {
@@ -968,9 +971,25 @@ int cpb_average_tiles_ex_device(const float* y, int B, int ntiles, int nch, int 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // vector path: the host vouches for the tile geometry (device arrays are not read back here)
     (void)max_cover;
-    const bool vec4 = x0_multiple_of_4 && nch <= 16 && (lx % 4 == 0) && (cx0 % 4 == 0) && (oW % 4 == 0) &&
+    const bool vec4 = x0_multiple_of_4 && (blend_eft_enabled() || nch <= 16) && (lx % 4 == 0) && (cx0 % 4 == 0) && (oW % 4 == 0) &&
                       (reinterpret_cast<uintptr_t>(y) % 16 == 0) && (reinterpret_cast<uintptr_t>(yf) % 16 == 0);
-    if (vec4) {
+    if (vec4 && blend_eft_enabled()) {
+        // float32 error-free blend: weight table and per-pixel reciprocal normaliser from two tiny kernels, scratch from
+        // the stream-ordered allocator (freed on the stream after the blend)
+        float* tab = nullptr;
+        const size_t nw = (size_t)ly * lx, nr = (size_t)oH * oW;
+        if (cudaMallocAsync(reinterpret_cast<void**>(&tab), (2 * nw + 2 * nr) * sizeof(float), st) != cudaSuccess) return (int)cudaGetLastError();
+        float* wh = tab; float* wl = tab + nw; float* rh = tab + 2 * nw; float* rl = rh + nr;
+        CPB_LAUNCH_COUNTED(k_blend_weights, dim3(blocks_for((long long)nw, 256)), dim3(256), 0, st, taper_y, taper_x, ly, lx, wh, wl);
+        CPB_LAUNCH_COUNTED(k_blend_rinv, dim3(blocks_for((long long)nr, 256)), dim3(256), 0, st, ntiles, ly, lx, y0, x0, taper_y, taper_x,
+                           cy0, cx0, oH, oW, rh, rl);
+        constexpr int G = 4;
+        const long long total = (long long)B * ((nch + G - 1) / G) * oH * (oW / 4);
+        CPB_LAUNCH_COUNTED(k_average_tiles_eft<G>, dim3(blocks_for(total, 256)), dim3(256), 0, st, y, B, ntiles, nch, ly, lx, y0, x0,
+                           flip, negate_flow, (const float*)wh, (const float*)wl, (const float*)rh, (const float*)rl, cy0, cx0, oH,
+                           oW, yf);
+        cudaFreeAsync(tab, st);
+    } else if (vec4) {
         const dim3 grid4(blocks_for((long long)B * oH * (oW / 4), 256));
 #define CPB_BLEND_ARGS y, B, ntiles, nch, ly, lx, y0, x0, flip, negate_flow, taper_y, taper_x, cy0, cx0, oH, oW, yf
         if (nch <= 4)      { CPB_LAUNCH_COUNTED(k_average_tiles_v4<4>, grid4, dim3(256), 0, st, CPB_BLEND_ARGS); }

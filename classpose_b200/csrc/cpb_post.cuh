@@ -349,6 +349,127 @@ k_average_tiles_v4(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int 
     }
 }
 
+// ---- blend without float64 on the per-element path ---------------------------------------------------------------
+// The reference accumulates acc = float32(double(acc) + double(v) * w) with a float64 weight w and ends with
+// float32(double(acc) / Navg).  Converting every element to float64 and back keeps the conversion (XU) pipe at 60-70 %
+// and the kernel at 40 % of the HBM roofline (profiles/r02: k_average_tiles_v4).  The same result comes out of float32
+// arithmetic with error-free transformations:
+//   w = wh + wl (two floats, |w - wh - wl| <= 2^-48 |w|),  v * wh = ph + pl exactly (one FMA),
+//   acc + ph = s + e exactly (two-sum),  acc' = RN32(s + (e + pl + v * wl))
+// which is the correctly rounded value of acc + v * w up to a perturbation of ~2^-23 ulp; numpy's double-rounded value can
+// differ from it only when the exact sum lies that close to a rounding boundary (probability ~1e-6 per operation).  The
+// final division uses r = 1 / Navg (float64, split the same way): acc * r = ph + pl exactly, out = RN32(ph + (pl + acc * rl)).
+// The weight table (wh, wl)[ly][lx] and the per-pixel (rh, rl)[oH][oW] depend on the geometry only and are built by two
+// tiny kernels per call.
+CPB_KERNEL k_blend_weights(const double* CPB_RESTRICT taper_y, const double* CPB_RESTRICT taper_x, int ly, int lx,
+                           float* CPB_RESTRICT wh, float* CPB_RESTRICT wl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ly * lx) return;
+    const int ry = i / lx, rx = i - ry * lx;
+    const double w = __dmul_rn(taper_y[ry], taper_x[rx]);
+    const float h = (float)w;
+    wh[i] = h; wl[i] = (float)__dsub_rn(w, (double)h);
+}
+
+CPB_KERNEL k_blend_rinv(int ntiles, int ly, int lx, const int* CPB_RESTRICT ty0, const int* CPB_RESTRICT tx0,
+                        const double* CPB_RESTRICT taper_y, const double* CPB_RESTRICT taper_x, int cy0, int cx0, int oH, int oW,
+                        float* CPB_RESTRICT rh, float* CPB_RESTRICT rl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= oH * oW) return;
+    const int Y = i / oW, X = i - Y * oW;
+    const int gy = Y + cy0, gx = X + cx0;
+    double navg = 0.0;
+    for (int j = 0; j < ntiles; j++) {
+        const int ry = gy - ty0[j], rx = gx - tx0[j];
+        if (ry < 0 || ry >= ly || rx < 0 || rx >= lx) continue;
+        navg = __dadd_rn(navg, __dmul_rn(taper_y[ry], taper_x[rx]));
+    }
+    const double r = __ddiv_rn(1.0, navg);
+    const float h = (float)r;
+    rh[i] = h; rl[i] = (float)__dsub_rn(r, (double)h);
+}
+
+CPB_DEVICE void cpb_eft_acc(float& acc, float v, float wh, float wl) {
+    const float ph = __fmul_rn(v, wh);
+    float pl = __fmaf_rn(v, wh, -ph);
+    pl = __fmaf_rn(v, wl, pl);
+    const float s = __fadd_rn(acc, ph);
+    const float bb = __fsub_rn(s, acc);
+    const float e = __fadd_rn(__fsub_rn(acc, __fsub_rn(s, bb)), __fsub_rn(ph, bb));
+    acc = __fadd_rn(s, __fadd_rn(e, pl));
+}
+
+CPB_DEVICE float cpb_eft_scale(float acc, float rh, float rl) {
+    const float ph = __fmul_rn(acc, rh);
+    float pl = __fmaf_rn(acc, rh, -ph);
+    pl = __fmaf_rn(acc, rl, pl);
+    return __fadd_rn(ph, pl);
+}
+
+// one thread per 4 consecutive output pixels of one row and a group of NCH channels (same geometry requirements as
+// k_average_tiles_v4: lx, crop offset, output width and every window origin x0 multiples of 4)
+template <int NCH>
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_average_tiles_eft(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly, int lx,
+                    const int* CPB_RESTRICT ty0, const int* CPB_RESTRICT tx0, const int* CPB_RESTRICT flip, int negate_flow,
+                    const float* CPB_RESTRICT wh, const float* CPB_RESTRICT wl, const float* CPB_RESTRICT rh,
+                    const float* CPB_RESTRICT rl, int cy0, int cx0, int oH, int oW, float* CPB_RESTRICT yf) {
+    const int oW4 = oW >> 2;
+    const int ngrp = (nch + NCH - 1) / NCH;
+    const long long total = (long long)B * ngrp * oH * oW4;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const int X4 = (int)(g % oW4);
+    const int Y = (int)((g / oW4) % oH);
+    const int cg = (int)((g / ((long long)oW4 * oH)) % ngrp);
+    const int b = (int)(g / ((long long)oW4 * oH * ngrp));
+    const int gy = Y + cy0, gx = X4 * 4 + cx0;
+    const int c0 = cg * NCH;
+    float acc[NCH][4];
+    #pragma unroll
+    for (int q = 0; q < NCH; q++) { acc[q][0] = 0.f; acc[q][1] = 0.f; acc[q][2] = 0.f; acc[q][3] = 0.f; }
+    const size_t plane = (size_t)ly * lx;
+    for (int j = 0; j < ntiles; j++) {
+        const int ry = gy - ty0[j], rx = gx - tx0[j];
+        if (ry < 0 || ry >= ly || rx < 0 || rx >= lx) continue;
+        const int f = flip[j];
+        const int sy = (f & 1) ? ly - 1 - ry : ry;
+        const int sx = (f & 2) ? lx - 4 - rx : rx;           // first of the 4 source pixels (reversed if flipped)
+        const float* src = y + (((size_t)b * ntiles + j) * nch + c0) * plane + (size_t)sy * lx + sx;
+        const float4 h4 = *reinterpret_cast<const float4*>(wh + (size_t)ry * lx + rx);
+        const float4 l4 = *reinterpret_cast<const float4*>(wl + (size_t)ry * lx + rx);
+        float4 v4[NCH];
+        #pragma unroll
+        for (int q = 0; q < NCH; q++)
+            v4[q] = (c0 + q < nch) ? *reinterpret_cast<const float4*>(src + q * plane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        #pragma unroll
+        for (int q = 0; q < NCH; q++) {
+            const int ch = c0 + q;
+            float v[4];
+            if (f & 2) { v[0] = v4[q].w; v[1] = v4[q].z; v[2] = v4[q].y; v[3] = v4[q].x; }
+            else       { v[0] = v4[q].x; v[1] = v4[q].y; v[2] = v4[q].z; v[3] = v4[q].w; }
+            if (negate_flow && ((ch == 0 && (f & 1)) || (ch == 1 && (f & 2)))) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; v[3] = -v[3]; }
+            cpb_eft_acc(acc[q][0], v[0], h4.x, l4.x);
+            cpb_eft_acc(acc[q][1], v[1], h4.y, l4.y);
+            cpb_eft_acc(acc[q][2], v[2], h4.z, l4.z);
+            cpb_eft_acc(acc[q][3], v[3], h4.w, l4.w);
+        }
+    }
+    const float4 r_h = *reinterpret_cast<const float4*>(rh + (size_t)Y * oW + X4 * 4);
+    const float4 r_l = *reinterpret_cast<const float4*>(rl + (size_t)Y * oW + X4 * 4);
+    #pragma unroll
+    for (int q = 0; q < NCH; q++) {
+        if (c0 + q < nch) {
+            float4 o;
+            o.x = cpb_eft_scale(acc[q][0], r_h.x, r_l.x);
+            o.y = cpb_eft_scale(acc[q][1], r_h.y, r_l.y);
+            o.z = cpb_eft_scale(acc[q][2], r_h.z, r_l.z);
+            o.w = cpb_eft_scale(acc[q][3], r_h.w, r_l.w);
+            *reinterpret_cast<float4*>(yf + (((size_t)b * nch + c0 + q) * oH + Y) * oW + X4 * 4) = o;
+        }
+    }
+}
+
 // k_label_offsets: single block; offsets[b] = base + sum(counts[0..b)), total = sum(counts).
 CPB_KERNEL k_label_offsets(const int* CPB_RESTRICT counts, int B, long long base,
                            long long* CPB_RESTRICT offsets, long long* CPB_RESTRICT total) {

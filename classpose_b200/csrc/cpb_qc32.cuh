@@ -578,7 +578,8 @@ k_flow_err32(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, i
                 for (int q4 = 0; q4 < 4; q4++) {
                     if (ny[q4] < 0 || ny[q4] >= H || nx[q4] < 0 || nx[q4] >= W) continue;
                     const int v = L[ny[q4] * W + nx[q4]];
-                    if (cpb_foreign_live(v, l, alive)) cpb_q32_queue64(q, b, v, (size_t)b * LC + v);
+                    // (labels beyond the warp kernels always get their float64 T from the block kernel k_diffuse)
+                    if (cpb_foreign_live(v, l, alive) && (info[v] & 7) != CPB_Q32_CLSBIG) cpb_q32_queue64(q, b, v, (size_t)b * LC + v);
                 }
             }
         }

@@ -99,6 +99,9 @@ void cpb_debug_set_follow_merge(int mode);
 #define CPB_SWITCH_VOTE_FUSED 3     /* CPB_VOTE_FUSED: class vote folded into the final label pass */
 #define CPB_SWITCH_QC_SCREEN 4      /* CPB_QC_SCREEN: float32 screen with a proven error bound in front of the float64
                                        flow check; labels it cannot decide take the float64 path (same removal set) */
+#define CPB_SWITCH_BLEND_EFT 5      /* CPB_BLEND_EFT: taper blend in float32 with error-free transformations (0: float64
+                                       arithmetic per element, numpy's literal sequence; results agree to one ulp on
+                                       ~1e-6 of the elements) */
 void cpb_debug_set_switch(int which, int value);
 /* number of kernels this library has launched in this process (statistics for the benchmark) */
 long long cpb_debug_launch_count(void);

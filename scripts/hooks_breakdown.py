@@ -41,3 +41,6 @@ cm8 = plan.vote(l3)
 print("class image uint8 -> int64       %7.1f us" % bench(lambda: cm8.astype(np.int64)))
 print("hook C total (cached labels)     %7.1f us" % bench(lambda: models.compute_class_masks(m, lg)))
 print("hook C total (general path)      %7.1f us" % bench(lambda: models.compute_class_masks(m.copy(), lg), n=50))
+import torch
+st = eng.profile_stages(torch.from_numpy(t["dP"][None]).cuda(), torch.from_numpy(t["cellprob"][None]).cuda(), None)
+print("single-tile stage times (us):", {k: round(1e3 * v, 1) for k, v in st.items() if v > 0}, "sum", round(1e3 * sum(st.values()), 1))

@@ -305,6 +305,14 @@ def case_flow_qc_screen_is_decision_exact(be):
         lab = inv.reshape(lab.shape).astype(np.int32)
         if lab.max() > 0:
             jobs.append((lab, (5.0 * dynamics.masks_to_flows(lab) + rng.normal(0, 1.2, size=(2,) + lab.shape)).astype(np.float32)))
+    # a label beyond the warp kernels (44 px wide: block kernels, float64 only) in flat contact with small ones: the small
+    # neighbours find no float32 T for it and must fall back together with whatever they touch
+    yy, xx = np.mgrid[0:96, 0:128]
+    seeds = [(48, 48, 22), (48, 78, 9), (20, 40, 9), (78, 60, 8), (30, 100, 7), (44, 98, 7), (80, 20, 6)]
+    d = np.stack([(yy - a) ** 2 + (xx - b_) ** 2 for a, b_, _ in seeds])
+    near = d.argmin(0)
+    lab = np.where(d.min(0) <= np.array([r * r for _, _, r in seeds])[near], near + 1, 0).astype(np.int32)
+    jobs.append((lab, (5.0 * dynamics.masks_to_flows(lab) + rng.normal(0, 0.8, size=(2,) + lab.shape)).astype(np.float32)))
     n_screened = n_left = n_total = 0
     try:
         for lab, dP in jobs:
@@ -515,15 +523,27 @@ def case_average_tiles(be):
         ty, tx = btf.taper_1d(256, 256)
         out = be.average_tiles(y[None], geo["y0"], geo["x0"], geo["flip"], nch == 3 and augment, ty, tx, Ly, Lx,
                                (0, 0, 0, 0))
+        # default vector path: float32 arithmetic with error-free transformations -- within 1e-6 of numpy's float64
+        # accumulate everywhere and bit-identical on (far) more than 99.9 % of the elements
         np.testing.assert_allclose(out[0], ref, rtol=0, atol=1e-6)
-        assert np.mean(out[0] == ref) > 0.999
+        assert np.mean(out[0] == ref) > 0.9999, np.mean(out[0] == ref)
+        ulp = np.spacing(np.abs(ref).astype(np.float32))
+        assert (np.abs(out[0] - ref) <= ulp).all()
         crop = (8, 8, 8, 8)
         outc = be.average_tiles(y[None], geo["y0"], geo["x0"], geo["flip"], nch == 3 and augment, ty, tx, Ly, Lx, crop)
         np.testing.assert_array_equal(outc[0], out[0][:, 8:-8, 8:-8])
-        # the scalar kernel (no geometry promises) gives bit-identical results to the 128-bit one
+        # CPB_BLEND_EFT=0: numpy's literal float64 sequence per element; the scalar kernel (no geometry promises) and
+        # the 128-bit one are then bit-identical to each other and > 99.9 % identical to the oracle
+        try:
+            be.set_switch(5, 0)
+            out64 = be.average_tiles(y[None], geo["y0"], geo["x0"], geo["flip"], nch == 3 and augment, ty, tx, Ly, Lx, crop)
+        finally:
+            be.set_switch(5, -1)
         outs = be.average_tiles(y[None], geo["y0"], geo["x0"], geo["flip"], nch == 3 and augment, ty, tx, Ly, Lx, crop,
                                 vector=False)
-        np.testing.assert_array_equal(outs, outc)
+        np.testing.assert_array_equal(outs, out64)
+        np.testing.assert_allclose(out64[0], ref[:, 8:-8, 8:-8], rtol=0, atol=1e-6)
+        assert np.mean(out64[0] == ref[:, 8:-8, 8:-8]) > 0.999
     # odd geometry: origins not multiples of 4 -> scalar path only
     y = rng.normal(size=(2, 3, 2, 30, 50)).astype(np.float32)
     y0, x0 = np.array([0, 7, 11]), np.array([0, 9, 3])

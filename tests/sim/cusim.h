@@ -54,6 +54,8 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpy
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { *p = malloc(n); return *p ? 0 : 2; }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "cusim"; }

@@ -197,6 +197,36 @@ def test_single_tile_fast_path_graph_and_identity_cache():
     assert not cmz.any() and uz.tolist() == [0]
 
 
+def test_touching_workload_screen_equals_float64_path():
+    """The hostile generator (Voronoi-clipped touching cells, 15 % of them with noise for flows, a 43-px cell every 8th tile,
+    a ring every 16th): the float32 flow-check screen -- isolated labels in registers, labels in contact through the
+    float32 T plane -- must give exactly the label images of the float64-only path, and must actually decide most labels."""
+    import torch
+    from classpose_b200 import synth
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    data = synth.make_batch(48, 256, 256, 7, seed=5, device=eng.device, style="touching", chunk=16)
+    dP, cp, lg = data["dP"], data["cellprob"], data["logits"]
+    try:
+        eng.lib.cpb_debug_set_switch(4, 0)
+        m0, c0, cc0, _ = eng.compute_masks_batch(dP, cp, lg)
+        torch.cuda.synchronize()
+        eng.lib.cpb_debug_set_switch(4, 1)
+        m1, c1, cc1, _ = eng.compute_masks_batch(dP, cp, lg)
+        torch.cuda.synchronize()
+    finally:
+        eng.lib.cpb_debug_set_switch(4, -1)
+    assert torch.equal(m0, m1) and torch.equal(c0, c1) and torch.equal(cc0, cc1)
+    _, qc = eng.profile_stages(dP, cp, lg, with_qc=True)
+    assert qc["screen_decided"] > 3 * qc["float64_labels"], qc
+    assert int(c1.sum()) > 48 * 40           # the tiles do hold cells after the flow check
+    # and the oracle agrees on a few of them
+    for b in (0, 3, 5):
+        ref = odyn.resize_and_compute_masks(dP[b].cpu().numpy(), cp[b].cpu().numpy())
+        r = metrics.match_instances(ref, m1[b].cpu().numpy())
+        assert r["f1"] >= 0.99, (b, r)
+
+
 def test_concurrent_calls_from_two_threads():
     """The reference runs two inference threads per process; calls must be re-entrant."""
     import threading
