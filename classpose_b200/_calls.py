@@ -64,7 +64,7 @@ class Calls:
                                                         C.byref(prm), self._p(masks), self._p(counts),
                                                         self._p(cell_class), None, self._p(ws), n, self.stream(), ms)
         check(rc, "cpb_compute_masks_profiled_device")
-        qc = (C.c_int32 * 16)()
+        qc = (C.c_int32 * 24)()
         self.lib.cpb_debug_qc_stats(qc)
         stats = {"screen_jobs": int(qc[0]), "float64_labels": int(qc[2]), "screen_decided": int(qc[4]),
                  "screen_undecided": int(qc[5])}

@@ -3,7 +3,7 @@
 // mutable state; every call runs on the caller's stream with the caller's workspace.
 #include "classpose_b200.h"
 
-#define CPB_QCTR_INTS 16
+#define CPB_QCTR_INTS 24
 #include "cpb_platform.h"
 #include "cpb_common.cuh"
 #include "cpb_flow.cuh"
@@ -415,7 +415,7 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
         cudaMemsetAsync(w.t.niter, 0, B * sizeof(int), st);
         CPB_LAUNCH_COUNTED(k_qc_scan32, dim3(tile_slices(H, W), B), dim3(256), 0, st, masks, H, W, w.t, w.q, w.todo, todo_n, screen);
         CPB_CHECK_LAUNCH();
-        CPB_LAUNCH_COUNTED(k_qc_pack, dim3(B), dim3(128), 0, st, w.t, w.q);
+        CPB_LAUNCH_COUNTED(k_qc_pack, dim3(B), dim3(32 * CPB_Q32_NCLS), 0, st, w.t, w.q);
         CPB_CHECK_LAUNCH();
         CPB_LAUNCH_COUNTED(k_centres, dim3(sm_count() * 8), dim3(CPB_QC_THREADS), 0, st, masks, H, W, w.t, 1, big);
         CPB_CHECK_LAUNCH();
@@ -983,11 +983,23 @@ int cpb_average_tiles_ex_device(const float* y, int B, int ntiles, int nch, int 
         CPB_LAUNCH_COUNTED(k_blend_weights, dim3(blocks_for((long long)nw, 256)), dim3(256), 0, st, taper_y, taper_x, ly, lx, wh, wl);
         CPB_LAUNCH_COUNTED(k_blend_rinv, dim3(blocks_for((long long)nr, 256)), dim3(256), 0, st, ntiles, ly, lx, y0, x0, taper_y, taper_x,
                            cy0, cx0, oH, oW, rh, rl);
-        constexpr int G = 4;
-        const long long total = (long long)B * ((nch + G - 1) / G) * oH * (oW / 4);
-        CPB_LAUNCH_COUNTED(k_average_tiles_eft<G>, dim3(blocks_for(total, 256)), dim3(256), 0, st, y, B, ntiles, nch, ly, lx, y0, x0,
-                           flip, negate_flow, (const float*)wh, (const float*)wl, (const float*)rh, (const float*)rl, cy0, cx0, oH,
-                           oW, yf);
+        // channel groups of at most 5 (register budget), none of them padded: 3 -> 3, 5 -> 5, 7 -> 4 + 3, 10 -> 5 + 5
+        const dim3 grid(blocks_for((long long)B * oH * (oW / 4), 256));
+#define CPB_EFT_LAUNCH(N) CPB_LAUNCH_COUNTED(k_average_tiles_eft<N>, grid, dim3(256), 0, st, y, B, ntiles, nch, c0, ly, lx, y0, x0, flip, \
+                           negate_flow, (const float*)wh, (const float*)wl, (const float*)rh, (const float*)rl, cy0, cx0, oH, oW, yf)
+        for (int c0 = 0; c0 < nch;) {
+            const int rem = nch - c0;
+            const int n = rem <= 5 ? rem : (rem == 6 ? 3 : (rem == 7 ? 4 : 5));
+            switch (n) {
+                case 1: CPB_EFT_LAUNCH(1); break;
+                case 2: CPB_EFT_LAUNCH(2); break;
+                case 3: CPB_EFT_LAUNCH(3); break;
+                case 4: CPB_EFT_LAUNCH(4); break;
+                default: CPB_EFT_LAUNCH(5); break;
+            }
+            c0 += n;
+        }
+#undef CPB_EFT_LAUNCH
         cudaFreeAsync(tab, st);
     } else if (vec4) {
         const dim3 grid4(blocks_for((long long)B * oH * (oW / 4), 256));

@@ -389,14 +389,16 @@ CPB_KERNEL k_blend_rinv(int ntiles, int ly, int lx, const int* CPB_RESTRICT ty0,
     rh[i] = h; rl[i] = (float)__dsub_rn(r, (double)h);
 }
 
-CPB_DEVICE void cpb_eft_acc(float& acc, float v, float wh, float wl) {
-    const float ph = __fmul_rn(v, wh);
-    float pl = __fmaf_rn(v, wh, -ph);
-    pl = __fmaf_rn(v, wl, pl);
-    const float s = __fadd_rn(acc, ph);
-    const float bb = __fsub_rn(s, acc);
-    const float e = __fadd_rn(__fsub_rn(acc, __fsub_rn(s, bb)), __fsub_rn(ph, bb));
-    acc = __fadd_rn(s, __fadd_rn(e, pl));
+// two pixels per instruction (packed f32x2: every half is an ordinary IEEE round-to-nearest operation).
+// nwh = -wh, so that v * nwh = -(v * wh) exactly and pl = fma(v, wh, -ph) needs no packed negation.
+CPB_DEVICE void cpb_eft_acc2(pf2& acc, pf2 v, pf2 wh, pf2 nwh, pf2 wl) {
+    const pf2 ph = pf2_mul(v, wh);
+    pf2 pl = pf2_fma(v, wh, pf2_mul(v, nwh));
+    pl = pf2_fma(v, wl, pl);
+    const pf2 s = pf2_add(acc, ph);
+    const pf2 bb = pf2_sub(s, acc);
+    const pf2 e = pf2_add(pf2_sub(acc, pf2_sub(s, bb)), pf2_sub(ph, bb));
+    acc = pf2_add(s, pf2_add(e, pl));
 }
 
 CPB_DEVICE float cpb_eft_scale(float acc, float rh, float rl) {
@@ -406,28 +408,27 @@ CPB_DEVICE float cpb_eft_scale(float acc, float rh, float rl) {
     return __fadd_rn(ph, pl);
 }
 
-// one thread per 4 consecutive output pixels of one row and a group of NCH channels (same geometry requirements as
-// k_average_tiles_v4: lx, crop offset, output width and every window origin x0 multiples of 4)
+// one thread per 4 consecutive output pixels of one row and NCH channels starting at c0 (same geometry requirements as
+// k_average_tiles_v4: lx, crop offset, output width and every window origin x0 multiples of 4).  The flip / sign cases
+// are warp-uniform branches (every thread of a warp sees the same tile), a sign change is folded into the weights
+// ((-v) * w == v * (-w) exactly).
 template <int NCH>
-CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
-k_average_tiles_eft(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int ly, int lx,
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, (NCH > 4 ? 2 : 4))
+k_average_tiles_eft(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int c0, int ly, int lx,
                     const int* CPB_RESTRICT ty0, const int* CPB_RESTRICT tx0, const int* CPB_RESTRICT flip, int negate_flow,
                     const float* CPB_RESTRICT wh, const float* CPB_RESTRICT wl, const float* CPB_RESTRICT rh,
                     const float* CPB_RESTRICT rl, int cy0, int cx0, int oH, int oW, float* CPB_RESTRICT yf) {
     const int oW4 = oW >> 2;
-    const int ngrp = (nch + NCH - 1) / NCH;
-    const long long total = (long long)B * ngrp * oH * oW4;
+    const long long total = (long long)B * oH * oW4;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total) return;
     const int X4 = (int)(g % oW4);
     const int Y = (int)((g / oW4) % oH);
-    const int cg = (int)((g / ((long long)oW4 * oH)) % ngrp);
-    const int b = (int)(g / ((long long)oW4 * oH * ngrp));
+    const int b = (int)(g / ((long long)oW4 * oH));
     const int gy = Y + cy0, gx = X4 * 4 + cx0;
-    const int c0 = cg * NCH;
-    float acc[NCH][4];
+    pf2 acc[NCH][2];
     #pragma unroll
-    for (int q = 0; q < NCH; q++) { acc[q][0] = 0.f; acc[q][1] = 0.f; acc[q][2] = 0.f; acc[q][3] = 0.f; }
+    for (int q = 0; q < NCH; q++) { acc[q][0] = pf2_make(0.f, 0.f); acc[q][1] = pf2_make(0.f, 0.f); }
     const size_t plane = (size_t)ly * lx;
     for (int j = 0; j < ntiles; j++) {
         const int ry = gy - ty0[j], rx = gx - tx0[j];
@@ -436,37 +437,36 @@ k_average_tiles_eft(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int
         const int sy = (f & 1) ? ly - 1 - ry : ry;
         const int sx = (f & 2) ? lx - 4 - rx : rx;           // first of the 4 source pixels (reversed if flipped)
         const float* src = y + (((size_t)b * ntiles + j) * nch + c0) * plane + (size_t)sy * lx + sx;
-        const float4 h4 = *reinterpret_cast<const float4*>(wh + (size_t)ry * lx + rx);
-        const float4 l4 = *reinterpret_cast<const float4*>(wl + (size_t)ry * lx + rx);
         float4 v4[NCH];
         #pragma unroll
-        for (int q = 0; q < NCH; q++)
-            v4[q] = (c0 + q < nch) ? *reinterpret_cast<const float4*>(src + q * plane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < NCH; q++) v4[q] = *reinterpret_cast<const float4*>(src + q * plane);
+        const float4 h4 = *reinterpret_cast<const float4*>(wh + (size_t)ry * lx + rx);
+        const float4 l4 = *reinterpret_cast<const float4*>(wl + (size_t)ry * lx + rx);
+        const pf2 h01 = pf2_make(h4.x, h4.y), h23 = pf2_make(h4.z, h4.w), l01 = pf2_make(l4.x, l4.y), l23 = pf2_make(l4.z, l4.w);
+        const pf2 n01 = pf2_make(-h4.x, -h4.y), n23 = pf2_make(-h4.z, -h4.w), m01 = pf2_make(-l4.x, -l4.y), m23 = pf2_make(-l4.z, -l4.w);
         #pragma unroll
         for (int q = 0; q < NCH; q++) {
             const int ch = c0 + q;
-            float v[4];
-            if (f & 2) { v[0] = v4[q].w; v[1] = v4[q].z; v[2] = v4[q].y; v[3] = v4[q].x; }
-            else       { v[0] = v4[q].x; v[1] = v4[q].y; v[2] = v4[q].z; v[3] = v4[q].w; }
-            if (negate_flow && ((ch == 0 && (f & 1)) || (ch == 1 && (f & 2)))) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; v[3] = -v[3]; }
-            cpb_eft_acc(acc[q][0], v[0], h4.x, l4.x);
-            cpb_eft_acc(acc[q][1], v[1], h4.y, l4.y);
-            cpb_eft_acc(acc[q][2], v[2], h4.z, l4.z);
-            cpb_eft_acc(acc[q][3], v[3], h4.w, l4.w);
+            const bool neg = negate_flow && ((ch == 0 && (f & 1)) || (ch == 1 && (f & 2)));       // warp-uniform
+            pf2 va, vb;
+            if (f & 2) { va = pf2_make(v4[q].w, v4[q].z); vb = pf2_make(v4[q].y, v4[q].x); }
+            else       { va = pf2_make(v4[q].x, v4[q].y); vb = pf2_make(v4[q].z, v4[q].w); }
+            if (neg) { cpb_eft_acc2(acc[q][0], va, n01, h01, m01); cpb_eft_acc2(acc[q][1], vb, n23, h23, m23); }
+            else     { cpb_eft_acc2(acc[q][0], va, h01, n01, l01); cpb_eft_acc2(acc[q][1], vb, h23, n23, l23); }
         }
     }
     const float4 r_h = *reinterpret_cast<const float4*>(rh + (size_t)Y * oW + X4 * 4);
     const float4 r_l = *reinterpret_cast<const float4*>(rl + (size_t)Y * oW + X4 * 4);
     #pragma unroll
     for (int q = 0; q < NCH; q++) {
-        if (c0 + q < nch) {
-            float4 o;
-            o.x = cpb_eft_scale(acc[q][0], r_h.x, r_l.x);
-            o.y = cpb_eft_scale(acc[q][1], r_h.y, r_l.y);
-            o.z = cpb_eft_scale(acc[q][2], r_h.z, r_l.z);
-            o.w = cpb_eft_scale(acc[q][3], r_h.w, r_l.w);
-            *reinterpret_cast<float4*>(yf + (((size_t)b * nch + c0 + q) * oH + Y) * oW + X4 * 4) = o;
-        }
+        float a0, a1, a2, a3;
+        pf2_get(acc[q][0], a0, a1); pf2_get(acc[q][1], a2, a3);
+        float4 o;
+        o.x = cpb_eft_scale(a0, r_h.x, r_l.x);
+        o.y = cpb_eft_scale(a1, r_h.y, r_l.y);
+        o.z = cpb_eft_scale(a2, r_h.z, r_l.z);
+        o.w = cpb_eft_scale(a3, r_h.w, r_l.w);
+        *reinterpret_cast<float4*>(yf + (((size_t)b * nch + c0 + q) * oH + Y) * oW + X4 * 4) = o;
     }
 }
 

@@ -34,9 +34,10 @@
 
 #define CPB_Q32_MAXSUB 8
 #define CPB_Q32_COLS 64            // columns of a job strip (two per lane); column 63 stays empty
-#define CPB_Q32_NCLS 4             // register-row classes NR = 9, 13, 17, 21 (centre row RC = NR / 2 = 4, 6, 8, 10)
-#define CPB_Q32_CLS64 4            // info class of labels left to the float64 warp kernel
-#define CPB_Q32_CLSBIG 5           // info class of labels left to the block kernels
+#define CPB_Q32_NCLS 6             // register-row classes NR = 9, 13, 17, 21, 25, 29 (centre row RC = NR / 2 = 4 .. 14)
+#define CPB_Q32_MAXNR 29
+#define CPB_Q32_CLS64 6            // info class of labels left to the float64 warp kernel
+#define CPB_Q32_CLSBIG 7           // info class of labels left to the block kernels
 
 #define CPB_QI_CLEAN 8             // info bit: no pixel of another live label in the bbox grown by one
 #define CPB_QI_T32 16              // info bit: the screen wrote this label's float32 T to the global plane
@@ -45,9 +46,9 @@
 // counters: [0] jobs appended, [1] jobs pulled, [2] float64 list appended, [3] float64 list pulled,
 //           [4] labels decided by the screen, [5] labels the screen left undecided (statistics),
 //           [6] contact list appended, [7] contact list pulled,
-//           [8..11] jobs per class, [12..15] scatter cursors of k_q32_sort
+//           [8..13] jobs per class, [14..19] scatter cursors of k_q32_sort
 #ifndef CPB_QCTR_INTS
-#define CPB_QCTR_INTS 16
+#define CPB_QCTR_INTS 24
 #endif
 
 struct Q32 {
@@ -57,7 +58,7 @@ struct Q32 {
     int4* sorted;     // [B*LC]  the same jobs, tallest class first (k_q32_sort)
     int2* l64;        // [B*LC]  (tile, label) for the float64 warp kernel
     int2* lc;         // [B*LC]  (tile, label): screened labels in contact with another label (k_flow_err32)
-    int* cls_cnt;     // [B*4]   screened labels per tile and class
+    int* cls_cnt;     // [B*6]   screened labels per tile and class
     float* T32;       // [B*N]   float32 T of the screened labels in contact (their neighbours read it)
     int* ctr;         // [CPB_QCTR_INTS]
 };
@@ -69,7 +70,7 @@ CPB_DEVICE void cpb_q32_queue64(const Q32& q, int b, int l, size_t k) {
 
 CPB_DEVICE int cpb_q32_class(int cr, int h) {
     const int rho = max(cr, h - 1 - cr);
-    return rho <= 4 ? 0 : rho <= 6 ? 1 : rho <= 8 ? 2 : rho <= 10 ? 3 : CPB_Q32_CLS64;
+    return rho <= 4 ? 0 : rho <= 6 ? 1 : rho <= 8 ? 2 : rho <= 10 ? 3 : rho <= 12 ? 4 : rho <= 14 ? 5 : CPB_Q32_CLS64;
 }
 
 // ---- k_qc_scan32: one warp per label, grid (slices, B) ------------------------------------------------------
@@ -185,9 +186,9 @@ k_qc_scan32(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, Q32 q, int
     if (lane == 0 && ext > 0) atomicMax(&t.niter[b], ext);
 }
 
-// ---- k_qc_pack: one block of four warps per tile -------------------------------------------------------------
+// ---- k_qc_pack: one block of CPB_Q32_NCLS warps per tile -----------------------------------------------------
 //  the screen's labels grouped by class into q.ent; warp c packs class c greedily into jobs of up to 8 labels / 63 columns
-CPB_KERNEL CPB_LAUNCH_BOUNDS(128, 8)
+CPB_KERNEL CPB_LAUNCH_BOUNDS(32 * CPB_Q32_NCLS, 8)
 k_qc_pack(LabelTables t, Q32 q) {
     CPB_SHARED int s_base[CPB_Q32_NCLS], s_pos[CPB_Q32_NCLS];
     const int b = blockIdx.x, LC = t.LC;
@@ -235,7 +236,7 @@ CPB_KERNEL k_q32_sort(Q32 q) {
         const int4 jb = q.jobs[i];
         int base = 0;
         for (int c = CPB_Q32_NCLS - 1; c > jb.w; c--) base += q.ctr[8 + c];
-        q.sorted[base + atomicAdd(&q.ctr[12 + jb.w], 1)] = jb;
+        q.sorted[base + atomicAdd(&q.ctr[14 + jb.w], 1)] = jb;
     }
 }
 
@@ -246,12 +247,16 @@ CPB_DEVICE pf2 pf2_make(float x, float y) { pf2 r; r.x = x; r.y = y; return r; }
 CPB_DEVICE void pf2_get(pf2 a, float& x, float& y) { x = a.x; y = a.y; }
 CPB_DEVICE pf2 pf2_add(pf2 a, pf2 b) { return pf2_make(a.x + b.x, a.y + b.y); }
 CPB_DEVICE pf2 pf2_mul(pf2 a, pf2 b) { return pf2_make(a.x * b.x, a.y * b.y); }
+CPB_DEVICE pf2 pf2_sub(pf2 a, pf2 b) { return pf2_make(a.x - b.x, a.y - b.y); }
+CPB_DEVICE pf2 pf2_fma(pf2 a, pf2 b, pf2 c) { return pf2_make(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
 #else
 typedef u64 pf2;
 CPB_DEVICE pf2 pf2_make(float x, float y) { return cpb_pk(x, y); }
 CPB_DEVICE void pf2_get(pf2 a, float& x, float& y) { cpb_upk(a, x, y); }
 CPB_DEVICE pf2 pf2_add(pf2 a, pf2 b) { return cpb_add2(a, b); }
 CPB_DEVICE pf2 pf2_mul(pf2 a, pf2 b) { return cpb_mul2(a, b); }
+CPB_DEVICE pf2 pf2_sub(pf2 a, pf2 b) { return cpb_sub2(a, b); }
+CPB_DEVICE pf2 pf2_fma(pf2 a, pf2 b, pf2 c) { return cpb_fma2(a, b, c); }
 #endif
 
 // approximate reciprocal / square roots (MUFU, <= 2 ulp): their error is part of the bound's slack below
@@ -309,15 +314,18 @@ struct Q32Cols { int l[2], x[2], yb[2]; float inj[2]; };
 // n_it iterations and goes back to the tile at the end as (member ? T : -0.0f) -- the sign bit carries membership.
 // Only this part is instantiated per row class; the set-up and the error pass are rolled loops shared by all classes
 // (fully unrolled they are ~5000 instructions per class, which the instruction cache does not forgive).
-template <int NR>
+template <int NR, bool MREG>       // MREG: M in registers (NR <= 21); otherwise M is re-read from the tile every row
 CPB_DEVICE void cpb_q32_iterate(float2* S, float inj0, float inj1, int n_it) {
     constexpr int RC = NR / 2;
+    constexpr int NM = MREG ? NR : 1;
     const int lane = threadIdx.x & 31;
-    pf2 T[NR], M[NR];
+    pf2 T[NR], M[NM];
     #pragma unroll
     for (int r = 0; r < NR; r++) {
-        const float2 m = S[(r + 1) * 32 + lane];
-        M[r] = pf2_make(m.x, m.y);
+        if (MREG) {
+            const float2 m = S[(r + 1) * 32 + lane];
+            M[r] = pf2_make(m.x, m.y);
+        }
         T[r] = pf2_make(0.f, 0.f);
     }
     const pf2 J = pf2_make(inj0, inj1);
@@ -335,7 +343,10 @@ CPB_DEVICE void cpb_q32_iterate(float2* S, float inj0, float inj1, int n_it) {
             const float ly = __shfl_sync(CPB_FULL, vy, lm);          // column 2j-1
             const float rx = __shfl_sync(CPB_FULL, vx, lp);          // column 2j+2
             const float s = __fadd_rn(vx, vy);
-            T[r] = pf2_mul(pf2_add(pf2_make(s, s), pf2_make(ly, rx)), M[r]);    // ({s, s} is a broadcast operand)
+            pf2 m;
+            if (MREG) m = M[r];
+            else { const float2 mm = S[(r + 1) * 32 + lane]; m = pf2_make(mm.x, mm.y); }
+            T[r] = pf2_mul(pf2_add(pf2_make(s, s), pf2_make(ly, rx)), m);    // ({s, s} is a broadcast operand)
             vcur = vnext;
         }
     }
@@ -343,14 +354,15 @@ CPB_DEVICE void cpb_q32_iterate(float2* S, float inj0, float inj1, int n_it) {
     for (int r = 0; r < NR; r++) {
         float tx, ty, mx, my;
         pf2_get(T[r], tx, ty);
-        pf2_get(M[r], mx, my);
+        if (MREG) pf2_get(M[r], mx, my);
+        else { const float2 mm = S[(r + 1) * 32 + lane]; mx = mm.x; my = mm.y; }
         S[(r + 1) * 32 + lane] = make_float2(mx != 0.f ? tx : -0.0f, my != 0.f ? ty : -0.0f);
     }
 }
 
 CPB_DEVICE bool cpb_q32_member(float v) { return (__float_as_uint(v) >> 31) == 0u; }
 
-// One job: set-up (rolled), iteration (per class), error pass (rolled).  S: the warp's tile of (21 + 2) x 32 float2.
+// One job: set-up (rolled), iteration (per class), error pass (rolled).  S: the warp's tile of (29 + 2) x 32 float2.
 CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, const LabelTables& t,
                             const Q32& q, int b, int first, int nsub, int cls, double threshold, float2* S, int pack_err) {
     const int NR = 9 + 4 * cls, RC = NR / 2;
@@ -419,10 +431,12 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
     S[lane] = make_float2(-0.0f, -0.0f);
     S[(NR + 1) * 32 + lane] = make_float2(-0.0f, -0.0f);
     switch (cls) {              // each lane reads back only what it wrote: no warp barrier needed here
-        case 0: cpb_q32_iterate<9>(S, c.inj[0], c.inj[1], n_it); break;
-        case 1: cpb_q32_iterate<13>(S, c.inj[0], c.inj[1], n_it); break;
-        case 2: cpb_q32_iterate<17>(S, c.inj[0], c.inj[1], n_it); break;
-        default: cpb_q32_iterate<21>(S, c.inj[0], c.inj[1], n_it); break;
+        case 0: cpb_q32_iterate<9, true>(S, c.inj[0], c.inj[1], n_it); break;
+        case 1: cpb_q32_iterate<13, true>(S, c.inj[0], c.inj[1], n_it); break;
+        case 2: cpb_q32_iterate<17, true>(S, c.inj[0], c.inj[1], n_it); break;
+        case 3: cpb_q32_iterate<21, true>(S, c.inj[0], c.inj[1], n_it); break;
+        case 4: cpb_q32_iterate<25, false>(S, c.inj[0], c.inj[1], n_it); break;
+        default: cpb_q32_iterate<29, false>(S, c.inj[0], c.inj[1], n_it); break;
     }
     __syncwarp();
     // flow error and its bound from the tile
@@ -489,7 +503,7 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
 CPB_KERNEL CPB_LAUNCH_BOUNDS(128, CPB_Q32_MINBLOCKS)
 k_diffuse32(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, LabelTables t, Q32 q, double threshold,
             int pack_err) {
-    CPB_SHARED float2 s_tile[4][(21 + 2) * 32];
+    CPB_SHARED float2 s_tile[4][(CPB_Q32_MAXNR + 2) * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int njobs = q.ctr[0];
     for (;;) {

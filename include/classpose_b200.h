@@ -105,7 +105,7 @@ void cpb_debug_set_follow_merge(int mode);
 void cpb_debug_set_switch(int which, int value);
 /* number of kernels this library has launched in this process (statistics for the benchmark) */
 long long cpb_debug_launch_count(void);
-/* flow-check counters of the last cpb_compute_masks_profiled_device call in this process, 16 ints: [0] float32 screen
+/* flow-check counters of the last cpb_compute_masks_profiled_device call in this process, 24 ints: [0] float32 screen
  * jobs, [2] labels that took the float64 warp kernel (contact, too large for the screen, or undecided), [4] labels the
  * screen decided, [5] labels the screen left undecided (statistics for the benchmark and the tests) */
 void cpb_debug_qc_stats(int32_t* out);

@@ -218,7 +218,7 @@ def test_touching_workload_screen_equals_float64_path():
         eng.lib.cpb_debug_set_switch(4, -1)
     assert torch.equal(m0, m1) and torch.equal(c0, c1) and torch.equal(cc0, cc1)
     _, qc = eng.profile_stages(dP, cp, lg, with_qc=True)
-    assert qc["screen_decided"] > 3 * qc["float64_labels"], qc
+    assert qc["screen_decided"] > 2 * qc["float64_labels"], qc
     assert int(c1.sum()) > 48 * 40           # the tiles do hold cells after the flow check
     # and the oracle agrees on a few of them
     for b in (0, 3, 5):
