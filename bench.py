@@ -595,7 +595,7 @@ def brief_extras(eng, dev, peak):
     driver's line carries them: tiles/s, cells/s, per-stage device times, flow-check statistics."""
     import torch
     out = {}
-    for name, B in (("wsi", 512), ("tta", 128), ("dense", 64), ("touching", 512)):
+    for name, B in (("wsi", 512), ("tta", 256), ("dense", 64), ("touching", 512)):
         try:
             cfg, step, (dP, cellprob, logits), extra = build_extra(eng, dev, name, B, seed=99)
             for _ in range(3):
