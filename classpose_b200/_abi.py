@@ -74,6 +74,8 @@ SIGNATURES = {
     "cpb_remove_border_instances_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "cpb_average_tiles_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "cpb_average_tiles_ex_device": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "cpb_eval_tail_device": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I,
+                                       C.POINTER(Params), _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "cpb_cell_contours_device": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _Z, _P]),
     "cpb_dedup_workspace_bytes": (_Z, [_L]),
     "cpb_dedup_cells_device": (C.c_int, [_P, _P, _P, _L, _D, _P, _P, _P, _Z, _P]),

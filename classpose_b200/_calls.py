@@ -162,6 +162,34 @@ class Calls:
         self.mem.keep_alive(y, y0, x0, flip, taper_y, taper_x)
         return yf
 
+    def eval_tail(self, y_flows, y_logits, y0, x0, flip, augment, taper_y, taper_x, Ly, Lx, crop, params: Params | None = None,
+                  want_class_masks=False):
+        """Fused tail of ClassposeModel.eval on the network's sub-tile outputs (cpb_eval_tail_device).
+        Returns (masks, counts, cell_class, class_masks, dP, cellprob, logits)."""
+        B, nt, three, ly, lx = y_flows.shape
+        assert three == 3
+        Cc = 0 if y_logits is None else int(y_logits.shape[2])
+        cy0, cy1, cx0, cx1 = crop
+        H, W = Ly - cy0 - cy1, Lx - cx0 - cx1
+        prm = params or make_params()
+        LC = self.label_capacity(H, W)
+        dP = self.mem.empty((B, 2, H, W), "float32")
+        cellprob = self.mem.empty((B, H, W), "float32")
+        logits = self.mem.empty((B, Cc, H, W), "float32") if Cc else None
+        masks = self.mem.empty((B, H, W), "int32")
+        counts = self.mem.empty((B,), "int32")
+        cell_class = self.mem.zeros((B, LC), "int32") if Cc else None
+        class_masks = self.mem.empty((B, H, W), "uint8") if (Cc and want_class_masks) else None
+        ws, n = self._ws(B, H, W, Cc, 0)
+        rc = self.lib.cpb_eval_tail_device(self._p(y_flows), self._p(y_logits), B, nt, Cc, ly, lx, self._p(y0), self._p(x0),
+                                           self._p(flip), 1 if augment else 0, self._p(taper_y), self._p(taper_x), int(Ly),
+                                           int(Lx), cy0, cy1, cx0, cx1, C.byref(prm), self._p(dP), self._p(cellprob),
+                                           self._p(logits), self._p(masks), self._p(counts), self._p(cell_class),
+                                           self._p(class_masks), self._p(ws), n, self.stream())
+        check(rc, "cpb_eval_tail_device")
+        self.mem.keep_alive(ws, y_flows, y_logits, y0, x0, flip, taper_y, taper_x)
+        return masks, counts, cell_class, class_masks, dP, cellprob, logits
+
     def cell_contours(self, masks, lcap, points_cap=None):
         """PostProcessor features per label: dict(npoints, offsets, total, points, feat, perimeter, valid)."""
         B, H, W = masks.shape

@@ -37,7 +37,16 @@ def eval_tail(y_tiles, nclasses, pads, geo, augment=False, device=None, want_cla
     x4, cover = btf.tile_cover(geo["y0"], geo["x0"], ly, lx, geo["Ly"], geo["Lx"])
     g = [eng._dev(geo[k], torch.int32) for k in ("y0", "x0", "flip")]
     tyd, txd = eng._dev(ty, torch.float64), eng._dev(tx, torch.float64)
+    H, W = geo["Ly"] - pads[0] - pads[1], geo["Lx"] - pads[2] - pads[3]
+    from ._abi import make_params
     with torch.cuda.device(eng.device):
+        if x4 and lx % 4 == 0 and pads[2] % 4 == 0 and W % 64 == 0:
+            # one library call: the flow-map blend is fused with the cellprob threshold (foreground list, scaled flow
+            # field and zeroed labels come out of the blend itself), then the mask path and the vote
+            masks, counts, cell_class, class_masks, dP, cellprob, _ = eng.calls.eval_tail(
+                flows, logits, g[0], g[1], g[2], bool(augment), tyd, txd, geo["Ly"], geo["Lx"], tuple(int(p) for p in pads),
+                make_params(**params), want_class_masks)
+            return masks, counts, cell_class, class_masks, dP, cellprob
         yf = eng.calls.average_tiles(flows, g[0], g[1], g[2], bool(augment), tyd, txd, geo["Ly"], geo["Lx"], tuple(pads),
                                      x4, cover)
         yc = None

@@ -287,11 +287,13 @@ int run_map_stats(const Workspace& w, int32_t* lab, int B, int H, int W, int nch
 // zero_out != NULL (fused path): the prep kernel zeroes that label image instead of marking background in p_final
 int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B, int H, int W, int niter,
                float thr, int32_t* pfinal, float* pfloat, int* hist, cudaStream_t st, int32_t* zero_out = nullptr,
-               float* dP_copy = nullptr) {
+               float* dP_copy = nullptr, bool prep_done = false) {
     const long long BN = (long long)B * H * W;
     prof_begin(w.prof, S_PREP);
-    cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
-    cudaMemsetAsync(w.t.fail, 0, B * sizeof(int), st);
+    if (!prep_done) {
+        cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
+        cudaMemsetAsync(w.t.fail, 0, B * sizeof(int), st);
+    }
     if (hist) cudaMemsetAsync(hist, 0, BN * sizeof(int), st);
     const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
     // tap indices are formed in float32 (exact below 2^24): one tile of more than ~4090 x 4090 pixels is out of range
@@ -301,7 +303,9 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     const bool vec4 = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(dP) % 16 == 0) &&
                       (reinterpret_cast<uintptr_t>(cellprob) % 16 == 0) && (reinterpret_cast<uintptr_t>(bg_out) % 16 == 0);
     if (dP_copy && !(vec4 && reinterpret_cast<uintptr_t>(dP_copy) % 16 == 0)) return CPB_E_ARG;   // (only the host path asks)
-    if (vec4) {
+    if (prep_done) {
+        // (k_blend_prep already wrote the flow field, the foreground list and the zeroed label image)
+    } else if (vec4) {
         const int patch = (W % 64 == 0) ? 1 : 0;
         const long long nblk = patch ? (long long)B * ((H + 2 + 15) / 16) * (W / 64)
                                      : (long long)blocks_for((long long)B * (H + 2) * (W / 4), 256);
@@ -680,7 +684,7 @@ int cpb_remove_border_instances_device(int32_t* masks, int B, int H, int W, int 
 static int compute_masks_impl(const float* dP, const float* cellprob, const float* logits, int B, int H, int W,
                              int C, const cpb_params* prm, int32_t* masks, int32_t* counts, int32_t* cell_class,
                              uint8_t* class_masks, void* workspace, size_t workspace_bytes, void* stream, Prof* prof,
-                             float* dP_copy = nullptr) {
+                             float* dP_copy = nullptr, bool prep_done = false) {
     if (!dP || !cellprob || !prm || !masks || !counts) return CPB_E_ARG;
     if (logits && (!cell_class || C < 1 || C > 255)) return CPB_E_ARG;
     if (prm->niter < 0) return CPB_E_ARG;
@@ -690,7 +694,8 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     int e;
     const long long BN = (long long)B * H * W;
     // (2) Euler integration + end-point histogram
-    e = run_follow(w, dP, cellprob, B, H, W, prm->niter, prm->cellprob_threshold, w.pfinal, nullptr, w.hist, st, masks, dP_copy);
+    e = run_follow(w, dP, cellprob, B, H, W, prm->niter, prm->cellprob_threshold, w.pfinal, nullptr, w.hist, st, masks, dP_copy,
+                   prep_done);
     if (e) return e;
     if (dP_copy) dP = dP_copy;          // every later reader (flow check) sits on a foreground pixel
     // (3) seeds -> raw labels (seed order + 1) and their statistics; ids after get_masks live in t.remap
@@ -1015,6 +1020,49 @@ int cpb_average_tiles_ex_device(const float* y, int B, int ntiles, int nch, int 
     }
     CPB_CHECK_LAUNCH();
     return 0;
+}
+
+int cpb_eval_tail_device(const float* y_flows, const float* y_logits, int B, int ntiles, int C, int ly, int lx,
+                         const int32_t* y0, const int32_t* x0, const int32_t* flip, int augment, const double* taper_y,
+                         const double* taper_x, int Ly, int Lx, int cy0, int cy1, int cx0, int cx1, const cpb_params* prm,
+                         float* dP, float* cellprob, float* logits, int32_t* masks, int32_t* counts, int32_t* cell_class,
+                         uint8_t* class_masks, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!y_flows || !y0 || !x0 || !flip || !taper_y || !taper_x || !prm || !dP || !cellprob || !masks || !counts) return CPB_E_ARG;
+    if (y_logits && (!logits || !cell_class || C < 1 || C > 255)) return CPB_E_ARG;
+    const int H = Ly - cy0 - cy1, W = Lx - cx0 - cx1;
+    if (ntiles <= 0 || ly <= 0 || lx <= 0 || cy0 < 0 || cx0 < 0) return CPB_E_ARG;
+    // the fused kernel's geometry promises (the WSI path: 256-px sub-tiles, 8 / 16-px pads): otherwise CPB_E_ARG and the
+    // caller composes cpb_average_tiles_ex_device + cpb_compute_masks_device itself
+    if (lx % 4 || cx0 % 4 || W % 64 || H < 2 || reinterpret_cast<uintptr_t>(y_flows) % 16 || reinterpret_cast<uintptr_t>(dP) % 16 ||
+        reinterpret_cast<uintptr_t>(cellprob) % 16 || reinterpret_cast<uintptr_t>(masks) % 16)
+        return CPB_E_ARG;
+    CPB_PROLOGUE(y_logits ? C : 0, 0)
+    if ((long long)(H + 2) * (W + 2 * CPB_FLOW_PADX) >= (1LL << 24)) return CPB_E_RANGE;
+    int e;
+    if (y_logits) {          // class logits: un-flip + blend (transforms/transforms.py:4-21, core.py:218-220)
+        e = cpb_average_tiles_ex_device(y_logits, B, ntiles, C, ly, lx, y0, x0, flip, 0, taper_y, taper_x, Ly, Lx, cy0, cy1, cx0,
+                                        cx1, logits, 1, 0, stream);
+        if (e) return e;
+    }
+    float* tab = nullptr;
+    const size_t nw = (size_t)ly * lx, nr = (size_t)H * W;
+    if (cudaMallocAsync(reinterpret_cast<void**>(&tab), (2 * nw + 2 * nr) * sizeof(float), st) != cudaSuccess) return (int)cudaGetLastError();
+    float* wh = tab; float* wl = tab + nw; float* rh = tab + 2 * nw; float* rl = rh + nr;
+    CPB_LAUNCH_COUNTED(k_blend_weights, dim3(blocks_for((long long)nw, 256)), dim3(256), 0, st, taper_y, taper_x, ly, lx, wh, wl);
+    CPB_LAUNCH_COUNTED(k_blend_rinv, dim3(blocks_for((long long)nr, 256)), dim3(256), 0, st, ntiles, ly, lx, y0, x0, taper_y, taper_x,
+                       cy0, cx0, H, W, rh, rl);
+    cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
+    cudaMemsetAsync(w.t.fail, 0, B * sizeof(int), st);
+    const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
+    const long long nblk = (long long)B * ((H + 15) / 16) * (W / 64);
+    CPB_LAUNCH_COUNTED(k_blend_prep, dim3((unsigned)nblk), dim3(256), 0, st, y_flows, B, ntiles, ly, lx, y0, x0, flip, augment ? 1 : 0,
+                       (const float*)wh, (const float*)wl, (const float*)rh, (const float*)rl, cy0, cx0, H, W,
+                       prm->cellprob_threshold, sx, sy, dP, cellprob, reinterpret_cast<float4*>(w.flow),
+                       reinterpret_cast<int4*>(masks), w.list, w.list_n);
+    cudaFreeAsync(tab, st);
+    CPB_CHECK_LAUNCH();
+    return compute_masks_impl(dP, cellprob, y_logits ? logits : nullptr, B, H, W, C, prm, masks, counts, cell_class, class_masks,
+                              workspace, workspace_bytes, stream, nullptr, nullptr, true);
 }
 
 int cpb_label_offsets_device(const int32_t* counts, int B, int64_t base, int64_t* offsets, int64_t* total,

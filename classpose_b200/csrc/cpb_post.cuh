@@ -391,8 +391,14 @@ CPB_KERNEL k_blend_rinv(int ntiles, int ly, int lx, const int* CPB_RESTRICT ty0,
 
 // two pixels per instruction (packed f32x2: every half is an ordinary IEEE round-to-nearest operation).
 // nwh = -wh, so that v * nwh = -(v * wh) exactly and pl = fma(v, wh, -ph) needs no packed negation.
+// ph is formed by SCALAR multiplies: ptxas contracts a packed mul.rn.f32x2 that feeds a packed add / sub into FFMA2
+// (despite the .rn), which would turn s = RN(acc + RN(v * wh)) into RN(acc + v * wh) and break the two-sum that follows
+// -- seen on the B200: only 83 % of the elements were bit-identical to numpy with the packed multiply, all of them
+// with the scalar one.
 CPB_DEVICE void cpb_eft_acc2(pf2& acc, pf2 v, pf2 wh, pf2 nwh, pf2 wl) {
-    const pf2 ph = pf2_mul(v, wh);
+    float v0, v1, h0, h1;
+    pf2_get(v, v0, v1); pf2_get(wh, h0, h1);
+    const pf2 ph = pf2_make(__fmul_rn(v0, h0), __fmul_rn(v1, h1));
     pf2 pl = pf2_fma(v, wh, pf2_mul(v, nwh));
     pl = pf2_fma(v, wl, pl);
     const pf2 s = pf2_add(acc, ph);
@@ -468,6 +474,111 @@ k_average_tiles_eft(const float* CPB_RESTRICT y, int B, int ntiles, int nch, int
         o.w = cpb_eft_scale(a3, r_h.w, r_l.w);
         *reinterpret_cast<float4*>(yf + (((size_t)b * nch + c0 + q) * oH + Y) * oW + X4 * 4) = o;
     }
+}
+
+// ---- blend of the flow map FUSED with the cellprob threshold (north_star (1); SURVEY 8b: average_tiles(...,
+// cellprob_threshold) -> yf + foreground) ---------------------------------------------------------------------------
+// The flow map of run_net has three channels (dY, dX, cellprob: core.py:215-216).  One thread blends all three for its
+// 4 pixels (error-free float32 accumulate as above) and, holding them in registers, also does everything the first
+// pass of the mask path would re-read them for: foreground = cellprob > threshold, the masked / scaled zero-padded flow
+// field of follow_flows, the compacted foreground list (block scan + one atomic per block, blocks in 16 x 64 patch
+// order so that a run of the list holds whole cells) and the zeroed label image.  dP / cellprob are written once, for
+// the flow check and the caller; k_prep_flow_v4 never runs on this path.
+// Requirements (checked by the host): lx, crop offset, every x0 multiples of 4, oW % 64 == 0.
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_blend_prep(const float* CPB_RESTRICT y, int B, int ntiles, int ly, int lx, const int* CPB_RESTRICT ty0,
+             const int* CPB_RESTRICT tx0, const int* CPB_RESTRICT flip, int negate_flow, const float* CPB_RESTRICT wh,
+             const float* CPB_RESTRICT wl, const float* CPB_RESTRICT rh, const float* CPB_RESTRICT rl, int cy0, int cx0,
+             int oH, int oW, float thr, float sxs, float sys, float* CPB_RESTRICT dP, float* CPB_RESTRICT cellprob,
+             float4* CPB_RESTRICT flow, int4* CPB_RESTRICT labels, unsigned* CPB_RESTRICT list, unsigned* CPB_RESTRICT list_n) {
+    CPB_SHARED int s_scan[33];
+    CPB_SHARED unsigned s_base;
+    constexpr int NCH = 3;
+    const int W4 = oW >> 2, N = oH * oW;
+    const int Wp4 = (oW + 2 * CPB_FLOW_PADX) >> 1;           // padded row pitch in float4 (2 pixels each)
+    const int pbx = W4 >> 4, pby = (oH + 15) >> 4;
+    const int blk = blockIdx.x;
+    const int b = blk / (pbx * pby);
+    const int rem = blk - b * (pbx * pby);
+    const int Y = (rem / pbx) * 16 + (threadIdx.x >> 4);
+    const int X4 = (rem % pbx) * 16 + (threadIdx.x & 15);
+    const bool in = b < B && Y < oH;
+    int nfg = 0;
+    unsigned gi0 = 0;
+    bool f0 = false, f1 = false, f2 = false, f3 = false;
+    if (in) {
+        const int gy = Y + cy0, gx = X4 * 4 + cx0;
+        pf2 acc[NCH][2];
+        #pragma unroll
+        for (int q = 0; q < NCH; q++) { acc[q][0] = pf2_make(0.f, 0.f); acc[q][1] = pf2_make(0.f, 0.f); }
+        const size_t plane = (size_t)ly * lx;
+        for (int j = 0; j < ntiles; j++) {
+            const int ry = gy - ty0[j], rx = gx - tx0[j];
+            if (ry < 0 || ry >= ly || rx < 0 || rx >= lx) continue;
+            const int f = flip[j];
+            const int sy = (f & 1) ? ly - 1 - ry : ry;
+            const int sx = (f & 2) ? lx - 4 - rx : rx;
+            const float* src = y + ((size_t)b * ntiles + j) * NCH * plane + (size_t)sy * lx + sx;
+            float4 v4[NCH];
+            #pragma unroll
+            for (int q = 0; q < NCH; q++) v4[q] = *reinterpret_cast<const float4*>(src + q * plane);
+            const float4 h4 = *reinterpret_cast<const float4*>(wh + (size_t)ry * lx + rx);
+            const float4 l4 = *reinterpret_cast<const float4*>(wl + (size_t)ry * lx + rx);
+            const pf2 h01 = pf2_make(h4.x, h4.y), h23 = pf2_make(h4.z, h4.w), l01 = pf2_make(l4.x, l4.y), l23 = pf2_make(l4.z, l4.w);
+            const pf2 n01 = pf2_make(-h4.x, -h4.y), n23 = pf2_make(-h4.z, -h4.w), m01 = pf2_make(-l4.x, -l4.y), m23 = pf2_make(-l4.z, -l4.w);
+            #pragma unroll
+            for (int q = 0; q < NCH; q++) {
+                const bool neg = negate_flow && ((q == 0 && (f & 1)) || (q == 1 && (f & 2)));
+                pf2 va, vb;
+                if (f & 2) { va = pf2_make(v4[q].w, v4[q].z); vb = pf2_make(v4[q].y, v4[q].x); }
+                else       { va = pf2_make(v4[q].x, v4[q].y); vb = pf2_make(v4[q].z, v4[q].w); }
+                if (neg) { cpb_eft_acc2(acc[q][0], va, n01, h01, m01); cpb_eft_acc2(acc[q][1], vb, n23, h23, m23); }
+                else     { cpb_eft_acc2(acc[q][0], va, h01, n01, l01); cpb_eft_acc2(acc[q][1], vb, h23, n23, l23); }
+            }
+        }
+        const float4 r_h = *reinterpret_cast<const float4*>(rh + (size_t)Y * oW + X4 * 4);
+        const float4 r_l = *reinterpret_cast<const float4*>(rl + (size_t)Y * oW + X4 * 4);
+        float4 o[NCH];
+        #pragma unroll
+        for (int q = 0; q < NCH; q++) {
+            float a0, a1, a2, a3;
+            pf2_get(acc[q][0], a0, a1); pf2_get(acc[q][1], a2, a3);
+            o[q].x = cpb_eft_scale(a0, r_h.x, r_l.x); o[q].y = cpb_eft_scale(a1, r_h.y, r_l.y);
+            o[q].z = cpb_eft_scale(a2, r_h.z, r_l.z); o[q].w = cpb_eft_scale(a3, r_h.w, r_l.w);
+        }
+        const size_t pix = (size_t)Y * oW + X4 * 4;
+        *reinterpret_cast<float4*>(dP + ((size_t)b * 2 + 0) * N + pix) = o[0];
+        *reinterpret_cast<float4*>(dP + ((size_t)b * 2 + 1) * N + pix) = o[1];
+        *reinterpret_cast<float4*>(cellprob + (size_t)b * N + pix) = o[2];
+        // ---- what k_prep_flow_v4 does with these three values
+        f0 = o[2].x > thr; f1 = o[2].y > thr; f2 = o[2].z > thr; f3 = o[2].w > thr;
+        const float2 a0 = cpb_scaled_flow(o[0].x, o[1].x, f0, sxs, sys), a1 = cpb_scaled_flow(o[0].y, o[1].y, f1, sxs, sys);
+        const float2 a2 = cpb_scaled_flow(o[0].z, o[1].z, f2, sxs, sys), a3 = cpb_scaled_flow(o[0].w, o[1].w, f3, sxs, sys);
+        float4* row = flow + ((size_t)b * (oH + 2) + Y + 1) * Wp4;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        row[1 + 2 * X4] = make_float4(a0.x, a0.y, a1.x, a1.y);
+        row[2 + 2 * X4] = make_float4(a2.x, a2.y, a3.x, a3.y);
+        if (X4 == 0) row[0] = z;
+        if (X4 == W4 - 1) row[Wp4 - 1] = z;
+        if (Y == 0 || Y == oH - 1) {                                    // the zero rows above / below the tile
+            float4* prow = flow + ((size_t)b * (oH + 2) + (Y == 0 ? 0 : oH + 1)) * Wp4;
+            prow[1 + 2 * X4] = z; prow[2 + 2 * X4] = z;
+            if (X4 == 0) prow[0] = z;
+            if (X4 == W4 - 1) prow[Wp4 - 1] = z;
+        }
+        labels[((size_t)b * N + pix) >> 2] = make_int4(0, 0, 0, 0);
+        gi0 = (unsigned)b * (unsigned)N + (unsigned)pix;
+        nfg = (int)f0 + (int)f1 + (int)f2 + (int)f3;
+    }
+    int tot;
+    const int incl = cpb_block_scan_incl(nfg, s_scan, &tot);
+    if (threadIdx.x == 0 && tot > 0) s_base = atomicAdd(list_n, (unsigned)tot);
+    __syncthreads();
+    unsigned op = s_base + (unsigned)(incl - nfg);
+    if (f0) list[op++] = gi0;
+    if (f1) list[op++] = gi0 + 1;
+    if (f2) list[op++] = gi0 + 2;
+    if (f3) list[op++] = gi0 + 3;
 }
 
 // k_label_offsets: single block; offsets[b] = base + sum(counts[0..b)), total = sum(counts).

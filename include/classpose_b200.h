@@ -237,6 +237,25 @@ int cpb_average_tiles_ex_device(const float* y, int B, int ntiles, int nch, int 
                                 int Ly, int Lx, int cy0, int cy1, int cx0, int cx1, float* yf,
                                 int x0_multiple_of_4, int max_cover, void* stream);
 
+/* ---- next row N3 / north_star (1): the tail of ClassposeModel.eval on the network's sub-tile outputs -------------
+ * Replaces core.py:197-231 (un-flip, average_tiles of the flow map and of the class logits, crop) + models.py:750-770
+ * (masks, class vote) in one call on device data.  The blend of the flow map is FUSED with the cellprob threshold: the
+ * thread that blends (dY, dX, cellprob) of a pixel group also emits the foreground list, the masked / scaled flow field of
+ * follow_flows and the zeroed label image, so the blended maps are never re-read by a separate first pass.
+ *   y_flows  [B,ntiles,3,ly,lx] float32 (dY, dX, cellprob per sub-tile, as the network emits them)
+ *   y_logits [B,ntiles,C,ly,lx] float32 or NULL
+ *   y0/x0/flip [ntiles], taper_y [ly], taper_x [lx], (Ly, Lx), crop as in cpb_average_tiles_device; augment != 0 = --tta
+ *   out: dP [B,2,H,W], cellprob [B,H,W], logits [B,C,H,W] (blended, cropped; H = Ly-cy0-cy1, W = Lx-cx0-cx1), and the
+ *        outputs of cpb_compute_masks_device.
+ * Geometry the fused kernel needs: lx % 4 == 0, cx0 % 4 == 0, every x0 % 4 == 0 (host's promise), W % 64 == 0;
+ * otherwise CPB_E_ARG (compose cpb_average_tiles_ex_device + cpb_compute_masks_device instead). */
+int cpb_eval_tail_device(const float* y_flows, const float* y_logits, int B, int ntiles, int C, int ly, int lx,
+                         const int32_t* y0, const int32_t* x0, const int32_t* flip, int augment,
+                         const double* taper_y, const double* taper_x, int Ly, int Lx, int cy0, int cy1,
+                         int cx0, int cx1, const cpb_params* prm, float* dP, float* cellprob, float* logits,
+                         int32_t* masks, int32_t* counts, int32_t* cell_class, uint8_t* class_masks,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- next row N1: PostProcessor features on the device --------------------------------------------
  * Replaces the per-cell host loop of PostProcessor.__call__ (predict_wsi.py:595-656): ndimage.find_objects,
  * cv2.findContours(cell_mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE)[0] and the shapely polygon measures.

@@ -63,6 +63,14 @@ class _Base:
         out = self._calls().compute_masks(self._in(dP), self._in(cp), self._in(logits), prm, want_class_masks)
         return tuple(_np(o) for o in out)
 
+    def eval_tail(self, y_flows, y_logits, y0, x0, flip, augment, ty, tx, Ly, Lx, crop, want_class_masks=False, **kw):
+        from classpose_b200._abi import make_params
+        out = self._calls().eval_tail(self._in(y_flows), self._in(y_logits), self._in(np.asarray(y0, np.int32)),
+                                      self._in(np.asarray(x0, np.int32)), self._in(np.asarray(flip, np.int32)), augment,
+                                      self._in(np.asarray(ty, np.float64)), self._in(np.asarray(tx, np.float64)), Ly, Lx, crop,
+                                      make_params(**kw), want_class_masks)
+        return tuple(_np(o) for o in out)
+
     def cell_contours(self, masks, lcap, points_cap=None):
         out = self._calls().cell_contours(self._in(masks), lcap, points_cap)
         return {k: _np(v) for k, v in out.items()}

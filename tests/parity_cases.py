@@ -615,6 +615,57 @@ def case_fused_baseline_config_shapes(be):
         assert abs(nnew - nref) <= max(1, 0.001 * nref), (C, nref, nnew)
 
 
+def case_eval_tail_blend_fused_with_threshold(be):
+    """north_star (1): the tail of ClassposeModel.eval on the network's sub-tile outputs in ONE library call -- the blend of the
+    flow map emits the foreground list / scaled flow field / zeroed labels itself (no separate first pass).  Must equal the
+    composition `blend -> compute_masks` of the same library bit for bit, and the reference's host sequence on the oracle."""
+    from classpose_b200 import transforms as btf
+    t = std_tile(23, C=5)
+    C = 5
+    for augment in (True, False):
+        pads = btf.get_pad_yx(256, 256, min_size=(256, 256))
+        Ly, Lx = 256 + pads[0] + pads[1], 256 + pads[2] + pads[3]
+        geo = btf.tile_geometry(Ly, Lx, 256, augment=augment)
+        full = np.zeros((C + 3, Ly, Lx), np.float32)
+        full[:C, pads[0]:pads[0] + 256, pads[2]:pads[2] + 256] = t["logits"]
+        full[C:C + 2, pads[0]:pads[0] + 256, pads[2]:pads[2] + 256] = t["dP"]
+        full[C + 2, pads[0]:pads[0] + 256, pads[2]:pads[2] + 256] = t["cellprob"]
+        nt = len(geo["y0"])
+        tiles = np.zeros((nt, C + 3, 256, 256), np.float32)
+        for j, (y0, x0, f) in enumerate(zip(geo["y0"], geo["x0"], geo["flip"])):
+            s_ = full[:, y0:y0 + 256, x0:x0 + 256].copy()
+            if f & 1:
+                s_ = s_[:, ::-1]; s_[C] *= -1
+            if f & 2:
+                s_ = s_[:, :, ::-1]; s_[C + 1] *= -1
+            tiles[j] = s_
+        yfl, ycl = f32(tiles[None, :, C:]), f32(tiles[None, :, :C])
+        ty, tx = btf.taper_1d(256, 256)
+        masks, counts, cc, cm, dP, cp, lg = be.eval_tail(yfl, ycl, geo["y0"], geo["x0"], geo["flip"], augment, ty, tx, Ly, Lx,
+                                                         tuple(int(p) for p in pads), want_class_masks=True)
+        # the same library, composed from its parts
+        yf = be.average_tiles(yfl, geo["y0"], geo["x0"], geo["flip"], augment, ty, tx, Ly, Lx, tuple(int(p) for p in pads))
+        yc = be.average_tiles(ycl, geo["y0"], geo["x0"], geo["flip"], False, ty, tx, Ly, Lx, tuple(int(p) for p in pads))
+        np.testing.assert_array_equal(dP[0], yf[0, :2]); np.testing.assert_array_equal(cp[0], yf[0, 2])
+        np.testing.assert_array_equal(lg, yc)
+        m2, c2, cc2, cm2 = be.compute_masks(f32(yf[:, :2]), f32(yf[:, 2]), f32(yc), want_class_masks=True)
+        np.testing.assert_array_equal(masks, m2); np.testing.assert_array_equal(counts, c2)
+        np.testing.assert_array_equal(cm, cm2)
+        # the reference's host sequence on the oracle
+        y5 = tiles[:, C:].reshape(geo["ny"], geo["nx"], 3, 256, 256).copy()
+        c5 = tiles[:, :C].reshape(geo["ny"], geo["nx"], C, 256, 256).copy()
+        if augment:
+            y5 = otf.unaugment_tiles(y5); c5 = classpose_ref.unaugment_class_tiles(c5)
+        ysub = [[a, a + 256] for a in geo["y0"]]; xsub = [[a, a + 256] for a in geo["x0"]]
+        ryf = otf.average_tiles(y5.reshape(-1, 3, 256, 256), ysub, xsub, Ly, Lx)[:, pads[0]:Ly - pads[1], pads[2]:Lx - pads[3]]
+        ryc = otf.average_tiles(c5.reshape(-1, C, 256, 256), ysub, xsub, Ly, Lx)[:, pads[0]:Ly - pads[1], pads[2]:Lx - pads[3]]
+        np.testing.assert_allclose(dP[0], ryf[:2], rtol=1e-6, atol=1e-6)
+        ref = dynamics.resize_and_compute_masks(ryf[:2], ryf[2])
+        ref_cm, _ = classpose_ref.compute_class_masks(ref, ryc[:, None])
+        r = metrics.class_agreement(ref, ref_cm, masks[0], cm[0].astype(np.int64))
+        assert r["f1"] >= 0.995 and not r["class_mismatch"] and r["n_pred"] == r["n_true"], r
+
+
 def case_fused_generic_class_count(be):
     """A class count that has no specialised final+vote instance (C = 4; the reference's configs use 5, 7, 10) on a
     tile whose pixel count is a multiple of 4, so the vote still rides on the final pass (generic kernel)."""
@@ -916,6 +967,7 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_f
              case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_flow_qc_screen_is_decision_exact,
              case_fill_holes_exact, case_fill_holes_oversized_label, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes, case_fused_baseline_config_shapes,
+             case_eval_tail_blend_fused_with_threshold,
              case_fused_generic_class_count, case_fused_switch_matrix, case_fused_odd_width, case_fused_empty_and_params, case_fused_min_size_zero_keeps_upstream_ids,
              case_fused_qc_then_positional_size_filter,
              case_cell_contours_match_cv2, case_prepare_tiles, case_dedup_overlapping_tiles, case_dedup_random_points_components,
