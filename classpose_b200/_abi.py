@@ -58,7 +58,7 @@ SIGNATURES = {
     "cpb_compute_masks_host_ex": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _P, _P, _P, _P, C.POINTER(HostOptions)]),
     "cpb_tile_plan_create": (C.c_int, [_I, _I, C.POINTER(Params), _I, C.POINTER(C.c_void_p)]),
     "cpb_tile_plan_destroy": (None, [_P]),
-    "cpb_tile_plan_dP": (_P, [_P]),
+    "cpb_tile_plan_dp": (_P, [_P]),
     "cpb_tile_plan_cellprob": (_P, [_P]),
     "cpb_tile_plan_masks": (_P, [_P]),
     "cpb_tile_plan_run": (C.c_int, [_P, C.POINTER(C.c_int32)]),
@@ -85,7 +85,7 @@ SIGNATURES = {
 
 # entry points that exist only in the CUDA build (host-buffer path does real H2D/D2H copies)
 CUDA_ONLY = {"cpb_compute_masks_host", "cpb_compute_masks_host_ex", "cpb_tile_plan_create", "cpb_tile_plan_destroy",
-             "cpb_tile_plan_dP", "cpb_tile_plan_cellprob", "cpb_tile_plan_masks", "cpb_tile_plan_run", "cpb_tile_plan_logits",
+             "cpb_tile_plan_dp", "cpb_tile_plan_cellprob", "cpb_tile_plan_masks", "cpb_tile_plan_run", "cpb_tile_plan_logits",
              "cpb_tile_plan_vote"}
 
 

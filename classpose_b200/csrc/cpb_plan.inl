@@ -130,7 +130,7 @@ void cpb_tile_plan_destroy(cpb_tile_plan* p) {
     delete p;
 }
 
-float* cpb_tile_plan_dP(cpb_tile_plan* p) { return p ? p->h_dP : nullptr; }
+float* cpb_tile_plan_dp(cpb_tile_plan* p) { return p ? p->h_dP : nullptr; }
 float* cpb_tile_plan_cellprob(cpb_tile_plan* p) { return p ? p->h_cp : nullptr; }
 const int32_t* cpb_tile_plan_masks(cpb_tile_plan* p) { return p ? p->h_masks : nullptr; }
 

@@ -41,7 +41,7 @@ class TilePlan:
         check(self.lib.cpb_tile_plan_create(H, W, C.byref(prm), int(eng.device.index), C.byref(handle)), "cpb_tile_plan_create")
         self.handle = handle
         self._finalizer = weakref.finalize(self, self.lib.cpb_tile_plan_destroy, handle)
-        self.h_dP = _view(self.lib.cpb_tile_plan_dP(handle), (2, H, W), np.float32)
+        self.h_dP = _view(self.lib.cpb_tile_plan_dp(handle), (2, H, W), np.float32)
         self.h_cp = _view(self.lib.cpb_tile_plan_cellprob(handle), (H, W), np.float32)
         self.h_masks = _view(self.lib.cpb_tile_plan_masks(handle), (H, W), np.int32)
         self.h_lg = None                # numpy view of the logits staging buffer

@@ -145,7 +145,7 @@ int cpb_compute_masks_host_ex(const float* dP, const float* cellprob, const floa
  * "upload -> fused path -> download" and "upload logits -> vote on the labels still on the device -> download", so a
  * call costs one copy into the staging buffer, one graph launch and one synchronise.  One plan per host thread and
  * tile shape; the calls of one plan must not overlap.
- *   cpb_tile_plan_dP / _cellprob   pinned float32 [2,H,W] / [H,W] the caller fills before cpb_tile_plan_run
+ *   cpb_tile_plan_dp / _cellprob   pinned float32 [2,H,W] / [H,W] the caller fills before cpb_tile_plan_run
  *   cpb_tile_plan_masks            pinned int32 [H,W], valid after cpb_tile_plan_run until the next run
  *   cpb_tile_plan_logits(p, C)     pinned float32 [C,H,W] to fill before cpb_tile_plan_vote (sets up the vote for C classes)
  *   cpb_tile_plan_vote             class image uint8 [H,W] and per-instance classes (first min(lcap, 1024) entries),
@@ -153,7 +153,7 @@ int cpb_compute_masks_host_ex(const float* dP, const float* cellprob, const floa
 typedef struct cpb_tile_plan cpb_tile_plan;
 int  cpb_tile_plan_create(int H, int W, const cpb_params* prm, int device, cpb_tile_plan** out);
 void cpb_tile_plan_destroy(cpb_tile_plan* plan);
-float* cpb_tile_plan_dP(cpb_tile_plan* plan);
+float* cpb_tile_plan_dp(cpb_tile_plan* plan);
 float* cpb_tile_plan_cellprob(cpb_tile_plan* plan);
 const int32_t* cpb_tile_plan_masks(cpb_tile_plan* plan);
 int  cpb_tile_plan_run(cpb_tile_plan* plan, int32_t* count);
