@@ -177,6 +177,7 @@ void ensure_attributes() {
     if (g_attr_done[dev].load(std::memory_order_acquire)) return;
     cudaFuncSetAttribute(k_fill_holes, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CPB_FILL_WORDS * 4);
     cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, kVoteSmemIntsMax * 4);
+    cudaFuncSetAttribute(k_follow_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_FS_WIN * CPB_FS_WIN * 8);
     g_attr_done[dev].store(1, std::memory_order_release);      // (setting them twice from two threads is harmless)
 }
 int sm_count() {
@@ -196,13 +197,14 @@ int sm_count() { return 4; }
 #endif
 
 // follow_flows variant: 2 = trajectory pool with many merge points (default), 1 = two merge points per 256-pixel
-// chunk, 0 = plain kernel; CPB_FOLLOW_MERGE in the environment or cpb_debug_set_follow_merge (A/B measurements
-// and tests).  Results are bit-identical in every mode.
+// chunk, 0 = plain kernel, 3 = plain kernel with the flow window of every 32 x 32 patch staged by TMA bulk copies
+// (the north-star experiment, needs cellprob: fused path and cpb_follow_flows_device); CPB_FOLLOW_MERGE in the
+// environment or cpb_debug_set_follow_merge (A/B measurements and tests).  Results are bit-identical in every mode.
 std::atomic<int> g_follow_merge{-1};     // -1: take CPB_FOLLOW_MERGE from the environment
 int follow_merge_mode() {
     const int v = g_follow_merge.load(std::memory_order_relaxed);
     if (v >= 0) return v;
-    static const int env = [] { const char* e = getenv("CPB_FOLLOW_MERGE"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }();
+    static const int env = [] { const char* e = getenv("CPB_FOLLOW_MERGE"); return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2; }();
     return env;
 }
 
@@ -325,6 +327,16 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     // the pool kernel forms the tap index with an FADD (1.5 * 2^23 + index): the padded tile must stay below 2^22
     // pixels (about 2040 x 2040); larger tiles take the two-point merge kernel, whose index is a float -> int conversion
     const bool pool_ok = (long long)(H + 2) * (W + 2 * CPB_FLOW_PADX) < (1LL << 22);
+#ifndef CPB_SIM
+    if (mode == 3) {
+        ensure_attributes();
+        const int pb = ((W + CPB_FS_PATCH - 1) / CPB_FS_PATCH) * ((H + CPB_FS_PATCH - 1) / CPB_FS_PATCH);
+        CPB_LAUNCH_COUNTED(k_follow_staged, dim3((unsigned)((long long)B * pb)), dim3(256), CPB_FS_WIN * CPB_FS_WIN * 8, st, w.flow,
+                           cellprob, thr, B, H, W, niter, pfinal, pfloat, hist);
+        CPB_CHECK_LAUNCH();
+        return 0;
+    }
+#endif
     if (mode == 2 && niter >= 32 && pool_ok) {
         // one block per chunk of the list (blocks past the end of the list exit at once)
 #ifdef CPB_SIM

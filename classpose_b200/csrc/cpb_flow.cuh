@@ -279,6 +279,116 @@ k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// k_follow_staged (A/B experiment, CPB_FOLLOW_MERGE=3; north_star (2) names "tiles staged by TMA"): the plain kernel's
+// arithmetic, with the flow window of a 32 x 32 pixel patch staged into shared memory by the TMA engine
+// (cp.async.bulk global -> shared, one bulk copy per window row, completion on an mbarrier; UBLKCP in the SASS) for
+// the first CPB_FS_STEPS Euler steps.  A tap whose 2 x 2 cell lies inside the staged window comes from shared
+// memory, any other from global memory, so the result is bit-identical to k_follow whatever a trajectory does.
+// Measured against k_follow on the B200: the staging does not pay -- the kernel is bound by issue
+// slots, an LDS costs the slot of the L1-hit LDG it replaces, and the window test adds instructions.
+#define CPB_FS_PATCH 32
+#define CPB_FS_HALO 24
+#define CPB_FS_STEPS 24
+#define CPB_FS_WIN (CPB_FS_PATCH + 2 * CPB_FS_HALO)            // 80 rows x 80 columns of float2 = 51,200 bytes
+
+#ifndef CPB_SIM
+CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
+k_follow_staged(const float2* CPB_RESTRICT flow, const float* CPB_RESTRICT cellprob, float thr, int B, int H, int W,
+                int niter, int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float2* s_win = reinterpret_cast<float2*>(s_raw);
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int N = H * W, Wp = W + 2 * CPB_FLOW_PADX, Np = (H + 2) * Wp;
+    const int pbx = (W + CPB_FS_PATCH - 1) / CPB_FS_PATCH, pby = (H + CPB_FS_PATCH - 1) / CPB_FS_PATCH;
+    const int b = blockIdx.x / (pbx * pby);
+    const int rem = blockIdx.x - b * (pbx * pby);
+    const int py0 = (rem / pbx) * CPB_FS_PATCH, px0 = (rem % pbx) * CPB_FS_PATCH;
+    // window in PADDED coordinates (row yp = y + 1, column xp = x + PADX), clipped to the padded tile, even start column
+    const int wy0 = max(py0 + 1 - CPB_FS_HALO, 0), wy1 = min(py0 + 1 + CPB_FS_PATCH + CPB_FS_HALO, H + 2);
+    const int wx0 = max(px0 + CPB_FLOW_PADX - CPB_FS_HALO, 0) & ~1;
+    const int wx1 = min(wx0 + CPB_FS_WIN, Wp);
+    const int wcols = (wx1 - wx0) & ~1, wrows = wy1 - wy0;
+    const float2* tile = flow + (size_t)b * Np;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned row_bytes = (unsigned)wcols * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(row_bytes * (unsigned)wrows) : "memory");
+        for (int r = 0; r < wrows; r++) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_win + r * CPB_FS_WIN);
+            const float2* src = tile + (size_t)(wy0 + r) * Wp + wx0;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
+        }
+    }
+    {   // every thread waits for the bytes to land (phase 0)
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
+    const float fW = 0.5f * (float)W, fH = 0.5f * (float)H;
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const float2* f = tile + Wp + CPB_FLOW_PADX;                 // pixel (0, 0) of the padded tile
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < (CPB_FS_PATCH * CPB_FS_PATCH) / 256; k++) {
+        const int i = threadIdx.x + k * 256;
+        const int y = py0 + i / CPB_FS_PATCH, x = px0 + (i % CPB_FS_PATCH);
+        const bool act = y < H && x < W && cellprob[(size_t)b * N + y * W + x] > thr;
+        const unsigned amask = __ballot_sync(CPB_FULL, act);
+        if (!act) continue;
+        float px = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, wm1), 2.f), 1.f);
+        float py = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, hm1), 2.f), 1.f);
+        const int nst = min(CPB_FS_STEPS, niter);
+        for (int t = 0; t < nst; t++) {
+            // same operations as cpb_euler_step_t<0, false>, taps from the window when the 2 x 2 cell is inside it
+            const float ix = fmaf(px + 1.f, fW, -0.5f), iy = fmaf(py + 1.f, fH, -0.5f);
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            const int tx = (int)fx0 + CPB_FLOW_PADX, ty = (int)fy0 + 1;          // padded coordinates of the NW tap
+            float2 vnw, vne, vsw, vse;
+            if (tx >= wx0 && tx + 1 < wx0 + wcols && ty >= wy0 && ty + 1 < wy1) {
+                const float2* r0 = s_win + (ty - wy0) * CPB_FS_WIN + (tx - wx0);
+                vnw = r0[0]; vne = r0[1]; vsw = r0[CPB_FS_WIN]; vse = r0[CPB_FS_WIN + 1];
+            } else {
+                const float2* r0 = f + ((int)fy0 * Wp + (int)fx0);
+                vnw = __ldg(r0); vne = __ldg(r0 + 1); vsw = __ldg(r0 + Wp); vse = __ldg(r0 + Wp + 1);
+            }
+            const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+            const float wnw = (fx1 - ix) * (fy1 - iy), wne = (ix - fx0) * (fy1 - iy);
+            const float wsw = (fx1 - ix) * (iy - fy0), wse = (ix - fx0) * (iy - fy0);
+            float ox = vnw.x * wnw, oy = vnw.y * wnw;
+            ox = fmaf(vne.x, wne, ox); oy = fmaf(vne.y, wne, oy);
+            ox = fmaf(vsw.x, wsw, ox); oy = fmaf(vsw.y, wsw, oy);
+            ox = fmaf(vse.x, wse, ox); oy = fmaf(vse.y, wse, oy);
+            px = fminf(fmaxf(px + ox, -1.f), 1.f);
+            py = fminf(fmaxf(py + oy, -1.f), 1.f);
+        }
+        for (int t = nst; t < niter; t++) cpb_euler_step(f, Wp, fH, fW, px, py);
+        const float ex = __fmul_rn(__fmul_rn(__fadd_rn(px, 1.f), 0.5f), wm1);
+        const float ey = __fmul_rn(__fmul_rn(__fadd_rn(py, 1.f), 0.5f), hm1);
+        int xi = __float2int_rz(ex), yi = __float2int_rz(ey);
+        xi = min(max(xi, 0), W - 1);
+        yi = min(max(yi, 0), H - 1);
+        const int r = y * W + x;
+        pfinal[(size_t)b * N + r] = (yi << 16) | xi;
+        if (pfloat) {
+            pfloat[((size_t)b * 2 + 0) * N + r] = ey;
+            pfloat[((size_t)b * 2 + 1) * N + r] = ex;
+        }
+        if (hist) {
+            const int key = b * N + yi * W + xi;
+            const unsigned peers = __match_any_sync(amask, key);
+            if (lane == __ffs((int)peers) - 1) atomicAdd(&hist[key], __popc(peers));
+        }
+    }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
 // k_follow_merge: same integration, with exact trajectory merging.  The Euler map is deterministic, so two
 // pixels of a tile whose float32 positions are bitwise equal at some step stay equal forever; pixels of a cell
 // fall into the same attractor and do become bitwise equal (about a third of the trajectories of a 256-pixel

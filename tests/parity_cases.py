@@ -101,7 +101,7 @@ def case_follow_flows_merge_is_exact(be):
             be.set_follow_merge(0)
             p0, f0 = be.follow_flows(a, b, 200, 0.0, want_float=True)
             fg = b > 0
-            for mode in (1, 2):       # two merge points per 256-pixel chunk; trajectory pool
+            for mode in (1, 2, 3):    # two merge points per 256-pixel chunk; trajectory pool; TMA-staged plain kernel (GPU)
                 be.set_follow_merge(mode)
                 p1, f1 = be.follow_flows(a, b, 200, 0.0, want_float=True)
                 np.testing.assert_array_equal(p0, p1)
