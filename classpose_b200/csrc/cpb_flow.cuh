@@ -335,12 +335,30 @@ k_follow_staged(const float2* CPB_RESTRICT flow, const float* CPB_RESTRICT cellp
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
     const float2* f = tile + Wp + CPB_FLOW_PADX;                 // pixel (0, 0) of the padded tile
     const int lane = threadIdx.x & 31;
+    // the patch's foreground pixels, compacted (full warps, like the list the other kernels walk)
+    __shared__ unsigned short s_idx[CPB_FS_PATCH * CPB_FS_PATCH];
+    __shared__ int s_scan[33];
+    __shared__ int s_nfg;
+    if (threadIdx.x == 0) s_nfg = 0;
+    __syncthreads();
     for (int k = 0; k < (CPB_FS_PATCH * CPB_FS_PATCH) / 256; k++) {
         const int i = threadIdx.x + k * 256;
         const int y = py0 + i / CPB_FS_PATCH, x = px0 + (i % CPB_FS_PATCH);
-        const bool act = y < H && x < W && cellprob[(size_t)b * N + y * W + x] > thr;
+        const bool fg = y < H && x < W && cellprob[(size_t)b * N + y * W + x] > thr;
+        int tot;
+        const int incl = cpb_block_scan_incl(fg ? 1 : 0, s_scan, &tot);
+        if (fg) s_idx[s_nfg + incl - 1] = (unsigned short)i;
+        __syncthreads();
+        if (threadIdx.x == 0) s_nfg += tot;
+        __syncthreads();
+    }
+    const int nfg = s_nfg;
+    for (int e = threadIdx.x; e < ((nfg + 31) & ~31); e += 256) {
+        const bool act = e < nfg;
         const unsigned amask = __ballot_sync(CPB_FULL, act);
         if (!act) continue;
+        const int i = s_idx[e];
+        const int y = py0 + i / CPB_FS_PATCH, x = px0 + (i % CPB_FS_PATCH);
         float px = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, wm1), 2.f), 1.f);
         float py = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, hm1), 2.f), 1.f);
         const int nst = min(CPB_FS_STEPS, niter);
