@@ -318,7 +318,8 @@ def run_ours(args):
     hcp = torch.empty(cellprob.shape, dtype=torch.float32, pin_memory=True); hcp.copy_(cellprob)
     hlg = torch.empty(logits.shape, dtype=torch.float32, pin_memory=True); hlg.copy_(logits)
     LC = eng.label_capacity(H, W)
-    outbuf = {"masks": torch.empty((B, H, W), dtype=torch.int32, pin_memory=True),
+    # label images come back as uint16, the dtype Cellpose (and so the reference) returns below 65,536 labels
+    outbuf = {"masks": torch.empty((B, H, W), dtype=torch.uint16, pin_memory=True),
               "counts": torch.empty((B,), dtype=torch.int32, pin_memory=True),
               "cell_class": torch.zeros((B, LC), dtype=torch.int32, pin_memory=True)}
     torch.cuda.synchronize()
@@ -339,7 +340,7 @@ def run_ours(args):
         one call overlaps the steady state of the other."""
         def call(lo, hi, ob):
             eng.compute_masks_host(hdP[lo:hi], hcp[lo:hi], hlg[lo:hi], out=ob, tiles_per_chunk=args.chunk,
-                                   logits_mode=logits_mode, flows_mode=flows_mode, **PARAMS)
+                                   logits_mode=logits_mode, flows_mode=flows_mode, masks_u16=True, **PARAMS)
         if threads == 1:
             parts = [(0, B, outbuf)]
         else:
@@ -368,7 +369,7 @@ def run_ours(args):
     e2e_upload_s = time_e2e("upload", "upload")
     e2e_lg_s = time_e2e("auto", "upload")
     e2e_s = time_e2e("auto", "auto")    # the API default: pinned logits / flows are read in place where they are needed
-    same = bool((outbuf["masks"][:8].to(dev) == out[0][:8]).all().item())
+    same = bool((outbuf["masks"][:8].to(torch.int32).to(dev) == out[0][:8]).all().item())
     same = same and bool((outbuf["cell_class"][:8, :64].to(dev) == out[2][:8, :64]).all().item())
     fg4 = float((out[0].reshape(-1, 4) > 0).any(dim=1).float().mean().item())
     fgrp = float((cellprob.reshape(-1, 4) > PARAMS["cellprob_threshold"]).any(dim=1).float().mean().item())
@@ -376,7 +377,7 @@ def run_ours(args):
     # in place: 16 bytes per class for every 4-pixel group that holds a cell, 32 bytes of flow per group with foreground
     mapped_up = int(B * N * C * 4 * fg4) + int(B * N * 8 * fgrp)
     h2d = copied_up + mapped_up
-    d2h = B * N * 4 + B * 4 + B * min(LC, 512) * 4
+    d2h = B * N * 2 + B * 4 + B * min(LC, 512) * 4
 
     if rank != 0:
         if world > 1:

@@ -34,8 +34,8 @@
 
 #define CPB_Q32_MAXSUB 8
 #define CPB_Q32_COLS 64            // columns of a job strip (two per lane); column 63 stays empty
-#define CPB_Q32_NCLS 6             // register-row classes NR = 9, 13, 17, 21, 25, 29 (centre row RC = NR / 2 = 4 .. 14)
-#define CPB_Q32_MAXNR 29
+#define CPB_Q32_NCLS 6             // register-row classes NR = 9, 13, 17, 21, 25, 31 (centre row RC = NR / 2 = 4 .. 15)
+#define CPB_Q32_MAXNR 31
 #define CPB_Q32_CLS64 6            // info class of labels left to the float64 warp kernel
 #define CPB_Q32_CLSBIG 7           // info class of labels left to the block kernels
 
@@ -70,7 +70,7 @@ CPB_DEVICE void cpb_q32_queue64(const Q32& q, int b, int l, size_t k) {
 
 CPB_DEVICE int cpb_q32_class(int cr, int h) {
     const int rho = max(cr, h - 1 - cr);
-    return rho <= 4 ? 0 : rho <= 6 ? 1 : rho <= 8 ? 2 : rho <= 10 ? 3 : rho <= 12 ? 4 : rho <= 14 ? 5 : CPB_Q32_CLS64;
+    return rho <= 4 ? 0 : rho <= 6 ? 1 : rho <= 8 ? 2 : rho <= 10 ? 3 : rho <= 12 ? 4 : rho <= 15 ? 5 : CPB_Q32_CLS64;
 }
 
 // ---- k_qc_scan32: one warp per label, grid (slices, B) ------------------------------------------------------
@@ -362,10 +362,10 @@ CPB_DEVICE void cpb_q32_iterate(float2* S, float inj0, float inj1, int n_it) {
 
 CPB_DEVICE bool cpb_q32_member(float v) { return (__float_as_uint(v) >> 31) == 0u; }
 
-// One job: set-up (rolled), iteration (per class), error pass (rolled).  S: the warp's tile of (29 + 2) x 32 float2.
+// One job: set-up (rolled), iteration (per class), error pass (rolled).  S: the warp's tile of (31 + 2) x 32 float2.
 CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, int W, const LabelTables& t,
                             const Q32& q, int b, int first, int nsub, int cls, double threshold, float2* S, int pack_err) {
-    const int NR = 9 + 4 * cls, RC = NR / 2;
+    const int NR = cls < 5 ? 9 + 4 * cls : CPB_Q32_MAXNR, RC = NR / 2;
     const int lane = threadIdx.x & 31;
     const int N = H * W, LC = t.LC;
     const int* L = lab + (size_t)b * N;
@@ -436,7 +436,7 @@ CPB_DEVICE void cpb_q32_run(const int* CPB_RESTRICT lab, const float* CPB_RESTRI
         case 2: cpb_q32_iterate<17, true>(S, c.inj[0], c.inj[1], n_it); break;
         case 3: cpb_q32_iterate<21, true>(S, c.inj[0], c.inj[1], n_it); break;
         case 4: cpb_q32_iterate<25, false>(S, c.inj[0], c.inj[1], n_it); break;
-        default: cpb_q32_iterate<29, false>(S, c.inj[0], c.inj[1], n_it); break;
+        default: cpb_q32_iterate<31, false>(S, c.inj[0], c.inj[1], n_it); break;
     }
     __syncwarp();
     // flow error and its bound from the tile

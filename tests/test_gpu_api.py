@@ -197,6 +197,35 @@ def test_single_tile_fast_path_graph_and_identity_cache():
     assert not cmz.any() and uz.tolist() == [0]
 
 
+def test_tile_plans_from_two_threads():
+    """The reference's two inference threads (predict_wsi.py:728-797), each calling hook A then hook C per tile: the
+    per-thread plans (CUDA graphs on their own streams) must not disturb each other, also while plans are being created."""
+    import threading
+    from classpose_b200 import models
+    tiles = [pc.std_tile(s_) for s_ in (1, 3, 4, 6)]
+    want = []
+    for t in tiles:
+        m = models.compute_masks(t["dP"][:, None], t["cellprob"][None], (1, 256, 256), False, 200, 0.0, 0.4, 15, 0.4, 0.0, None)
+        cm, _ = models.compute_class_masks(m, t["logits"][:, None])
+        want.append((m.copy(), cm.copy()))
+    errors = []
+
+    def work(k):
+        try:
+            for rep in range(6):
+                i = (k + rep) % len(tiles)
+                t = tiles[i]
+                m = models.compute_masks(t["dP"][:, None], t["cellprob"][None], (1, 256, 256), False, 200, 0.0, 0.4, 15, 0.4, 0.0, None)
+                cm, _ = models.compute_class_masks(m, t["logits"][:, None])
+                np.testing.assert_array_equal(m, want[i][0])
+                np.testing.assert_array_equal(cm, want[i][1])
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=work, args=(k,)) for k in range(3)]
+    [t_.start() for t_ in th]; [t_.join() for t_ in th]
+    assert not errors, errors
+
+
 def test_touching_workload_screen_equals_float64_path():
     """The hostile generator (Voronoi-clipped touching cells, 15 % of them with noise for flows, a 43-px cell every 8th tile,
     a ring every 16th): the float32 flow-check screen -- isolated labels in registers, labels in contact through the
