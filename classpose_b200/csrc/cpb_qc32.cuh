@@ -559,7 +559,38 @@ k_flow_err32(const int* CPB_RESTRICT lab, const float* CPB_RESTRICT dP, int H, i
         const float eta = (float)(1.02 * (xk + xk * xk) + 1e-9);
         float sc = 0.f, sb = 0.f;
         bool missing = false;
-        if (lane < w) {
+        if (w <= 30) {
+            // lane = column x0 - 1 + lane of the bbox grown by one; three rows (label's effective T, "no float32 T" mark)
+            // slide through registers, left / right neighbours come by shuffle: ~4 loads per row and lane, none dependent
+            const int xg = x0 - 1 + lane;
+            const bool col_ok = lane < w + 2 && xg >= 0 && xg < W;
+            float t_prev = 0.f, t_cur = 0.f, t_next = 0.f;
+            bool m_prev = false, m_cur = false, m_next = false, mem_cur = false, mem_next = false;
+            for (int ry = -2; ry < h; ry++) {
+                // load row ry + 1 into "next" (row ry is "cur", row ry - 1 is "prev"); the first two rounds only fill the window
+                const int yn = y0 + ry + 1;
+                float tn = 0.f; bool mn = false, memn = false;
+                if (ry + 1 <= h && col_ok && yn >= 0 && yn < H) {
+                    const int p = yn * W + xg;
+                    const int v = L[p];
+                    if (v == l) { tn = Tb[p]; memn = true; }
+                    else if (cpb_foreign_live(v, l, alive)) {
+                        if (info[v] & CPB_QI_T32) tn = Tb[p]; else mn = true;
+                    }
+                }
+                t_prev = t_cur; m_prev = m_cur;
+                t_cur = t_next; m_cur = m_next; mem_cur = mem_next;
+                t_next = tn; m_next = mn; mem_next = memn;
+                // neighbours of row ry ("cur"); every lane takes part in the shuffles
+                const float lf = __shfl_up_sync(CPB_FULL, t_cur, 1), rt = __shfl_down_sync(CPB_FULL, t_cur, 1);
+                const int mlf = __shfl_up_sync(CPB_FULL, (int)m_cur, 1), mrt = __shfl_down_sync(CPB_FULL, (int)m_cur, 1);
+                if (ry >= 0 && ry < h && mem_cur) {          // member lanes are 1 .. w: both shuffles have a source
+                    missing |= m_prev || m_next || mlf != 0 || mrt != 0;
+                    const int p = (y0 + ry) * W + xg;
+                    cpb_q32_pixel(t_prev, t_next, lf, rt, dPy[p], dPx[p], eta, sc, sb);
+                }
+            }
+        } else if (lane < w) {
             const int x = x0 + lane;
             for (int r = 0; r < h; r++) {
                 const int y = y0 + r, p = y * W + x;
