@@ -92,6 +92,17 @@ def test_border_and_fill_wrappers(golden_dir):
     lab = pc.nested_rings().astype(np.uint16)
     np.testing.assert_array_equal(butils.fill_holes_and_remove_small_masks(lab.copy(), 15),
                                   outils.fill_holes_and_remove_small_masks(lab.copy(), 15))
+    # dtypes the int32 device path cannot hold: surviving pixels -- every channel -- must keep their exact values
+    rng = np.random.default_rng(2)
+    base = pc.random_label_image(rng, 40, 56, 12)
+    for dtype, scale, off in ((np.float64, 1.5, 0.25), (np.int64, 1, 2 ** 33), (np.uint32, 1, 2 ** 31 + 5), (np.int16, 1, 0)):
+        inst = np.where(base > 0, base.astype(np.int64) * scale + off, 0).astype(dtype)
+        for nch in (0, 3):
+            a = inst.copy() if nch == 0 else np.stack([inst] + [rng.integers(1, 9, size=inst.shape).astype(dtype) for _ in range(nch - 1)], axis=-1)
+            want = classpose_ref.remove_border_instances(a.copy())
+            got = bmetrics.remove_border_instances(a)
+            assert got is a and got.dtype == dtype
+            np.testing.assert_array_equal(got, want)
 
 
 def test_host_buffer_path_matches_device_path():
