@@ -167,6 +167,32 @@ def test_install_on_a_package_tree_with_the_reference_import_style(tmp_path, mon
         sys.modules.pop(m, None)
 
 
+def test_border_removal_keeps_caller_dtype_and_values(monkeypatch):
+    """Host side of remove_border_instances (metrics/pq.py:65-92): only int32 ids travel to the device; float masks and ids
+    beyond int32 go through ranks, and the caller's array is edited in place in its own dtype.  The device call is replaced
+    by the oracle here (no GPU), which leaves exactly the host logic under test."""
+    import parity_cases as pc
+    from classpose_b200 import metrics as bm
+    from oracle import classpose_ref
+
+    class FakeEngine:
+        def remove_border_instances(self, ids, lcap, nch=1):
+            assert ids.dtype == np.int32 and nch == 1 and ids.max() < lcap
+            return torch.from_numpy(classpose_ref.remove_border_instances(ids[0].copy())[None])
+    monkeypatch.setattr(bm, "get_engine", lambda device=None: FakeEngine())
+    rng = np.random.default_rng(2)
+    base = pc.random_label_image(rng, 40, 56, 12)
+    for dtype, scale, off in ((np.float64, 1.5, 0.25), (np.int64, 1, 2 ** 33), (np.uint32, 1, 2 ** 31 + 5), (np.int16, 1, 0)):
+        inst = np.where(base > 0, base.astype(np.int64) * scale + off, 0).astype(dtype)
+        for nch in (0, 3):
+            a = inst.copy() if nch == 0 else np.stack([inst] + [rng.integers(1, 9, size=inst.shape).astype(dtype)
+                                                                 for _ in range(nch - 1)], axis=-1)
+            want = classpose_ref.remove_border_instances(a.copy())
+            got = bm.remove_border_instances(a)
+            assert got is a and got.dtype == dtype
+            np.testing.assert_array_equal(got, want)
+
+
 def test_reference_signatures_are_honoured():
     import inspect
     from classpose_b200 import dynamics, models
