@@ -537,6 +537,10 @@ def build_extra(eng, dev, workload, B, seed):
         extra["blend_max_abs_err_vs_unblended"] = float((eng.calls.average_tiles(
             y_flow, g["y0"], g["x0"], g["flip"], True, tyd, txd, Ly, Lx, pad)[:, :2] - dP).abs().max().item())
         extra["cells_vs_unblended"] = [int(out[1].sum().item()), int(ref[1].sum().item())]
+        for _ in range(3):      # warm-up (stream-ordered allocator pool, clocks)
+            eng.calls.average_tiles(y_flow, g["y0"], g["x0"], g["flip"], True, tyd, txd, Ly, Lx, pad, x4, cover)
+            eng.calls.average_tiles(y_cls, g["y0"], g["x0"], g["flip"], False, tyd, txd, Ly, Lx, pad, x4, cover)
+        torch.cuda.synchronize()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev[0].record()
         for _ in range(3):
@@ -553,7 +557,7 @@ def build_extra(eng, dev, workload, B, seed):
     return cfg, step, (dP, cellprob, logits), extra
 
 
-def hooks_e2e(host_tiles, threads=2, n=200):
+def hooks_e2e(host_tiles, threads=2, n=400):
     """Numpy in / numpy out through the callables install() puts in place of the reference's (hooks A and C), one tile per
     call as predict_wsi.py:749-756 does: single-thread latency and the throughput of `threads` host threads."""
     import numpy as np
@@ -566,7 +570,7 @@ def hooks_e2e(host_tiles, threads=2, n=200):
                                  PARAMS["flow_threshold"], PARAMS["min_size"], PARAMS["max_size_fraction"], 0.0, None)
         cm, _ = models.compute_class_masks(m, lg)
         return m
-    for i in range(8):
+    for i in range(40):
         one(i)
     lat = []
     for i in range(n):
@@ -577,7 +581,7 @@ def hooks_e2e(host_tiles, threads=2, n=200):
 
     def worker(k):
         try:
-            for i in range(4):
+            for i in range(40):           # plan creation (graph capture, pinned allocations) and warm-up
                 one(i)
             bar.wait(timeout=120)
             for i in range(n):
