@@ -842,8 +842,6 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
 }
 
 
-extern "C" {
-
 #ifndef CPB_SIM
 namespace {
 struct PartStreams {            // helper streams and events of one host thread (created on first use, per device)
@@ -878,40 +876,52 @@ thread_local PartStreams tl_parts;
 }  // namespace
 #endif
 
-int cpb_compute_masks_device(const float* dP, const float* cellprob, const float* logits, int B, int H, int W,
-                             int C, const cpb_params* prm, int32_t* masks, int32_t* counts, int32_t* cell_class,
-                             uint8_t* class_masks, void* workspace, size_t workspace_bytes, void* stream) {
+// fork / join: part(b0, nb, ws, ws_bytes, stream) runs sub-batch [b0, b0 + nb) of the call; part 0 stays on the caller's
+// stream, the others run on this thread's helper streams behind an event, and the caller's stream waits for all of them.
+// Still one asynchronous, stream-ordered call for the caller.  Not used while the caller's stream is being captured.
+template <class F>
+static int run_in_parts(int B, int H, int W, int C, void* workspace, size_t workspace_bytes, void* stream, F&& part) {
 #ifndef CPB_SIM
     const int np = batch_parts(B);
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(reinterpret_cast<cudaStream_t>(stream), &cap);
-    if (np > 1 && dP && cellprob && prm && masks && counts && workspace && cap == cudaStreamCaptureStatusNone && tl_parts.ensure()) {
-        // fork: part 0 stays on the caller's stream, the others run on helper streams behind an event; join at the end.
-        // Still asynchronous for the caller, who sees one stream-ordered call.
+    if (cudaStreamIsCapturing(reinterpret_cast<cudaStream_t>(stream), &cap) != cudaSuccess) cudaGetLastError();
+    if (np > 1 && workspace && cap == cudaStreamCaptureStatusNone && tl_parts.ensure()) {
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-        const size_t N = (size_t)H * W;
-        const int LC = cpb_label_capacity(H, W);
         char* ws = reinterpret_cast<char*>(workspace);
         size_t off = 0;
         cudaEventRecord(tl_parts.ready, st);
         int rc = 0;
         for (int k = 0; k < np && rc == 0; k++) {
             const int b0 = part_begin(B, np, k), nb = part_begin(B, np, k + 1) - b0;
-            const size_t need = carve(nullptr, nb, H, W, logits ? C : 0, 0).bytes + 2 * kAlign;
+            const size_t need = carve(nullptr, nb, H, W, C, 0).bytes + 2 * kAlign;
             if (off + need > workspace_bytes) { rc = CPB_E_WORKSPACE; break; }
             cudaStream_t sk = k == 0 ? st : tl_parts.helper[k - 1];
             if (k > 0) cudaStreamWaitEvent(sk, tl_parts.ready, 0);
-            rc = compute_masks_impl(dP + (size_t)b0 * 2 * N, cellprob + (size_t)b0 * N, logits ? logits + (size_t)b0 * C * N : nullptr, nb,
-                                    H, W, C, prm, masks + (size_t)b0 * N, counts + b0, cell_class ? cell_class + (size_t)b0 * LC : nullptr,
-                                    class_masks ? class_masks + (size_t)b0 * N : nullptr, ws + off, need, sk, nullptr);
+            rc = part(b0, nb, static_cast<void*>(ws + off), need, static_cast<void*>(sk));
             if (k > 0) { cudaEventRecord(tl_parts.done[k - 1], sk); cudaStreamWaitEvent(st, tl_parts.done[k - 1], 0); }
             off += need;
         }
         return rc;
     }
 #endif
-    return compute_masks_impl(dP, cellprob, logits, B, H, W, C, prm, masks, counts, cell_class, class_masks, workspace,
-                              workspace_bytes, stream, nullptr);
+    return part(0, B, workspace, workspace_bytes, stream);
+}
+
+extern "C" {
+
+int cpb_compute_masks_device(const float* dP, const float* cellprob, const float* logits, int B, int H, int W,
+                             int C, const cpb_params* prm, int32_t* masks, int32_t* counts, int32_t* cell_class,
+                             uint8_t* class_masks, void* workspace, size_t workspace_bytes, void* stream) {
+    if (B <= 0 || H < 2 || W < 2) return CPB_E_ARG;
+    const size_t N = (size_t)H * W;
+    const int LC = cpb_label_capacity(H, W);
+    return run_in_parts(B, H, W, logits ? C : 0, workspace, workspace_bytes, stream,
+                        [&](int b0, int nb, void* ws, size_t ws_bytes, void* st) {
+        return compute_masks_impl(dP ? dP + (size_t)b0 * 2 * N : nullptr, cellprob ? cellprob + (size_t)b0 * N : nullptr,
+                                  logits ? logits + (size_t)b0 * C * N : nullptr, nb, H, W, C, prm, masks ? masks + (size_t)b0 * N : nullptr,
+                                  counts ? counts + b0 : nullptr, cell_class ? cell_class + (size_t)b0 * LC : nullptr,
+                                  class_masks ? class_masks + (size_t)b0 * N : nullptr, ws, ws_bytes, st, nullptr);
+    });
 }
 
 int cpb_num_stages(void) { return S_COUNT; }
@@ -1123,39 +1133,68 @@ int cpb_eval_tail_device(const float* y_flows, const float* y_logits, int B, int
     if (!y_flows || !y0 || !x0 || !flip || !taper_y || !taper_x || !prm || !dP || !cellprob || !masks || !counts) return CPB_E_ARG;
     if (y_logits && (!logits || !cell_class || C < 1 || C > 255)) return CPB_E_ARG;
     const int H = Ly - cy0 - cy1, W = Lx - cx0 - cx1;
-    if (ntiles <= 0 || ly <= 0 || lx <= 0 || cy0 < 0 || cx0 < 0) return CPB_E_ARG;
+    if (B <= 0 || ntiles <= 0 || ly <= 0 || lx <= 0 || cy0 < 0 || cx0 < 0 || !workspace) return CPB_E_ARG;
     // the fused kernel's geometry promises (the WSI path: 256-px sub-tiles, 8 / 16-px pads): otherwise CPB_E_ARG and the
     // caller composes cpb_average_tiles_ex_device + cpb_compute_masks_device itself
     if (lx % 4 || cx0 % 4 || W % 64 || H < 2 || reinterpret_cast<uintptr_t>(y_flows) % 16 || reinterpret_cast<uintptr_t>(dP) % 16 ||
         reinterpret_cast<uintptr_t>(cellprob) % 16 || reinterpret_cast<uintptr_t>(masks) % 16)
         return CPB_E_ARG;
-    CPB_PROLOGUE(y_logits ? C : 0, 0)
+    { int e_ = check_geom(B, H, W); if (e_) return e_; }
     if ((long long)(H + 2) * (W + 2 * CPB_FLOW_PADX) >= (1LL << 24)) return CPB_E_RANGE;
-    int e;
-    if (y_logits) {          // class logits: un-flip + blend (transforms/transforms.py:4-21, core.py:218-220)
-        e = cpb_average_tiles_ex_device(y_logits, B, ntiles, C, ly, lx, y0, x0, flip, 0, taper_y, taper_x, Ly, Lx, cy0, cy1, cx0,
-                                        cx1, logits, 1, 0, stream);
-        if (e) return e;
-    }
+    ensure_attributes();
+    cudaStream_t st0 = reinterpret_cast<cudaStream_t>(stream);
+    // weight table and reciprocal normaliser depend on the geometry only: built once, before the batch is cut into parts
     float* tab = nullptr;
-    const size_t nw = (size_t)ly * lx, nr = (size_t)H * W;
-    if (cudaMallocAsync(reinterpret_cast<void**>(&tab), (2 * nw + 2 * nr) * sizeof(float), st) != cudaSuccess) return (int)cudaGetLastError();
+    const size_t nw = (size_t)ly * lx, nr = (size_t)H * W, N = nr;
+    if (cudaMallocAsync(reinterpret_cast<void**>(&tab), (2 * nw + 2 * nr) * sizeof(float), st0) != cudaSuccess) return (int)cudaGetLastError();
     float* wh = tab; float* wl = tab + nw; float* rh = tab + 2 * nw; float* rl = rh + nr;
-    CPB_LAUNCH_COUNTED(k_blend_weights, dim3(blocks_for((long long)nw, 256)), dim3(256), 0, st, taper_y, taper_x, ly, lx, wh, wl);
-    CPB_LAUNCH_COUNTED(k_blend_rinv, dim3(blocks_for((long long)nr, 256)), dim3(256), 0, st, ntiles, ly, lx, y0, x0, taper_y, taper_x,
+    CPB_LAUNCH_COUNTED(k_blend_weights, dim3(blocks_for((long long)nw, 256)), dim3(256), 0, st0, taper_y, taper_x, ly, lx, wh, wl);
+    CPB_LAUNCH_COUNTED(k_blend_rinv, dim3(blocks_for((long long)nr, 256)), dim3(256), 0, st0, ntiles, ly, lx, y0, x0, taper_y, taper_x,
                        cy0, cx0, H, W, rh, rl);
-    cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
-    cudaMemsetAsync(w.t.fail, 0, B * sizeof(int), st);
+    const int LC = cpb_label_capacity(H, W);
+    const size_t tplane = (size_t)ntiles * ly * lx;
     const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
-    const long long nblk = (long long)B * ((H + 15) / 16) * (W / 64);
-    CPB_LAUNCH_COUNTED(k_blend_prep, dim3((unsigned)nblk), dim3(256), 0, st, y_flows, B, ntiles, ly, lx, y0, x0, flip, augment ? 1 : 0,
-                       (const float*)wh, (const float*)wl, (const float*)rh, (const float*)rl, cy0, cx0, H, W,
-                       prm->cellprob_threshold, sx, sy, dP, cellprob, reinterpret_cast<float4*>(w.flow),
-                       reinterpret_cast<int4*>(masks), w.list, w.list_n);
-    cudaFreeAsync(tab, st);
-    CPB_CHECK_LAUNCH();
-    return compute_masks_impl(dP, cellprob, y_logits ? logits : nullptr, B, H, W, C, prm, masks, counts, cell_class, class_masks,
-                              workspace, workspace_bytes, stream, nullptr, nullptr, true);
+    const int rc = run_in_parts(B, H, W, y_logits ? C : 0, workspace, workspace_bytes, stream,
+                                [&](int b0, int nb, void* ws, size_t ws_bytes, void* stp) -> int {
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stp);
+        const uintptr_t wsa = (reinterpret_cast<uintptr_t>(ws) + kAlign - 1) / kAlign * kAlign;
+        Workspace w = carve(reinterpret_cast<void*>(wsa), nb, H, W, y_logits ? C : 0, 0);
+        if (w.bytes + (wsa - reinterpret_cast<uintptr_t>(ws)) > ws_bytes) return CPB_E_WORKSPACE;
+        float* dPp = dP + (size_t)b0 * 2 * N; float* cpp = cellprob + (size_t)b0 * N;
+        float* lgp = y_logits ? logits + (size_t)b0 * C * N : nullptr;
+        int32_t* mp = masks + (size_t)b0 * N;
+        if (y_logits) {          // class logits: un-flip + blend (transforms/transforms.py:4-21, core.py:218-220)
+            const dim3 grid(blocks_for((long long)nb * H * (W / 4), 256));
+            const float* ysrc = y_logits + (size_t)b0 * C * tplane;
+#define CPB_EFT_LAUNCH(Nc) CPB_LAUNCH_COUNTED(k_average_tiles_eft<Nc>, grid, dim3(256), 0, st, ysrc, nb, ntiles, C, c0, ly, lx, y0, x0, flip, \
+                           0, (const float*)wh, (const float*)wl, (const float*)rh, (const float*)rl, cy0, cx0, H, W, lgp)
+            for (int c0 = 0; c0 < C;) {
+                const int rem = C - c0;
+                const int n = rem <= 5 ? rem : (rem == 6 ? 3 : (rem == 7 ? 4 : 5));
+                switch (n) {
+                    case 1: CPB_EFT_LAUNCH(1); break;
+                    case 2: CPB_EFT_LAUNCH(2); break;
+                    case 3: CPB_EFT_LAUNCH(3); break;
+                    case 4: CPB_EFT_LAUNCH(4); break;
+                    default: CPB_EFT_LAUNCH(5); break;
+                }
+                c0 += n;
+            }
+#undef CPB_EFT_LAUNCH
+        }
+        cudaMemsetAsync(w.list_n, 0, 64 * sizeof(unsigned), st);
+        cudaMemsetAsync(w.t.fail, 0, nb * sizeof(int), st);
+        const long long nblk = (long long)nb * ((H + 15) / 16) * (W / 64);
+        CPB_LAUNCH_COUNTED(k_blend_prep, dim3((unsigned)nblk), dim3(256), 0, st, y_flows + (size_t)b0 * 3 * tplane, nb, ntiles, ly, lx, y0, x0,
+                           flip, augment ? 1 : 0, (const float*)wh, (const float*)wl, (const float*)rh, (const float*)rl, cy0, cx0, H, W,
+                           prm->cellprob_threshold, sx, sy, dPp, cpp, reinterpret_cast<float4*>(w.flow), reinterpret_cast<int4*>(mp),
+                           w.list, w.list_n);
+        CPB_CHECK_LAUNCH();
+        return compute_masks_impl(dPp, cpp, lgp, nb, H, W, C, prm, mp, counts + b0, cell_class ? cell_class + (size_t)b0 * LC : nullptr,
+                                  class_masks ? class_masks + (size_t)b0 * N : nullptr, ws, ws_bytes, stp, nullptr, nullptr, true);
+    });
+    cudaFreeAsync(tab, st0);          // (the caller's stream has joined every part by now)
+    return rc;
 }
 
 int cpb_label_offsets_device(const int32_t* counts, int B, int64_t base, int64_t* offsets, int64_t* total,
