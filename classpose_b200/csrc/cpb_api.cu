@@ -239,9 +239,10 @@ FollowSchedule follow_schedule(int niter) {
 //   CPB_QC_FUSED=0       every label's flow error from T in global memory (k_flow_err) instead of the diffusion tile
 //   CPB_VOTE_FUSED=0     class vote as its own pass over the finished label image
 //   CPB_QC_SCREEN=0      every label through the float64 diffusion (no float32 screen in front of it)
+//   CPB_FOLLOW_SMALL=0   1024-entry chunks in the trajectory pool for every batch size (1: 256-entry chunks for a handful of tiles)
 //   CPB_BLEND_EFT=0      blend with float64 arithmetic per element (numpy's literal op sequence) instead of the float32
 //                        error-free form (identical up to ~1e-6 of the elements by one ulp)
-std::atomic<int> g_switch[6] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
+std::atomic<int> g_switch[7] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
 bool switch_on(int which, const char* env_name) {
     int v = g_switch[which].load(std::memory_order_relaxed);
     if (v < 0) {
@@ -255,6 +256,7 @@ bool qc_fused_enabled() { return switch_on(CPB_SWITCH_QC_FUSED, "CPB_QC_FUSED");
 bool vote_fused_enabled() { return switch_on(CPB_SWITCH_VOTE_FUSED, "CPB_VOTE_FUSED"); }
 bool qc_screen_enabled() { return switch_on(CPB_SWITCH_QC_SCREEN, "CPB_QC_SCREEN"); }
 bool blend_eft_enabled() { return switch_on(CPB_SWITCH_BLEND_EFT, "CPB_BLEND_EFT"); }
+bool follow_small_enabled() { return switch_on(CPB_SWITCH_FOLLOW_SMALL, "CPB_FOLLOW_SMALL"); }
 // value 2 (tests only): the screen also runs when the caller asks for the per-label errors, and reports
 // (float32 error, bound) bit-packed into the float64 error of the labels it decided
 bool qc_screen_debug() { return g_switch[CPB_SWITCH_QC_SCREEN].load(std::memory_order_relaxed) == 2; }
@@ -351,19 +353,24 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     }
 #endif
     if (mode == 2 && niter >= 32 && pool_ok) {
-        // one block per chunk of the list (blocks past the end of the list exit at once)
+        // one block per chunk of the list (blocks past the end of the list exit at once).  A handful of tiles (the
+        // numpy hooks hand over one) cannot fill the GPU with 1024-entry chunks: 256-entry chunks give four times
+        // the blocks and one trajectory per thread, i.e. a quarter of the serial Euler steps per thread
+        const bool small = BN <= (long long)CPB_FP_POOL * 4 * sm_count() && follow_small_enabled();
+        const int pool = small ? CPB_FP_POOL_SMALL : CPB_FP_POOL;
 #ifdef CPB_SIM
-        const unsigned pgrid = (unsigned)std::min<long long>(blocks_for(BN, CPB_FP_POOL), 8);
+        const unsigned pgrid = (unsigned)std::min<long long>(blocks_for(BN, pool), 8);
 #else
-        const unsigned pgrid = blocks_for(BN, CPB_FP_POOL);
+        const unsigned pgrid = blocks_for(BN, pool);
 #endif
+#define CPB_LAUNCH_POOL(WPv, POOLv) CPB_LAUNCH_COUNTED((k_follow_pool<WPv, POOLv>), dim3(pgrid), dim3(CPB_FP_THREADS), 0, st, w.flow, \
+                               w.list, w.list_n, H, W, niter, follow_schedule(niter), pfinal, pfloat, hist)
         if (W == 256) {       // the WSI tile width: row pitch as an immediate
-            CPB_LAUNCH_COUNTED(k_follow_pool<256 + 2 * CPB_FLOW_PADX>, dim3(pgrid), dim3(CPB_FP_THREADS), 0, st, w.flow, w.list,
-                               w.list_n, H, W, niter, follow_schedule(niter), pfinal, pfloat, hist);
+            if (small) CPB_LAUNCH_POOL(256 + 2 * CPB_FLOW_PADX, CPB_FP_POOL_SMALL); else CPB_LAUNCH_POOL(256 + 2 * CPB_FLOW_PADX, CPB_FP_POOL);
         } else {
-            CPB_LAUNCH_COUNTED(k_follow_pool<0>, dim3(pgrid), dim3(CPB_FP_THREADS), 0, st, w.flow, w.list, w.list_n, H, W, niter,
-                               follow_schedule(niter), pfinal, pfloat, hist);
+            if (small) CPB_LAUNCH_POOL(0, CPB_FP_POOL_SMALL); else CPB_LAUNCH_POOL(0, CPB_FP_POOL);
         }
+#undef CPB_LAUNCH_POOL
     } else if (mode >= 1 && niter >= 32 && B < (1 << 28)) {
         // merge points at a quarter and a half of the integration (48 and 96 of 200 steps)
         CPB_LAUNCH_COUNTED(k_follow_merge, dim3(grid), dim3(CPB_FM_THREADS), 0, st, w.flow, w.list, w.list_n, H, W, niter,
@@ -929,7 +936,7 @@ const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames
 void cpb_debug_set_follow_merge(int mode) { g_follow_merge.store(mode, std::memory_order_relaxed); }
 void cpb_debug_set_switch(int which, int value) {
     if (which == CPB_SWITCH_FOLLOW_MERGE) g_follow_merge.store(value, std::memory_order_relaxed);
-    else if (which > 0 && which < 6) g_switch[which].store(value, std::memory_order_relaxed);
+    else if (which > 0 && which < 7) g_switch[which].store(value, std::memory_order_relaxed);
 }
 long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void cpb_debug_qc_stats(int32_t* out) {

@@ -151,6 +151,8 @@ k_prep_flow_v4(const float4* CPB_RESTRICT dP, const float4* CPB_RESTRICT cellpro
 CPB_DEVICE u64 cpb_pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 CPB_DEVICE void cpb_upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 CPB_DEVICE u64 cpb_add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+CPB_DEVICE u64 cpb_add2_rm(u64 a, u64 b) { u64 r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+CPB_DEVICE float cpb_clamp1(float v) { float r; asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(1.0f)); return r; }
 CPB_DEVICE u64 cpb_sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 CPB_DEVICE u64 cpb_mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 CPB_DEVICE u64 cpb_fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
@@ -160,17 +162,60 @@ CPB_DEVICE u64 cpb_fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, 
 // The four taps of the previous step: a trajectory that has reached its sink keeps sampling the same 2 x 2 cell
 // (sub-pixel steps), so the gathers -- the L1 data pipe is the busiest unit of the packed kernel, ~3 wavefronts per
 // scattered 8-byte load -- are skipped while the tap index does not change.  Same values, same arithmetic.
-struct EulerTaps { int key; float2 nw, ne, sw, se; };
+struct EulerTaps { int key; float2 nw, ne, sw, se; u64 pm, mp, one0; };   // pm .. one0: constant pairs (cpb_taps_init)
 #define CPB_TAPS_NONE 0x7fffffff
 
+// CPB_EULER_VARIANT (compile time, A/B only; all bit-identical; follow_flows stage per 1024 conic tiles,
+// profiles/r02/ab_euler_variants.txt): 0 round-1 form, 29 instructions of which 10 packed, 2.09 ms; 1 (default) the same
+// with a one-instruction clamp, 27 / 10, 2.04 ms; 2 also FADD2.RM floor and paired tap distances, 25 / 15, 2.13 ms;
+// 3 all scalar, 37 / 0, 2.35 ms.  A packed instruction holds the fmaheavy pipe for two cycles (FFMA2 : FFMA = 1.98 : 1
+// in tests/studies/f32x2_issue.cu), so packing pays for operations that would otherwise be two instructions, and
+// turning scalar work into extra packed work (variant 2) does not.
+#ifndef CPB_EULER_VARIANT
+#define CPB_EULER_VARIANT 1
+#endif
 template <int WP, bool PACKED>
 CPB_DEVICE void cpb_euler_step_t(const float2* CPB_RESTRICT f, int Wp_rt, float fH, float fW, float& px, float& py,
                                  EulerTaps& tp) {
     const int Wp = WP > 0 ? WP : Wp_rt;
 #ifndef CPB_SIM
   if (PACKED) {
+#if CPB_EULER_VARIANT == 3
+    // all-scalar form of the same step (tap reuse, FADD-formed tap index, one-instruction clamp): the A/B that
+    // separates "fewer instructions" from "fewer issue cycles" for the packed forms
+    const float ix = fmaf(__fadd_rn(px, 1.f), fW, -0.5f), iy = fmaf(__fadd_rn(py, 1.f), fH, -0.5f);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int key = __float_as_int(fmaf(fy0, (float)Wp, __fadd_rn(fx0, 12582912.f)));
+    if (key != tp.key) {
+        const float2* r0 = f + key;
+        const float2* r1 = r0 + Wp;
+        tp.nw = __ldg(r0); tp.ne = __ldg(r0 + 1); tp.sw = __ldg(r1); tp.se = __ldg(r1 + 1);
+        tp.key = key;
+    }
+    const float ax1 = __fsub_rn(__fadd_rn(fx0, 1.f), ix), ay1 = __fsub_rn(__fadd_rn(fy0, 1.f), iy);
+    const float ax0 = __fsub_rn(ix, fx0), ay0 = __fsub_rn(iy, fy0);
+    const float wnw = __fmul_rn(ax1, ay1), wne = __fmul_rn(ax0, ay1);
+    const float wsw = __fmul_rn(ax1, ay0), wse = __fmul_rn(ax0, ay0);
+    float ox = __fmul_rn(tp.nw.x, wnw), oy = __fmul_rn(tp.nw.y, wnw);
+    ox = fmaf(tp.ne.x, wne, ox); oy = fmaf(tp.ne.y, wne, oy);
+    ox = fmaf(tp.sw.x, wsw, ox); oy = fmaf(tp.sw.y, wsw, oy);
+    ox = fmaf(tp.se.x, wse, ox); oy = fmaf(tp.se.y, wse, oy);
+    px = cpb_clamp1(__fadd_rn(px, ox));
+    py = cpb_clamp1(__fadd_rn(py, oy));
+#else
     // same operations, same order, two lanes (x, y) per instruction
     const u64 i2 = cpb_fma2(cpb_add2(cpb_pk(px, py), cpb_pk(1.f, 1.f)), cpb_pk(fW, fH), cpb_pk(-0.5f, -0.5f));
+#if CPB_EULER_VARIANT == 2
+    // floor without the XU pipe: i + 1.5 * 2^23 rounded toward -inf is exactly 1.5 * 2^23 + floor(i) (floats of that
+    // binade are the integers, -0.5 <= i < 2^22), and subtracting the constant again is exact -- FADD2.RM + FADD2
+    // instead of two FRND, and the x half of t2 is already the biased column the tap index needs.
+    const u64 t2 = cpb_add2_rm(i2, cpb_pk(12582912.f, 12582912.f));
+    const u64 f0 = cpb_add2(t2, cpb_pk(-12582912.f, -12582912.f));
+    float tx, ty, fx0, fy0;
+    cpb_upk(t2, tx, ty);
+    cpb_upk(f0, fx0, fy0);
+    const int key = __float_as_int(fmaf(fy0, (float)Wp, tx));
+#else
     float ix, iy;
     cpb_upk(i2, ix, iy);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
@@ -178,26 +223,51 @@ CPB_DEVICE void cpb_euler_step_t(const float2* CPB_RESTRICT f, int Wp_rt, float 
     // tap index: fy0 * Wp + fx0 is an exact small integer; adding 1.5 * 2^23 leaves it in the low mantissa bits, so
     // the float -> int conversion (XU pipe) becomes an FADD.  `f` arrives biased by -0x4B400000 elements.
     const int key = __float_as_int(fmaf(fy0, (float)Wp, fx0 + 12582912.f));
-    const u64 f1 = cpb_add2(f0, cpb_pk(1.f, 1.f));
+#endif
     if (key != tp.key) {
         const float2* r0 = f + key;
         const float2* r1 = r0 + Wp;
         tp.nw = __ldg(r0); tp.ne = __ldg(r0 + 1); tp.sw = __ldg(r1); tp.se = __ldg(r1 + 1);
         tp.key = key;
     }
+    float wnw, wne, wsw, wse;
+#if CPB_EULER_VARIANT == 2
+    // the two tap distances of an axis as ONE pair {f1 - i, i - f0}: {f0 + 1, -f0} is exact, and an fma whose
+    // product is +-i is the subtraction itself (one rounding); a pair times a broadcast weight then gives two of
+    // the four bilinear weights per FMUL2
+    float ix, iy;
+    cpb_upk(i2, ix, iy);
+    const u64 pm = tp.pm, mp = tp.mp, one0 = tp.one0;      // {1, -1}, {-1, 1}, {1, 0}
+    const u64 ax = cpb_fma2(cpb_pk(ix, ix), mp, cpb_fma2(cpb_pk(fx0, fx0), pm, one0));   // {ax1, ax0}
+    const u64 ay = cpb_fma2(cpb_pk(iy, iy), mp, cpb_fma2(cpb_pk(fy0, fy0), pm, one0));   // {ay1, ay0}
+    float ay1, ay0;
+    cpb_upk(ay, ay1, ay0);
+    cpb_upk(cpb_mul2(ax, cpb_pk(ay1, ay1)), wnw, wne);
+    cpb_upk(cpb_mul2(ax, cpb_pk(ay0, ay0)), wsw, wse);
+#else
+    const u64 f1 = cpb_add2(f0, cpb_pk(1.f, 1.f));
     float ax1, ay1, ax0, ay0;
     cpb_upk(cpb_sub2(f1, i2), ax1, ay1);          // (fx1 - ix, fy1 - iy)
     cpb_upk(cpb_sub2(i2, f0), ax0, ay0);          // (ix - fx0, iy - fy0)
-    const float wnw = __fmul_rn(ax1, ay1), wne = __fmul_rn(ax0, ay1);
-    const float wsw = __fmul_rn(ax1, ay0), wse = __fmul_rn(ax0, ay0);
+    wnw = __fmul_rn(ax1, ay1); wne = __fmul_rn(ax0, ay1);
+    wsw = __fmul_rn(ax1, ay0); wse = __fmul_rn(ax0, ay0);
+#endif
     u64 o = cpb_mul2(cpb_pk(tp.nw.x, tp.nw.y), cpb_pk(wnw, wnw));   // 0 + v*w
     o = cpb_fma2(cpb_pk(tp.ne.x, tp.ne.y), cpb_pk(wne, wne), o);
     o = cpb_fma2(cpb_pk(tp.sw.x, tp.sw.y), cpb_pk(wsw, wsw), o);
     o = cpb_fma2(cpb_pk(tp.se.x, tp.se.y), cpb_pk(wse, wse), o);
     float nx, ny;
     cpb_upk(cpb_add2(cpb_pk(px, py), o), nx, ny);
+#if CPB_EULER_VARIANT == 0
     px = fminf(fmaxf(nx, -1.f), 1.f);
     py = fminf(fmaxf(ny, -1.f), 1.f);
+#else
+    // clamp to [-1, 1] in one instruction per coordinate: min(|n|, 1) with the sign of n (FMNMX.XORSIGN) is
+    // fmin(fmax(n, -1), 1) for every n, signed zeros included
+    px = cpb_clamp1(nx);
+    py = cpb_clamp1(ny);
+#endif
+#endif
     return;
   }
 #endif
@@ -586,9 +656,8 @@ k_follow_merge(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT lis
 // plain kernel (two merge points over 256 pixels: ~60 %).  Which duplicate survives depends on the CAS race, but
 // duplicates hold the same bits, so the output is bit-identical to k_follow.
 #define CPB_FP_THREADS 256
-#define CPB_FP_POOL 1024
-#define CPB_FP_PER (CPB_FP_POOL / CPB_FP_THREADS)
-#define CPB_FP_SLOTS 2048
+#define CPB_FP_POOL 1024        // entries of the foreground list per block (throughput form)
+#define CPB_FP_POOL_SMALL 256   // latency form for a handful of tiles: one trajectory per thread, four times the blocks
 #define CPB_FP_MAXMERGE 16
 
 struct FollowSchedule { int n; int at[CPB_FP_MAXMERGE]; };   // merge points (step numbers), ascending, < niter
@@ -596,27 +665,28 @@ struct FollowSchedule { int n; int at[CPB_FP_MAXMERGE]; };   // merge points (st
 #ifndef CPB_FP_MINBLOCKS
 #define CPB_FP_MINBLOCKS 6
 #endif
-template <int WP>
+template <int WP, int POOL>
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FP_THREADS, CPB_FP_MINBLOCKS)
 k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
               const unsigned* CPB_RESTRICT list_n, int H, int W, int niter, FollowSchedule sch,
               int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
-    CPB_SHARED float2 s_pos[CPB_FP_POOL];               // position of live trajectory i
-    CPB_SHARED int s_tile[CPB_FP_POOL];                 // its tile
-    CPB_SHARED int s_slot[CPB_FP_SLOTS];                // hash slot -> trajectory index (-1 empty)
-    CPB_SHARED unsigned short s_cur[CPB_FP_POOL];       // pixel -> live trajectory
-    CPB_SHARED unsigned short s_new[CPB_FP_POOL];       // trajectory -> index after the merge
+    constexpr int PER = POOL / CPB_FP_THREADS, SLOTS = 2 * POOL;
+    CPB_SHARED float2 s_pos[POOL];               // position of live trajectory i
+    CPB_SHARED int s_tile[POOL];                 // its tile
+    CPB_SHARED int s_slot[SLOTS];                // hash slot -> trajectory index (-1 empty)
+    CPB_SHARED unsigned short s_cur[POOL];       // pixel -> live trajectory
+    CPB_SHARED unsigned short s_new[POOL];       // trajectory -> index after the merge
     CPB_SHARED int s_scan[33];
     const unsigned total = *list_n;
     const int N = H * W, Wp = W + 2 * CPB_FLOW_PADX, Np = (H + 2) * Wp;
     const float fW = 0.5f * (float)W, fH = 0.5f * (float)H;      // halved: see cpb_euler_step
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
     const int t = threadIdx.x, lane = t & 31;
-    for (unsigned i0 = blockIdx.x * CPB_FP_POOL; i0 < total; i0 += gridDim.x * CPB_FP_POOL) {
-        const int n0 = (int)min((unsigned)CPB_FP_POOL, total - i0);
-        unsigned gi[CPB_FP_PER];
+    for (unsigned i0 = blockIdx.x * POOL; i0 < total; i0 += gridDim.x * POOL) {
+        const int n0 = (int)min((unsigned)POOL, total - i0);
+        unsigned gi[PER];
 #pragma unroll
-        for (int k = 0; k < CPB_FP_PER; k++) {
+        for (int k = 0; k < PER; k++) {
             const int i = t + k * CPB_FP_THREADS;
             gi[k] = 0;
             if (i < n0) {
@@ -633,6 +703,14 @@ k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list
         }
         __syncthreads();
         int n = n0, step = 0;
+        EulerTaps tp;
+#if !defined(CPB_SIM) && CPB_EULER_VARIANT == 2
+        // the constant pairs of variant 2 stay in registers only if they are built from a per-thread run-time value
+        // (ptxas folds literals back into immediates / uniform registers and rebuilds the pairs with moves every step)
+        const bool tv = __float_as_int(s_pos[t].x) != 0x7fc00123, tw = __float_as_int(s_pos[t].y) != 0x7fc00123;   // always true
+        const float c1 = tv ? 1.f : 2.f, cm1 = tv ? -1.f : 2.f, c0 = tw ? 0.f : 2.f, d1 = tw ? 1.f : 2.f;
+        tp.pm = cpb_pk(c1, cm1); tp.mp = cpb_pk(cm1, c1); tp.one0 = cpb_pk(d1, c0);
+#endif
         for (int m = 0; m <= sch.n; m++) {
             const int until = m < sch.n ? sch.at[m] : niter;
             // ---- integrate the live trajectories from `step` to `until`
@@ -643,7 +721,6 @@ k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list
                 f -= 0x4B400000;       // bias of the FADD-based tap index (see cpb_euler_step_t)
                 asm volatile("" : "+l"(f));
 #endif
-                EulerTaps tp;
                 tp.key = CPB_TAPS_NONE;
                 for (int s = step; s < until; s++) cpb_euler_step_t<WP, true>(f, Wp, fH, fW, p.x, p.y, tp);
                 s_pos[i] = p;
@@ -652,16 +729,16 @@ k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list
             if (m == sch.n) break;
             // ---- merge: thread t owns trajectories [t*per, t*per + per)
             // table of the smallest power of two >= 2n slots (load factor <= 1/2)
-            const int smask = n <= 32 ? 63 : min(CPB_FP_SLOTS, 1 << (33 - __clz(n - 1))) - 1;
+            const int smask = n <= 32 ? 63 : min(SLOTS, 1 << (33 - __clz(n - 1))) - 1;
             for (int i = t; i <= smask; i += CPB_FP_THREADS) s_slot[i] = -1;
             __syncthreads();                                  // positions written, table cleared
-            const int per = (n + CPB_FP_THREADS - 1) / CPB_FP_THREADS;   // <= CPB_FP_PER
-            int rep[CPB_FP_PER];                              // -1: owner, else the trajectory it duplicates
-            float2 mp[CPB_FP_PER];
-            int mt[CPB_FP_PER];
+            const int per = (n + CPB_FP_THREADS - 1) / CPB_FP_THREADS;   // <= PER
+            int rep[PER];                              // -1: owner, else the trajectory it duplicates
+            float2 mp[PER];
+            int mt[PER];
             int owners = 0;
 #pragma unroll
-            for (int k = 0; k < CPB_FP_PER; k++) {
+            for (int k = 0; k < PER; k++) {
                 const int i = t * per + k;
                 rep[k] = -2;
                 if (k < per && i < n) {
@@ -683,21 +760,21 @@ k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list
             int tot;
             int idx = cpb_block_scan_incl(owners, s_scan, &tot) - owners;     // contains __syncthreads()
 #pragma unroll
-            for (int k = 0; k < CPB_FP_PER; k++)
+            for (int k = 0; k < PER; k++)
                 if (rep[k] == -1) s_new[t * per + k] = (unsigned short)(idx++);
             __syncthreads();                                  // owners' new indices visible; all keys were read
             idx -= owners;
 #pragma unroll
-            for (int k = 0; k < CPB_FP_PER; k++) {
+            for (int k = 0; k < PER; k++) {
                 if (rep[k] == -1) { s_pos[idx] = mp[k]; s_tile[idx] = mt[k]; idx++; }
             }
             // (duplicates resolve through their representative after the owners' entries are final)
-            unsigned short dupnew[CPB_FP_PER];
+            unsigned short dupnew[PER];
 #pragma unroll
-            for (int k = 0; k < CPB_FP_PER; k++) dupnew[k] = rep[k] >= 0 ? s_new[rep[k]] : (unsigned short)0;
+            for (int k = 0; k < PER; k++) dupnew[k] = rep[k] >= 0 ? s_new[rep[k]] : (unsigned short)0;
             __syncthreads();
 #pragma unroll
-            for (int k = 0; k < CPB_FP_PER; k++)
+            for (int k = 0; k < PER; k++)
                 if (rep[k] >= 0) s_new[t * per + k] = dupnew[k];
             __syncthreads();
             for (int i = t; i < n0; i += CPB_FP_THREADS) s_cur[i] = s_new[s_cur[i]];
@@ -707,7 +784,7 @@ k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list
         __syncthreads();                                      // final positions visible
         // ---- every pixel reads the end point of the trajectory it was merged into
 #pragma unroll
-        for (int k = 0; k < CPB_FP_PER; k++) {
+        for (int k = 0; k < PER; k++) {
             const int i = t + k * CPB_FP_THREADS;
             const bool act = i < n0;
             const unsigned amask = __ballot_sync(CPB_FULL, act);

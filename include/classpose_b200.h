@@ -102,6 +102,8 @@ void cpb_debug_set_follow_merge(int mode);
 #define CPB_SWITCH_BLEND_EFT 5      /* CPB_BLEND_EFT: taper blend in float32 with error-free transformations (0: float64
                                        arithmetic per element, numpy's literal sequence; results agree to one ulp on
                                        ~1e-6 of the elements) */
+#define CPB_SWITCH_FOLLOW_SMALL 6   /* CPB_FOLLOW_SMALL: 256-entry chunks in the trajectory pool when the batch is a handful of
+                                       tiles (latency form; 0: 1024-entry chunks always) */
 void cpb_debug_set_switch(int which, int value);
 /* number of kernels this library has launched in this process (statistics for the benchmark) */
 long long cpb_debug_launch_count(void);

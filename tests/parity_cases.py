@@ -96,19 +96,30 @@ def case_follow_flows_merge_is_exact(be):
     dP = f32(np.stack([t["dP"] for t in tiles])); cp = f32(np.stack([t["cellprob"] for t in tiles]))
     rng = np.random.default_rng(5)
     small_dP = f32(rng.normal(0, 2.0, size=(96, 2, 16, 16))); small_cp = f32(rng.normal(-1.0, 1.0, size=(96, 16, 16)))
+    # drift tiles: a constant flow towards each border (plus noise) parks every trajectory on the clamp at +-1 and on
+    # the i = -0.5 / L - 0.5 sampling positions -- the corner cases of the packed step's FADD.RM floor and
+    # FMNMX.XORSIGN clamp, which must equal floorf / fmin(fmax()) of the scalar kernel
+    drift = np.zeros((8, 2, 64, 64), np.float32)
+    for k, (vy, vx) in enumerate(((5, 0), (-5, 0), (0, 5), (0, -5), (5, 5), (-5, -5), (5, -5), (-5, 5))):
+        drift[k, 0] = vy; drift[k, 1] = vx
+    drift = f32(drift + rng.normal(0, 0.7, size=drift.shape)); drift_cp = f32(np.ones((8, 64, 64)))
     try:
-        for a, b in ((dP, cp), (small_dP, small_cp)):
+        for a, b in ((dP, cp), (small_dP, small_cp), (drift, drift_cp)):
             be.set_follow_merge(0)
             p0, f0 = be.follow_flows(a, b, 200, 0.0, want_float=True)
             fg = b > 0
-            for mode in (1, 2, 3):    # two merge points per 256-pixel chunk; trajectory pool; TMA-staged plain kernel (GPU)
+            # two merge points per 256-pixel chunk; trajectory pool with 1024- and with 256-entry chunks (switch 6);
+            # TMA-staged plain kernel (GPU)
+            for mode, small in ((1, -1), (2, 0), (2, 1), (3, -1)):
                 be.set_follow_merge(mode)
+                be.set_switch(6, small)
                 p1, f1 = be.follow_flows(a, b, 200, 0.0, want_float=True)
                 np.testing.assert_array_equal(p0, p1)
                 np.testing.assert_array_equal(f0[:, 0][fg], f1[:, 0][fg])
                 np.testing.assert_array_equal(f0[:, 1][fg], f1[:, 1][fg])
     finally:
         be.set_follow_merge(-1)
+        be.set_switch(6, -1)
 
 
 def case_follow_flows_large_tiles(be):
