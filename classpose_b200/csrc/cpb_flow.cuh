@@ -656,7 +656,9 @@ k_follow_merge(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT lis
 // plain kernel (two merge points over 256 pixels: ~60 %).  Which duplicate survives depends on the CAS race, but
 // duplicates hold the same bits, so the output is bit-identical to k_follow.
 #define CPB_FP_THREADS 256
+#ifndef CPB_FP_POOL
 #define CPB_FP_POOL 1024        // entries of the foreground list per block (throughput form)
+#endif
 #define CPB_FP_POOL_SMALL 256   // latency form for a handful of tiles: one trajectory per thread, four times the blocks
 #define CPB_FP_MAXMERGE 16
 
