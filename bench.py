@@ -432,7 +432,7 @@ def run_ours(args):
                 "note": "follow_flows (200 dependent Euler steps per foreground pixel, ~300 flop per byte) is issue-bound (75 % of the "
                         "issue slots, DRAM at 3 % of peak); the flow check (float32 register-resident screen) is shuffle / issue "
                         "bound.  The HBM fraction is reported as required; the pipe utilisations and the kernels that ARE HBM "
-                        "streams (prep 65 %, final+vote 78 %, blend 71-86 % of the measured copy peak, by ncu DRAM bytes) are in "
+                        "streams (prep 83 %, final+vote 78 %, blend 71-86 % of the measured copy peak, by ncu DRAM bytes) are in "
                         "DESIGN.md section 4"}
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample of the same workload

@@ -15,11 +15,15 @@
 #define CPB_FLOW_PADX 2
 
 CPB_DEVICE float2 cpb_scaled_flow(float dy, float dx, bool fg, float sx, float sy) {
-    // (dP * fg) / 5.  then  *= 2/(L-1)   -- each a separately rounded float32 op
-    const float m = fg ? 1.0f : 0.0f;
-    // (a three-operation exact x / 5 -- tests/studies/div5_exhaustive.cu, 0 mismatches over all float32 -- is no
-    //  faster than the division by a constant nvcc emits: 0.44 ms vs 0.42 ms)
-    return make_float2(__fmul_rn(__fdiv_rn(__fmul_rn(dx, m), 5.0f), sx), __fmul_rn(__fdiv_rn(__fmul_rn(dy, m), 5.0f), sy));
+    // (dP * fg) / 5.  then  *= 2/(L-1)   -- each a separately rounded float32 op.  Background is 0 whatever dP holds
+    // (the reference's dP * 0 keeps the sign of dP on its zero, which no later operation can see), and it must not reach
+    // the division: nvcc's division by a constant tests its operands with FCHK and a ZERO numerator takes the slow
+    // path (a call, ~60 instructions) -- four pixels in five are background.  Foreground lanes divide dP itself,
+    // background lanes a harmless 5, and the select picks.
+    // (a three-operation exact x / 5 -- tests/studies/div5_exhaustive.cu, 0 mismatches over all float32 -- is the
+    //  alternative without FCHK)
+    const float qx = __fmul_rn(__fdiv_rn(fg ? dx : 5.0f, 5.0f), sx), qy = __fmul_rn(__fdiv_rn(fg ? dy : 5.0f, 5.0f), sy);
+    return make_float2(fg ? qx : 0.0f, fg ? qy : 0.0f);
 }
 
 // k_prep_flow: one thread per padded pixel (any W).  Also writes bg_value on background (-1: the p_final contract;
