@@ -377,6 +377,13 @@ def run_ours(args):
     # in place: 16 bytes per class for every 4-pixel group that holds a cell, 32 bytes of flow per group with foreground
     mapped_up = int(B * N * C * 4 * fg4) + int(B * N * 8 * fgrp)
     h2d = copied_up + mapped_up
+    # what the link actually carries: kernel reads of host memory move 64-byte half lines (tests/studies/zerocopy_bw.cu),
+    # i.e. every 16-pixel aligned run that holds a cell (logits, per class) / foreground (flows, per component)
+    moved_up = None
+    if W % 16 == 0:
+        cell16 = float((out[0].reshape(-1, 16) > 0).any(dim=1).float().mean().item())
+        fg16 = float((cellprob.reshape(-1, 16) > PARAMS["cellprob_threshold"]).any(dim=1).float().mean().item())
+        moved_up = copied_up + int(B * N * C * 4 * cell16) + int(B * N * 8 * fg16)
     d2h = B * N * 2 + B * 4 + B * min(LC, 512) * 4
 
     if rank != 0:
@@ -461,6 +468,9 @@ def run_ours(args):
                           "foreground, logits where it holds a cell); one host thread, one call per step",
                 "h2d_copied_bytes": copied_up, "h2d_mapped_bytes_min": mapped_up,
                 "pcie_gbs": h2d / e2e_s / 1e9, "pcie_peak_gbs": pcie_peak, "pcie_frac": h2d / e2e_s / 1e9 / pcie_peak,
+                "h2d_moved_bytes_64B_lines": moved_up,
+                "pcie_link_gbs": (moved_up / e2e_s / 1e9) if moved_up else None,
+                "pcie_link_frac": (moved_up / e2e_s / 1e9 / pcie_peak) if moved_up else None,
                 "variants": {
                     "upload_everything": {"value": world * B / e2e_upload_s, "ms_per_step": e2e_upload_s * 1e3,
                                           "h2d_bytes_per_step": B * (3 + C) * N * 4,
