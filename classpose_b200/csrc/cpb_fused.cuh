@@ -9,26 +9,45 @@
 // k_lookup_list: grid-stride over the compacted foreground list (full warps).  raw label = painted
 // label at the pixel's end point; statistics of the raw labels go to the tables.  `lab` must be
 // zeroed beforehand (background stays 0).
+#ifndef CPB_LK_ILP
+#define CPB_LK_ILP 4
+#endif
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_lookup_list(const unsigned* CPB_RESTRICT list, const unsigned* CPB_RESTRICT list_n,
               const int* CPB_RESTRICT pfinal, const int* CPB_RESTRICT M, int H, int W,
               int* CPB_RESTRICT lab, LabelTables t) {
     const unsigned total = *list_n;
     const int N = H * W;
-    for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {
-        const unsigned i = i0 + threadIdx.x;
-        int l = 0, b = 0, r = 0, y = 0, x = 0;
-        if (i < total) {
-            const unsigned gi = list[i];
-            b = (int)(gi / (unsigned)N);
-            r = (int)(gi - (unsigned)b * (unsigned)N);
-            const int pf = pfinal[gi];
-            l = max(-M[(size_t)b * N + (pf >> 16) * W + (pf & 0xffff)], 0);      // painted histogram, see k_seeds
-            lab[gi] = l;
-            y = r / W; x = r - y * W;
+    // CPB_LK_ILP list entries per thread and round, each level of the dependent chain (list -> end point -> painted
+    // label) loaded for all of them before the next: the kernel is a chain of memory latencies otherwise
+    for (unsigned i0 = blockIdx.x * blockDim.x * CPB_LK_ILP; i0 < total; i0 += gridDim.x * blockDim.x * CPB_LK_ILP) {
+        unsigned gi[CPB_LK_ILP];
+        int pf[CPB_LK_ILP], l[CPB_LK_ILP], b[CPB_LK_ILP];
+        #pragma unroll
+        for (int j = 0; j < CPB_LK_ILP; j++) {
+            const unsigned i = i0 + j * blockDim.x + threadIdx.x;
+            gi[j] = i < total ? list[i] : 0xffffffffu;
         }
-        cpb_stats_accum(t, b, l, r, y, x);      // (a block-level shared-memory merge before the L2 atomics was slower:
-                                                //  0.355 ms vs 0.261 ms, three block barriers per 256 pixels)
+        #pragma unroll
+        for (int j = 0; j < CPB_LK_ILP; j++) {
+            b[j] = gi[j] != 0xffffffffu ? (int)(gi[j] / (unsigned)N) : 0;
+            pf[j] = gi[j] != 0xffffffffu ? pfinal[gi[j]] : 0;
+        }
+        #pragma unroll
+        for (int j = 0; j < CPB_LK_ILP; j++)
+            l[j] = gi[j] != 0xffffffffu ? max(-M[(size_t)b[j] * N + (pf[j] >> 16) * W + (pf[j] & 0xffff)], 0) : 0;   // painted histogram, see k_seeds
+        #pragma unroll
+        for (int j = 0; j < CPB_LK_ILP; j++) {
+            if (i0 + j * blockDim.x >= total) break;                      // uniform: the whole block is past the list
+            int r = 0, y = 0, x = 0;
+            if (gi[j] != 0xffffffffu) {
+                r = (int)(gi[j] - (unsigned)b[j] * (unsigned)N);
+                lab[gi[j]] = l[j];
+                y = r / W; x = r - y * W;
+            }
+            cpb_stats_accum(t, b[j], l[j], r, y, x);      // (a block-level shared-memory merge before the L2 atomics was slower:
+                                                          //  0.355 ms vs 0.261 ms, three block barriers per 256 pixels)
+        }
     }
 }
 
