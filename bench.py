@@ -436,11 +436,11 @@ def run_ours(args):
                 "whole_path_achieved_GBs": whole_bytes / (ms_step * 1e-3) / 1e9,
                 "whole_path_frac": whole_bytes / (ms_step * 1e-3) / 1e9 / peak,
                 "streaming_stages": stage_hbm,
-                "note": "follow_flows (200 dependent Euler steps per foreground pixel, ~300 flop per byte) is issue-bound (75 % of the "
-                        "issue slots, DRAM at 3 % of peak); the flow check (float32 register-resident screen) is shuffle / issue "
-                        "bound.  The HBM fraction is reported as required; the pipe utilisations and the kernels that ARE HBM "
-                        "streams (prep 83 %, final+vote 78 %, blend 71-86 % of the measured copy peak, by ncu DRAM bytes) are in "
-                        "DESIGN.md section 4"}
+                "note": "follow_flows (200 dependent Euler steps per foreground pixel, ~300 flop per byte) is bound by its instruction "
+                        "mix (73 % of the issue slots, FP32 pipe 63 % of cycles, DRAM at 3 % of peak); the flow check (float32 "
+                        "register-resident screen) is shuffle / issue bound.  The HBM fraction is reported as required; the pipe "
+                        "utilisations and the kernels that ARE HBM streams (prep 97 %, final+vote 78 %, blend 71-86 % of the "
+                        "measured copy peak, by ncu DRAM bytes) are in DESIGN.md section 4"}
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample of the same workload
     cores = os.cpu_count() or 1
@@ -551,13 +551,15 @@ def build_extra(eng, dev, workload, B, seed):
             eng.calls.average_tiles(y_flow, g["y0"], g["x0"], g["flip"], True, tyd, txd, Ly, Lx, pad, x4, cover)
             eng.calls.average_tiles(y_cls, g["y0"], g["x0"], g["flip"], False, tyd, txd, Ly, Lx, pad, x4, cover)
         torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        ev[0].record()
-        for _ in range(3):
+        reps = []
+        for _ in range(7):      # median of single repetitions: the pair is ~1 ms of GPU time behind six python calls
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
             eng.calls.average_tiles(y_flow, g["y0"], g["x0"], g["flip"], True, tyd, txd, Ly, Lx, pad, x4, cover)
             eng.calls.average_tiles(y_cls, g["y0"], g["x0"], g["flip"], False, tyd, txd, Ly, Lx, pad, x4, cover)
-        ev[1].record(); torch.cuda.synchronize()
-        blend_ms = ev[0].elapsed_time(ev[1]) / 3
+            ev[1].record(); torch.cuda.synchronize()
+            reps.append(ev[0].elapsed_time(ev[1]))
+        blend_ms = statistics.median(reps)
         blend_bytes = B * (3 + Cc) * 4 * (nt * 256 * 256 + Hh * Ww)
         extra["blend_ms"] = blend_ms
         extra["blend_GBs"] = blend_bytes / (blend_ms * 1e-3) / 1e9

@@ -306,6 +306,26 @@ def test_device_synth_and_batch_consistency():
         assert metrics.match_instances(ref, masks[b].cpu().numpy())["f1"] >= 0.995
 
 
+def test_batch_parts_with_ragged_sizes():
+    """The C API cuts batches of >= 256 tiles into up to four parts that run on forked streams (run_in_parts).  Batch
+    sizes that do not divide evenly (389 -> 129 + 130 + 130, 257 -> 128 + 129) must give, tile for tile, what calls
+    small enough to stay one part give."""
+    import torch
+    from classpose_b200 import synth
+    from classpose_b200.engine import get_engine
+    eng = get_engine()
+    d = synth.make_batch(389, 256, 256, 7, seed=31)
+    for B in (389, 257):
+        masks, counts, cc, _ = eng.compute_masks_batch(d["dP"][:B], d["cellprob"][:B], d["logits"][:B])
+        for lo in range(0, B, 100):
+            hi = min(B, lo + 100)
+            m1, c1, cc1, _ = eng.compute_masks_batch(d["dP"][lo:hi], d["cellprob"][lo:hi], d["logits"][lo:hi])
+            assert torch.equal(m1, masks[lo:hi]) and torch.equal(c1, counts[lo:hi])
+            used = torch.arange(cc1.shape[1], device=cc1.device).view(1, -1) <= c1.view(-1, 1)     # entries 0..count
+            assert torch.equal(cc1[used], cc[lo:hi][used])
+    assert int(counts.min()) > 0
+
+
 def test_full_size_batch_properties():
     """BASELINE configs[1] size (1024 conic tiles): size-independent properties of the result.
     labels contiguous 1..counts[b]; every instance within [min_size, 0.4*N]; classes in range; a tile gives the
