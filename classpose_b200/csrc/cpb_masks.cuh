@@ -64,21 +64,20 @@ CPB_DEVICE void cpb_block_rank(const u64* CPB_RESTRICT keys, int n, int* CPB_RES
     __syncthreads();
 }
 
-CPB_DEVICE int cpb_hist_at(const int* CPB_RESTRICT h, int H, int W, int y, int x) {
-    return (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(&h[y * W + x]) : 0;
-}
-
 // k_seed_scan + k_seeds (one block per tile).
-//  1. seeds = pixels with h > 10 that equal the maximum of their 5x5 neighbourhood (k_seed_scan, below)
+//  1. seeds = pixels with h > 10 (k_seed_scan collects them) that equal the maximum of their 5x5 neighbourhood (first
+//     step of k_seeds)
 //  2. order: ascending count, ties by raster position (stable sort of a raster-ordered list)
 //  3. each seed grows inside its 11x11 window: 5 x { 3x3 dilation ; &= h > 2 }
 //  4. paint label = order+1; later (larger) labels overwrite.  The labels are painted INTO the histogram as
 //     negative numbers (atomicMin of -label): only pixels with h > 2 are ever painted and the only reads that
 //     follow are "h > 2" tests, which a painted pixel passes by construction -- so no separate label plane has to
 //     be zeroed, written and read.  Afterwards hist[p] < 0 means label -hist[p], anything else label 0.
-// k_seed_scan: the whole batch as one stream (one thread per 4 pixels, 128-bit loads when vec != 0): pixels with
-// h > 10 that equal the maximum of their 5x5 neighbourhood are appended to their tile's candidate list
-// (cand_count must be zeroed).  The histogram is almost everywhere 0, so nearly every thread stops after its load.
+// k_seed_scan: the whole batch as one stream (one thread per 4 pixels, 128-bit loads when vec != 0): every pixel
+// with h > 10 is appended to its tile's candidate list (cand_count must be zeroed; at most N / 11 < LC pixels of a tile
+// can hold more than 10 end points).  The histogram is almost everywhere 0, so nearly every thread stops after its
+// load; the 5 x 5 maximum test of the candidates -- 25 scattered loads for the few lanes of a warp that hold one --
+// is left to k_seeds, where the candidates are compact (in this kernel it cost more than the stream itself).
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_seed_scan(const int* CPB_RESTRICT hist, int B, int H, int W, int LC, int vec, u64* CPB_RESTRICT seed_key,
             int* CPB_RESTRICT cand_count) {
@@ -97,20 +96,11 @@ k_seed_scan(const int* CPB_RESTRICT hist, int B, int H, int W, int LC, int vec, 
     const long long g0 = vec ? 4 * q : q;
     const int b = (int)(g0 / N);
     const int p0 = (int)(g0 - (long long)b * N);
-    const int* h = hist + (size_t)b * N;
     for (int e = 0; e < (vec ? 4 : 1); e++) {
         const int v = vals[e];
         if (v <= CPB_SEED_MIN) continue;
-        const int p = p0 + e;
-        const int y = p / W, x = p - y * W;
-        bool ismax = true;
-        for (int dy = -2; dy <= 2 && ismax; dy++)
-            for (int dx = -2; dx <= 2; dx++)
-                if (cpb_hist_at(h, H, W, y + dy, x + dx) > v) { ismax = false; break; }
-        if (ismax) {
-            const int k = atomicAdd(&cand_count[b], 1);
-            if (k < LC) seed_key[(size_t)b * LC + k] = ((u64)(unsigned)v << 32) | (unsigned)p;
-        }
+        const int k = atomicAdd(&cand_count[b], 1);
+        if (k < LC) seed_key[(size_t)b * LC + k] = ((u64)(unsigned)v << 32) | (unsigned)(p0 + e);
     }
 }
 
@@ -123,7 +113,32 @@ k_seeds(int* hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
     u64* keys = seed_key + (size_t)b * LC;
     int* labs = seed_lab + (size_t)b * LC;
     int* Mb = hist + (size_t)b * N;
-    const int n = min(cand_count[b], LC - 1);
+    // candidates (h > 10) -> seeds: those that equal the maximum of their 5 x 5 neighbourhood, compacted in place a
+    // block-width at a time (a round only writes below the positions it has already read; nothing is painted yet)
+    CPB_SHARED int s_cscan[33];
+    const int nc = min(cand_count[b], LC - 1);
+    int n = 0;
+    for (int k0 = 0; k0 < nc; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        u64 key = 0;
+        bool ismax = false;
+        if (k < nc) {
+            key = keys[k];
+            const int v = (int)(key >> 32), p = (int)(key & 0xffffffffu);
+            const int y = p / W, x = p - y * W;
+            ismax = true;
+            for (int dy = -2; dy <= 2 && ismax; dy++)
+                for (int dx = -2; dx <= 2; dx++) {
+                    const int yy = y + dy, xx = x + dx;     // plain loads: this kernel writes the plane further down
+                    if (yy >= 0 && yy < H && xx >= 0 && xx < W && Mb[yy * W + xx] > v) { ismax = false; break; }
+                }
+        }
+        int tot;
+        const int incl = cpb_block_scan_incl(ismax ? 1 : 0, s_cscan, &tot);      // barriers: every key of the round is read
+        if (ismax) keys[n + incl - 1] = key;
+        n += tot;
+        __syncthreads();
+    }
     if (threadIdx.x == 0) nseeds[b] = n;
     cpb_block_rank(keys, n, labs, s_keys);
 
