@@ -239,10 +239,12 @@ FollowSchedule follow_schedule(int niter) {
 //   CPB_QC_FUSED=0       every label's flow error from T in global memory (k_flow_err) instead of the diffusion tile
 //   CPB_VOTE_FUSED=0     class vote as its own pass over the finished label image
 //   CPB_QC_SCREEN=0      every label through the float64 diffusion (no float32 screen in front of it)
+//   CPB_SEED_CANDS=0     seed candidates (bins with more than 10 end points) found by streaming the histogram (k_seed_scan)
+//                        instead of being listed by the kernel that counts the end points
 //   CPB_FOLLOW_SMALL=0   1024-entry chunks in the trajectory pool for every batch size (1: 256-entry chunks for a handful of tiles)
 //   CPB_BLEND_EFT=0      blend with float64 arithmetic per element (numpy's literal op sequence) instead of the float32
 //                        error-free form (identical up to ~1e-6 of the elements by one ulp)
-std::atomic<int> g_switch[7] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
+std::atomic<int> g_switch[8] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
 bool switch_on(int which, const char* env_name) {
     int v = g_switch[which].load(std::memory_order_relaxed);
     if (v < 0) {
@@ -256,6 +258,7 @@ bool qc_fused_enabled() { return switch_on(CPB_SWITCH_QC_FUSED, "CPB_QC_FUSED");
 bool vote_fused_enabled() { return switch_on(CPB_SWITCH_VOTE_FUSED, "CPB_VOTE_FUSED"); }
 bool qc_screen_enabled() { return switch_on(CPB_SWITCH_QC_SCREEN, "CPB_QC_SCREEN"); }
 bool blend_eft_enabled() { return switch_on(CPB_SWITCH_BLEND_EFT, "CPB_BLEND_EFT"); }
+bool seed_cands_enabled() { return switch_on(CPB_SWITCH_SEED_CANDS, "CPB_SEED_CANDS"); }
 bool follow_small_enabled() { return switch_on(CPB_SWITCH_FOLLOW_SMALL, "CPB_FOLLOW_SMALL"); }
 // value 2 (tests only): the screen also runs when the caller asks for the per-label errors, and reports
 // (float32 error, bound) bit-packed into the float64 error of the labels it decided
@@ -304,7 +307,7 @@ int run_map_stats(const Workspace& w, int32_t* lab, int B, int H, int W, int nch
 // zero_out != NULL (fused path): the prep kernel zeroes that label image instead of marking background in p_final
 int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B, int H, int W, int niter,
                float thr, int32_t* pfinal, float* pfloat, int* hist, cudaStream_t st, int32_t* zero_out = nullptr,
-               float* dP_copy = nullptr, bool prep_done = false) {
+               float* dP_copy = nullptr, bool prep_done = false, bool seed_cands = false) {
     const long long BN = (long long)B * H * W;
     prof_begin(w.prof, S_PREP);
     if (!prep_done) {
@@ -312,6 +315,12 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
         cudaMemsetAsync(w.t.fail, 0, B * sizeof(int), st);
     }
     if (hist) cudaMemsetAsync(hist, 0, BN * sizeof(int), st);
+    // seed candidates (pixels whose bin passes 10 end points) are listed by the counting kernel: see cpb_hist_count
+    SeedCands cands{nullptr, nullptr, 0};
+    if (hist && seed_cands) {
+        cands = SeedCands{w.skey, w.t.misc, w.t.LC};
+        cudaMemsetAsync(w.t.misc, 0, B * sizeof(int), st);
+    }
     const float sx = (float)(2.0 / (double)(W - 1)), sy = (float)(2.0 / (double)(H - 1));
     // tap indices are formed in float32 (exact below 2^24): one tile of more than ~4090 x 4090 pixels is out of range
     if ((long long)(H + 2) * (W + 2 * CPB_FLOW_PADX) >= (1LL << 24)) return CPB_E_RANGE;
@@ -347,7 +356,7 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
         ensure_attributes();
         const int pb = ((W + CPB_FS_PATCH - 1) / CPB_FS_PATCH) * ((H + CPB_FS_PATCH - 1) / CPB_FS_PATCH);
         CPB_LAUNCH_COUNTED(k_follow_staged, dim3((unsigned)((long long)B * pb)), dim3(256), CPB_FS_WIN * CPB_FS_WIN * 8, st, w.flow,
-                           cellprob, thr, B, H, W, niter, pfinal, pfloat, hist);
+                           cellprob, thr, B, H, W, niter, pfinal, pfloat, hist, cands);
         CPB_CHECK_LAUNCH();
         return 0;
     }
@@ -364,7 +373,7 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
         const unsigned pgrid = blocks_for(BN, pool);
 #endif
 #define CPB_LAUNCH_POOL(WPv, POOLv) CPB_LAUNCH_COUNTED((k_follow_pool<WPv, POOLv>), dim3(pgrid), dim3(CPB_FP_THREADS), 0, st, w.flow, \
-                               w.list, w.list_n, H, W, niter, follow_schedule(niter), pfinal, pfloat, hist)
+                               w.list, w.list_n, H, W, niter, follow_schedule(niter), pfinal, pfloat, hist, cands)
         if (W == 256) {       // the WSI tile width: row pitch as an immediate
             if (small) CPB_LAUNCH_POOL(256 + 2 * CPB_FLOW_PADX, CPB_FP_POOL_SMALL); else CPB_LAUNCH_POOL(256 + 2 * CPB_FLOW_PADX, CPB_FP_POOL);
         } else {
@@ -374,23 +383,25 @@ int run_follow(const Workspace& w, const float* dP, const float* cellprob, int B
     } else if (mode >= 1 && niter >= 32 && B < (1 << 28)) {
         // merge points at a quarter and a half of the integration (48 and 96 of 200 steps)
         CPB_LAUNCH_COUNTED(k_follow_merge, dim3(grid), dim3(CPB_FM_THREADS), 0, st, w.flow, w.list, w.list_n, H, W, niter,
-                           (niter * 6) / 25, (niter * 12) / 25, pfinal, pfloat, hist);
+                           (niter * 6) / 25, (niter * 12) / 25, pfinal, pfloat, hist, cands);
     } else {
         CPB_LAUNCH_COUNTED(k_follow, dim3(grid), dim3(256), 0, st, w.flow, w.list, w.list_n, H, W, niter, pfinal, pfloat,
-                           hist);
+                           hist, cands);
     }
     CPB_CHECK_LAUNCH();
     return 0;
 }
 
 // end-point histogram in w.hist -> seed labels painted into it, seed count per tile in t.lbound
-int run_seeds(const Workspace& w, int B, int H, int W, cudaStream_t st) {
+int run_seeds(const Workspace& w, int B, int H, int W, cudaStream_t st, bool have_cands = false) {
     const long long BN = (long long)B * H * W;
     const int vec = ((long long)H * W % 4 == 0) && (reinterpret_cast<uintptr_t>(w.hist) % 16 == 0) ? 1 : 0;
-    cudaMemsetAsync(w.t.misc, 0, B * sizeof(int), st);                 // candidate counters
-    CPB_LAUNCH_COUNTED(k_seed_scan, dim3(blocks_for(vec ? BN / 4 : BN, 256)), dim3(256), 0, st, (const int*)w.hist, B, H, W,
-                       w.t.LC, vec, w.skey, w.t.misc);
-    CPB_CHECK_LAUNCH();
+    if (!have_cands) {      // (the fused path's counting kernel has listed the candidates already: cpb_hist_count)
+        cudaMemsetAsync(w.t.misc, 0, B * sizeof(int), st);                 // candidate counters
+        CPB_LAUNCH_COUNTED(k_seed_scan, dim3(blocks_for(vec ? BN / 4 : BN, 256)), dim3(256), 0, st, (const int*)w.hist, B, H, W,
+                           w.t.LC, vec, w.skey, w.t.misc);
+        CPB_CHECK_LAUNCH();
+    }
     CPB_LAUNCH_COUNTED(k_seeds, dim3(B), dim3(table_threads(H, W)), 0, st, w.hist, H, W, w.t.LC, w.skey, w.sidx, w.t.lbound,
                        (const int*)w.t.misc);
     CPB_CHECK_LAUNCH();
@@ -731,13 +742,14 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
     int e;
     const long long BN = (long long)B * H * W;
     // (2) Euler integration + end-point histogram
+    const bool seed_cands = seed_cands_enabled();
     e = run_follow(w, dP, cellprob, B, H, W, prm->niter, prm->cellprob_threshold, w.pfinal, nullptr, w.hist, st, masks, dP_copy,
-                   prep_done);
+                   prep_done, seed_cands);
     if (e) return e;
     if (dP_copy) dP = dP_copy;          // every later reader (flow check) sits on a foreground pixel
     // (3) seeds -> raw labels (seed order + 1) and their statistics; ids after get_masks live in t.remap
     prof_begin(w.prof, S_SEEDS);
-    { int e_ = run_seeds(w, B, H, W, st); if (e_) return e_; }
+    { int e_ = run_seeds(w, B, H, W, st, seed_cands); if (e_) return e_; }
     prof_end(w.prof, S_SEEDS);
     prof_begin(w.prof, S_LOOKUP);
     e = run_init_tables(w, B, st); if (e) return e;
@@ -936,7 +948,7 @@ const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames
 void cpb_debug_set_follow_merge(int mode) { g_follow_merge.store(mode, std::memory_order_relaxed); }
 void cpb_debug_set_switch(int which, int value) {
     if (which == CPB_SWITCH_FOLLOW_MERGE) g_follow_merge.store(value, std::memory_order_relaxed);
-    else if (which > 0 && which < 7) g_switch[which].store(value, std::memory_order_relaxed);
+    else if (which > 0 && which < 8) g_switch[which].store(value, std::memory_order_relaxed);
 }
 long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void cpb_debug_qc_stats(int32_t* out) {

@@ -6,6 +6,7 @@
 #define CPB_IMAX 0x7fffffff
 
 typedef unsigned long long u64;
+#define CPB_SEED_MIN 10      // get_masks: a seed collects more than this many end points
 
 // Per-tile, per-label tables (struct of arrays, each [B][LC]); entry 0 is background.
 struct LabelTables {

@@ -14,6 +14,20 @@
 // of every row 16-byte aligned for the vectorised writer.
 #define CPB_FLOW_PADX 2
 
+// End-point histogram with seed candidates on the side.  get_masks needs the pixels that collect more than 10 end points;
+// the increment that takes a bin from <= 10 to > 10 happens exactly once per such pixel, so the kernel that counts can
+// list them (tile-local pixel index; k_seeds reads the final count) and nobody has to stream the whole histogram to
+// find them afterwards.  count == NULL: plain counting.
+struct SeedCands { u64* key; int* count; int LC; };
+CPB_DEVICE void cpb_hist_count(int* CPB_RESTRICT hist, int key, int cnt, int b, int p, const SeedCands& c) {
+    if (c.count == nullptr) { atomicAdd(&hist[key], cnt); return; }
+    const int old = atomicAdd(&hist[key], cnt);
+    if (old <= CPB_SEED_MIN && old + cnt > CPB_SEED_MIN) {
+        const int k = atomicAdd(&c.count[b], 1);
+        if (k < c.LC) c.key[(size_t)b * c.LC + k] = (u64)(unsigned)p;
+    }
+}
+
 CPB_DEVICE float2 cpb_scaled_flow(float dy, float dx, bool fg, float sx, float sy) {
     // (dP * fg) / 5.  then  *= 2/(L-1)   -- each a separately rounded float32 op.  Background is 0 whatever dP holds
     // (the reference's dP * 0 keeps the sign of dP on its zero, which no later operation can see), and it must not reach
@@ -310,7 +324,7 @@ CPB_DEVICE void cpb_euler_step(const float2* CPB_RESTRICT f, int Wp, float fH, f
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, CPB_F_MINBLOCKS)
 k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
          const unsigned* CPB_RESTRICT list_n, int H, int W, int niter,
-         int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
+         int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist, SeedCands cands) {
     const unsigned total = *list_n;
     const int N = H * W, Wp = W + 2 * CPB_FLOW_PADX, Np = (H + 2) * Wp;
     const float fW = 0.5f * (float)W, fH = 0.5f * (float)H;      // halved: see cpb_euler_step
@@ -347,7 +361,7 @@ k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
         if (hist) {
             const int key = b * N + yi * W + xi;
             const unsigned peers = __match_any_sync(amask, key);
-            if (lane == __ffs((int)peers) - 1) atomicAdd(&hist[key], __popc(peers));
+            if (lane == __ffs((int)peers) - 1) cpb_hist_count(hist, key, __popc(peers), b, yi * W + xi, cands);
         }
     }
 }
@@ -368,7 +382,7 @@ k_follow(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
 #ifndef CPB_SIM
 CPB_KERNEL CPB_LAUNCH_BOUNDS(256, 4)
 k_follow_staged(const float2* CPB_RESTRICT flow, const float* CPB_RESTRICT cellprob, float thr, int B, int H, int W,
-                int niter, int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
+                int niter, int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist, SeedCands cands) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     float2* s_win = reinterpret_cast<float2*>(s_raw);
     __shared__ __align__(8) unsigned long long s_bar;
@@ -474,7 +488,7 @@ k_follow_staged(const float2* CPB_RESTRICT flow, const float* CPB_RESTRICT cellp
         if (hist) {
             const int key = b * N + yi * W + xi;
             const unsigned peers = __match_any_sync(amask, key);
-            if (lane == __ffs((int)peers) - 1) atomicAdd(&hist[key], __popc(peers));
+            if (lane == __ffs((int)peers) - 1) cpb_hist_count(hist, key, __popc(peers), b, yi * W + xi, cands);
         }
     }
 }
@@ -534,7 +548,7 @@ CPB_DEVICE int cpb_block_merge(u64 key, int nact, bool unique, u64* s_keys, int*
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FM_THREADS, CPB_FM_MINBLOCKS)
 k_follow_merge(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
                const unsigned* CPB_RESTRICT list_n, int H, int W, int niter, int m1, int m2,
-               int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
+               int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist, SeedCands cands) {
     CPB_SHARED u64 s_keys[CPB_FM_SLOTS];
     CPB_SHARED int s_own[CPB_FM_SLOTS];
     CPB_SHARED float2 s_pos[CPB_FM_THREADS];
@@ -641,7 +655,7 @@ k_follow_merge(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT lis
             if (hist) {
                 const int hkey = b * N + yi * W + xi;
                 const unsigned peers = __match_any_sync(amask, hkey);
-                if (lane == __ffs((int)peers) - 1) atomicAdd(&hist[hkey], __popc(peers));
+                if (lane == __ffs((int)peers) - 1) cpb_hist_count(hist, hkey, __popc(peers), b, yi * W + xi, cands);
             }
         }
         __syncthreads();
@@ -675,7 +689,7 @@ template <int WP, int POOL>
 CPB_KERNEL CPB_LAUNCH_BOUNDS(CPB_FP_THREADS, CPB_FP_MINBLOCKS)
 k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list,
               const unsigned* CPB_RESTRICT list_n, int H, int W, int niter, FollowSchedule sch,
-              int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist) {
+              int* CPB_RESTRICT pfinal, float* CPB_RESTRICT pfloat, int* CPB_RESTRICT hist, SeedCands cands) {
     constexpr int PER = POOL / CPB_FP_THREADS, SLOTS = 2 * POOL;
     CPB_SHARED float2 s_pos[POOL];               // position of live trajectory i
     CPB_SHARED int s_tile[POOL];                 // its tile
@@ -813,7 +827,7 @@ k_follow_pool(const float2* CPB_RESTRICT flow, const unsigned* CPB_RESTRICT list
                 if (hist) {
                     const int hkey = b * N + yi * W + xi;
                     const unsigned peers = __match_any_sync(amask, hkey);
-                    if (lane == __ffs((int)peers) - 1) atomicAdd(&hist[hkey], __popc(peers));
+                    if (lane == __ffs((int)peers) - 1) cpb_hist_count(hist, hkey, __popc(peers), b, yi * W + xi, cands);
                 }
             }
         }

@@ -6,7 +6,6 @@
 #pragma once
 #include "cpb_common.cuh"
 
-#define CPB_SEED_MIN 10
 #define CPB_GROW_MIN 2
 #define CPB_RANK_CHUNK 2048
 
@@ -100,7 +99,7 @@ k_seed_scan(const int* CPB_RESTRICT hist, int B, int H, int W, int LC, int vec, 
         const int v = vals[e];
         if (v <= CPB_SEED_MIN) continue;
         const int k = atomicAdd(&cand_count[b], 1);
-        if (k < LC) seed_key[(size_t)b * LC + k] = ((u64)(unsigned)v << 32) | (unsigned)(p0 + e);
+        if (k < LC) seed_key[(size_t)b * LC + k] = (u64)(unsigned)(p0 + e);      // (k_seeds reads the count itself)
     }
 }
 
@@ -123,8 +122,9 @@ k_seeds(int* hist, int H, int W, int LC, u64* CPB_RESTRICT seed_key,
         u64 key = 0;
         bool ismax = false;
         if (k < nc) {
-            key = keys[k];
-            const int v = (int)(key >> 32), p = (int)(key & 0xffffffffu);
+            const int p = (int)(keys[k] & 0xffffffffu);       // candidate: a pixel with h > 10 (from the counting
+            const int v = Mb[p];                              // kernel or from k_seed_scan)
+            key = ((u64)(unsigned)v << 32) | (unsigned)p;
             const int y = p / W, x = p - y * W;
             ismax = true;
             for (int dy = -2; dy <= 2 && ismax; dy++)

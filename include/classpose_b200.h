@@ -104,6 +104,8 @@ void cpb_debug_set_follow_merge(int mode);
                                        ~1e-6 of the elements) */
 #define CPB_SWITCH_FOLLOW_SMALL 6   /* CPB_FOLLOW_SMALL: 256-entry chunks in the trajectory pool when the batch is a handful of
                                        tiles (latency form; 0: 1024-entry chunks always) */
+#define CPB_SWITCH_SEED_CANDS 7     /* CPB_SEED_CANDS: the trajectory kernel lists the bins that pass 10 end points while it counts
+                                       them (0: a separate pass streams the whole histogram to find them) */
 void cpb_debug_set_switch(int which, int value);
 /* number of kernels this library has launched in this process (statistics for the benchmark) */
 long long cpb_debug_launch_count(void);

@@ -699,11 +699,18 @@ def case_fused_switch_matrix(be):
                         for vote in (0, 1):
                             be.set_follow_merge(follow)
                             be.set_switch(1, queue); be.set_switch(2, qc); be.set_switch(3, vote)
+                            # switch 7: seed candidates listed by the counting kernel / found by streaming the histogram
+                            be.set_switch(7, (queue + qc + vote) & 1)
                             m, c, cc, _ = be.compute_masks(dP, cp, lg, want_class_masks=False)
                             outs[(t_i, follow, queue, qc, vote)] = (m.copy(), c.copy(), cc[0, :int(c[0]) + 1].copy())
+            for follow in (1, 2, 3):          # every counting kernel with the candidate list on and off
+                for cands in (0, 1):
+                    be.set_follow_merge(follow); be.set_switch(7, cands)
+                    m, c, cc, _ = be.compute_masks(dP, cp, lg, want_class_masks=False)
+                    outs[(t_i, follow, 9, 9, cands)] = (m.copy(), c.copy(), cc[0, :int(c[0]) + 1].copy())
     finally:
         be.set_follow_merge(-1)
-        for sw in (1, 2, 3):
+        for sw in (1, 2, 3, 7):
             be.set_switch(sw, -1)
     for t_i in range(len(tiles)):
         m0, c0, cc0 = outs[(t_i, 0, 0, 0, 0)]
