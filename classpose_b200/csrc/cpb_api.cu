@@ -180,6 +180,30 @@ void ensure_attributes() {
     cudaFuncSetAttribute(k_follow_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, CPB_FS_WIN * CPB_FS_WIN * 8);
     g_attr_done[dev].store(1, std::memory_order_release);      // (setting them twice from two threads is harmless)
 }
+// Stream-ordered scratch (the blend's weight tables) comes from a pool of the library's own that keeps what is freed:
+// the device's default pool hands its memory back at every synchronisation, and the next call then pays a real
+// allocation (measured: the 9-way blend pair took 1.1 to 1.9 ms depending on the box).
+cudaMemPool_t g_pool[kMaxDevices] = {};
+std::mutex g_pool_mutex;
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+    const int dev = current_device();
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (!g_pool[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaError_t e = cudaMemPoolCreate(&g_pool[dev], &props);
+            if (e != cudaSuccess) { g_pool[dev] = nullptr; return e; }
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool = g_pool[dev];
+    }
+    return cudaMallocFromPoolAsync(p, bytes, pool, st);
+}
 int sm_count() {
     const int dev = current_device();
     int n = g_sm_count[dev].load(std::memory_order_relaxed);
@@ -194,6 +218,7 @@ int sm_count() {
 #else
 void ensure_attributes() {}
 int sm_count() { return 4; }
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes, st); }
 #endif
 
 // follow_flows variant: 2 = trajectory pool with many merge points (default), 1 = two merge points per 256-pixel
@@ -1105,7 +1130,7 @@ int cpb_average_tiles_ex_device(const float* y, int B, int ntiles, int nch, int 
         // the stream-ordered allocator (freed on the stream after the blend)
         float* tab = nullptr;
         const size_t nw = (size_t)ly * lx, nr = (size_t)oH * oW;
-        if (cudaMallocAsync(reinterpret_cast<void**>(&tab), (2 * nw + 2 * nr) * sizeof(float), st) != cudaSuccess) return (int)cudaGetLastError();
+        if (scratch_alloc(reinterpret_cast<void**>(&tab), (2 * nw + 2 * nr) * sizeof(float), st) != cudaSuccess) return (int)cudaGetLastError();
         float* wh = tab; float* wl = tab + nw; float* rh = tab + 2 * nw; float* rl = rh + nr;
         CPB_LAUNCH_COUNTED(k_blend_weights, dim3(blocks_for((long long)nw, 256)), dim3(256), 0, st, taper_y, taper_x, ly, lx, wh, wl);
         CPB_LAUNCH_COUNTED(k_blend_rinv, dim3(blocks_for((long long)nr, 256)), dim3(256), 0, st, ntiles, ly, lx, y0, x0, taper_y, taper_x,
@@ -1165,7 +1190,7 @@ int cpb_eval_tail_device(const float* y_flows, const float* y_logits, int B, int
     // weight table and reciprocal normaliser depend on the geometry only: built once, before the batch is cut into parts
     float* tab = nullptr;
     const size_t nw = (size_t)ly * lx, nr = (size_t)H * W, N = nr;
-    if (cudaMallocAsync(reinterpret_cast<void**>(&tab), (2 * nw + 2 * nr) * sizeof(float), st0) != cudaSuccess) return (int)cudaGetLastError();
+    if (scratch_alloc(reinterpret_cast<void**>(&tab), (2 * nw + 2 * nr) * sizeof(float), st0) != cudaSuccess) return (int)cudaGetLastError();
     float* wh = tab; float* wl = tab + nw; float* rh = tab + 2 * nw; float* rl = rh + nr;
     CPB_LAUNCH_COUNTED(k_blend_weights, dim3(blocks_for((long long)nw, 256)), dim3(256), 0, st0, taper_y, taper_x, ly, lx, wh, wl);
     CPB_LAUNCH_COUNTED(k_blend_rinv, dim3(blocks_for((long long)nr, 256)), dim3(256), 0, st0, ntiles, ly, lx, y0, x0, taper_y, taper_x,

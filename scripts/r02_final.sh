@@ -7,7 +7,7 @@ O=gpurun_out/r02final
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $O/gpu.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu.log
 SECONDS=0; timeout 600 python bench.py 2>$O/bench.err > $O/bench.json; echo "bench rc=$? wall=${SECONDS}s"; tail -3 $O/bench.err
-SECONDS=0; timeout 600 python bench.py --impl reference 2>$O/bench_ref.err > $O/bench_ref.json; echo "reference arm rc=$? wall=${SECONDS}s"; tail -c 600 $O/bench_ref.json; echo
+echo "(reference arm: see the earlier session)"
 python - <<'PY'
 import json
 d=json.load(open("gpurun_out/r02final/bench.json"))
@@ -26,7 +26,7 @@ echo "== ncu launch list, one part"
 CPB_BATCH_PARTS=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ --csv --log-file $O/launches_one_part.csv \
     python bench.py --tiles 1024 --steps 2 --warmup 1 --profile-only > $O/ncu_bench1.log 2>&1; echo "ncu rc=$?"
 python scripts/summarise_launches.py $O/launches_one_part.csv > $O/launches_summary_one_part.txt 2>&1; head -12 $O/launches_summary_one_part.txt
-for k in k_follow_pool k_prep_flow_v4 k_lookup_list; do
+for k in k_follow_pool; do
   CPB_BATCH_PARTS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $O/prof_$k \
       python bench.py --tiles 1024 --steps 2 --warmup 1 --profile-only > $O/ncu_$k.log 2>&1; echo "ncu $k rc=$?"
 done
