@@ -407,6 +407,56 @@ def case_fill_holes_oversized_label(be):
     assert cnt[0] == ref.max()
 
 
+def fill_from_input_image(lab):
+    """The hole-fill semantic of the kernels, restated for the one configuration in which it differs from upstream:
+    every label's holes are taken from the INPUT image (a pixel enclosed by several labels goes to the one with the
+    largest bounding box, the outermost), whereas upstream fills label by label in id order on the image as the
+    earlier fills left it.  New ids as upstream's loop counter with min_size <= 0: rank of the id among those present."""
+    from scipy.ndimage import binary_fill_holes, find_objects
+    out = lab.copy()
+    best = np.zeros(lab.shape, np.int64)
+    for i, slc in enumerate(find_objects(lab)):
+        if slc is None:
+            continue
+        m = lab == (i + 1)
+        hole = binary_fill_holes(m) & ~m
+        area = (slc[0].stop - slc[0].start) * (slc[1].stop - slc[1].start)
+        key = (area << 32) | (i + 1)
+        take = hole & (key > best)
+        best[take] = key
+        out[take] = i + 1
+    ids = np.unique(lab); ids = ids[ids != 0]
+    lut = np.zeros(int(lab.max()) + 1, lab.dtype)
+    lut[ids] = np.arange(1, len(ids) + 1)
+    return lut[out]
+
+
+def case_fill_holes_label_partly_inside_a_hole(be):
+    """KNOWN DEVIATION, found by tests/studies/fuzz_sim.py and documented in INTEGRATION.md section 4: label 3 is a ring
+    of which one side lies inside a hole of label 2 (which in turn has a piece inside the ring).  Upstream processes
+    label 2 first, its fill cuts the ring open, and the ring then encloses nothing; the kernels take both labels' holes
+    from the input image, so the ring still fills its interior.  The case pins the kernels' behaviour (and that the two
+    differ on exactly the ring's interior), so that a change of either side is noticed."""
+    lab = np.array([[0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+                    [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+                    [0, 0, 12, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+                    [0, 12, 12, 12, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+                    [0, 0, 12, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+                    [0, 8, 2, 2, 2, 3, 3, 3, 0, 0, 0, 0, 0],
+                    [8, 8, 8, 2, 3, 2, 2, 2, 3, 0, 0, 0, 0],
+                    [7, 7, 7, 2, 3, 2, 2, 2, 3, 0, 0, 0, 0],
+                    [7, 7, 7, 2, 3, 2, 2, 2, 3, 11, 11, 11, 0],
+                    [7, 7, 7, 2, 2, 3, 3, 3, 0, 11, 11, 11, 0],
+                    [8, 8, 8, 2, 2, 2, 2, 2, 0, 11, 11, 11, 0],
+                    [0, 8, 2, 2, 2, 2, 2, 0, 0, 0, 0, 0, 0]], np.int32)
+    upstream = outils.fill_holes_and_remove_small_masks(lab.copy(), -1)
+    expected = fill_from_input_image(lab)
+    out, _ = be.fill_holes_and_remove_small_masks(c32(lab[None]).copy(), int(lab.max()) + 2, -1)
+    np.testing.assert_array_equal(out[0], expected)
+    differ = out[0] != upstream
+    assert differ.sum() == 9 and differ[6:9, 5:8].all()          # the ring's interior, nothing else
+
+
 def random_label_image(rng, H, W, n, gaps=True):
     """Random discs, rings (holes, some with a cell inside), slabs and specks painted over each other, with
     non-contiguous ids when `gaps`: the shapes the table-driven relabelling has to get right."""
@@ -984,7 +1034,7 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_f
              case_follow_flows_large_tiles, case_get_masks_exact,
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
              case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_flow_qc_screen_is_decision_exact,
-             case_fill_holes_exact, case_fill_holes_oversized_label, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
+             case_fill_holes_exact, case_fill_holes_oversized_label, case_fill_holes_label_partly_inside_a_hole, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
              case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes, case_fused_baseline_config_shapes,
              case_eval_tail_blend_fused_with_threshold,
              case_fused_generic_class_count, case_fused_switch_matrix, case_fused_odd_width, case_fused_empty_and_params, case_fused_min_size_zero_keeps_upstream_ids,
