@@ -9,7 +9,10 @@ Targets, all exact comparisons:
   class vote           random labels / logits with exact ties                                   vs oracle.classpose_ref
   border removal       random label images, 1 and 3 channels                                    vs oracle.classpose_ref
   flow check           random label images + random flows: removal set                          vs oracle.dynamics
-  fused path           every A/B switch combination gives one result; fused == stage by stage   (library vs itself)
+  fused path           every A/B switch combination gives one result                             (library vs itself)
+  contours             random label images: point lists, area, bbox                             vs cv2.findContours
+  masks_to_flows       random label images: <= 1e-12                                            vs oracle.dynamics
+  average_tiles        random tile geometry / channels / TTA flips: <= 1e-6                     vs oracle.transforms
 """
 from __future__ import annotations
 
@@ -200,7 +203,81 @@ def fuzz_fused(be, rng):
         np.testing.assert_array_equal(cc, outs[0][2])
 
 
-TARGETS = [fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
+def fuzz_contours(be, rng):
+    """Point lists of every label against cv2.findContours(cell, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE)[0] on the label's
+    crop -- the call the reference's PostProcessor makes -- plus pixel area and bbox."""
+    import cv2
+    from scipy.ndimage import find_objects
+    H, W = random_shape(rng)
+    lab = random_labels(rng, H, W, int(rng.integers(1, 10)))
+    if rng.random() < 0.3:                                   # specks and diagonal chains
+        n = int(rng.integers(1, 12))
+        lab[rng.integers(0, H, n), rng.integers(0, W, n)] = int(lab.max()) + 1
+    out = be.cell_contours(c32(lab[None]), int(lab.max()) + 2)
+    total = 0
+    for l, slc in enumerate(find_objects(lab), start=1):
+        if slc is None:
+            assert out["npoints"][0, l] == 0
+            continue
+        ys, xs = slc
+        cell = lab[ys, xs] == l
+        cs = cv2.findContours(np.uint8(cell), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]
+        ref = cs[0][:, 0] + np.array([xs.start, ys.start])
+        n, off = int(out["npoints"][0, l]), int(out["offsets"][0, l])
+        assert off == total
+        total += n
+        np.testing.assert_array_equal(out["points"][off:off + n], ref, err_msg=f"label {l}")
+        f = out["feat"][0, l]
+        assert f[0] == cell.sum() and (f[1], f[2] + 1, f[3], f[4] + 1) == (ys.start, ys.stop, xs.start, xs.stop)
+    assert int(out["total"][0]) == total
+
+
+def fuzz_masks_to_flows(be, rng):
+    H, W = random_shape(rng)
+    lab = outils.renumber(random_labels(rng, H, W, int(rng.integers(1, 8))))
+    if lab.max() == 0:
+        return
+    mu = be.masks_to_flows(c32(lab[None]), int(lab.max()) + 2)
+    ref = dynamics.masks_to_flows(lab)
+    assert np.abs(mu[0] - ref).max() <= 1e-12
+
+
+def fuzz_average_tiles(be, rng):
+    """Taper blend of sub-tiles with random geometry (tile sizes 16 .. 48, images up to ~3 tiles a side, with and
+    without the TTA flips, 1 .. 6 channels) against the oracle's float64 accumulate: <= 1e-6."""
+    from classpose_b200 import transforms as btf
+    from oracle import transforms as otf
+    bsize = int(rng.choice([16, 20, 24, 32, 48]))
+    augment = bool(rng.random() < 0.5)
+    Ly = int(rng.integers(bsize, 3 * bsize)); Lx = int(rng.integers(bsize, 3 * bsize))
+    if rng.random() < 0.5:
+        Lx = Lx // 4 * 4
+    geo = btf.tile_geometry(Ly, Lx, bsize, augment=augment, tile_overlap=float(rng.choice([0.1, 0.25, 0.5])))
+    Ly, Lx, ly, lx = geo["Ly"], geo["Lx"], geo["ly"], geo["lx"]
+    nt = geo["ny"] * geo["nx"]
+    nch = int(rng.integers(1, 7))
+    negate = augment and nch == 3 and bool(rng.random() < 0.7)           # flow maps: dY / dX change sign with the flip
+    y = rng.normal(size=(nt, nch, ly, lx)).astype(np.float32)
+    y5 = y.reshape(geo["ny"], geo["nx"], nch, ly, lx).copy()
+    if augment:
+        y5 = otf.unaugment_tiles(y5) if negate else classpose_ref.unaugment_class_tiles(y5)
+    ysub = [[a, a + ly] for a in geo["y0"]]
+    xsub = [[a, a + lx] for a in geo["x0"]]
+    ref = _average_tiles_ref(y5.reshape(nt, nch, ly, lx), ysub, xsub, Ly, Lx, ly, lx)
+    ty, tx = btf.taper_1d(ly, lx)
+    out = be.average_tiles(y[None], geo["y0"], geo["x0"], geo["flip"], negate, ty, tx, Ly, Lx, (0, 0, 0, 0),
+                           vector=bool(rng.random() < 0.7))
+    np.testing.assert_allclose(out[0], ref, rtol=1e-6, atol=1e-6)
+
+
+def _average_tiles_ref(y, ysub, xsub, Ly, Lx, ly, lx):
+    """cellpose.transforms.average_tiles for any tile size (the oracle's version, like upstream, builds its mask for
+    the tile size of y)."""
+    from oracle import transforms as otf
+    return otf.average_tiles(y, ysub, xsub, Ly, Lx)
+
+
+TARGETS = [fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
 
 
 def run(seconds=60.0, seed=0, targets=TARGETS, be=None, verbose=True):
