@@ -12,6 +12,8 @@ Targets, all exact comparisons:
   fused path           every A/B switch combination gives one result                             (library vs itself)
   contours             random label images: point lists, area, bbox                             vs cv2.findContours
   masks_to_flows       random label images: <= 1e-12                                            vs oracle.dynamics
+  prepare_tiles        random images / tile sizes / TTA: bit-exact                              vs oracle.transforms
+  dedup                random cell centres (ties, chains): keep flags                          vs oracle.dedup
   average_tiles        random tile geometry / channels / TTA flips: <= 1e-6                     vs oracle.transforms
 """
 from __future__ import annotations
@@ -277,7 +279,44 @@ def _average_tiles_ref(y, ysub, xsub, Ly, Lx, ly, lx):
     return otf.average_tiles(y, ysub, xsub, Ly, Lx)
 
 
-TARGETS = [fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
+def fuzz_prepare_tiles(be, rng):
+    """Percentile normalisation + pad + sub-tiles (with the TTA flips) on random small images and tile sizes."""
+    from classpose_b200 import transforms as btf
+    from oracle import transforms as otf
+    bsize = int(rng.choice([16, 32, 48]))
+    H = int(rng.integers(8, 3 * bsize)); W = int(rng.integers(8, 3 * bsize)); C = int(rng.integers(1, 4))
+    kind = rng.random()
+    if kind < 0.4:
+        img = rng.integers(0, 256, size=(H, W, C)).astype(np.float32)         # uint8-valued: many equal values
+    elif kind < 0.8:
+        img = rng.normal(100, 30, size=(H, W, C)).astype(np.float32)
+    else:
+        img = rng.gamma(2.0, 30.0, size=(H, W, C)).astype(np.float32)
+    if rng.random() < 0.3:
+        img[..., int(rng.integers(0, C))] = float(rng.integers(0, 200))       # constant channel
+    augment = bool(rng.random() < 0.5)
+    ref, ysub, xsub, pads = otf.prepare_tiles(img, bsize, augment=augment)
+    geo = btf.tile_geometry(H + pads[0] + pads[1], W + pads[2] + pads[3], bsize, augment=augment)
+    tiles, lowhigh, code = be.prepare_tiles(f32(img[None]), pads, geo["y0"], geo["x0"], geo["flip"], geo["ly"], geo["lx"])
+    assert tiles.shape[1:] == ref.shape
+    np.testing.assert_array_equal(tiles[0], ref)
+
+
+def fuzz_dedup(be, rng):
+    """Overlap de-duplication: keep flags against the connected-components rule of the oracle."""
+    from oracle import dedup as odedup
+    n = int(rng.integers(1, 400))
+    extent = float(rng.choice([5.0, 40.0, 200.0, 2000.0]))
+    centers = rng.uniform(0, extent, size=(n, 2)) - extent / 3
+    if rng.random() < 0.3:
+        centers = np.round(centers)                                             # exact ties in distance
+    sizes = rng.integers(10, 20, size=n).astype(np.float64)
+    md = float(rng.choice([7.5, 7.5, 1.0, 30.0]))
+    keep, _ = be.dedup_cells(centers[:, 0], centers[:, 1], sizes, md)
+    np.testing.assert_array_equal(keep.astype(bool), odedup.components_keep_largest(centers, sizes, md))
+
+
+TARGETS = [fuzz_prepare_tiles, fuzz_dedup, fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
 
 
 def run(seconds=60.0, seed=0, targets=TARGETS, be=None, verbose=True):
