@@ -12,6 +12,7 @@ Targets, all exact comparisons:
   fused path           every A/B switch combination gives one result                             (library vs itself)
   contours             random label images: point lists, area, bbox                             vs cv2.findContours
   masks_to_flows       random label images: <= 1e-12                                            vs oracle.dynamics
+  eval_tail            blend fused with the threshold + masks + classes in one call             vs blend -> compute_masks (library)
   prepare_tiles        random images / tile sizes / TTA: bit-exact                              vs oracle.transforms
   dedup                random cell centres (ties, chains): keep flags                          vs oracle.dedup
   average_tiles        random tile geometry / channels / TTA flips: <= 1e-6                     vs oracle.transforms
@@ -316,7 +317,49 @@ def fuzz_dedup(be, rng):
     np.testing.assert_array_equal(keep.astype(bool), odedup.components_keep_largest(centers, sizes, md))
 
 
-TARGETS = [fuzz_prepare_tiles, fuzz_dedup, fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
+def fuzz_eval_tail(be, rng):
+    """cpb_eval_tail_device (blend fused with the threshold, then masks and classes, one call) against the composition
+    blend -> compute_masks of the same library, bit for bit, on random small geometries."""
+    from classpose_b200 import transforms as btf
+    W = int(rng.choice([64, 128])); H = int(rng.integers(16, 72))
+    bsize = int(rng.choice([32, 48, 64]))
+    augment = bool(rng.random() < 0.5)
+    pads = (int(rng.integers(0, 9)), int(rng.integers(0, 9)), int(rng.choice([0, 4, 8])), int(rng.choice([0, 4, 8, 12])))
+    Ly, Lx = H + pads[0] + pads[1], W + pads[2] + pads[3]
+    geo = btf.tile_geometry(Ly, Lx, bsize, augment=augment, tile_overlap=float(rng.choice([0.1, 0.3])))
+    if (geo["Ly"], geo["Lx"]) != (Ly, Lx) or geo["lx"] % 4 or (np.asarray(geo["x0"]) % 4).any():
+        return
+    ly, lx, nt = geo["ly"], geo["lx"], len(geo["y0"])
+    C = int(rng.choice([2, 5, 7]))
+    lab = outils.renumber(random_labels(rng, Ly, Lx, int(rng.integers(1, 7))))
+    mu = dynamics.masks_to_flows(lab) if lab.max() > 0 else np.zeros((2, Ly, Lx))
+    full = np.zeros((C + 3, Ly, Lx), np.float32)
+    full[:C] = rng.normal(0, 1, size=(C, Ly, Lx))
+    full[C:C + 2] = 5.0 * mu + rng.normal(0, 0.7, size=mu.shape)
+    full[C + 2] = np.where(lab > 0, 4.0, -4.0) + rng.normal(0, 1.5, size=lab.shape)
+    tiles = np.zeros((nt, C + 3, ly, lx), np.float32)
+    for j, (y0, x0, f) in enumerate(zip(geo["y0"], geo["x0"], geo["flip"])):
+        s_ = full[:, y0:y0 + ly, x0:x0 + lx].copy()
+        if f & 1:
+            s_ = s_[:, ::-1]; s_[C] *= -1
+        if f & 2:
+            s_ = s_[:, :, ::-1]; s_[C + 1] *= -1
+        tiles[j] = s_ + rng.normal(0, 0.05, size=s_.shape).astype(np.float32)       # sub-tiles disagree slightly
+    yfl, ycl = f32(tiles[None, :, C:]), f32(tiles[None, :, :C])
+    ty, tx = btf.taper_1d(ly, lx)
+    kw = dict(niter=int(rng.choice([200, 50])), flow_threshold=float(rng.choice([0.4, 0.0])), min_size=int(rng.choice([15, 3])))
+    masks, counts, cc, cm, dP, cp, lg = be.eval_tail(yfl, ycl, geo["y0"], geo["x0"], geo["flip"], augment, ty, tx, Ly, Lx,
+                                                     pads, want_class_masks=True, **kw)
+    yf = be.average_tiles(yfl, geo["y0"], geo["x0"], geo["flip"], augment, ty, tx, Ly, Lx, pads)
+    yc = be.average_tiles(ycl, geo["y0"], geo["x0"], geo["flip"], False, ty, tx, Ly, Lx, pads)
+    np.testing.assert_array_equal(dP[0], yf[0, :2]); np.testing.assert_array_equal(cp[0], yf[0, 2])
+    np.testing.assert_array_equal(lg, yc)
+    m2, c2, cc2, cm2 = be.compute_masks(f32(yf[:, :2]), f32(yf[:, 2]), f32(yc), want_class_masks=True, **kw)
+    np.testing.assert_array_equal(masks, m2); np.testing.assert_array_equal(counts, c2)
+    np.testing.assert_array_equal(cm, cm2)
+
+
+TARGETS = [fuzz_eval_tail, fuzz_prepare_tiles, fuzz_dedup, fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
 
 
 def run(seconds=60.0, seed=0, targets=TARGETS, be=None, verbose=True):
