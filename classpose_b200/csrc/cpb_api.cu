@@ -98,6 +98,8 @@ struct Workspace {
     int* jobs;           // [B+1] diffusion job offsets, 2 queue counters, 2 counts of `todo` (front / back)
     int2* todo;          // [B*LC] (tile, label) work list of the block-per-label kernels
     Q32 q;               // float32 flow-check screen: label info, class lists, job queue, float64 list, counters
+    int* cover;          // [B*LC] exact hole fill (CPB_FILL_EXACT): pixels a label loses to other labels' fills
+    int* seq;            // [B]    tiles whose fill is replayed sequentially
     LabelTables t;
     size_t bytes;
     Prof* prof;          // optional stage timing
@@ -139,6 +141,7 @@ Workspace carve(void* base, int B, int H, int W, int C, int lcap) {
     t.done = c.take<int>(BL);
     t.lbound = c.take<int>(B); t.nlab = c.take<int>(B); t.niter = c.take<int>(B); t.misc = c.take<int>(B);
     t.fail = c.take<int>(B);
+    w.cover = c.take<int>(BL); w.seq = c.take<int>(B);
     w.bytes = c.off;
     return w;
 }
@@ -264,12 +267,15 @@ FollowSchedule follow_schedule(int niter) {
 //   CPB_QC_FUSED=0       every label's flow error from T in global memory (k_flow_err) instead of the diffusion tile
 //   CPB_VOTE_FUSED=0     class vote as its own pass over the finished label image
 //   CPB_QC_SCREEN=0      every label through the float64 diffusion (no float32 screen in front of it)
+//   CPB_FILL_EXACT=1     (default 0) replay upstream's label-by-label hole fill on tiles in which a label lies partly inside
+//                        another label's hole (the one configuration where taking every label's holes from the input
+//                        image differs from it); simulator-validated only
 //   CPB_SEED_CANDS=0     seed candidates (bins with more than 10 end points) found by streaming the histogram (k_seed_scan)
 //                        instead of being listed by the kernel that counts the end points
 //   CPB_FOLLOW_SMALL=0   1024-entry chunks in the trajectory pool for every batch size (1: 256-entry chunks for a handful of tiles)
 //   CPB_BLEND_EFT=0      blend with float64 arithmetic per element (numpy's literal op sequence) instead of the float32
 //                        error-free form (identical up to ~1e-6 of the elements by one ulp)
-std::atomic<int> g_switch[8] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
+std::atomic<int> g_switch[9] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
 bool switch_on(int which, const char* env_name) {
     int v = g_switch[which].load(std::memory_order_relaxed);
     if (v < 0) {
@@ -283,6 +289,12 @@ bool qc_fused_enabled() { return switch_on(CPB_SWITCH_QC_FUSED, "CPB_QC_FUSED");
 bool vote_fused_enabled() { return switch_on(CPB_SWITCH_VOTE_FUSED, "CPB_VOTE_FUSED"); }
 bool qc_screen_enabled() { return switch_on(CPB_SWITCH_QC_SCREEN, "CPB_QC_SCREEN"); }
 bool blend_eft_enabled() { return switch_on(CPB_SWITCH_BLEND_EFT, "CPB_BLEND_EFT"); }
+// default OFF (the only switch that is): the exact replay for tangled labels has run on the simulator only
+bool fill_exact_enabled() {
+    int v = g_switch[CPB_SWITCH_FILL_EXACT].load(std::memory_order_relaxed);
+    if (v < 0) { const char* e = getenv("CPB_FILL_EXACT"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v != 0;
+}
 bool seed_cands_enabled() { return switch_on(CPB_SWITCH_SEED_CANDS, "CPB_SEED_CANDS"); }
 bool follow_small_enabled() { return switch_on(CPB_SWITCH_FOLLOW_SMALL, "CPB_FOLLOW_SMALL"); }
 // value 2 (tests only): the screen also runs when the caller asks for the per-label errors, and reports
@@ -539,6 +551,20 @@ int run_flow_qc(const Workspace& w, const int32_t* masks, const float* dP, int B
     return 0;
 }
 
+// exact hole fill for tangled labels (see k_fill_sequential): detection + replay on the proposal plane in place
+int run_fill_exact(const Workspace& w, const int32_t* masks, int B, int H, int W, bool order_by_remap, cudaStream_t st) {
+    cudaMemsetAsync(w.cover, 0, (size_t)B * w.t.LC * sizeof(int), st);
+    cudaMemsetAsync(w.seq, 0, B * sizeof(int), st);
+    CPB_LAUNCH_COUNTED(k_fill_cover, dim3(tile_slices(H, W), B), dim3(256), 0, st, masks, (const u64*)w.holekey, H, W, w.t, w.cover);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_fill_conflict, dim3(B), dim3(256), 0, st, w.t, (const int*)w.cover, w.seq);
+    CPB_CHECK_LAUNCH();
+    CPB_LAUNCH_COUNTED(k_fill_sequential, dim3(B), dim3(32), 0, st, masks, H, W, w.t, (const int*)w.seq, order_by_remap ? 1 : 0,
+                       w.M, w.hist, w.pfinal, w.sinv, w.holekey);
+    CPB_CHECK_LAUNCH();
+    return 0;
+}
+
 // fill_holes_and_remove_small_masks on `masks` whose statistics are NOT yet in the tables
 int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int min_size, int32_t* counts,
                    bool have_stats, cudaStream_t st) {
@@ -561,6 +587,7 @@ int run_fill_small(const Workspace& w, int32_t* masks, int B, int H, int W, int 
     CPB_LAUNCH_COUNTED(k_fill_holes, dim3(kLabelBlocksPerTile, B), dim3(CPB_FILL_THREADS), 2 * CPB_FILL_WORDS * 4, st,
                masks, H, W, w.t, w.holekey, fill_pool(w, B, H, W), 1, (LabelWork{nullptr, nullptr, 0, 0}), CPB_FILL_BOTH);
     CPB_CHECK_LAUNCH();
+    if (fill_exact_enabled()) { e = run_fill_exact(w, masks, B, H, W, false, st); if (e) return e; }
     prof_end(w.prof, S_FILL);
     e = run_map_stats(w, masks, B, H, W, 1, nullptr, nullptr, w.holekey, true, st, S_MAP3); if (e) return e;
     if (mode == 1) {
@@ -819,6 +846,7 @@ static int compute_masks_impl(const float* dP, const float* cellprob, const floa
                 CPB_CHECK_LAUNCH();
             }
         }
+        if (fill_exact_enabled()) { e = run_fill_exact(w, masks, B, H, W, true, st); if (e) return e; }
         prof_end(w.prof, S_FILL);
         prof_begin(w.prof, S_MAP3);
         CPB_LAUNCH_COUNTED(k_recount_reset, dim3(B), dim3(256), 0, st, w.t);
@@ -973,7 +1001,7 @@ const char* cpb_stage_name(int i) { return (i >= 0 && i < S_COUNT) ? kStageNames
 void cpb_debug_set_follow_merge(int mode) { g_follow_merge.store(mode, std::memory_order_relaxed); }
 void cpb_debug_set_switch(int which, int value) {
     if (which == CPB_SWITCH_FOLLOW_MERGE) g_follow_merge.store(value, std::memory_order_relaxed);
-    else if (which > 0 && which < 8) g_switch[which].store(value, std::memory_order_relaxed);
+    else if (which > 0 && which < 9) g_switch[which].store(value, std::memory_order_relaxed);
 }
 long long cpb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void cpb_debug_qc_stats(int32_t* out) {

@@ -184,13 +184,15 @@ k_final(int* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, int B, int H, in
     const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= total) return;
     const int b = (int)(gi / N);
-    int l = lab[gi];
+    const int was = lab[gi];
+    int l = was;
     if (holekey && t.misc[b] != 0) {
         const u64 hk = holekey[gi];
         if (hk) l = (int)(hk & 0xffffffffu);
     }
     const int out = l > 0 ? t.remap[(size_t)b * t.LC + l] : 0;
-    if (out != l) lab[gi] = out;
+    if (out != was) lab[gi] = out;      // (compared with what the pixel HOLDS: a filled hole whose label keeps its number
+                                        //  under the remap used to be skipped -- found by tests/studies/fuzz_sim.py)
     if (gi - (long long)b * N == 0) {
         const int n = t.nlab[b];
         if (counts_out) counts_out[b] = n;

@@ -173,6 +173,105 @@ k_fill_holes_warp(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, u64*
     }
 }
 
+// ---- exact hole fill for tangled labels (CPB_FILL_EXACT, default off: validated on the simulator only) ----------
+// The proposals above take every label's holes from the input image.  Upstream fills label by label in id order on
+// the image as the earlier fills left it; the two differ only when a label loses SOME of its pixels to another
+// label's fill and survives (it is then cut before its own turn).  k_fill_cover counts, per label, the pixels it
+// loses to the proposals; k_fill_conflict flags the tiles in which a label loses some but not all of them; and
+// k_fill_sequential replays upstream's loop on those tiles (one thread per tile: they are rare, and a sequential
+// replay is the specification) and rewrites their proposal plane with the result.
+CPB_KERNEL k_fill_cover(const int* CPB_RESTRICT lab, const u64* CPB_RESTRICT holekey, int H, int W, LabelTables t,
+                        int* CPB_RESTRICT cover) {
+    const int b = blockIdx.y;
+    if (t.misc[b] == 0) return;                 // no proposal anywhere in this tile
+    const int N = H * W, LC = t.LC;
+    const int* L = lab + (size_t)b * N;
+    const u64* HK = holekey + (size_t)b * N;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
+        const u64 hk = HK[r];
+        if (hk == 0) continue;
+        const int o = L[r];
+        if (o > 0 && o < LC && o != (int)(hk & 0xffffffffu)) atomicAdd(&cover[(size_t)b * LC + o], 1);
+    }
+}
+
+CPB_KERNEL k_fill_conflict(LabelTables t, const int* CPB_RESTRICT cover, int* CPB_RESTRICT seq) {
+    const int b = blockIdx.x;
+    if (t.misc[b] == 0) return;
+    const int LC = t.LC, lb = min(t.lbound[b], LC - 1);
+    for (int l = 1 + threadIdx.x; l <= lb; l += blockDim.x) {
+        const size_t k = (size_t)b * LC + l;
+        const int c = cover[k];
+        if (c > 0 && c < t.cnt[k] && (t.alive == nullptr || t.alive[k] != 0)) seq[b] = 1;
+    }
+}
+
+// order_by_remap != 0 (fused path): the image holds raw labels and upstream's id of raw label l at this point is
+// t.remap[l]; otherwise (stage call) the image holds those ids themselves.  state / mark / stack: three scratch
+// planes of N ints per tile; inv: LC ints per tile.
+CPB_KERNEL k_fill_sequential(const int* CPB_RESTRICT lab, int H, int W, LabelTables t, const int* CPB_RESTRICT seq,
+                             int order_by_remap, int* CPB_RESTRICT state_, int* CPB_RESTRICT mark_,
+                             int* CPB_RESTRICT stack_, int* CPB_RESTRICT inv_, u64* CPB_RESTRICT holekey) {
+    const int b = blockIdx.x;
+    if (seq[b] == 0 || threadIdx.x != 0) return;
+    const int N = H * W, LC = t.LC, lb = min(t.lbound[b], LC - 1);
+    const int* L = lab + (size_t)b * N;
+    int* state = state_ + (size_t)b * N;
+    int* mark = mark_ + (size_t)b * N;
+    int* stack = stack_ + (size_t)b * N;
+    int* inv = inv_ + (size_t)b * LC;
+    u64* HK = holekey + (size_t)b * N;
+    // labels on the image before the fill: everything the size filter in front of it left alive
+    for (int p = 0; p < N; p++) {
+        const int o = L[p];
+        const bool on = o > 0 && o <= lb && (t.alive == nullptr || t.alive[(size_t)b * LC + o] != 0);
+        state[p] = on ? o : 0;
+        mark[p] = 0;
+    }
+    for (int i = 0; i <= lb; i++) inv[i] = 0;
+    for (int l = 1; l <= lb; l++) {
+        const size_t k = (size_t)b * LC + l;
+        if (t.cnt[k] <= 0 || (t.alive != nullptr && t.alive[k] == 0)) continue;
+        const int id = order_by_remap ? t.remap[k] : l;
+        if (id >= 1 && id <= lb) inv[id] = l;
+    }
+    for (int id = 1; id <= lb; id++) {
+        const int l = inv[id];
+        if (l == 0) continue;
+        const size_t k = (size_t)b * LC + l;
+        const int y0 = t.ymin[k], y1 = t.ymax[k], x0 = t.xmin[k], x1 = t.xmax[k];
+        if (y1 - y0 < 2 || x1 - x0 < 2) continue;             // a crop under 3 x 3 encloses nothing
+        // flood the crop from its border through pixels that are not l (4-connectivity)
+        int sp = 0;
+        for (int y = y0; y <= y1; y++)
+            for (int x = x0; x <= x1; x++) {
+                if (y != y0 && y != y1 && x != x0 && x != x1) continue;
+                const int p = y * W + x;
+                if (state[p] != l && mark[p] != id) { mark[p] = id; stack[sp++] = p; }
+            }
+        while (sp > 0) {
+            const int p = stack[--sp];
+            const int y = p / W, x = p - y * W;
+            if (y > y0) { const int q = p - W; if (state[q] != l && mark[q] != id) { mark[q] = id; stack[sp++] = q; } }
+            if (y < y1) { const int q = p + W; if (state[q] != l && mark[q] != id) { mark[q] = id; stack[sp++] = q; } }
+            if (x > x0) { const int q = p - 1; if (state[q] != l && mark[q] != id) { mark[q] = id; stack[sp++] = q; } }
+            if (x < x1) { const int q = p + 1; if (state[q] != l && mark[q] != id) { mark[q] = id; stack[sp++] = q; } }
+        }
+        for (int y = y0; y <= y1; y++)
+            for (int x = x0; x <= x1; x++) {
+                const int p = y * W + x;
+                if (state[p] != l && mark[p] != id) state[p] = l;      // enclosed: the label takes it
+            }
+    }
+    // the proposal plane of the tile, rewritten: a pixel whose owner changed carries its new owner
+    for (int p = 0; p < N; p++) {
+        const int o = L[p];
+        const bool on = o > 0 && o <= lb && (t.alive == nullptr || t.alive[(size_t)b * LC + o] != 0);
+        const int was = on ? o : 0;
+        HK[p] = state[p] != was ? ((1ull << 32) | (u64)(unsigned)state[p]) : 0ull;
+    }
+}
+
 // k_vote: one block per tile.  Per-pixel arg-max over the C logits (first maximum wins),
 // histogram (instance, class) in shared memory, per-instance arg-max (first maximum wins).
 // Falls back to a global table when (lbound+1)*C ints exceed the shared-memory budget.

@@ -106,6 +106,9 @@ void cpb_debug_set_follow_merge(int mode);
                                        tiles (latency form; 0: 1024-entry chunks always) */
 #define CPB_SWITCH_SEED_CANDS 7     /* CPB_SEED_CANDS: the trajectory kernel lists the bins that pass 10 end points while it counts
                                        them (0: a separate pass streams the whole histogram to find them) */
+#define CPB_SWITCH_FILL_EXACT 8     /* CPB_FILL_EXACT (default 0, unlike the others): replay upstream's label-by-label hole fill on
+                                       tiles where a label lies partly inside another label's hole; validated on the CPU
+                                       simulator only, see INTEGRATION.md section 4 */
 void cpb_debug_set_switch(int which, int value);
 /* number of kernels this library has launched in this process (statistics for the benchmark) */
 long long cpb_debug_launch_count(void);

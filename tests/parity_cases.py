@@ -455,6 +455,16 @@ def case_fill_holes_label_partly_inside_a_hole(be):
     np.testing.assert_array_equal(out[0], expected)
     differ = out[0] != upstream
     assert differ.sum() == 9 and differ[6:9, 5:8].all()          # the ring's interior, nothing else
+    if be.name == "sim":
+        # CPB_FILL_EXACT (switch 8, default off): tiles with such a label are replayed label by label -- upstream's result.
+        # Validated on the simulator (thousands of tangled images, tests/studies/fuzz_sim.py); it has not run on hardware
+        # yet, which is why it is off by default and why this half of the case is simulator-only.
+        try:
+            be.set_switch(8, 1)
+            exact, _ = be.fill_holes_and_remove_small_masks(c32(lab[None]).copy(), int(lab.max()) + 2, -1)
+        finally:
+            be.set_switch(8, -1)
+        np.testing.assert_array_equal(exact[0], upstream)
 
 
 def random_label_image(rng, H, W, n, gaps=True):
@@ -726,6 +736,17 @@ def case_eval_tail_blend_fused_with_threshold(be):
         ref_cm, _ = classpose_ref.compute_class_masks(ref, ryc[:, None])
         r = metrics.class_agreement(ref, ref_cm, masks[0], cm[0].astype(np.int64))
         assert r["f1"] >= 0.995 and not r["class_mismatch"] and r["n_pred"] == r["n_true"], r
+
+
+def case_fused_equals_stages_on_odd_tiles(be):
+    """Regression (found by tests/studies/fuzz_sim.py): tiles whose pixel count is not a multiple of 4 take the scalar
+    final pass, which skipped a filled hole whenever its label kept its number under the final remap.  The fused path
+    must equal the composition of the stage entry points bit for bit on messy inputs of odd shapes."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "studies"))
+    import fuzz_sim
+    for it in (25, 34, 100, 106, 3, 7):              # the first four are the inputs that exposed it
+        fuzz_sim.fuzz_fused_equals_stages(be, np.random.default_rng([99, it]))
 
 
 def case_fused_generic_class_count(be):
@@ -1035,7 +1056,7 @@ ALL_CASES = [case_follow_flows, case_follow_flows_few_iters_exact, case_follow_f
              case_get_masks_plateaus_and_ties, case_get_masks_no_seeds, case_masks_to_flows_exact,
              case_remove_bad_flow_masks_exact, case_flow_qc_fused_equals_unfused, case_flow_qc_screen_is_decision_exact,
              case_fill_holes_exact, case_fill_holes_oversized_label, case_fill_holes_label_partly_inside_a_hole, case_random_label_images, case_random_flow_qc, case_class_vote_reference_vectors,
-             case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes, case_fused_baseline_config_shapes,
+             case_border_reference_vectors, case_average_tiles, case_fused_path, case_fused_path_other_shapes, case_fused_baseline_config_shapes, case_fused_equals_stages_on_odd_tiles,
              case_eval_tail_blend_fused_with_threshold,
              case_fused_generic_class_count, case_fused_switch_matrix, case_fused_odd_width, case_fused_empty_and_params, case_fused_min_size_zero_keeps_upstream_ids,
              case_fused_qc_then_positional_size_filter,

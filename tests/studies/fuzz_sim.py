@@ -10,6 +10,8 @@ Targets, all exact comparisons:
   border removal       random label images, 1 and 3 channels                                    vs oracle.classpose_ref
   flow check           random label images + random flows: removal set                          vs oracle.dynamics
   fused path           every A/B switch combination gives one result                             (library vs itself)
+  exact replay         CPB_FILL_EXACT=1: hole fill equal to upstream on tangled label images too, stage call and fused path (planted labels)
+  fused == stages      fused path vs follow -> get_masks -> flow check -> fill through the stage calls  (library vs itself)
   contours             random label images: point lists, area, bbox                             vs cv2.findContours
   masks_to_flows       random label images: <= 1e-12                                            vs oracle.dynamics
   eval_tail            blend fused with the threshold + masks + classes in one call             vs blend -> compute_masks (library)
@@ -359,7 +361,104 @@ def fuzz_eval_tail(be, rng):
     np.testing.assert_array_equal(cm, cm2)
 
 
-TARGETS = [fuzz_eval_tail, fuzz_prepare_tiles, fuzz_dedup, fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
+def stages_composed(be, dP, cp, kw):
+    """follow_flows -> get_masks -> remove_bad_flow_masks -> fill_holes_and_remove_small_masks through the stage-by-stage
+    entry points (each of them compared with the oracle by its own target)."""
+    pf, _ = be.follow_flows(dP[None], cp[None], kw["niter"], kw["cellprob_threshold"])
+    m, _ = be.get_masks(pf, kw["max_size_fraction"])
+    if kw["flow_threshold"] > 0 and m.max() > 0:
+        m, _ = be.remove_bad_flow_masks(c32(m), dP[None], int(m.max()) + 2, kw["flow_threshold"])
+    m, _ = be.fill_holes_and_remove_small_masks(c32(m), int(m.max()) + 2, kw["min_size"])
+    return m
+
+
+def fuzz_fused_equals_stages(be, rng):
+    """The fused path (raw labels + table relabelling, one final pixel pass) against the composition of the stage entry
+    points, bit for bit, on messy inputs: noisy flows, ragged foreground, odd tile shapes (pixel counts that are not a
+    multiple of 4 take the scalar final pass -- this target found that it skipped a filled hole whose label keeps its
+    number under the remap)."""
+    H, W = random_shape(rng, vec_bias=0.7)
+    H, W = max(H, 16), max(W, 16)
+    lab = outils.renumber(random_labels(rng, H, W, int(rng.integers(2, 9))))
+    mu = dynamics.masks_to_flows(lab) if lab.max() > 0 else np.zeros((2, H, W))
+    dP = (5.0 * mu + rng.normal(0, rng.uniform(0.3, 2.5), size=mu.shape)).astype(np.float32)
+    cp = (np.where(lab > 0, 4.0, -4.0) + rng.normal(0, 2.0, size=lab.shape)).astype(np.float32)
+    kw = dict(niter=int(rng.choice([200, 60])), cellprob_threshold=0.0, flow_threshold=float(rng.choice([0.0, 3.0, 0.4])),
+              min_size=int(rng.choice([15, 3, -1, 0])), max_size_fraction=0.4)
+    m0, _, _, _ = be.compute_masks(dP[None], cp[None], None, **kw)
+    np.testing.assert_array_equal(m0, stages_composed(be, dP, cp, kw))
+
+
+def planted_labels(rng):
+    """dP / cellprob that push a chosen -- tangled -- label image through get_masks: every pixel of label k jumps in ONE
+    Euler step (niter = 1, displacement dP / 5 pixels) onto a target pixel of its own, so the histogram has one bin per
+    label and the label image that comes out is the planted one."""
+    H = int(rng.integers(20, 44)); W = int(rng.integers(20, 44))
+    lab = random_labels(rng, H, W, int(rng.integers(2, 9)))
+    ids, cnt = np.unique(lab, return_counts=True)
+    for i, c in zip(ids, cnt):
+        if i != 0 and c < 11:
+            lab[lab == i] = 0                       # a seed needs more than 10 end points
+    lab = outils.renumber(lab)
+    n = int(lab.max())
+    slots = [(3 + 6 * j, 3 + 6 * i) for j in range((H - 4) // 6) for i in range((W - 4) // 6)]
+    if n == 0 or len(slots) < n:
+        return None
+    pick = rng.permutation(len(slots))[:n]
+    dP = np.zeros((2, H, W), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for k in range(1, n + 1):
+        ty, tx = slots[pick[k - 1]]
+        m = lab == k
+        dP[0][m] = 5.0 * (ty - yy[m] + 0.25); dP[1][m] = 5.0 * (tx - xx[m] + 0.25)
+    return dP, np.where(lab > 0, 4.0, -4.0).astype(np.float32)
+
+
+def fuzz_fused_planted_labels(be, rng):
+    """Tangled label images through the FUSED path against the oracle on the same end points: exact without the
+    replay unless a label lies partly inside another label's hole, always exact with it (switch 8, CPB_FILL_EXACT)."""
+    g = planted_labels(rng)
+    if g is None:
+        return
+    dP, cp = g
+    H, W = cp.shape
+    kw = dict(niter=1, cellprob_threshold=0.0, flow_threshold=0.0, min_size=int(rng.choice([-1, 0, 3, 15])), max_size_fraction=1.0)
+    try:
+        be.set_switch(8, 0); m0, _, _, _ = be.compute_masks(dP[None], cp[None], None, **kw)
+        be.set_switch(8, 1); m1, _, _, _ = be.compute_masks(dP[None], cp[None], None, **kw)
+        ms = stages_composed(be, dP, cp, kw)
+    finally:
+        be.set_switch(8, -1)
+    pf, _ = be.follow_flows(dP[None], cp[None], 1, 0.0)
+    ys, xs = np.nonzero(cp > 0)
+    pfin = np.stack([pf[0][ys, xs] >> 16, pf[0][ys, xs] & 0xffff]).astype(np.int32)
+    mo = dynamics.get_masks(pfin, (ys, xs), (H, W), max_size_fraction=1.0)
+    tangled = partly_swallowed(outils._drop_small(mo.copy(), kw["min_size"]) if kw["min_size"] > 0 else mo)
+    ref = outils.fill_holes_and_remove_small_masks(mo, kw["min_size"])
+    np.testing.assert_array_equal(m1[0], ref)
+    np.testing.assert_array_equal(m1, ms)
+    if tangled:
+        SKIPPED["partly_swallowed"] += 1
+    else:
+        np.testing.assert_array_equal(m0[0], ref)
+
+
+def fuzz_fill_holes_exact_replay(be, rng):
+    """fill_holes_and_remove_small_masks with the sequential replay on (switch 8): equal to upstream on EVERY label
+    image, tangled ones included."""
+    H, W = random_shape(rng)
+    lab = random_labels(rng, H, W, int(rng.integers(1, 10)))
+    min_size = int(rng.choice([15, 15, 1, 3, 40, 0, -1]))
+    ref = outils.fill_holes_and_remove_small_masks(lab.copy(), min_size)
+    try:
+        be.set_switch(8, 1)
+        out, _ = be.fill_holes_and_remove_small_masks(c32(lab[None]), int(lab.max()) + 2, min_size)
+    finally:
+        be.set_switch(8, -1)
+    np.testing.assert_array_equal(out[0], ref)
+
+
+TARGETS = [fuzz_fill_holes_exact_replay, fuzz_fused_planted_labels, fuzz_fused_equals_stages, fuzz_eval_tail, fuzz_prepare_tiles, fuzz_dedup, fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
 
 
 def run(seconds=60.0, seed=0, targets=TARGETS, be=None, verbose=True):
