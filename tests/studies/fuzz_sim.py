@@ -369,6 +369,8 @@ def stages_composed(be, dP, cp, kw):
     if kw["flow_threshold"] > 0 and m.max() > 0:
         m, _ = be.remove_bad_flow_masks(c32(m), dP[None], int(m.max()) + 2, kw["flow_threshold"])
     m, _ = be.fill_holes_and_remove_small_masks(c32(m), int(m.max()) + 2, kw["min_size"])
+    if kw.get("remove_border"):
+        m = be.remove_border_instances(c32(m), int(m.max()) + 2, 1)
     return m
 
 
@@ -385,6 +387,8 @@ def fuzz_fused_equals_stages(be, rng):
     cp = (np.where(lab > 0, 4.0, -4.0) + rng.normal(0, 2.0, size=lab.shape)).astype(np.float32)
     kw = dict(niter=int(rng.choice([200, 60])), cellprob_threshold=0.0, flow_threshold=float(rng.choice([0.0, 3.0, 0.4])),
               min_size=int(rng.choice([15, 3, -1, 0])), max_size_fraction=0.4)
+    if rng.random() < 0.3:
+        kw["remove_border"] = True
     m0, _, _, _ = be.compute_masks(dP[None], cp[None], None, **kw)
     np.testing.assert_array_equal(m0, stages_composed(be, dP, cp, kw))
 
