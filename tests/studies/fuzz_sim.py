@@ -11,6 +11,7 @@ Targets, all exact comparisons:
   flow check           random label images + random flows: removal set                          vs oracle.dynamics
   fused path           every A/B switch combination gives one result                             (library vs itself)
   exact replay         CPB_FILL_EXACT=1: hole fill equal to upstream on tangled label images too, stage call and fused path (planted labels)
+  batch consistency    a batch of different tiles equals the tiles one by one                    (library vs itself)
   fused == stages      fused path vs follow -> get_masks -> flow check -> fill through the stage calls  (library vs itself)
   contours             random label images: point lists, area, bbox                             vs cv2.findContours
   masks_to_flows       random label images: <= 1e-12                                            vs oracle.dynamics
@@ -170,7 +171,12 @@ def fuzz_flow_qc(be, rng):
     dP = np.where(mix, rng.normal(0, 3.0, size=mu.shape), 5.0 * mu).astype(np.float32)
     thr = float(rng.choice([0.4, 0.4, 0.1, 1.0]))
     ref = dynamics.remove_bad_flow_masks(lab.copy(), dP, threshold=thr)
-    out, _ = be.remove_bad_flow_masks(c32(lab[None]), f32(dP[None]), int(lab.max()) + 2, thr)
+    out, _ = be.remove_bad_flow_masks(c32(lab[None]).copy(), f32(dP[None]), int(lab.max()) + 2, thr)   # (in place on the simulator)
+    if rng.random() < 0.5:                                   # the per-label errors themselves (float64 path): <= 1e-9
+        err_ref, _ = dynamics.flow_error(lab, dP)
+        out2, err = be.remove_bad_flow_masks(c32(lab[None]).copy(), f32(dP[None]), int(lab.max()) + 2, thr, want_err=True)
+        assert np.abs(err[0, 1:len(err_ref) + 1] - err_ref).max() < 1e-9
+        np.testing.assert_array_equal(out2, out)
     # the library keeps the ids of the survivors or renumbers like the reference: compare as sets of pixels per survivor
     np.testing.assert_array_equal(out[0] > 0, ref > 0)
     np.testing.assert_array_equal(outils.renumber(out[0].astype(np.int32)), outils.renumber(ref.astype(np.int32)))
@@ -462,7 +468,31 @@ def fuzz_fill_holes_exact_replay(be, rng):
     np.testing.assert_array_equal(out[0], ref)
 
 
-TARGETS = [fuzz_fill_holes_exact_replay, fuzz_fused_planted_labels, fuzz_fused_equals_stages, fuzz_eval_tail, fuzz_prepare_tiles, fuzz_dedup, fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
+def fuzz_batch_consistency(be, rng):
+    """A batch of 2 .. 4 different tiles through the fused path (with classes) equals the tiles one by one: label images,
+    counts, and the class of every cell."""
+    H, W = random_shape(rng, vec_bias=0.7)
+    H, W = max(H, 16), max(W, 16)
+    B = int(rng.integers(2, 5)); C = int(rng.choice([2, 5, 7]))
+    dP = np.zeros((B, 2, H, W), np.float32); cp = np.zeros((B, H, W), np.float32)
+    for b in range(B):
+        lab = outils.renumber(random_labels(rng, H, W, int(rng.integers(0, 8)))) if rng.random() < 0.9 else np.zeros((H, W), np.int32)
+        mu = dynamics.masks_to_flows(lab) if lab.max() > 0 else np.zeros((2, H, W))
+        dP[b] = 5.0 * mu + rng.normal(0, rng.uniform(0.2, 1.5), size=mu.shape)
+        cp[b] = np.where(lab > 0, 4.0, -4.0) + rng.normal(0, 1.5, size=lab.shape)
+    lg = rng.normal(0, 1.0, size=(B, C, H, W)).astype(np.float32)
+    kw = dict(niter=int(rng.choice([200, 50])), flow_threshold=float(rng.choice([0.4, 0.0, 2.0])), min_size=int(rng.choice([15, 3, -1])))
+    m, c, cc, cm = be.compute_masks(dP, cp, lg, want_class_masks=bool(rng.random() < 0.5), **kw)
+    for b in range(B):
+        m1, c1, cc1, cm1 = be.compute_masks(dP[b:b + 1], cp[b:b + 1], lg[b:b + 1], want_class_masks=cm is not None, **kw)
+        np.testing.assert_array_equal(m[b], m1[0]); assert c[b] == c1[0]
+        n = max(int(c1[0]), 0)
+        np.testing.assert_array_equal(cc[b, :n + 1], cc1[0, :n + 1])
+        if cm is not None:
+            np.testing.assert_array_equal(cm[b], cm1[0])
+
+
+TARGETS = [fuzz_batch_consistency, fuzz_fill_holes_exact_replay, fuzz_fused_planted_labels, fuzz_fused_equals_stages, fuzz_eval_tail, fuzz_prepare_tiles, fuzz_dedup, fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
 
 
 def run(seconds=60.0, seed=0, targets=TARGETS, be=None, verbose=True):
