@@ -43,9 +43,11 @@ def f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def random_shape(rng, vec_bias=0.5):
+def random_shape(rng, vec_bias=0.5, big=0.0):
     H = int(rng.integers(6, 44))
     W = int(rng.integers(6, 44))
+    if rng.random() < big:                        # several 1024-entry chunks of the foreground list, several blocks per pass
+        H = int(rng.integers(60, 120)); W = int(rng.integers(60, 120))
     if rng.random() < vec_bias:
         W = max(8, W // 4 * 4)
     return H, W
@@ -385,9 +387,9 @@ def fuzz_fused_equals_stages(be, rng):
     points, bit for bit, on messy inputs: noisy flows, ragged foreground, odd tile shapes (pixel counts that are not a
     multiple of 4 take the scalar final pass -- this target found that it skipped a filled hole whose label keeps its
     number under the remap)."""
-    H, W = random_shape(rng, vec_bias=0.7)
+    H, W = random_shape(rng, vec_bias=0.7, big=0.15)
     H, W = max(H, 16), max(W, 16)
-    lab = outils.renumber(random_labels(rng, H, W, int(rng.integers(2, 9))))
+    lab = outils.renumber(random_labels(rng, H, W, int(rng.integers(2, 9 if H < 60 else 30))))
     mu = dynamics.masks_to_flows(lab) if lab.max() > 0 else np.zeros((2, H, W))
     dP = (5.0 * mu + rng.normal(0, rng.uniform(0.3, 2.5), size=mu.shape)).astype(np.float32)
     cp = (np.where(lab > 0, 4.0, -4.0) + rng.normal(0, 2.0, size=lab.shape)).astype(np.float32)
