@@ -397,8 +397,18 @@ def fuzz_fused_equals_stages(be, rng):
               min_size=int(rng.choice([15, 3, -1, 0])), max_size_fraction=0.4)
     if rng.random() < 0.3:
         kw["remove_border"] = True
-    m0, _, _, _ = be.compute_masks(dP[None], cp[None], None, **kw)
-    np.testing.assert_array_equal(m0, stages_composed(be, dP, cp, kw))
+    C = int(rng.choice([0, 2, 5, 7, 10]))
+    lg = rng.normal(0, 1.0, size=(1, C, H, W)).astype(np.float32) if C else None
+    want_cm = bool(C and rng.random() < 0.5)
+    m0, c0, cc0, cm0 = be.compute_masks(dP[None], cp[None], lg, want_class_masks=want_cm, **kw)
+    ms = stages_composed(be, dP, cp, kw)
+    np.testing.assert_array_equal(m0, ms)
+    if C:                   # classes of the cells: the fused vote (riding on the final pass or not) against the stage call
+        cc1, cm1 = be.class_vote(c32(ms), lg, int(ms.max()) + 2, want_class_masks=True)
+        n = int(ms.max())
+        np.testing.assert_array_equal(cc0[0, 1:n + 1], cc1[0, 1:n + 1])
+        if want_cm:
+            np.testing.assert_array_equal(cm0, cm1)
 
 
 def planted_labels(rng):
