@@ -11,6 +11,7 @@ Targets, all exact comparisons:
   flow check           random label images + random flows: removal set                          vs oracle.dynamics
   fused path           every A/B switch combination gives one result                             (library vs itself)
   exact replay         CPB_FILL_EXACT=1: hole fill equal to upstream on tangled label images too, stage call and fused path (planted labels)
+  follow_flows         1 .. 4 Euler steps on random flows, any tile shape: truncated end points         vs oracle (torch grid_sample)
   batch consistency    a batch of different tiles equals the tiles one by one                    (library vs itself)
   fused == stages      fused path vs follow -> get_masks -> flow check -> fill through the stage calls  (library vs itself)
   contours             random label images: point lists, area, bbox                             vs cv2.findContours
@@ -504,7 +505,27 @@ def fuzz_batch_consistency(be, rng):
             np.testing.assert_array_equal(cm[b], cm1[0])
 
 
-TARGETS = [fuzz_batch_consistency, fuzz_fill_holes_exact_replay, fuzz_fused_planted_labels, fuzz_fused_equals_stages, fuzz_eval_tail, fuzz_prepare_tiles, fuzz_dedup, fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
+def fuzz_follow_flows_few_steps(be, rng):
+    """Euler integration against the oracle (torch-CPU grid_sample) for 1 .. 4 steps, where rounding cannot amplify:
+    truncated end points equal (at most one pixel in a thousand may sit on a truncation boundary), any tile shape --
+    widths that are not a multiple of 4 take the scalar prep kernel."""
+    H, W = random_shape(rng)
+    H, W = max(H, 8), max(W, 8)
+    dP = rng.normal(0, rng.uniform(0.5, 6.0), size=(2, H, W)).astype(np.float32)
+    cp = rng.normal(0.5, 1.5, size=(H, W)).astype(np.float32)
+    niter = int(rng.integers(1, 5))
+    fg = cp > 0
+    if fg.sum() == 0:
+        return
+    p = dynamics.follow_flows(dP * fg / 5.0, np.nonzero(fg), niter).int().numpy()
+    pf, _ = be.follow_flows(f32(dP[None]), f32(cp[None]), niter, 0.0)
+    ys, xs = np.nonzero(fg)
+    assert (pf[0][~fg] == -1).all()
+    eq = ((pf[0][ys, xs] >> 16) == p[0]) & ((pf[0][ys, xs] & 0xFFFF) == p[1])
+    assert (~eq).sum() <= max(1, len(ys) // 1000), (int((~eq).sum()), len(ys))
+
+
+TARGETS = [fuzz_follow_flows_few_steps, fuzz_batch_consistency, fuzz_fill_holes_exact_replay, fuzz_fused_planted_labels, fuzz_fused_equals_stages, fuzz_eval_tail, fuzz_prepare_tiles, fuzz_dedup, fuzz_average_tiles, fuzz_contours, fuzz_masks_to_flows, fuzz_get_masks, fuzz_fill_holes, fuzz_class_vote, fuzz_border, fuzz_flow_qc, fuzz_fused]
 
 
 def run(seconds=60.0, seed=0, targets=TARGETS, be=None, verbose=True):
