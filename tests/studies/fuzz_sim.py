@@ -398,6 +398,10 @@ def fuzz_fused_equals_stages(be, rng):
               min_size=int(rng.choice([15, 3, -1, 0])), max_size_fraction=0.4)
     if rng.random() < 0.3:
         kw["remove_border"] = True
+    if rng.random() < 0.3:                          # other thresholds, a short integration (plain Euler kernel), size caps
+        kw["cellprob_threshold"] = float(rng.choice([0.5, -1.0, 2.0]))
+        kw["niter"] = int(rng.choice([10, 31, 32, 200]))
+        kw["max_size_fraction"] = float(rng.choice([0.4, 0.1, 1.0]))
     C = int(rng.choice([0, 2, 5, 7, 10]))
     lg = rng.normal(0, 1.0, size=(1, C, H, W)).astype(np.float32) if C else None
     want_cm = bool(C and rng.random() < 0.5)
