@@ -91,8 +91,9 @@ int cpb_compute_masks_profiled_device(const float* dP, const float* cellprob, co
  * 0 = plain kernel, -1 = CPB_FOLLOW_MERGE from the environment.  All give bit-identical results; the switch
  * exists for A/B measurements and tests. */
 void cpb_debug_set_follow_merge(int mode);
-/* A/B switches of the fused path (value 1 = on, 0 = off, -1 = environment variable of the same name, default on).
- * Every setting gives the same results; they exist for measurements and tests. */
+/* A/B switches of the fused path (value 1 = on, 0 = off, -1 = environment variable of the same name, default on
+ * unless stated).  Every setting gives the same results (CPB_BLEND_EFT: to one ulp; CPB_FILL_EXACT: see below); they
+ * exist for measurements and tests. */
 #define CPB_SWITCH_FOLLOW_MERGE 0   /* CPB_FOLLOW_MERGE: values 0 / 1 / 2 as cpb_debug_set_follow_merge */
 #define CPB_SWITCH_DIFFUSE_QUEUE 1  /* CPB_DIFFUSE_QUEUE: diffusion warps pull label pairs from a queue */
 #define CPB_SWITCH_QC_FUSED 2       /* CPB_QC_FUSED: flow error of isolated labels inside the diffusion warp */
