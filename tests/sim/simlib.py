@@ -16,6 +16,10 @@ SIM_LIB = os.path.join(HERE, "libcpb_sim.so")
 
 
 def build(force=False):
+    # CPB_SIM_LIB: a pre-built variant of the library, e.g. one compiled with -fsanitize=address (then run python with
+    # LD_PRELOAD=$(gcc -print-file-name=libasan.so) and ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0)
+    if os.environ.get("CPB_SIM_LIB"):
+        return os.environ["CPB_SIM_LIB"]
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "cusim.h"),
                                                                  os.path.join(ROOT, "include", "classpose_b200.h")]
     if not force and os.path.exists(SIM_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(SIM_LIB) for d in deps):
